@@ -1,0 +1,304 @@
+"""halo2_vectordb_b200 -- B200 (sm_100a) backend for the KZG-commit / EvaluationDomain hot path of
+erhant/halo2-vectordb's keygen / prove flow (/root/reference/src/scaffold/mod.rs:273,296).
+
+This module is the Python host-side mirror of the upstream interface the C ABI (include/h2v.h)
+stands in for -- halo2-axiom `arithmetic::{best_multiexp, best_fft}`, `poly::kzg::commitment::ParamsKZG`
+and `poly::domain::EvaluationDomain` -- with the same names, argument meaning and error behaviour
+(upstream `assert!` panics become `ValueError`).  It is a thin ctypes layer: all arithmetic runs in
+libh2v.so's CUDA kernels.  There is no CPU fallback and nothing here imports `oracle/`; if the
+native library is missing, importing the compute API raises.
+
+Data convention = halo2curves: numpy uint64 arrays of little-endian limbs in Montgomery form,
+Fr (n, 4), G1Affine (n, 8), G1 Jacobian (12,).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libh2v.so")
+
+H2V_BASIS_MONOMIAL, H2V_BASIS_LAGRANGE = 0, 1
+OP_LAGRANGE_TO_COEFF, OP_COEFF_TO_LAGRANGE, OP_COEFF_TO_EXTENDED, OP_EXTENDED_TO_COEFF, OP_DIVIDE_BY_VANISHING = range(5)
+KERNEL_CLASSES = ["msm_digits", "msm_scan", "msm_scatter", "msm_accumulate", "msm_finish", "msm_reduce", "msm_final", "ntt"]
+
+# every symbol include/h2v.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "h2v_init", "h2v_device_count", "h2v_last_error", "h2v_version",
+    "h2v_srs_load", "h2v_srs_free", "h2v_commit", "h2v_commit_batch", "h2v_commit_batch_dev", "h2v_best_multiexp",
+    "h2v_best_fft", "h2v_domain_new", "h2v_domain_free", "h2v_domain_k", "h2v_domain_extended_k", "h2v_domain_constant",
+    "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
+    "h2v_divide_by_vanishing_poly", "h2v_domain_transform_batch", "h2v_domain_transform_dev",
+    "h2v_selftest_field", "h2v_selftest_group", "h2v_selftest_imad_peak", "h2v_launch_count", "h2v_last_kernel_ms",
+]
+
+
+class H2VError(RuntimeError):
+    pass
+
+
+_lib = None
+_u64p = C.POINTER(C.c_uint64)
+
+
+def lib():
+    """Load libh2v.so (built in-tree by halo2_vectordb_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise H2VError(f"{LIB_PATH} is missing: run `python -m halo2_vectordb_b200.build` "
+                           "(there is no CPU fallback for this path)")
+        L = C.CDLL(LIB_PATH)
+        L.h2v_last_error.restype = C.c_char_p
+        L.h2v_version.restype = C.c_char_p
+        L.h2v_launch_count.restype = C.c_uint64
+        L.h2v_domain_k.restype = C.c_uint32
+        L.h2v_domain_extended_k.restype = C.c_uint32
+        L.h2v_domain_k.argtypes = [C.c_void_p]
+        L.h2v_domain_extended_k.argtypes = [C.c_void_p]
+        L.h2v_init.argtypes = [C.c_int]
+        L.h2v_srs_load.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.h2v_srs_free.argtypes = [C.c_void_p]
+        L.h2v_srs_free.restype = None
+        L.h2v_commit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.h2v_commit_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t, C.c_void_p]
+        L.h2v_commit_batch_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
+        L.h2v_best_multiexp.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.h2v_best_fft.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.h2v_domain_new.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.h2v_domain_free.argtypes = [C.c_void_p]
+        L.h2v_domain_free.restype = None
+        L.h2v_domain_constant.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        for name in ("h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_divide_by_vanishing_poly"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
+        for name in ("h2v_coeff_to_extended", "h2v_extended_to_coeff"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.h2v_domain_transform_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t]
+        L.h2v_domain_transform_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]
+        L.h2v_selftest_field.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.h2v_selftest_group.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.h2v_selftest_imad_peak.argtypes = [C.POINTER(C.c_double)]
+        L.h2v_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        msg = lib().h2v_last_error().decode(errors="replace")
+        if rc == -1:
+            raise ValueError(msg)      # upstream: assert!/panic on a malformed argument
+        raise H2VError(msg)            # CUDA failure: hard error, never a fallback
+
+
+def _fr(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.ndim != 2 or a.shape[1] != 4 or (n is not None and a.shape[0] != n):
+        raise ValueError(f"expected Fr array of shape ({'n' if n is None else n}, 4), got {a.shape}")
+    return a
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def init(device=0):
+    _check(lib().h2v_init(device))
+
+
+def device_count():
+    return lib().h2v_device_count()
+
+
+def launch_count():
+    return int(lib().h2v_launch_count())
+
+
+def last_kernel_ms():
+    buf = (C.c_float * 8)()
+    _check(lib().h2v_last_kernel_ms(buf))
+    return dict(zip(KERNEL_CLASSES, [float(x) for x in buf]))
+
+
+def imad_peak():
+    out = C.c_double()
+    _check(lib().h2v_selftest_imad_peak(C.byref(out)))
+    return out.value
+
+
+# ----------------------------------------------------------------------------- arithmetic.rs
+def best_multiexp(coeffs, bases):
+    """halo2-axiom arithmetic.rs `best_multiexp(coeffs, bases) -> C::Curve` (Jacobian, 12 limbs)."""
+    coeffs = _fr(coeffs)
+    bases = np.ascontiguousarray(bases, dtype=np.uint64)
+    if bases.ndim != 2 or bases.shape[1] != 8:
+        raise ValueError(f"expected G1Affine array of shape (n, 8), got {bases.shape}")
+    if coeffs.shape[0] != bases.shape[0]:
+        raise ValueError("best_multiexp: assertion failed: coeffs.len() == bases.len()")
+    out = np.zeros(12, dtype=np.uint64)
+    _check(lib().h2v_best_multiexp(_ptr(coeffs), _ptr(bases), coeffs.shape[0], _ptr(out)))
+    return out
+
+
+def best_fft(a, omega, log_n):
+    """halo2-axiom arithmetic.rs `best_fft(a, omega, log_n)`; returns the transformed copy."""
+    a = np.array(_fr(a), copy=True)
+    if a.shape[0] != 1 << log_n:
+        raise ValueError("best_fft: assertion failed: a.len() == 1 << log_n")
+    omega = np.ascontiguousarray(omega, dtype=np.uint64).reshape(4)
+    _check(lib().h2v_best_fft(_ptr(a), _ptr(omega), log_n))
+    return a
+
+
+# ----------------------------------------------------------------------------- poly/kzg/commitment.rs
+class ParamsKZG:
+    """halo2-axiom `ParamsKZG<Bn256>` restricted to the commit path: {k, n, g, g_lagrange}."""
+
+    def __init__(self, k, g=None, g_lagrange=None):
+        self.k, self.n = k, 1 << k
+        self._h = C.c_void_p()
+        ptrs = []
+        for b in (g, g_lagrange):
+            if b is None:
+                ptrs.append(None)
+                continue
+            b = np.ascontiguousarray(b, dtype=np.uint64)
+            if b.shape != (self.n, 8):
+                raise ValueError(f"expected ({self.n}, 8) G1Affine bases, got {b.shape}")
+            ptrs.append(b)
+        _check(lib().h2v_srs_load(k, None if ptrs[0] is None else _ptr(ptrs[0]),
+                                  None if ptrs[1] is None else _ptr(ptrs[1]), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().h2v_srs_free(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _commit(self, basis, poly):
+        poly = _fr(poly)
+        out = np.zeros(8, dtype=np.uint64)
+        _check(lib().h2v_commit(self._h, basis, _ptr(poly), poly.shape[0], _ptr(out)))
+        return out
+
+    def commit(self, poly, blind=None):
+        """`commit(&poly, _blind)`: monomial basis; the blind is ignored by KZG upstream. Affine (8,)."""
+        return self._commit(H2V_BASIS_MONOMIAL, poly)
+
+    def commit_lagrange(self, poly, blind=None):
+        return self._commit(H2V_BASIS_LAGRANGE, poly)
+
+    def commit_batch(self, polys, basis=H2V_BASIS_LAGRANGE):
+        """Commit a list of equal-length columns against one basis in a single call -> (n_polys, 8)."""
+        cols = [_fr(p) for p in polys]
+        if not cols:
+            return np.zeros((0, 8), dtype=np.uint64)
+        ln = cols[0].shape[0]
+        if any(c.shape[0] != ln for c in cols):
+            raise ValueError("commit_batch: columns must have equal length")
+        arr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        out = np.zeros((len(cols), 8), dtype=np.uint64)
+        _check(lib().h2v_commit_batch(self._h, basis, arr, len(cols), ln, _ptr(out)))
+        return out
+
+    def commit_batch_dev(self, d_polys_ptr, col_stride, n_polys, length, d_out_ptr, basis=H2V_BASIS_LAGRANGE):
+        """Device-resident columns (raw device pointers, e.g. torch tensor .data_ptr())."""
+        _check(lib().h2v_commit_batch_dev(self._h, basis, d_polys_ptr, col_stride, n_polys, length, d_out_ptr))
+
+
+# ----------------------------------------------------------------------------- poly/domain.rs
+class EvaluationDomain:
+    """halo2-axiom `EvaluationDomain::new(j, k)` and its transforms."""
+
+    _CONST = ["omega", "omega_inv", "extended_omega", "extended_omega_inv", "g_coset", "g_coset_inv",
+              "ifft_divisor", "extended_ifft_divisor"]
+
+    def __init__(self, j, k):
+        self._h = C.c_void_p()
+        _check(lib().h2v_domain_new(j, k, C.byref(self._h)))
+        self.j, self.k, self.n = j, k, 1 << k
+        self.extended_k = int(lib().h2v_domain_extended_k(self._h))
+        self.extended_n = 1 << self.extended_k
+        for i, name in enumerate(self._CONST):
+            setattr(self, name, self._constant(i))
+        self.t_evaluations = [self._constant(8 + i) for i in range(1 << (self.extended_k - k))]
+
+    def _constant(self, which):
+        out = np.zeros(4, dtype=np.uint64)
+        _check(lib().h2v_domain_constant(self._h, which, _ptr(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().h2v_domain_free(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def get_quotient_poly_degree(self):
+        return self.j - 1
+
+    def lagrange_to_coeff(self, a):
+        a = np.array(_fr(a, self.n), copy=True)
+        _check(lib().h2v_lagrange_to_coeff(self._h, _ptr(a)))
+        return a
+
+    def coeff_to_lagrange(self, a):
+        a = np.array(_fr(a, self.n), copy=True)
+        _check(lib().h2v_coeff_to_lagrange(self._h, _ptr(a)))
+        return a
+
+    def coeff_to_extended(self, a):
+        a = _fr(a, self.n)
+        out = np.zeros((self.extended_n, 4), dtype=np.uint64)
+        _check(lib().h2v_coeff_to_extended(self._h, _ptr(a), _ptr(out)))
+        return out
+
+    def extended_to_coeff(self, a):
+        a = _fr(a, self.extended_n)
+        out = np.zeros((self.n * (self.j - 1), 4), dtype=np.uint64)
+        _check(lib().h2v_extended_to_coeff(self._h, _ptr(a), _ptr(out)))
+        return out
+
+    def divide_by_vanishing_poly(self, a):
+        a = np.array(_fr(a, self.extended_n), copy=True)
+        _check(lib().h2v_divide_by_vanishing_poly(self._h, _ptr(a)))
+        return a
+
+    def transform_batch(self, op, cols):
+        """One EvaluationDomain op over a list of independent columns (host arrays) -> list of arrays."""
+        nin = self.extended_n if op in (OP_EXTENDED_TO_COEFF, OP_DIVIDE_BY_VANISHING) else self.n
+        nout = (self.extended_n if op == OP_COEFF_TO_EXTENDED else
+                self.n * (self.j - 1) if op in (OP_EXTENDED_TO_COEFF, OP_DIVIDE_BY_VANISHING) else self.n)
+        ins = [_fr(c, nin) for c in cols]
+        outs = [np.zeros((nout, 4), dtype=np.uint64) for _ in ins]
+        if ins:
+            ia = (C.c_void_p * len(ins))(*[c.ctypes.data for c in ins])
+            oa = (C.c_void_p * len(ins))(*[c.ctypes.data for c in outs])
+            _check(lib().h2v_domain_transform_batch(self._h, op, ia, oa, len(ins)))
+        return outs
+
+    def transform_dev(self, op, d_in_ptr, in_stride, d_out_ptr, out_stride, n_cols):
+        _check(lib().h2v_domain_transform_dev(self._h, op, d_in_ptr, in_stride, d_out_ptr, out_stride, n_cols))
+
+
+# ----------------------------------------------------------------------------- device self-tests
+def selftest_field(field, op, a, b=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros_like(a)
+    bp = None
+    if b is not None:
+        b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+        bp = _ptr(b)
+    _check(lib().h2v_selftest_field(field, op, _ptr(a), bp, a.shape[0], _ptr(out)))
+    return out
+
+
+def selftest_group(mode, p, q):
+    p = np.ascontiguousarray(p, dtype=np.uint64).reshape(-1, 8)
+    q = np.ascontiguousarray(q, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros_like(p)
+    _check(lib().h2v_selftest_group(mode, _ptr(p), _ptr(q), p.shape[0], _ptr(out)))
+    return out

@@ -1,0 +1,348 @@
+// ff.cuh -- BN254 Fr / Fq arithmetic, 8 x 32-bit limbs, Montgomery form (R = 2^256).
+//
+// Replaces (device side) halo2curves bn256::{Fr,Fq} `mul/add/sub/neg/square/invert`
+// (reached from /root/reference/src/scaffold/mod.rs:273,296).
+// Memory layout is byte-identical to halo2curves' `[u64;4]` little-endian Montgomery limbs, so
+// host slices cross the C ABI without conversion.
+//
+// Device path: interleaved (CIOS) Montgomery product on two accumulators -- one holding the
+// products of the even limbs of `a`, one the odd limbs, the second offset by 32 bits -- so every
+// 64-bit partial product lands on an aligned limb pair and a whole row is one carry chain of
+// mad.lo.cc / madc.hi.cc pairs, which ptxas fuses into IMAD.WIDE.U32(.X) on sm_100a.
+// 8*16 wide multiply-adds + 8 low multiplies (the Montgomery quotients) = 136 per product.
+// Host path (same file, !__CUDA_ARCH__): portable u64 arithmetic, used for domain constants and
+// by the host-side unit checks.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define H2V_HD __host__ __device__ __forceinline__
+#define H2V_D __device__ __forceinline__
+#else
+#define H2V_HD inline
+#define H2V_D inline
+#endif
+
+namespace h2v {
+
+struct alignas(16) fe {
+    uint32_t v[8];
+};
+
+// ------------------------------------------------------------------ field parameters
+// SURVEY.md App. B; re-derived in oracle/pyref.py, checked by tests/test_oracle.py::test_constants
+struct FqP {
+    static H2V_HD uint32_t m(int i) {
+        return i == 0 ? 0xd87cfd47u : i == 1 ? 0x3c208c16u : i == 2 ? 0x6871ca8du : i == 3 ? 0x97816a91u
+             : i == 4 ? 0x8181585du : i == 5 ? 0xb85045b6u : i == 6 ? 0xe131a029u : 0x30644e72u;
+    }
+    static H2V_HD uint32_t inv() { return 0xe4866389u; }   // -p^{-1} mod 2^32
+    static H2V_HD uint32_t r1(int i) {                      // R mod p
+        return i == 0 ? 0xc58f0d9du : i == 1 ? 0xd35d438du : i == 2 ? 0xf5c70b3du : i == 3 ? 0x0a78eb28u
+             : i == 4 ? 0x7879462cu : i == 5 ? 0x666ea36fu : i == 6 ? 0x9a07df2fu : 0x0e0a77c1u;
+    }
+    static H2V_HD uint32_t r2(int i) {                      // R^2 mod p
+        return i == 0 ? 0x538afa89u : i == 1 ? 0xf32cfc5bu : i == 2 ? 0xd44501fbu : i == 3 ? 0xb5e71911u
+             : i == 4 ? 0x0a417ff6u : i == 5 ? 0x47ab1effu : i == 6 ? 0xcab8351fu : 0x06d89f71u;
+    }
+};
+struct FrP {
+    static H2V_HD uint32_t m(int i) {
+        return i == 0 ? 0xf0000001u : i == 1 ? 0x43e1f593u : i == 2 ? 0x79b97091u : i == 3 ? 0x2833e848u
+             : i == 4 ? 0x8181585du : i == 5 ? 0xb85045b6u : i == 6 ? 0xe131a029u : 0x30644e72u;
+    }
+    static H2V_HD uint32_t inv() { return 0xefffffffu; }   // -r^{-1} mod 2^32
+    static H2V_HD uint32_t r1(int i) {
+        return i == 0 ? 0x4ffffffbu : i == 1 ? 0xac96341cu : i == 2 ? 0x9f60cd29u : i == 3 ? 0x36fc7695u
+             : i == 4 ? 0x7879462eu : i == 5 ? 0x666ea36fu : i == 6 ? 0x9a07df2fu : 0x0e0a77c1u;
+    }
+    static H2V_HD uint32_t r2(int i) {
+        return i == 0 ? 0xae216da7u : i == 1 ? 0x1bb8e645u : i == 2 ? 0xe35c59e3u : i == 3 ? 0x53fe3ab1u
+             : i == 4 ? 0x53bb8085u : i == 5 ? 0x8c49833du : i == 6 ? 0x7f4e44a5u : 0x0216d0b1u;
+    }
+};
+
+// ------------------------------------------------------------------ small helpers
+H2V_HD fe fe_zero() {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = 0;
+    return r;
+}
+template <class F> H2V_HD fe fe_one() {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = F::r1(i);
+    return r;
+}
+H2V_HD bool fe_is_zero(const fe &a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o |= a.v[i];
+    return o == 0;
+}
+H2V_HD bool fe_eq(const fe &a, const fe &b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o |= a.v[i] ^ b.v[i];
+    return o == 0;
+}
+
+// ------------------------------------------------------------------ add / sub
+#ifdef __CUDA_ARCH__
+// r = a + b (no reduction); both < 2^255 so no carry out of limb 7
+__device__ __forceinline__ void raw_add(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+}
+// r = a - b, returns borrow mask (0xffffffff if a < b)
+__device__ __forceinline__ uint32_t raw_sub(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    uint32_t bw;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(bw)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return bw;
+}
+#else
+inline void raw_add(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    uint64_t c = 0;
+    for (int i = 0; i < 8; ++i) {
+        c += (uint64_t)a[i] + b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+}
+inline uint32_t raw_sub(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    uint64_t bw = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint64_t d = (uint64_t)a[i] - b[i] - bw;
+        r[i] = (uint32_t)d;
+        bw = (d >> 32) & 1;
+    }
+    return bw ? 0xffffffffu : 0u;
+}
+#endif
+
+// if t >= m: t -= m   (t < 2m on entry)
+template <class F> H2V_HD void fe_reduce_once(fe &t) {
+    uint32_t mm[8], d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mm[i] = F::m(i);
+    uint32_t bw = raw_sub(d, t.v, mm);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.v[i] = bw ? t.v[i] : d[i];
+}
+template <class F> H2V_HD fe fe_add(const fe &a, const fe &b) {
+    fe r;
+    raw_add(r.v, a.v, b.v);
+    fe_reduce_once<F>(r);
+    return r;
+}
+template <class F> H2V_HD fe fe_sub(const fe &a, const fe &b) {
+    fe r;
+    uint32_t bw = raw_sub(r.v, a.v, b.v);
+    uint32_t mm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mm[i] = F::m(i) & bw;
+    raw_add(r.v, r.v, mm);
+    return r;
+}
+template <class F> H2V_HD fe fe_neg(const fe &a) {
+    if (fe_is_zero(a)) return a;
+    fe r;
+    uint32_t mm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mm[i] = F::m(i);
+    raw_sub(r.v, mm, a.v);
+    return r;
+}
+template <class F> H2V_HD fe fe_dbl(const fe &a) { return fe_add<F>(a, a); }
+
+// ------------------------------------------------------------------ Montgomery product
+#ifdef __CUDA_ARCH__
+// acc[0..7] = sum_t (x[2t] * y) << (64 t)            (four independent 64-bit products)
+__device__ __forceinline__ void row_mul(uint32_t *acc, const uint32_t *x, uint32_t y) {
+    asm("mul.lo.u32 %0, %8, %12;\n\t"
+        "mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t"
+        "mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t"
+        "mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t"
+        "mul.hi.u32 %7, %11, %12;"
+        : "=&r"(acc[0]), "=&r"(acc[1]), "=&r"(acc[2]), "=&r"(acc[3]), "=&r"(acc[4]), "=&r"(acc[5]), "=&r"(acc[6]), "=&r"(acc[7])
+        : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(y));
+}
+// acc[0..7] += sum_t (x[2t] * y) << (64 t); returns the carry out of limb 7 (0 or 1)
+__device__ __forceinline__ uint32_t row_mad(uint32_t *acc, const uint32_t *x, uint32_t y) {
+    uint32_t c;
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=&r"(c)
+        : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(y));
+    return c;
+}
+// Shift-and-accumulate for the offset accumulator when its partner drops one limb:
+//   lo0 += stray (carry c0);  out[0..7] = {in[2..7],0,0} + sum_t (x[2t] * y) << (64 t) + c0
+__device__ __forceinline__ void row_mad_shift(uint32_t *out, const uint32_t *in, uint32_t &lo0, uint32_t stray,
+                                              const uint32_t *x, uint32_t y) {
+    asm("add.cc.u32 %8, %8, %9;\n\t"
+        "madc.lo.cc.u32 %0, %10, %14, %15;\n\t"
+        "madc.hi.cc.u32 %1, %10, %14, %16;\n\t"
+        "madc.lo.cc.u32 %2, %11, %14, %17;\n\t"
+        "madc.hi.cc.u32 %3, %11, %14, %18;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %19;\n\t"
+        "madc.hi.cc.u32 %5, %12, %14, %20;\n\t"
+        "madc.lo.cc.u32 %6, %13, %14, 0;\n\t"
+        "madc.hi.u32 %7, %13, %14, 0;"
+        : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "=&r"(out[7]),
+          "+r"(lo0)
+        : "r"(stray), "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(y),
+          "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]), "r"(in[7]));
+}
+
+// One CIOS row.  On entry (FIRST == false): T = lo + hi * 2^32 with lo[0] == 0 from the previous
+// reduction.  T <- (T >> 32) + a * bi, then T += q * m with q chosen so the low limb vanishes.
+// The accumulators swap roles: new lo = old hi, new hi = old lo >> 64, old lo[1] is the stray limb.
+template <class F, bool FIRST>
+__device__ __forceinline__ void mont_row(uint32_t *lo, uint32_t *hi, const uint32_t *a, uint32_t bi) {
+    // (lo, hi) are the accumulators in their roles for THIS row (caller swaps them every row).
+    uint32_t mm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mm[i] = F::m(i);
+    if (FIRST) {
+        row_mul(lo, a, bi);
+        row_mul(hi, a + 1, bi);
+    } else {
+        // on entry `hi` holds the OLD low accumulator (limb 0 is zero, limb 1 is the stray) and `lo` the old high one
+        uint32_t nh[8];
+        row_mad_shift(nh, hi, lo[0], hi[1], a + 1, bi);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hi[i] = nh[i];
+        uint32_t c = row_mad(lo, a, bi);
+        hi[7] += c;
+    }
+    uint32_t q = lo[0] * F::inv();
+    row_mad(hi, mm + 1, q);              // cannot carry out: T < 2 * 2^32 * m < 2^288
+    uint32_t c = row_mad(lo, mm, q);
+    hi[7] += c;
+}
+
+template <class F> __device__ __forceinline__ fe fe_mul(const fe &a, const fe &b) {
+    uint32_t e[8], o[8];
+    mont_row<F, true>(e, o, a.v, b.v[0]);
+    mont_row<F, false>(o, e, a.v, b.v[1]);
+    mont_row<F, false>(e, o, a.v, b.v[2]);
+    mont_row<F, false>(o, e, a.v, b.v[3]);
+    mont_row<F, false>(e, o, a.v, b.v[4]);
+    mont_row<F, false>(o, e, a.v, b.v[5]);
+    mont_row<F, false>(e, o, a.v, b.v[6]);
+    mont_row<F, false>(o, e, a.v, b.v[7]);
+    // after 8 rows: low accumulator = o (o[0] == 0), high = e.  result = e + (o >> 32)
+    fe r;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, 0;"
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7])
+        : "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]),
+          "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
+    fe_reduce_once<F>(r);
+    return r;
+}
+#else
+template <class F> inline fe fe_mul(const fe &a, const fe &b) {
+    uint32_t t[10] = {0};
+    for (int i = 0; i < 8; ++i) {
+        uint64_t c = 0;
+        for (int j = 0; j < 8; ++j) {
+            c += (uint64_t)a.v[j] * b.v[i] + t[j];
+            t[j] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[8];
+        t[8] = (uint32_t)c;
+        t[9] = (uint32_t)(c >> 32);
+        uint32_t q = t[0] * F::inv();
+        c = (uint64_t)q * F::m(0) + t[0];
+        c >>= 32;
+        for (int j = 1; j < 8; ++j) {
+            c += (uint64_t)q * F::m(j) + t[j];
+            t[j - 1] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[8];
+        t[7] = (uint32_t)c;
+        t[8] = t[9] + (uint32_t)(c >> 32);
+    }
+    fe r;
+    for (int i = 0; i < 8; ++i) r.v[i] = t[i];
+    fe_reduce_once<F>(r);   // t[8] == 0 here because m < 2^254
+    return r;
+}
+#endif
+template <class F> H2V_HD fe fe_sqr(const fe &a) { return fe_mul<F>(a, a); }
+
+template <class F> H2V_HD fe fe_to_mont(const fe &canon) {
+    fe r2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r2.v[i] = F::r2(i);
+    return fe_mul<F>(canon, r2);
+}
+template <class F> H2V_HD fe fe_from_mont(const fe &a) {
+    fe one = fe_zero();
+    one.v[0] = 1;
+    return fe_mul<F>(a, one);
+}
+// a^e, e given as 8 little-endian 32-bit limbs
+template <class F> H2V_HD fe fe_pow(const fe &a, const uint32_t *e, int nbits = 256) {
+    fe acc = fe_one<F>();
+    for (int i = nbits - 1; i >= 0; --i) {
+        acc = fe_sqr<F>(acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) acc = fe_mul<F>(acc, a);
+    }
+    return acc;
+}
+template <class F> H2V_HD fe fe_pow_u64(const fe &a, uint64_t e) {
+    uint32_t ee[8] = {(uint32_t)e, (uint32_t)(e >> 32), 0, 0, 0, 0, 0, 0};
+    return fe_pow<F>(a, ee, 64);
+}
+// a^(m-2) (Fermat); a == 0 -> 0
+template <class F> H2V_HD fe fe_inv(const fe &a) {
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = F::m(i);
+    e[0] -= 2;   // low limbs of p and r are >= 2
+    return fe_pow<F>(a, e, 254);
+}
+
+}  // namespace h2v

@@ -1,0 +1,945 @@
+// h2v.cu -- C ABI (include/h2v.h) over the sm_100a NTT / MSM kernels: handles, workspaces,
+// streams, host<->device staging.  No CPU fallback: every compute entry point needs a CUDA device.
+//
+// Host-side mirror of the upstream objects this library stands in for:
+//   h2v_srs     <-> halo2-axiom poly/kzg/commitment.rs ParamsKZG            (scaffold mod.rs:260)
+//   h2v_domain  <-> halo2-axiom poly/domain.rs EvaluationDomain             (scaffold mod.rs:273,296)
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "h2v.h"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+using namespace h2v;
+
+namespace {
+
+thread_local std::string g_err;
+int g_device = 0;
+std::atomic<uint64_t> g_launches{0};
+float g_last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+std::mutex g_ms_mu;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(x)                                                                                      \
+    do {                                                                                           \
+        cudaError_t e_ = (x);                                                                      \
+        if (e_ != cudaSuccess) return fail(H2V_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); \
+    } while (0)
+#define LAUNCHED()                                                                                  \
+    do {                                                                                            \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                         \
+        cudaError_t e_ = cudaGetLastError();                                                        \
+        if (e_ != cudaSuccess) return fail(H2V_ECUDA, "kernel launch failed (%s:%d): %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+int use_device() {
+    cudaError_t e = cudaSetDevice(g_device);
+    if (e != cudaSuccess) return fail(H2V_ECUDA, "cudaSetDevice(%d): %s (libh2v has no CPU fallback)", g_device, cudaGetErrorString(e));
+    return H2V_OK;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return H2V_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(H2V_ENOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        }
+        cap = bytes;
+        return H2V_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Timer {   // CUDA-event stopwatch on one stream, accumulating per kernel class
+    cudaStream_t st;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
+    explicit Timer(cudaStream_t s) : st(s) {}
+    void begin(int cls) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        spans.push_back({cls, {a, b}});
+    }
+    void end() { cudaEventRecord(spans.back().second.second, st); }
+    void collect(bool reset) {   // call after the stream is synchronised
+        std::lock_guard<std::mutex> lk(g_ms_mu);
+        if (reset)
+            for (float &v : g_last_ms) v = 0;
+        for (auto &s : spans) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, s.second.first, s.second.second);
+            g_last_ms[s.first] += ms;
+            cudaEventDestroy(s.second.first);
+            cudaEventDestroy(s.second.second);
+        }
+        spans.clear();
+    }
+};
+
+// ================================================================== NTT host side
+const size_t NTT_SMEM_BYTES = (2 * 2048 + H2V_NTT_PLANE_PAD) * 16;
+std::once_flag g_ntt_attr_once;
+
+struct NttPlan {
+    int P;
+    int S[4];
+};
+NttPlan ntt_plan(int L) {
+    NttPlan pl;
+    pl.P = (L + 8) / 9;
+    if (pl.P < 1) pl.P = 1;
+    int base = L / pl.P, rem = L % pl.P;
+    for (int i = 0; i < pl.P; ++i) pl.S[i] = base + (i < rem ? 1 : 0);
+    return pl;
+}
+
+// dst != src.  Columns are independent; pass 0 goes src -> dst, later passes run in place on dst.
+int run_ntt(cudaStream_t st, const fe *src, size_t src_stride, fe *dst, size_t dst_stride, int L, const fe *tw,
+            const fe *pre, uint32_t pre_mod, uint32_t n_in, const fe *post, uint32_t post_mod, uint32_t n_out,
+            size_t n_cols) {
+    if (n_cols == 0) return H2V_OK;
+    if ((const void *)src == (const void *)dst) return fail(H2V_EINVAL, "run_ntt: in-place transform needs distinct buffers");
+    std::call_once(g_ntt_attr_once, [] {
+        cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM_BYTES);
+    });
+    NttPass p;
+    memset(&p, 0, sizeof p);
+    p.tw = tw;
+    p.pre = pre;
+    p.pre_mod = pre_mod ? pre_mod : 1;
+    p.post = post;
+    p.post_mod = post_mod ? post_mod : 1;
+    p.n_in = n_in;
+    p.n_out = n_out;
+    p.L = L;
+    p.src_stride = src_stride;
+    p.dst_stride = dst_stride;
+    for (size_t c0 = 0; c0 < n_cols; c0 += 32768) {
+        unsigned cols = (unsigned)std::min<size_t>(32768, n_cols - c0);
+        p.src = src + c0 * src_stride;
+        p.dst = dst + c0 * dst_stride;
+        if (L <= 2) {
+            p.first = p.last = 1;
+            ntt_tiny_kernel<<<cols, 32, 0, st>>>(p);
+            LAUNCHED();
+            continue;
+        }
+        NttPlan pl = ntt_plan(L);
+        int t0 = 0;
+        for (int i = 0; i < pl.P; ++i) {
+            int S = pl.S[i];
+            p.S = S;
+            p.t0 = t0;
+            p.first = (i == 0);
+            p.last = (i == pl.P - 1);
+            p.logT = p.first ? std::min(11 - S, L - S) : std::min(11 - S, t0);
+            unsigned threads = 1u << (S + p.logT - 3);
+            unsigned tiles = 1u << (L - S - p.logT);
+            size_t smem = ((size_t)2 * (1u << (S + p.logT)) + H2V_NTT_PLANE_PAD) * 16;
+            ntt_pass_kernel<<<dim3(tiles, cols), threads, smem, st>>>(p);
+            LAUNCHED();
+            t0 += S;
+        }
+    }
+    return H2V_OK;
+}
+
+int build_twiddles(cudaStream_t st, DevBuf &buf, const fe &omega, int L) {
+    size_t half = L >= 1 ? ((size_t)1 << (L - 1)) : 1;
+    int rc = buf.ensure(std::max<size_t>(half, 1) * sizeof(fe));
+    if (rc) return rc;
+    TwiddleParams tp;
+    memset(&tp, 0, sizeof tp);
+    fe w = omega;
+    for (int b = 0; b < 28; ++b) {
+        tp.pows[b] = w;
+        w = fe_sqr<Fr>(w);
+    }
+    tp.half_n = (uint32_t)half;
+    twiddle_kernel<<<(unsigned)((half + 255) / 256), 256, 0, st>>>(buf.as<fe>(), tp);
+    LAUNCHED();
+    return H2V_OK;
+}
+
+fe fe_from_u64x4(const uint64_t *l) {
+    fe r;
+    memcpy(r.v, l, 32);
+    return r;
+}
+void fe_to_u64x4(const fe &a, uint64_t *l) { memcpy(l, a.v, 32); }
+fe fr_from_small(uint64_t x) {
+    fe c = fe_zero();
+    c.v[0] = (uint32_t)x;
+    c.v[1] = (uint32_t)(x >> 32);
+    return fe_to_mont<Fr>(c);
+}
+
+// Fr::ROOT_OF_UNITY (order 2^28) and Fr::ZETA, canonical -- SURVEY.md App. B
+const uint32_t FR_ROOT[8] = {0x60c37c9cu, 0xd34f1ed9u, 0xd39329c8u, 0x3215cf6du, 0x3dd31f74u, 0x98865ea9u, 0x166d18b7u, 0x03ddb9f5u};
+const uint32_t FR_ZETA[8] = {0x36636f23u, 0xb8ca0b2du, 0xec2bc5e9u, 0xcc37a73fu, 0x3fd84104u, 0x048b6e19u, 0xe131a029u, 0x30644e72u};
+const int FR_S = 28;
+
+}  // namespace
+
+struct h2v_domain {
+    uint32_t j, k, ek, nt;
+    fe omega, omega_inv, ext_omega, ext_omega_inv, g_coset, g_coset_inv, ifft_divisor, ext_ifft_divisor;
+    fe t_eval[64];
+    // device constants: [0..2] coset-in (1, z, z^2); [3] ifft_divisor; [4..6] ext_ifft_divisor * (1, z^2, z);
+    // [8 .. 8+nt) t_evaluations
+    DevBuf dconst;
+    DevBuf tw[4];   // 0: omega, 1: omega_inv, 2: ext_omega, 3: ext_omega_inv
+    bool tw_ready[4] = {false, false, false, false};
+    DevBuf stage_a, stage_b;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+};
+
+namespace {
+
+int domain_twiddles(h2v_domain *d, int which, const fe **out) {
+    if (!d->tw_ready[which]) {
+        const fe &w = which == 0 ? d->omega : which == 1 ? d->omega_inv : which == 2 ? d->ext_omega : d->ext_omega_inv;
+        int rc = build_twiddles(d->stream, d->tw[which], w, which < 2 ? (int)d->k : (int)d->ek);
+        if (rc) return rc;
+        d->tw_ready[which] = true;
+    }
+    *out = d->tw[which].as<fe>();
+    return H2V_OK;
+}
+
+// enqueue one EvaluationDomain transform on device-resident columns
+int domain_op_dev(h2v_domain *d, int op, const fe *in, size_t in_stride, fe *out, size_t out_stride, size_t n_cols) {
+    const fe *tw;
+    const fe *dc = d->dconst.as<fe>();
+    const uint32_t n = 1u << d->k, en = 1u << d->ek;
+    int rc;
+    switch (op) {
+    case H2V_OP_LAGRANGE_TO_COEFF:
+        if ((rc = domain_twiddles(d, 1, &tw))) return rc;
+        return run_ntt(d->stream, in, in_stride, out, out_stride, d->k, tw, nullptr, 1, n, dc + 3, 1, n, n_cols);
+    case H2V_OP_COEFF_TO_LAGRANGE:
+        if ((rc = domain_twiddles(d, 0, &tw))) return rc;
+        return run_ntt(d->stream, in, in_stride, out, out_stride, d->k, tw, nullptr, 1, n, nullptr, 1, n, n_cols);
+    case H2V_OP_COEFF_TO_EXTENDED:
+        if ((rc = domain_twiddles(d, 2, &tw))) return rc;
+        return run_ntt(d->stream, in, in_stride, out, out_stride, d->ek, tw, dc, 3, n, nullptr, 1, en, n_cols);
+    case H2V_OP_EXTENDED_TO_COEFF:
+        if ((rc = domain_twiddles(d, 3, &tw))) return rc;
+        return run_ntt(d->stream, in, in_stride, out, out_stride, d->ek, tw, nullptr, 1, en, dc + 4, 3, n * (d->j - 1), n_cols);
+    case H2V_OP_DIVIDE_BY_VANISHING:
+        if ((rc = domain_twiddles(d, 3, &tw))) return rc;
+        return run_ntt(d->stream, in, in_stride, out, out_stride, d->ek, tw, dc + 8, d->nt, en, dc + 4, 3, n * (d->j - 1), n_cols);
+    default:
+        return fail(H2V_EINVAL, "unknown domain op %d", op);
+    }
+}
+size_t op_in_len(const h2v_domain *d, int op) {
+    return (op == H2V_OP_EXTENDED_TO_COEFF || op == H2V_OP_DIVIDE_BY_VANISHING) ? ((size_t)1 << d->ek) : ((size_t)1 << d->k);
+}
+size_t op_out_len(const h2v_domain *d, int op) {
+    if (op == H2V_OP_COEFF_TO_EXTENDED) return (size_t)1 << d->ek;
+    if (op == H2V_OP_EXTENDED_TO_COEFF || op == H2V_OP_DIVIDE_BY_VANISHING) return ((size_t)1 << d->k) * (d->j - 1);
+    return (size_t)1 << d->k;
+}
+
+// ================================================================== MSM host side
+struct MsmCfg {
+    uint32_t c, W, G;
+};
+uint32_t windows_for(uint32_t c) { return (255 + c - 1) / c; }
+// cost model in group additions per column: bucket adds + ~3 per bucket for the reduction
+MsmCfg choose_cfg(size_t n, bool precomp) {
+    MsmCfg best = {1, 255, precomp ? 1u : 255u};
+    double best_cost = 1e300;
+    for (uint32_t c = 2; c <= 22; ++c) {
+        uint32_t W = windows_for(c);
+        double nb = (double)(1u << (c - 1));
+        double cost = precomp ? (double)W * n + 3.0 * nb : (double)W * (n + 3.0 * nb) + 10.0 * c * W;
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = {c, W, precomp ? 1u : W};
+        }
+    }
+    return best;
+}
+void fill_kadd(MsmShape &sh) {
+    // K = sum_{j<W} (2^(c-1) - 1) << (j c), as 9 x 32-bit limbs
+    uint32_t k[10] = {0};
+    uint64_t half = ((uint64_t)1 << (sh.c - 1)) - 1;
+    for (uint32_t j = 0; j < sh.W; ++j) {
+        uint32_t bit = j * sh.c, w = bit >> 5, s = bit & 31;
+        // add half << s at limb w (half < 2^21, so it spans at most 2 limbs)
+        unsigned __int128 v = (unsigned __int128)half << s;
+        uint64_t carry = 0;
+        for (uint32_t q = w; q < 10; ++q) {
+            uint64_t add = (uint64_t)(uint32_t)(v & 0xffffffffu);
+            v >>= 32;
+            uint64_t sum = (uint64_t)k[q] + add + carry;
+            k[q] = (uint32_t)sum;
+            carry = sum >> 32;
+            if (v == 0 && carry == 0) break;
+        }
+    }
+    for (int i = 0; i < 9; ++i) sh.kadd[i] = k[i];
+}
+
+struct MsmWorkspace {
+    DevBuf buf;
+};
+struct Carver {
+    char *base;
+    size_t off = 0;
+    explicit Carver(void *b) : base((char *)b) {}
+    template <class T> T *take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T *p = reinterpret_cast<T *>(base + off);
+        off += count * sizeof(T);
+        return p;
+    }
+};
+uint32_t pick_chunk(uint64_t max_entries) {
+    uint64_t c = max_entries / (148ull * 2048ull);
+    if (c < 4) c = 4;
+    if (c > 32) c = 32;
+    return (uint32_t)c;
+}
+struct MsmLayout {
+    size_t bytes;
+    uint32_t *keys, *counts, *offsets, *cursor;
+    uint2 *entries;
+    xyzz *buckets, *edges, *S[2], *A[2];
+    uint32_t nthreads, n_buckets, l1;
+};
+MsmLayout msm_layout(void *base, const MsmShape &sh, uint32_t cols) {
+    MsmLayout L;
+    Carver cv(base);
+    uint64_t ent = (uint64_t)cols * sh.W * sh.n;
+    L.n_buckets = cols * sh.G * sh.nb;
+    L.nthreads = (uint32_t)((ent + sh.chunk - 1) / sh.chunk);
+    L.l1 = (sh.nb + 31) / 32;
+    size_t l2 = (L.l1 + 31) / 32;
+    L.keys = cv.take<uint32_t>(ent);
+    L.counts = cv.take<uint32_t>(L.n_buckets);
+    L.offsets = cv.take<uint32_t>((size_t)L.n_buckets + 1);
+    L.cursor = cv.take<uint32_t>(L.n_buckets);
+    L.entries = cv.take<uint2>(ent);
+    L.buckets = cv.take<xyzz>(L.n_buckets);
+    L.edges = cv.take<xyzz>((size_t)2 * L.nthreads);
+    L.S[0] = cv.take<xyzz>((size_t)cols * sh.G * L.l1);
+    L.A[0] = cv.take<xyzz>((size_t)cols * sh.G * L.l1);
+    L.S[1] = cv.take<xyzz>((size_t)cols * sh.G * l2);
+    L.A[1] = cv.take<xyzz>((size_t)cols * sh.G * l2);
+    L.bytes = cv.off + 256;
+    return L;
+}
+
+const size_t MSM_WS_BUDGET = (size_t)6 << 30;   // per handle; columns per launch are sized to fit
+
+// d_scalars: n_cols columns of `len` Fr (Montgomery), col_stride apart.  points: bases (raw) or
+// window tables (precomputed, level stride `pstride`).  Results: affine and/or Jacobian per column.
+int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_stride, size_t n_cols, size_t len,
+            const affine *points, MsmCfg cfg, size_t pstride, affine *d_out_aff, jacobian *d_out_jac, Timer *tm) {
+    if (n_cols == 0) return H2V_OK;
+    if (len == 0) {   // empty sum = identity (zeros in both encodings)
+        if (d_out_aff) CU(cudaMemsetAsync(d_out_aff, 0, n_cols * sizeof(affine), st));
+        if (d_out_jac) CU(cudaMemsetAsync(d_out_jac, 0, n_cols * sizeof(jacobian), st));
+        return H2V_OK;
+    }
+    MsmShape sh;
+    memset(&sh, 0, sizeof sh);
+    sh.n = (uint32_t)len;
+    sh.c = cfg.c;
+    sh.W = cfg.W;
+    sh.G = cfg.G;
+    sh.nb = 1u << (cfg.c - 1);
+    sh.pstride = (uint32_t)pstride;
+    fill_kadd(sh);
+    // columns per launch: workspace budget, 2^31 entries, grid.z
+    size_t max_cols = std::min<size_t>(n_cols, 16384);
+    sh.chunk = pick_chunk((uint64_t)max_cols * sh.W * sh.n);
+    while (max_cols > 1) {
+        sh.chunk = pick_chunk((uint64_t)max_cols * sh.W * sh.n);
+        MsmLayout probe = msm_layout(nullptr, sh, (uint32_t)max_cols);
+        uint64_t ent = (uint64_t)max_cols * sh.W * sh.n;
+        uint64_t nbk = (uint64_t)max_cols * sh.G * sh.nb;
+        if (probe.bytes <= MSM_WS_BUDGET && ent < (1ull << 31) && nbk < (1ull << 31)) break;
+        max_cols = (max_cols + 1) / 2;
+    }
+    sh.chunk = pick_chunk((uint64_t)max_cols * sh.W * sh.n);
+    {
+        MsmLayout probe = msm_layout(nullptr, sh, (uint32_t)max_cols);
+        uint64_t ent = (uint64_t)max_cols * sh.W * sh.n;
+        if (ent >= (1ull << 32) - 64) return fail(H2V_EINVAL, "MSM too large: %llu bucket entries", (unsigned long long)ent);
+        int rc = ws.buf.ensure(probe.bytes);
+        if (rc) return rc;
+    }
+    for (size_t c0 = 0; c0 < n_cols; c0 += max_cols) {
+        uint32_t cols = (uint32_t)std::min(max_cols, n_cols - c0);
+        sh.n_cols = cols;
+        MsmLayout L = msm_layout(ws.buf.p, sh, cols);
+        const fe *sc = d_scalars + c0 * col_stride;
+        CU(cudaMemsetAsync(L.counts, 0, (size_t)L.n_buckets * sizeof(uint32_t), st));
+        unsigned gx = (unsigned)((len + 255) / 256);
+        if (tm) tm->begin(0);
+        msm_digits_kernel<<<dim3(gx, cols), 256, 0, st>>>(sc, col_stride, L.keys, L.counts, sh);
+        LAUNCHED();
+        if (tm) { tm->end(); tm->begin(1); }
+        msm_scan_kernel<<<1, 1024, 0, st>>>(L.counts, L.offsets, L.cursor, L.n_buckets);
+        LAUNCHED();
+        if (tm) { tm->end(); tm->begin(2); }
+        msm_scatter_kernel<<<dim3(gx, sh.W, cols), 256, 0, st>>>(L.keys, L.cursor, L.entries, sh);
+        LAUNCHED();
+        if (tm) { tm->end(); tm->begin(3); }
+        msm_accumulate_kernel<<<(L.nthreads + 127) / 128, 128, 0, st>>>(L.entries, L.offsets, L.n_buckets, points, L.buckets,
+                                                                        L.edges, sh.chunk);
+        LAUNCHED();
+        if (tm) { tm->end(); tm->begin(4); }
+        msm_finish_kernel<<<(L.n_buckets + 127) / 128, 128, 0, st>>>(L.offsets, L.n_buckets, L.edges, L.buckets, sh.chunk);
+        LAUNCHED();
+        if (tm) { tm->end(); tm->begin(5); }
+        // reduction tree over each (column, group)
+        const uint32_t n_inst = cols * sh.G;
+        const xyzz *Sin = L.buckets, *Ain = nullptr;
+        uint32_t cnt = sh.nb, shift = 0;
+        int pp = 0;
+        do {
+            uint32_t cnt_out = (cnt + 31) / 32;
+            uint32_t total = n_inst * cnt_out;
+            msm_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(Sin, Ain, L.S[pp], L.A[pp], cnt, cnt_out, n_inst, shift);
+            LAUNCHED();
+            Sin = L.S[pp];
+            Ain = L.A[pp];
+            pp ^= 1;
+            cnt = cnt_out;
+            shift += 5;
+        } while (cnt > 1);
+        if (tm) { tm->end(); tm->begin(6); }
+        msm_final_kernel<<<(cols + 31) / 32, 32, 0, st>>>(Sin, Ain, cols, sh.G, sh.c, d_out_aff ? d_out_aff + c0 : nullptr,
+                                                          d_out_jac ? d_out_jac + c0 : nullptr);
+        LAUNCHED();
+        if (tm) tm->end();
+    }
+    return H2V_OK;
+}
+
+}  // namespace
+
+struct h2v_srs {
+    uint32_t k;
+    size_t n;
+    DevBuf table[2];     // [basis]: W levels of n affine points (level 0 = the bases)
+    bool have[2] = {false, false};
+    MsmCfg cfg;
+    MsmWorkspace ws;
+    DevBuf stage, out;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+};
+
+// ================================================================== C ABI
+extern "C" {
+
+const char *h2v_last_error(void) { return g_err.c_str(); }
+const char *h2v_version(void) { return "h2v-b200 0.1 (sm_100a)"; }
+uint64_t h2v_launch_count(void) { return g_launches.load(); }
+
+int h2v_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int h2v_init(int device) {
+    int n = h2v_device_count();
+    if (n <= 0) return fail(H2V_ECUDA, "no CUDA device visible (libh2v has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(H2V_EINVAL, "device %d out of range (have %d)", device, n);
+    g_device = device;
+    CU(cudaSetDevice(device));
+    CU(cudaFree(0));
+    return H2V_OK;
+}
+int h2v_last_kernel_ms(float out[8]) {
+    std::lock_guard<std::mutex> lk(g_ms_mu);
+    memcpy(out, g_last_ms, sizeof g_last_ms);
+    return H2V_OK;
+}
+
+// ---------------------------------------------------------------- SRS / commit
+int h2v_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, h2v_srs_t *out) {
+    if (!out) return fail(H2V_EINVAL, "h2v_srs_load: out is NULL");
+    *out = nullptr;
+    if (k > 26) return fail(H2V_EINVAL, "h2v_srs_load: k = %u unsupported", k);
+    int rc = use_device();
+    if (rc) return rc;
+    h2v_srs *s = new h2v_srs();
+    s->k = k;
+    s->n = (size_t)1 << k;
+    s->cfg = choose_cfg(s->n, true);
+    // cap the table footprint at 24 GB per basis by shrinking the number of levels (bigger windows)
+    while ((size_t)s->cfg.W * s->n * sizeof(affine) > ((size_t)24 << 30) && s->cfg.c < 24) {
+        s->cfg.c++;
+        s->cfg.W = windows_for(s->cfg.c);
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(H2V_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    const uint64_t *src[2] = {g, g_lagrange};
+    for (int b = 0; b < 2; ++b) {
+        if (!src[b]) continue;
+        rc = s->table[b].ensure((size_t)s->cfg.W * s->n * sizeof(affine));
+        if (rc) { h2v_srs_free(s); return rc; }
+        e = cudaMemcpyAsync(s->table[b].p, src[b], s->n * sizeof(affine), cudaMemcpyHostToDevice, s->stream);
+        if (e != cudaSuccess) { h2v_srs_free(s); return fail(H2V_ECUDA, "SRS upload: %s", cudaGetErrorString(e)); }
+        for (uint32_t lvl = 1; lvl < s->cfg.W; ++lvl) {
+            msm_precompute_kernel<<<(unsigned)((s->n + 127) / 128), 128, 0, s->stream>>>(s->table[b].as<affine>(), (uint32_t)s->n, lvl,
+                                                                                        s->cfg.c);
+            g_launches.fetch_add(1);
+        }
+        s->have[b] = true;
+    }
+    e = cudaStreamSynchronize(s->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { h2v_srs_free(s); return fail(H2V_ECUDA, "SRS table build: %s", cudaGetErrorString(e)); }
+    *out = s;
+    return H2V_OK;
+}
+void h2v_srs_free(h2v_srs_t s) {
+    if (!s) return;
+    cudaSetDevice(g_device);
+    s->table[0].release();
+    s->table[1].release();
+    s->ws.buf.release();
+    s->stage.release();
+    s->out.release();
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int h2v_commit_batch_dev(h2v_srs_t s, int basis, const void *d_polys, size_t col_stride, size_t n_polys, size_t len,
+                         void *d_out_affine) {
+    if (!s) return fail(H2V_EINVAL, "commit: NULL srs");
+    if (basis != 0 && basis != 1) return fail(H2V_EINVAL, "commit: basis must be 0 or 1");
+    if (!s->have[basis]) return fail(H2V_EINVAL, "commit: basis %d was not loaded", basis);
+    if (len > s->n) return fail(H2V_EINVAL, "commit: poly length %zu exceeds n = %zu", len, s->n);
+    if (n_polys && (!d_polys || !d_out_affine)) return fail(H2V_EINVAL, "commit: NULL buffer");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    Timer tm(s->stream);
+    rc = run_msm(s->stream, s->ws, (const fe *)d_polys, col_stride, n_polys, len, s->table[basis].as<affine>(), s->cfg, s->n,
+                 (affine *)d_out_affine, nullptr, &tm);
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    tm.collect(true);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(H2V_ECUDA, "commit: %s", cudaGetErrorString(e));
+    return H2V_OK;
+}
+
+int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_t n_polys, size_t len, uint64_t *out_affine) {
+    if (!s) return fail(H2V_EINVAL, "commit: NULL srs");
+    if (basis != 0 && basis != 1) return fail(H2V_EINVAL, "commit: basis must be 0 or 1");
+    if (!s->have[basis]) return fail(H2V_EINVAL, "commit: basis %d was not loaded", basis);
+    if (len > s->n) return fail(H2V_EINVAL, "commit: poly length %zu exceeds n = %zu", len, s->n);
+    if (n_polys == 0) return H2V_OK;
+    if (!polys || !out_affine) return fail(H2V_EINVAL, "commit: NULL buffer");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    // stage at most ~1 GB of scalars at a time
+    size_t stride = std::max<size_t>(len, 1);
+    size_t per = std::max<size_t>(1, ((size_t)1 << 30) / (stride * sizeof(fe)));
+    per = std::min(per, n_polys);
+    if ((rc = s->stage.ensure(per * stride * sizeof(fe)))) return rc;
+    if ((rc = s->out.ensure(per * sizeof(affine)))) return rc;
+    for (size_t c0 = 0; c0 < n_polys; c0 += per) {
+        size_t cols = std::min(per, n_polys - c0);
+        for (size_t c = 0; c < cols; ++c) {
+            if (!polys[c0 + c] && len) return fail(H2V_EINVAL, "commit: polys[%zu] is NULL", c0 + c);
+            if (len) CU(cudaMemcpyAsync(s->stage.as<fe>() + c * stride, polys[c0 + c], len * sizeof(fe), cudaMemcpyHostToDevice, s->stream));
+        }
+        rc = run_msm(s->stream, s->ws, s->stage.as<fe>(), stride, cols, len, s->table[basis].as<affine>(), s->cfg, s->n,
+                     s->out.as<affine>(), nullptr, nullptr);
+        if (rc) { cudaStreamSynchronize(s->stream); return rc; }
+        CU(cudaMemcpyAsync(out_affine + 8 * c0, s->out.p, cols * sizeof(affine), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return H2V_OK;
+}
+int h2v_commit(h2v_srs_t s, int basis, const uint64_t *poly, size_t len, uint64_t out_affine[8]) {
+    const uint64_t *cols[1] = {poly};
+    return h2v_commit_batch(s, basis, cols, 1, len, out_affine);
+}
+
+int h2v_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t out_jacobian[12]) {
+    if (!out_jacobian) return fail(H2V_EINVAL, "best_multiexp: NULL output");
+    if (n && (!coeffs || !bases)) return fail(H2V_EINVAL, "best_multiexp: NULL input");
+    if (n >= ((size_t)1 << 27)) return fail(H2V_EINVAL, "best_multiexp: n = %zu unsupported", n);
+    int rc = use_device();
+    if (rc) return rc;
+    if (n == 0) {
+        memset(out_jacobian, 0, 96);
+        return H2V_OK;
+    }
+    static std::mutex mu;
+    static MsmWorkspace ws;
+    static DevBuf sc, pts, outb;
+    static cudaStream_t st = nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if ((rc = sc.ensure(n * sizeof(fe)))) return rc;
+    if ((rc = pts.ensure(n * sizeof(affine)))) return rc;
+    if ((rc = outb.ensure(sizeof(jacobian)))) return rc;
+    CU(cudaMemcpyAsync(sc.p, coeffs, n * sizeof(fe), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(pts.p, bases, n * sizeof(affine), cudaMemcpyHostToDevice, st));
+    MsmCfg cfg = choose_cfg(n, false);
+    rc = run_msm(st, ws, sc.as<fe>(), n, 1, n, pts.as<affine>(), cfg, n, nullptr, outb.as<jacobian>(), nullptr);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    CU(cudaMemcpyAsync(out_jacobian, outb.p, sizeof(jacobian), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return H2V_OK;
+}
+
+// ---------------------------------------------------------------- FFT / domain
+int h2v_best_fft(uint64_t *a, const uint64_t omega[4], uint32_t log_n) {
+    if (!a || !omega) return fail(H2V_EINVAL, "best_fft: NULL argument");
+    if (log_n > 27) return fail(H2V_EINVAL, "best_fft: log_n = %u unsupported", log_n);
+    int rc = use_device();
+    if (rc) return rc;
+    static std::mutex mu;
+    static DevBuf A, B, TW;
+    static cudaStream_t st = nullptr;
+    static fe cached_omega;
+    static int cached_L = -1;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    size_t n = (size_t)1 << log_n;
+    if ((rc = A.ensure(n * sizeof(fe)))) return rc;
+    if ((rc = B.ensure(n * sizeof(fe)))) return rc;
+    fe w = fe_from_u64x4(omega);
+    if (cached_L != (int)log_n || !fe_eq(w, cached_omega)) {   // twiddles are kept for repeated (omega, log_n)
+        if ((rc = build_twiddles(st, TW, w, (int)log_n))) return rc;
+        cached_L = (int)log_n;
+        cached_omega = w;
+    }
+    CU(cudaMemcpyAsync(A.p, a, n * sizeof(fe), cudaMemcpyHostToDevice, st));
+    rc = run_ntt(st, A.as<fe>(), n, B.as<fe>(), n, (int)log_n, TW.as<fe>(), nullptr, 1, (uint32_t)n, nullptr, 1, (uint32_t)n, 1);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    CU(cudaMemcpyAsync(a, B.p, n * sizeof(fe), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return H2V_OK;
+}
+
+int h2v_domain_new(uint32_t j, uint32_t k, h2v_domain_t *out) {
+    if (!out) return fail(H2V_EINVAL, "domain_new: out is NULL");
+    *out = nullptr;
+    if (j < 2) return fail(H2V_EINVAL, "domain_new: j = %u (need j >= 2)", j);
+    uint32_t ek = k;
+    while (((uint64_t)1 << ek) < ((uint64_t)1 << k) * (j - 1)) ++ek;
+    if (ek > 27 || ek - k > 6) return fail(H2V_EINVAL, "domain_new: extended_k = %u unsupported", ek);
+    int rc = use_device();
+    if (rc) return rc;
+    h2v_domain *d = new h2v_domain();
+    d->j = j;
+    d->k = k;
+    d->ek = ek;
+    d->nt = 1u << (ek - k);
+    fe root;
+    memcpy(root.v, FR_ROOT, 32);
+    root = fe_to_mont<Fr>(root);
+    d->ext_omega = root;
+    for (uint32_t i = ek; i < (uint32_t)FR_S; ++i) d->ext_omega = fe_sqr<Fr>(d->ext_omega);
+    d->omega = d->ext_omega;
+    for (uint32_t i = k; i < ek; ++i) d->omega = fe_sqr<Fr>(d->omega);
+    d->omega_inv = fe_inv<Fr>(d->omega);
+    d->ext_omega_inv = fe_inv<Fr>(d->ext_omega);
+    fe zeta;
+    memcpy(zeta.v, FR_ZETA, 32);
+    d->g_coset = fe_to_mont<Fr>(zeta);
+    d->g_coset_inv = fe_sqr<Fr>(d->g_coset);
+    d->ifft_divisor = fe_inv<Fr>(fr_from_small((uint64_t)1 << k));
+    d->ext_ifft_divisor = fe_inv<Fr>(fr_from_small((uint64_t)1 << ek));
+    fe cur = d->g_coset, one = fe_one<Fr>();
+    for (uint32_t i = 0; i < d->nt; ++i) {
+        fe v = fe_sub<Fr>(fe_pow_u64<Fr>(cur, (uint64_t)1 << k), one);
+        d->t_eval[i] = fe_inv<Fr>(v);
+        cur = fe_mul<Fr>(cur, d->ext_omega);
+    }
+    fe hc[8 + 64];
+    for (auto &x : hc) x = fe_zero();
+    hc[0] = one;
+    hc[1] = d->g_coset;
+    hc[2] = d->g_coset_inv;
+    hc[3] = d->ifft_divisor;
+    hc[4] = d->ext_ifft_divisor;
+    hc[5] = fe_mul<Fr>(d->ext_ifft_divisor, d->g_coset_inv);
+    hc[6] = fe_mul<Fr>(d->ext_ifft_divisor, d->g_coset);
+    for (uint32_t i = 0; i < d->nt; ++i) hc[8 + i] = d->t_eval[i];
+    cudaError_t e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        rc = d->dconst.ensure(sizeof hc);
+        if (rc) { h2v_domain_free(d); return rc; }
+        e = cudaMemcpy(d->dconst.p, hc, sizeof hc, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        h2v_domain_free(d);
+        return fail(H2V_ECUDA, "domain_new: %s", cudaGetErrorString(e));
+    }
+    *out = d;
+    return H2V_OK;
+}
+void h2v_domain_free(h2v_domain_t d) {
+    if (!d) return;
+    cudaSetDevice(g_device);
+    d->dconst.release();
+    for (auto &t : d->tw) t.release();
+    d->stage_a.release();
+    d->stage_b.release();
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+uint32_t h2v_domain_k(h2v_domain_t d) { return d ? d->k : 0; }
+uint32_t h2v_domain_extended_k(h2v_domain_t d) { return d ? d->ek : 0; }
+int h2v_domain_constant(h2v_domain_t d, int which, uint64_t out[4]) {
+    if (!d || !out) return fail(H2V_EINVAL, "domain_constant: NULL argument");
+    const fe *p = nullptr;
+    switch (which) {
+    case 0: p = &d->omega; break;
+    case 1: p = &d->omega_inv; break;
+    case 2: p = &d->ext_omega; break;
+    case 3: p = &d->ext_omega_inv; break;
+    case 4: p = &d->g_coset; break;
+    case 5: p = &d->g_coset_inv; break;
+    case 6: p = &d->ifft_divisor; break;
+    case 7: p = &d->ext_ifft_divisor; break;
+    default:
+        if (which >= 8 && (uint32_t)(which - 8) < d->nt) p = &d->t_eval[which - 8];
+    }
+    if (!p) return fail(H2V_EINVAL, "domain_constant: index %d out of range", which);
+    fe_to_u64x4(*p, out);
+    return H2V_OK;
+}
+
+int h2v_domain_transform_dev(h2v_domain_t d, int op, const void *d_in, size_t in_stride, void *d_out, size_t out_stride,
+                             size_t n_cols) {
+    if (!d) return fail(H2V_EINVAL, "transform: NULL domain");
+    if (n_cols && (!d_in || !d_out)) return fail(H2V_EINVAL, "transform: NULL buffer");
+    if (op < 0 || op > H2V_OP_DIVIDE_BY_VANISHING) return fail(H2V_EINVAL, "unknown domain op %d", op);
+    // the output column doubles as the work buffer of the in-place passes: it needs the full transform size
+    const size_t work_len = (size_t)1 << (op >= H2V_OP_COEFF_TO_EXTENDED ? d->ek : d->k);
+    if (in_stride < op_in_len(d, op) || out_stride < work_len)
+        return fail(H2V_EINVAL, "transform: stride shorter than the column (out_stride must cover 2^%s)",
+                    op >= H2V_OP_COEFF_TO_EXTENDED ? "extended_k" : "k");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(d->mu);
+    Timer tm(d->stream);
+    tm.begin(7);
+    rc = domain_op_dev(d, op, (const fe *)d_in, in_stride, (fe *)d_out, out_stride, n_cols);
+    tm.end();
+    cudaError_t e = cudaStreamSynchronize(d->stream);
+    tm.collect(true);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(H2V_ECUDA, "transform: %s", cudaGetErrorString(e));
+    return H2V_OK;
+}
+
+int h2v_domain_transform_batch(h2v_domain_t d, int op, const uint64_t *const *in, uint64_t *const *out, size_t n_cols) {
+    if (!d) return fail(H2V_EINVAL, "transform: NULL domain");
+    if (op < 0 || op > H2V_OP_DIVIDE_BY_VANISHING) return fail(H2V_EINVAL, "unknown domain op %d", op);
+    if (n_cols == 0) return H2V_OK;
+    if (!in || !out) return fail(H2V_EINVAL, "transform: NULL buffer");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(d->mu);
+    const size_t nin = op_in_len(d, op), nout = op_out_len(d, op);
+    const size_t out_stride = std::max(nout, (size_t)1 << (op >= H2V_OP_COEFF_TO_EXTENDED ? d->ek : d->k));
+    size_t per = std::max<size_t>(1, ((size_t)1 << 30) / (out_stride * sizeof(fe)));
+    per = std::min(per, n_cols);
+    if ((rc = d->stage_a.ensure(per * nin * sizeof(fe)))) return rc;
+    if ((rc = d->stage_b.ensure(per * out_stride * sizeof(fe)))) return rc;
+    for (size_t c0 = 0; c0 < n_cols; c0 += per) {
+        size_t cols = std::min(per, n_cols - c0);
+        for (size_t c = 0; c < cols; ++c) {
+            if (!in[c0 + c] || !out[c0 + c]) return fail(H2V_EINVAL, "transform: column %zu is NULL", c0 + c);
+            CU(cudaMemcpyAsync(d->stage_a.as<fe>() + c * nin, in[c0 + c], nin * sizeof(fe), cudaMemcpyHostToDevice, d->stream));
+        }
+        rc = domain_op_dev(d, op, d->stage_a.as<fe>(), nin, d->stage_b.as<fe>(), out_stride, cols);
+        if (rc) { cudaStreamSynchronize(d->stream); return rc; }
+        for (size_t c = 0; c < cols; ++c)
+            CU(cudaMemcpyAsync(out[c0 + c], d->stage_b.as<fe>() + c * out_stride, nout * sizeof(fe), cudaMemcpyDeviceToHost, d->stream));
+        CU(cudaStreamSynchronize(d->stream));
+    }
+    return H2V_OK;
+}
+static int one_col(h2v_domain_t d, int op, const uint64_t *in, uint64_t *out) {
+    const uint64_t *i1[1] = {in};
+    uint64_t *o1[1] = {out};
+    return h2v_domain_transform_batch(d, op, i1, o1, 1);
+}
+int h2v_lagrange_to_coeff(h2v_domain_t d, uint64_t *a) { return one_col(d, H2V_OP_LAGRANGE_TO_COEFF, a, a); }
+int h2v_coeff_to_lagrange(h2v_domain_t d, uint64_t *a) { return one_col(d, H2V_OP_COEFF_TO_LAGRANGE, a, a); }
+int h2v_coeff_to_extended(h2v_domain_t d, const uint64_t *in, uint64_t *out) { return one_col(d, H2V_OP_COEFF_TO_EXTENDED, in, out); }
+int h2v_extended_to_coeff(h2v_domain_t d, const uint64_t *in, uint64_t *out) { return one_col(d, H2V_OP_EXTENDED_TO_COEFF, in, out); }
+int h2v_divide_by_vanishing_poly(h2v_domain_t d, uint64_t *a) {
+    if (!d || !a) return fail(H2V_EINVAL, "divide_by_vanishing_poly: NULL argument");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(d->mu);
+    size_t en = (size_t)1 << d->ek;
+    if ((rc = d->stage_b.ensure(en * sizeof(fe)))) return rc;
+    CU(cudaMemcpyAsync(d->stage_b.p, a, en * sizeof(fe), cudaMemcpyHostToDevice, d->stream));
+    fr_scale_mod_kernel<<<dim3((unsigned)((en + 255) / 256), 1), 256, 0, d->stream>>>(d->stage_b.as<fe>(), en, d->dconst.as<fe>() + 8, d->nt,
+                                                                                     (uint32_t)en);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(a, d->stage_b.p, en * sizeof(fe), cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    return H2V_OK;
+}
+
+}  // extern "C"
+
+// ================================================================== self-tests
+namespace {
+template <class F> __global__ void selftest_field_kernel(int op, const fe *a, const fe *b, fe *o, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x = a[i], y = b ? b[i] : fe_zero(), r;
+    if (op == 0) r = fe_mul<F>(x, y);
+    else if (op == 1) r = fe_add<F>(x, y);
+    else if (op == 2) r = fe_sub<F>(x, y);
+    else r = fe_inv<F>(x);
+    o[i] = r;
+}
+__global__ void selftest_group_kernel(int mode, const affine *p, const affine *q, affine *o, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xyzz acc = xyzz_from_affine(p[i]);
+    if (mode == 0) {
+        xyzz_add_mixed(acc, q[i]);
+    } else if (mode == 1) {
+        // give the second operand a non-trivial ZZ by doubling and adding back: q' = 2q + (-q) = q
+        xyzz t = xyzz_from_affine(q[i]);
+        t = xyzz_double(t);
+        xyzz_add_mixed(t, affine_neg(q[i]));
+        xyzz_add(acc, t);
+    } else {
+        acc = xyzz_double(acc);
+    }
+    o[i] = xyzz_to_affine(acc);
+}
+__global__ void imad_probe_kernel(uint64_t *out, uint32_t iters, uint32_t seed) {
+    uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+    uint64_t acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = k + threadIdx.x;
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s ^= acc[k];
+    if (s == 0x1234567812345678ull) out[0] = s;   // keep the chain alive
+}
+}  // namespace
+
+extern "C" {
+int h2v_selftest_field(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out) {
+    int rc = use_device();
+    if (rc) return rc;
+    if (!a || !out || n == 0) return fail(H2V_EINVAL, "selftest_field: bad argument");
+    DevBuf A, B, O;
+    if ((rc = A.ensure(n * 32)) || (rc = B.ensure(n * 32)) || (rc = O.ensure(n * 32))) return rc;
+    CU(cudaMemcpy(A.p, a, n * 32, cudaMemcpyHostToDevice));
+    if (b) CU(cudaMemcpy(B.p, b, n * 32, cudaMemcpyHostToDevice));
+    unsigned g = (unsigned)((n + 127) / 128);
+    if (field == 0) selftest_field_kernel<FrP><<<g, 128>>>(op, A.as<fe>(), b ? B.as<fe>() : nullptr, O.as<fe>(), n);
+    else selftest_field_kernel<FqP><<<g, 128>>>(op, A.as<fe>(), b ? B.as<fe>() : nullptr, O.as<fe>(), n);
+    LAUNCHED();
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, O.p, n * 32, cudaMemcpyDeviceToHost));
+    A.release(); B.release(); O.release();
+    return H2V_OK;
+}
+int h2v_selftest_group(int mode, const uint64_t *p, const uint64_t *q, size_t n, uint64_t *out_affine) {
+    int rc = use_device();
+    if (rc) return rc;
+    if (!p || !q || !out_affine || n == 0) return fail(H2V_EINVAL, "selftest_group: bad argument");
+    DevBuf A, B, O;
+    if ((rc = A.ensure(n * 64)) || (rc = B.ensure(n * 64)) || (rc = O.ensure(n * 64))) return rc;
+    CU(cudaMemcpy(A.p, p, n * 64, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(B.p, q, n * 64, cudaMemcpyHostToDevice));
+    selftest_group_kernel<<<(unsigned)((n + 63) / 64), 64>>>(mode, A.as<affine>(), B.as<affine>(), O.as<affine>(), n);
+    LAUNCHED();
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out_affine, O.p, n * 64, cudaMemcpyDeviceToHost));
+    A.release(); B.release(); O.release();
+    return H2V_OK;
+}
+int h2v_selftest_imad_peak(double *out) {
+    int rc = use_device();
+    if (rc) return rc;
+    if (!out) return fail(H2V_EINVAL, "selftest_imad_peak: NULL");
+    DevBuf O;
+    if ((rc = O.ensure(64))) return rc;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, g_device));
+    const unsigned blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0));
+        imad_probe_kernel<<<blocks, threads>>>(O.as<uint64_t>(), iters, 12345u + rep);
+        LAUNCHED();
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double rate = (double)blocks * threads * iters * 8.0 / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    O.release();
+    *out = best;
+    return H2V_OK;
+}
+}

@@ -1,0 +1,120 @@
+/*
+ * h2v.h -- C ABI of libh2v.so: the B200 (sm_100a) backend for the KZG-commit and
+ * EvaluationDomain hot path underneath erhant/halo2-vectordb's keygen / prove flow.
+ *
+ * The reference has no FFI seam on this path: its scaffold (/root/reference/src/scaffold/mod.rs:273
+ * create_pk, :296 gen_snark_shplonk) calls in-process Rust generics of the un-vendored halo2-axiom
+ * crate (Cargo.toml:19-28).  Each entry point below names the upstream function a patched
+ * halo2-axiom would forward to it; INTEGRATION.md shows the Rust binding.
+ *
+ * Conventions (identical to halo2curves bn256, so Rust slices cross the boundary by pointer):
+ *   Fr / Fq element   4 x uint64_t little-endian limbs, MONTGOMERY form (R = 2^256)      32 B
+ *   G1Affine          {x, y} Fq                       identity = (0, 0)                  64 B
+ *   G1 (Jacobian)     {x, y, z} Fq                    identity z = 0                     96 B
+ * All pointers are HOST pointers unless the parameter name starts with `d_`.
+ * Return value: 0 on success, a negative H2V_E* code otherwise; h2v_last_error() (thread-local)
+ * describes the failure.  There is NO CPU fallback: without a usable CUDA device every compute
+ * entry point fails with H2V_ECUDA.  Entry points are thread-safe; calls on one handle serialise.
+ * One process drives one GPU (h2v_init), the multi-GPU layout is one process per GPU with
+ * polynomial columns partitioned across processes; no collective is needed.
+ */
+#ifndef H2V_H
+#define H2V_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H2V_OK 0
+#define H2V_EINVAL (-1)   /* bad argument (the reference would panic on the same input: assert_eq!(len, 1 << log_n) etc.) */
+#define H2V_ECUDA (-2)    /* CUDA runtime error or no device */
+#define H2V_ENOMEM (-3)
+
+#define H2V_BASIS_MONOMIAL 0 /* ParamsKZG::g          -> commit          */
+#define H2V_BASIS_LAGRANGE 1 /* ParamsKZG::g_lagrange -> commit_lagrange */
+
+typedef struct h2v_srs *h2v_srs_t;       /* device-resident ParamsKZG bases (+ window tables) */
+typedef struct h2v_domain *h2v_domain_t; /* EvaluationDomain: constants + device twiddles      */
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+/* Select the CUDA device this process drives (call once per process, before anything else;
+ * default device 0).  Mirrors nothing upstream: the reference is CPU-only. */
+int h2v_init(int device);
+int h2v_device_count(void);
+const char *h2v_last_error(void);
+const char *h2v_version(void);
+
+/* ---- KZG commit path ---------------------------------------------------------------------- */
+/* halo2-axiom poly/kzg/commitment.rs ParamsKZG {k, n, g, g_lagrange}: upload both bases
+ * (n = 2^k G1Affine each) and build the per-window tables 2^(jc) * B_i once.
+ * `g` or `g_lagrange` may be NULL if that basis is never used.  (scaffold: gen_srs, mod.rs:260) */
+int h2v_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, h2v_srs_t *out);
+void h2v_srs_free(h2v_srs_t srs);
+/* ParamsKZG::commit(poly, _blind) / commit_lagrange(poly, _blind) = best_multiexp(poly, bases[..len]);
+ * the Blind argument is ignored by KZG upstream, so it is not part of the ABI.  len <= 2^k.
+ * Output: the unique affine representative (G1::to_affine()). */
+int h2v_commit(h2v_srs_t srs, int basis, const uint64_t *poly, size_t len, uint64_t out_affine[8]);
+/* The same for `n_polys` columns in one call (create_proof commits every advice / lookup /
+ * permutation column against the same bases; this is the preferred entry point). polys[i] -> len Fr. */
+int h2v_commit_batch(h2v_srs_t srs, int basis, const uint64_t *const *polys, size_t n_polys, size_t len,
+                     uint64_t *out_affine /* n_polys x 8 */);
+/* Device-resident variant: d_polys = n_polys columns of `len` Fr, `col_stride` elements apart;
+ * d_out_affine = n_polys x 64 B on the device.  Asynchronous work is complete on return. */
+int h2v_commit_batch_dev(h2v_srs_t srs, int basis, const void *d_polys, size_t col_stride, size_t n_polys, size_t len,
+                         void *d_out_affine);
+/* halo2-axiom arithmetic.rs best_multiexp(coeffs, bases) -> C::Curve, exact shape: arbitrary bases,
+ * no handle, Jacobian result (any representative; compare after to_affine). */
+int h2v_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t out_jacobian[12]);
+
+/* ---- EvaluationDomain --------------------------------------------------------------------- */
+/* arithmetic.rs best_fft(a, omega, log_n): in place, natural order in and out. */
+int h2v_best_fft(uint64_t *a, const uint64_t omega[4], uint32_t log_n);
+/* poly/domain.rs EvaluationDomain::new(j, k) */
+int h2v_domain_new(uint32_t j, uint32_t k, h2v_domain_t *out);
+void h2v_domain_free(h2v_domain_t dom);
+uint32_t h2v_domain_k(h2v_domain_t dom);
+uint32_t h2v_domain_extended_k(h2v_domain_t dom);
+/* scalar getters: 0 omega, 1 omega_inv, 2 extended_omega, 3 extended_omega_inv, 4 g_coset, 5 g_coset_inv,
+ * 6 ifft_divisor, 7 extended_ifft_divisor, 8+i t_evaluations[i] */
+int h2v_domain_constant(h2v_domain_t dom, int which, uint64_t out[4]);
+/* EvaluationDomain::lagrange_to_coeff / coeff_to_lagrange (private fft/ifft on the 2^k domain); in place */
+int h2v_lagrange_to_coeff(h2v_domain_t dom, uint64_t *a);
+int h2v_coeff_to_lagrange(h2v_domain_t dom, uint64_t *a);
+/* EvaluationDomain::coeff_to_extended: in 2^k, out 2^extended_k */
+int h2v_coeff_to_extended(h2v_domain_t dom, const uint64_t *in, uint64_t *out);
+/* EvaluationDomain::extended_to_coeff: in 2^extended_k, out 2^k * (j-1) */
+int h2v_extended_to_coeff(h2v_domain_t dom, const uint64_t *in, uint64_t *out);
+/* EvaluationDomain::divide_by_vanishing_poly: in place on 2^extended_k */
+int h2v_divide_by_vanishing_poly(h2v_domain_t dom, uint64_t *a);
+/* batched over independent columns (host pointers, one per column) */
+#define H2V_OP_LAGRANGE_TO_COEFF 0
+#define H2V_OP_COEFF_TO_LAGRANGE 1
+#define H2V_OP_COEFF_TO_EXTENDED 2
+#define H2V_OP_EXTENDED_TO_COEFF 3
+#define H2V_OP_DIVIDE_BY_VANISHING 4 /* fused: divide_by_vanishing_poly then extended_to_coeff */
+int h2v_domain_transform_batch(h2v_domain_t dom, int op, const uint64_t *const *in, uint64_t *const *out, size_t n_cols);
+/* device-resident: columns `in_stride` / `out_stride` elements apart; d_in != d_out */
+int h2v_domain_transform_dev(h2v_domain_t dom, int op, const void *d_in, size_t in_stride, void *d_out, size_t out_stride,
+                             size_t n_cols);
+
+/* ---- device self-tests (used by tests/ to localise failures; not part of the drop-in surface) */
+/* out[i] = a[i] (op) b[i] computed by the device field routines; field 0 = Fr, 1 = Fq;
+ * op 0 mul, 1 add, 2 sub, 3 inverse (b ignored) */
+int h2v_selftest_field(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);
+/* out_affine[i] = affine(p[i] + q[i]) through the XYZZ mixed add (mode 0), full add (mode 1) or
+ * doubling of p (mode 2); p, q affine */
+int h2v_selftest_group(int mode, const uint64_t *p, const uint64_t *q, size_t n, uint64_t *out_affine);
+/* dependent-free IMAD.WIDE throughput probe: returns wide multiply-adds per second */
+int h2v_selftest_imad_peak(double *out_wmac_per_s);
+/* kernels launched by this process so far (for bench.py's gpu_launches) */
+uint64_t h2v_launch_count(void);
+/* device-side timing of the last commit_batch_dev / transform_dev call, in milliseconds per kernel class:
+ * MSM 0 digits 1 scan 2 scatter 3 accumulate 4 finish 5 reduce 6 final; NTT 7 */
+int h2v_last_kernel_ms(float out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
