@@ -1,0 +1,286 @@
+"""GPU parity: the CUDA path (through the C ABI of libh2v.so) against the CPU oracle, the committed
+golden vectors, and size-independent properties.  Bit-exact everywhere (integer arithmetic)."""
+import random
+
+import numpy as np
+import pytest
+
+from common import fr_arr, g1_arr, golden, ipt, ival
+from oracle import oracle as O
+from oracle import pyref as P
+
+pytestmark = pytest.mark.gpu
+
+FQ_ONE = O.to_mont(O.ints_to_limbs([1]), O.FQ)[0]
+
+
+def jac(aff):
+    z = FQ_ONE if np.asarray(aff).any() else np.zeros(4, dtype=np.uint64)
+    return np.concatenate([aff, z])
+
+
+# ----------------------------------------------------------------------------- field / group layer
+@pytest.mark.parametrize("field,nm", [(0, "fr"), (1, "fq")])
+def test_device_field_ops(h2v, field, nm):
+    mod = P.R if field == 0 else P.P
+    rnd = random.Random(field)
+    vals = [0, 1, mod - 1, mod - 2, 2, (1 << 253), mod >> 1] + [rnd.randrange(mod) for _ in range(2041)]
+    a = O.to_mont(O.ints_to_limbs(vals), field)
+    b = O.to_mont(O.ints_to_limbs(list(reversed(vals))), field)
+    for op, opn in ((0, "mul"), (1, "add"), (2, "sub")):
+        got = h2v.selftest_field(field, op, a, b)
+        exp = np.stack([O.field_op(f"{nm}_{opn}", a[i], b[i]) for i in range(len(a))])
+        assert (got == exp).all(), opn
+    got = h2v.selftest_field(field, 3, a[1:65])
+    exp = np.stack([O.field_op(f"{nm}_inv", a[i]) for i in range(1, 65)])
+    assert (got == exp).all()
+
+
+def test_device_group_law(h2v):
+    pts = O.gen_bases(64)
+    p, q = pts[:32].copy(), pts[32:].copy()
+    q[1] = p[1]                                            # P + P
+    x, y = O.g1_affine_to_ints(p[2])
+    q[2] = O.g1_affine_from_ints((x, (-y) % P.P))          # P + (-P)
+    q[3] = 0                                               # P + 0
+    p[4] = 0                                               # 0 + Q
+    p[5] = 0
+    q[5] = 0                                               # 0 + 0
+    for mode in (0, 1):
+        got = h2v.selftest_group(mode, p, q)
+        for i in range(32):
+            assert (got[i] == O.g1_to_affine(O.g1_add_mixed(jac(p[i]), q[i]))).all(), (mode, i)
+    got = h2v.selftest_group(2, p, q)
+    for i in range(32):
+        assert (got[i] == O.g1_to_affine(O.g1_double(jac(p[i])))).all(), i
+
+
+# ----------------------------------------------------------------------------- best_fft
+def test_best_fft_golden(h2v):
+    for v in golden()["fft"]:
+        a = fr_arr([ival(x) for x in v["a"]])
+        w = fr_arr([ival(v["omega"])])[0]
+        got = O.fr_to_ints(h2v.best_fft(a, w, v["log_n"]))
+        assert got == [ival(x) for x in v["out"]], v["log_n"]
+
+
+@pytest.mark.parametrize("log_n", list(range(0, 15)) + [16, 17, 18, 19])
+def test_best_fft_vs_oracle(h2v, log_n):
+    a = O.fr_fill(1 << log_n, 1000 + log_n, mode=log_n % 2)
+    w = fr_arr([P.omega_for(log_n)])[0]
+    assert (h2v.best_fft(a, w, log_n) == O.best_fft(a, w, log_n)).all()
+
+
+def test_best_fft_other_root_and_linearity(h2v):
+    L = 12
+    w = fr_arr([pow(P.omega_for(L), 5, P.R)])[0]           # another primitive 2^L-th root
+    a, b = O.fr_fill(1 << L, 1), O.fr_fill(1 << L, 2)
+    fa, fb = h2v.best_fft(a, w, L), h2v.best_fft(b, w, L)
+    assert (fa == O.best_fft(a, w, L)).all()
+    s = fr_arr([(x + y) % P.R for x, y in zip(O.fr_to_ints(a), O.fr_to_ints(b))])
+    fs = O.fr_to_ints(h2v.best_fft(s, w, L))
+    assert fs == [(x + y) % P.R for x, y in zip(O.fr_to_ints(fa), O.fr_to_ints(fb))]
+
+
+@pytest.mark.parametrize("log_n", [20, 22, 24])
+def test_best_fft_large_properties(h2v, log_n):
+    """Full-size sweep sizes: Horner spot checks against the definition + inverse round trip."""
+    n = 1 << log_n
+    a = O.fr_fill(n, 31 + log_n)
+    wi = P.omega_for(log_n)
+    w = fr_arr([wi])[0]
+    out = h2v.best_fft(a, w, log_n)
+    rnd = random.Random(log_n)
+    for j in [0, 1, n - 1] + rnd.sample(range(n), 3):
+        x = fr_arr([pow(wi, j, P.R)])[0]
+        assert (O.fr_eval_poly(a, x) == out[j]).all(), j
+    back = h2v.best_fft(out, fr_arr([pow(wi, -1, P.R)])[0], log_n)
+    ninv = fr_arr([pow(n, -1, P.R)])[0]
+    idx = [0, 5, n // 2, n - 1]
+    for j in idx:
+        assert (O.field_op("fr_mul", back[j], ninv) == a[j]).all()
+
+
+def test_best_fft_rejects_bad_length(h2v):
+    with pytest.raises(ValueError):
+        h2v.best_fft(O.fr_fill(12, 1), fr_arr([P.omega_for(4)])[0], 4)
+
+
+# ----------------------------------------------------------------------------- EvaluationDomain
+def test_domain_golden(h2v):
+    for v in golden()["domain"]:
+        d = h2v.EvaluationDomain(v["j"], v["k"])
+        assert d.extended_k == v["extended_k"]
+        for nm in ("omega", "omega_inv", "extended_omega", "extended_omega_inv", "g_coset", "g_coset_inv",
+                   "ifft_divisor", "extended_ifft_divisor"):
+            assert O.fr_to_ints(getattr(d, nm))[0] == ival(v[nm]), nm
+        assert [O.fr_to_ints(t)[0] for t in d.t_evaluations] == [ival(x) for x in v["t_evaluations"]]
+        a = fr_arr([ival(x) for x in v["a"]])
+        h = fr_arr([ival(x) for x in v["h"]])
+        assert O.fr_to_ints(d.lagrange_to_coeff(a)) == [ival(x) for x in v["lagrange_to_coeff"]]
+        assert O.fr_to_ints(d.coeff_to_lagrange(a)) == [ival(x) for x in v["coeff_to_lagrange"]]
+        assert O.fr_to_ints(d.coeff_to_extended(a)) == [ival(x) for x in v["coeff_to_extended"]]
+        assert O.fr_to_ints(d.divide_by_vanishing_poly(h)) == [ival(x) for x in v["divide_by_vanishing_poly"]]
+        assert O.fr_to_ints(d.extended_to_coeff(h)) == [ival(x) for x in v["extended_to_coeff"]]
+        d.close()
+
+
+@pytest.mark.parametrize("k", [3, 6, 9, 10, 13, 16])
+def test_domain_vs_oracle(h2v, k):
+    d, od = h2v.EvaluationDomain(4, k), O.EvaluationDomain(4, k)
+    a = O.fr_fill(1 << k, 70 + k, mode=1)
+    assert (d.lagrange_to_coeff(a) == od.lagrange_to_coeff(a)).all()
+    assert (d.coeff_to_lagrange(a) == od.coeff_to_lagrange(a)).all()
+    e, oe = d.coeff_to_extended(a), od.coeff_to_extended(a)
+    assert (e == oe).all()
+    h = O.fr_fill(1 << d.extended_k, 90 + k)
+    assert (d.extended_to_coeff(h) == od.extended_to_coeff(h)).all()
+    assert (d.divide_by_vanishing_poly(h) == od.divide_by_vanishing_poly(h)).all()
+    fused = d.transform_batch(h2v.OP_DIVIDE_BY_VANISHING, [h, e])
+    assert (fused[0] == od.extended_to_coeff(od.divide_by_vanishing_poly(h))).all()
+    assert (fused[1] == od.extended_to_coeff(od.divide_by_vanishing_poly(oe))).all()
+    d.close()
+
+
+def test_domain_batch_matches_single(h2v):
+    k = 11
+    d, od = h2v.EvaluationDomain(4, k), O.EvaluationDomain(4, k)
+    cols = [O.fr_fill(1 << k, 200 + i, mode=i % 2) for i in range(7)]
+    for op, f in ((h2v.OP_LAGRANGE_TO_COEFF, od.lagrange_to_coeff), (h2v.OP_COEFF_TO_LAGRANGE, od.coeff_to_lagrange),
+                  (h2v.OP_COEFF_TO_EXTENDED, od.coeff_to_extended)):
+        outs = d.transform_batch(op, cols)
+        for c, o in zip(cols, outs):
+            assert (o == f(c)).all()
+    assert d.transform_batch(h2v.OP_LAGRANGE_TO_COEFF, []) == []
+    d.close()
+
+
+def test_domain_roundtrip_k20(h2v):
+    """config 4 size: coset round trip extended_to_coeff(coeff_to_extended(a)) = a || 0 and iNTT(NTT) = id."""
+    d = h2v.EvaluationDomain(4, 20)
+    a = O.fr_fill(d.n, 2020, mode=1)
+    assert (d.coeff_to_lagrange(d.lagrange_to_coeff(a)) == a).all()
+    ext = d.coeff_to_extended(a)
+    back = d.extended_to_coeff(ext)
+    assert (back[: d.n] == a).all() and not back[d.n:].any()
+    # spot-check the coset evaluations against the definition: ext[i] = a(zeta * w_ext^i)
+    zeta, wext = O.fr_to_ints(d.g_coset)[0], O.fr_to_ints(d.extended_omega)[0]
+    for i in (0, 1, 12345, d.extended_n - 1):
+        x = fr_arr([zeta * pow(wext, i, P.R) % P.R])[0]
+        assert (O.fr_eval_poly(a, x) == ext[i]).all()
+    d.close()
+
+
+def test_domain_other_degrees_and_errors(h2v):
+    for j, k in ((2, 5), (3, 5), (5, 4), (9, 3)):
+        d, od = h2v.EvaluationDomain(j, k), O.EvaluationDomain(j, k)
+        assert d.extended_k == od.extended_k
+        a = O.fr_fill(1 << k, j * 100 + k)
+        e = d.coeff_to_extended(a)
+        assert (e == od.coeff_to_extended(a)).all()
+        assert (d.extended_to_coeff(e) == od.extended_to_coeff(e)).all()
+        d.close()
+    with pytest.raises(ValueError):
+        h2v.EvaluationDomain(4, 27)
+    d = h2v.EvaluationDomain(4, 4)
+    with pytest.raises(ValueError):
+        d.lagrange_to_coeff(O.fr_fill(15, 1))
+    d.close()
+
+
+# ----------------------------------------------------------------------------- best_multiexp
+def test_best_multiexp_golden(h2v):
+    for v in golden()["msm"]:
+        s = fr_arr([ival(x) for x in v["scalars"]])
+        b = g1_arr([ipt(p) for p in v["bases"]])
+        got = O.g1_affine_to_ints(O.g1_to_affine(h2v.best_multiexp(s, b)))
+        assert got == ipt(v["result"]), v["dist"]
+
+
+@pytest.mark.parametrize("n,mode", [(1, 0), (3, 0), (31, 1), (32, 0), (257, 1), (1000, 0), (4096, 1), (1 << 13, 0), (12345, 1)])
+def test_best_multiexp_vs_oracle(h2v, n, mode):
+    b = O.gen_bases(n)
+    s = O.fr_fill(n, 300 + n, mode=mode)
+    got = O.g1_to_affine(h2v.best_multiexp(s, b))
+    assert (got == O.best_multiexp_affine(s, b)).all()
+    assert (got == O.msm_closed_form(s)).all()
+
+
+def test_best_multiexp_edge_cases(h2v):
+    n = 512
+    b = O.gen_bases(n)
+    ident = np.zeros(8, dtype=np.uint64)
+    # empty input -> identity
+    e = h2v.best_multiexp(np.zeros((0, 4), dtype=np.uint64), np.zeros((0, 8), dtype=np.uint64))
+    assert (O.g1_to_affine(e) == ident).all()
+    # all-zero scalars -> identity
+    z = np.zeros((n, 4), dtype=np.uint64)
+    assert (O.g1_to_affine(h2v.best_multiexp(z, b)) == ident).all()
+    # all scalars r-1 (every signed digit path), all ones, one hot
+    for val in (P.R - 1, 1, (1 << 253) + 12345):
+        s = fr_arr([val] * n)
+        assert (O.g1_to_affine(h2v.best_multiexp(s, b)) == O.msm_closed_form(s)).all(), hex(val)
+    # all bases equal (P + P inside every bucket), bases containing identity and opposite pairs
+    g7 = O.g1_mul(O.g1_generator(), 7)
+    same = np.tile(g7, (n, 1))
+    s = O.fr_fill(n, 5, mode=1)
+    tot = sum(O.fr_to_ints(s)) % P.R
+    assert (O.g1_to_affine(h2v.best_multiexp(s, same)) == O.g1_mul(g7, tot)).all()
+    mixed = b.copy()
+    mixed[::3] = 0
+    x, y = O.g1_affine_to_ints(b[1])
+    mixed[4] = O.g1_affine_from_ints((x, (-y) % P.P))
+    assert (O.g1_to_affine(h2v.best_multiexp(s, mixed)) == O.best_multiexp_affine(s, mixed)).all()
+    with pytest.raises(ValueError):
+        h2v.best_multiexp(s[:10], b[:11])
+
+
+# ----------------------------------------------------------------------------- ParamsKZG commit path
+@pytest.mark.parametrize("k,ncols,mode", [(3, 2, 0), (8, 5, 1), (12, 6, 0), (13, 12, 1), (16, 3, 0)])
+def test_commit_vs_closed_form(h2v, k, ncols, mode):
+    n = 1 << k
+    b = O.gen_bases(n)
+    gm = O.gen_bases(n, a=12345677, b=987654321)
+    srs = h2v.ParamsKZG(k, gm, b)
+    cols = [O.fr_fill(n, 4000 + 17 * i + k, mode=mode, lookup_bits=12) for i in range(ncols)]
+    got = srs.commit_batch(cols)
+    for i, c in enumerate(cols):
+        assert (got[i] == O.msm_closed_form(c)).all(), i
+    # single-column entry points, both bases, short polynomial, oracle best_multiexp on the same inputs
+    assert (srs.commit_lagrange(cols[0]) == got[0]).all()
+    assert (srs.commit(cols[0]) == O.msm_closed_form(cols[0], a=12345677, b=987654321)).all()
+    ln = n // 2 + 1
+    assert (srs.commit_lagrange(cols[1][:ln]) == O.best_multiexp_affine(cols[1][:ln], b[:ln])).all()
+    assert (srs.commit_lagrange(np.zeros((n, 4), dtype=np.uint64)) == 0).all()
+    with pytest.raises(ValueError):
+        srs.commit_lagrange(np.zeros((n + 1, 4), dtype=np.uint64))
+    srs.close()
+
+
+def test_commit_linearity_and_checksum_k16(h2v):
+    """kmeans config size (n = 2^16): commit(a) + commit(b) = commit(a + b), and the batch agrees with itself."""
+    k, n = 16, 1 << 16
+    b = O.gen_bases(n)
+    srs = h2v.ParamsKZG(k, None, b)
+    a1, a2 = O.fr_fill(n, 1, mode=0), O.fr_fill(n, 2, mode=1, lookup_bits=15)
+    s = fr_arr([(x + y) % P.R for x, y in zip(O.fr_to_ints(a1), O.fr_to_ints(a2))])
+    c = srs.commit_batch([a1, a2, s, a1])
+    assert (c[0] == c[3]).all()
+    sum_pt = O.g1_to_affine(O.g1_add_mixed(jac(c[0]), c[1]))
+    assert (sum_pt == c[2]).all()
+    assert (c[0] == O.msm_closed_form(a1)).all() and (c[1] == O.msm_closed_form(a2)).all()
+    with pytest.raises(ValueError):
+        srs.commit(a1)   # monomial basis was not loaded
+    srs.close()
+
+
+def test_commit_k20_closed_form(h2v):
+    """config 4 size (n = 2^20), uniform and witness-like scalars."""
+    k, n = 20, 1 << 20
+    b = O.gen_bases(n)
+    srs = h2v.ParamsKZG(k, None, b)
+    cols = [O.fr_fill(n, 20, mode=0), O.fr_fill(n, 21, mode=1, lookup_bits=19)]
+    got = srs.commit_batch(cols)
+    for i, c in enumerate(cols):
+        assert (got[i] == O.msm_closed_form(c)).all(), i
+    srs.close()
