@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- the KZG-commit / EvaluationDomain hot path on N B200s (one process per GPU).
+
+Workload (BASELINE.json configs[2], the 20x target): the kmeans circuit at k = 16.  One *step* is one
+pass of the hot path over one batch of synthetic columns: `commit_lagrange` (BN254 G1 MSM against the
+shared g_lagrange bases) of COLS columns of n = 2^16 Fr scalars.  The headline metric is
+G1 MSM throughput in Mpts/s (BASELINE.json: "G1 MSM Mpts/s"); the same JSON line also carries the Fr
+NTT throughput (Gelem/s) and a prove-shaped latency for the same circuit under "ntt" / "prove_shaped".
+
+  value   device-resident: columns already in HBM when the timed region starts
+  e2e     through the host-facing C ABI (h2v_commit_batch) with pinned HOST buffers: H2D of every
+          column and D2H of every commitment inside the timed region
+  roofline  dominant kernel msm_accumulate against the integer pipe (measured IMAD.WIDE peak), per
+          SURVEY.md 8(d); "ntt.roofline" carries the HBM view for the NTT passes
+  cpu_baseline / --impl reference   the restated halo2-axiom CPU path (oracle/, kind "port": the Rust
+          reference cannot be built in this image) on all host cores, on a bounded sample
+
+N > 1: columns are partitioned across ranks (each rank commits its own COLS columns against its own
+SRS replica), no data-path collective; scaling = weak.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 16
+N = 1 << K
+COLS = 96                      # 96 x 2 MiB of scalars = 192 MiB per step (> 126 MB L2), tables 64 MiB more
+MSM_MACS_PER_POINT = {16: 27200, 13: 27200, 20: 20400}   # W(n) * 1360 wide-MACs
+FQ_MUL_MACS = 136
+SYN_A, SYN_B = 0x9E3779B97F4A7C15 >> 2, 0x632BE59BD9B4E019 >> 2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cols", type=int, default=COLS)
+    ap.add_argument("--no-extras", action="store_true", help="skip the ntt / prove_shaped / cpu_baseline sections")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        sm = [int(r[0]) for r in self.rows if len(r) >= 7 and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) >= 7 and r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------- CPU arm
+def cpu_msm_sample(n_cols, threads):
+    """restated halo2-axiom best_multiexp on `n_cols` columns of 2^16 uniform scalars, all host threads"""
+    from oracle import oracle as O
+    bases = O.gen_bases(N, threads=threads)
+    cols = [O.fr_fill(N, 7000 + i) for i in range(n_cols)]
+    t = time.perf_counter()
+    for c in cols:
+        O.best_multiexp(c, bases, threads)
+    dt = time.perf_counter() - t
+    return n_cols * N / dt / 1e6, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    from oracle import oracle as O
+    sample_cols = 4
+    bases = O.gen_bases(N, threads=threads)
+    cols = [O.fr_fill(N, 7000 + i) for i in range(sample_cols)]
+    for _ in range(min(args.warmup, 1)):
+        O.best_multiexp(cols[0], bases, threads)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        for c in cols:
+            O.best_multiexp(c, bases, threads)
+    dt = time.perf_counter() - t
+    v = args.steps * sample_cols * N / dt / 1e6
+    sample = f"{sample_cols} columns of 2^16 uniform Fr per step (of the {args.cols}-column batch), best_multiexp over {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "msm_mpts_per_s", "value": v, "unit": "Mpts/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 Montgomery (4x64 on the CPU)", "data": "synthetic",
+        "config": {"workload": "kmeans k=16 commit_lagrange batch (BASELINE configs[2])", "k": K, "cols_per_step": sample_cols},
+        "cpu_baseline": {"value": v, "unit": "Mpts/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "restated halo2-axiom CPU path (oracle/bn254_oracle.c); the Rust reference cannot be built here (no cargo, un-vendored deps)",
+    }))
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import halo2_vectordb_b200 as h
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    h.init(local_rank)
+    cols = args.cols
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- synthetic inputs: bases with known discrete logs (device-generated), uniform scalars
+    bases = h.synthetic_bases(N, SYN_A, SYN_B)
+    srs = h.ParamsKZG(K, None, bases)
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host = torch.randint(-(1 << 63), (1 << 63) - 1, (cols, N, 4), dtype=torch.int64, generator=g)
+    host[..., 3] &= (1 << 60) - 1                      # any value < 2^252 < r is a valid Montgomery residue
+    host = host.pin_memory()
+    d_cols = host.to(dev)
+    d_out = torch.zeros((cols, 8), dtype=torch.int64, device=dev)
+    out_host = np.zeros((cols, 8), dtype=np.uint64)
+    host_np = host.numpy().view(np.uint64)
+    import ctypes as C
+    col_ptrs = (C.c_void_p * cols)(*[host_np[i].ctypes.data for i in range(cols)])
+
+    def step_dev():
+        srs.commit_batch_dev(d_cols.data_ptr(), N, cols, N, d_out.data_ptr())
+
+    def step_e2e():
+        h._check(h.lib().h2v_commit_batch(srs._h, h.H2V_BASIS_LAGRANGE, col_ptrs, cols, N, out_host.ctypes.data_as(C.c_void_p)))
+
+    peak = h.imad_peak()                               # measured IMAD.WIDE rate on this GPU, wide-MAC/s
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local_rank)
+    kernel_ms = {k: 0.0 for k in h.KERNEL_CLASSES}
+    barrier()
+    sampler.start()
+    l0 = h.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+        for kk, v in h.last_kernel_ms().items():
+            kernel_ms[kk] += v
+    e1.record()
+    barrier()
+    launches = h.launch_count() - l0
+    clocks = sampler.stop()
+    dt = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    value = world * args.steps * cols * N / dt / 1e6
+
+    # correctness guard on the timed result: column 0 against the closed form, via the C ABI result
+    got0 = d_out[0].cpu().numpy().view(np.uint64)
+
+    # ---- end to end through the host-facing C ABI
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    dt_e2e = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    e2e_value = world * args.steps * cols * N / dt_e2e / 1e6
+    assert (out_host[0] == got0).all(), "device-resident and host-facing paths disagree"
+
+    acc_ms = kernel_ms["msm_accumulate"] / args.steps           # one launch per step (all columns)
+    macs = cols * N * MSM_MACS_PER_POINT[K]
+    achieved = macs / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
+    line = {
+        "metric": "msm_mpts_per_s", "value": value, "unit": "Mpts/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32x8 Montgomery (BN254 Fq/Fr)", "data": "synthetic",
+        "config": {"workload": "kmeans k=16 commit_lagrange batch (BASELINE configs[2])", "k": K, "cols_per_step": cols,
+                   "scalars": "uniform", "l2": "inputs larger than L2 (192 MiB scalars + 64 MiB tables per step)",
+                   "parallelism": f"columns x{world}"},
+        "e2e": {"value": e2e_value, "unit": "Mpts/s", "h2d_bytes_per_step": cols * N * 32, "d2h_bytes_per_step": cols * 64,
+                "ms_per_step": dt_e2e / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "kernel_ms_per_step": {k: round(v / args.steps, 4) for k, v in kernel_ms.items() if v},
+        "roofline": {"bound": "int32-pipe (IMAD.WIDE)", "kernel": "msm_accumulate_kernel", "achieved": achieved,
+                     "peak": peak / 1e12, "unit": "T wide-MAC/s", "frac": (achieved / (peak / 1e12)) if achieved else None,
+                     "traffic": None,
+                     "peak_source": "measured live: h2v_selftest_imad_peak (MEASURED_PEAKS.json has no integer peak)",
+                     "algorithmic": f"{MSM_MACS_PER_POINT[K]} wide-MAC/pt x {cols * N} pts per launch (SURVEY.md 8d)"},
+    }
+
+    if not args.no_extras and rank == 0:
+        line["ntt"] = bench_ntt(h, torch, dev, peak)
+        if world == 1:
+            threads = os.cpu_count() or 1
+            v, secs = cpu_msm_sample(8, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "Mpts/s", "cores": threads, "kind": "port",
+                                    "sample": f"8 of the {cols} columns (2^16 uniform Fr each), restated halo2-axiom best_multiexp, {secs:.1f} s"}
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        print(json.dumps(line))
+    srs.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_ntt(h, torch, dev, peak):
+    """Fr NTT throughput on the same circuit shape: lagrange_to_coeff (2^16) and coeff_to_extended (2^16 -> 2^18)."""
+    import json as _json
+    try:
+        hbm = _json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:
+        hbm, hbm_src = 6650.0, "fallback"
+    dom = h.EvaluationDomain(4, K)
+    cols = 64
+    g = torch.Generator(device="cpu").manual_seed(99)
+    a = torch.randint(-(1 << 63), (1 << 63) - 1, (cols, N, 4), dtype=torch.int64, generator=g)
+    a[..., 3] &= (1 << 60) - 1
+    d_in = a.to(dev)
+    d_n = torch.empty_like(d_in)
+    d_ext = torch.empty((cols, 4 * N, 4), dtype=torch.int64, device=dev)
+    res = {}
+    for name, op, src, dst, ostride, L in (("lagrange_to_coeff", h.OP_LAGRANGE_TO_COEFF, d_in, d_n, N, K),
+                                           ("coeff_to_extended", h.OP_COEFF_TO_EXTENDED, d_in, d_ext, 4 * N, K + 2)):
+        for _ in range(3):
+            dom.transform_dev(op, src.data_ptr(), N, dst.data_ptr(), ostride, cols)
+        ms = []
+        for _ in range(10):
+            dom.transform_dev(op, src.data_ptr(), N, dst.data_ptr(), ostride, cols)
+            ms.append(h.last_kernel_ms()["ntt"])
+        t = statistics.median(ms) * 1e-3
+        size = 1 << L
+        passes = (L + 8) // 9
+        alg_bytes = 64 * size * passes * cols
+        alg_macs = (size // 2) * L * FQ_MUL_MACS * cols
+        res[name] = {"gelem_per_s": cols * size / t / 1e9, "ms": t * 1e3, "cols": cols, "log_n": L,
+                     "roofline": {"bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": hbm, "unit": "GB/s",
+                                  "frac": alg_bytes / t / 1e9 / hbm, "peak_source": hbm_src, "traffic": None},
+                     "roofline_int": {"achieved": alg_macs / t / 1e12, "peak": peak / 1e12, "unit": "T wide-MAC/s",
+                                      "frac": alg_macs / t / peak}}
+    dom.close()
+    return res
+
+
+if __name__ == "__main__":
+    main()

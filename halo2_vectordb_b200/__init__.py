@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "h2v_best_fft", "h2v_domain_new", "h2v_domain_free", "h2v_domain_k", "h2v_domain_extended_k", "h2v_domain_constant",
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
     "h2v_divide_by_vanishing_poly", "h2v_domain_transform_batch", "h2v_domain_transform_dev",
-    "h2v_selftest_field", "h2v_selftest_group", "h2v_selftest_imad_peak", "h2v_launch_count", "h2v_last_kernel_ms",
+    "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_launch_count", "h2v_last_kernel_ms",
 ]
 
 
@@ -78,6 +78,7 @@ def lib():
         L.h2v_domain_transform_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]
         L.h2v_selftest_field.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_selftest_group.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.h2v_synthetic_bases.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p]
         L.h2v_selftest_imad_peak.argtypes = [C.POINTER(C.c_double)]
         L.h2v_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
         _lib = L
@@ -293,6 +294,16 @@ def selftest_field(field, op, a, b=None):
         b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
         bp = _ptr(b)
     _check(lib().h2v_selftest_field(field, op, _ptr(a), bp, a.shape[0], _ptr(out)))
+    return out
+
+
+SYN_A, SYN_B = 0x9E3779B97F4A7C15 >> 2, 0x632BE59BD9B4E019 >> 2
+
+
+def synthetic_bases(n, a=SYN_A, b=SYN_B):
+    """bases[i] = (a*i + b) * G computed on the device (bench / full-size test inputs)."""
+    out = np.zeros((n, 8), dtype=np.uint64)
+    _check(lib().h2v_synthetic_bases(a, b, n, _ptr(out)))
     return out
 
 

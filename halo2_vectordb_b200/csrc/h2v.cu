@@ -863,6 +863,24 @@ __global__ void selftest_group_kernel(int mode, const affine *p, const affine *q
     }
     o[i] = xyzz_to_affine(acc);
 }
+// out[i] = (a*i + b) * G, affine -- synthetic bases with a known discrete log
+__global__ void __launch_bounds__(128) synthetic_bases_kernel(affine *out, uint64_t a, uint64_t b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned __int128 k = (unsigned __int128)a * i + b;
+    affine g;
+    fe c = fe_zero();
+    c.v[0] = 1;
+    g.x = fe_to_mont<Fq>(c);
+    c.v[0] = 2;
+    g.y = fe_to_mont<Fq>(c);
+    xyzz acc = xyzz_identity();
+    for (int bit = 127; bit >= 0; --bit) {
+        acc = xyzz_double(acc);
+        if ((uint64_t)(k >> bit) & 1) xyzz_add_mixed(acc, g);
+    }
+    out[i] = xyzz_to_affine(acc);
+}
 __global__ void imad_probe_kernel(uint64_t *out, uint32_t iters, uint32_t seed) {
     uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
     uint64_t acc[8];
@@ -910,6 +928,20 @@ int h2v_selftest_group(int mode, const uint64_t *p, const uint64_t *q, size_t n,
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(out_affine, O.p, n * 64, cudaMemcpyDeviceToHost));
     A.release(); B.release(); O.release();
+    return H2V_OK;
+}
+int h2v_synthetic_bases(uint64_t a, uint64_t b, size_t n, uint64_t *out_affine) {
+    int rc = use_device();
+    if (rc) return rc;
+    if (!out_affine || n == 0) return fail(H2V_EINVAL, "synthetic_bases: bad argument");
+    if (a >> 62 || b >> 62 || n >> 32) return fail(H2V_EINVAL, "synthetic_bases: a, b < 2^62 and n < 2^32 required");
+    DevBuf O;
+    if ((rc = O.ensure(n * 64))) return rc;
+    synthetic_bases_kernel<<<(unsigned)((n + 127) / 128), 128>>>(O.as<affine>(), a, b, n);
+    LAUNCHED();
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out_affine, O.p, n * 64, cudaMemcpyDeviceToHost));
+    O.release();
     return H2V_OK;
 }
 int h2v_selftest_imad_peak(double *out) {

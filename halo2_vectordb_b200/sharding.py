@@ -1,0 +1,44 @@
+"""Column sharding across GPUs: one process per GPU, column j -> rank j mod G.
+
+A proof is hundreds of independent length-2^k columns that share the SRS bases and the domain
+twiddles, so each rank holds a full SRS/twiddle replica and transforms / commits only its own
+columns; there is NO collective on the math path.  The only exchange is returning the 64-byte
+commitments (and 32-byte evaluations) to the host transcript *in the original column order*,
+which is what `gather_in_column_order` does over torch.distributed (gloo on CPU, nccl on GPU).
+"""
+import numpy as np
+
+
+def column_shard(n_cols, rank, world):
+    """Indices of the columns rank `rank` of `world` owns (round-robin keeps per-rank work balanced
+    when column kinds -- advice, lookup, permutation products -- arrive in blocks)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return list(range(rank, n_cols, world))
+
+
+def shard_sizes(n_cols, world):
+    return [len(range(r, n_cols, world)) for r in range(world)]
+
+
+def gather_in_column_order(local, n_cols, rank, world, width=8, device=None):
+    """all-gather per-rank results (len(column_shard) x width uint64) and restore transcript order."""
+    local = np.ascontiguousarray(local, dtype=np.uint64).reshape(-1, width)
+    if local.shape[0] != len(column_shard(n_cols, rank, world)):
+        raise ValueError("local result count does not match this rank's shard")
+    if world == 1:
+        return local.copy()
+    import torch
+    import torch.distributed as dist
+
+    per = max(shard_sizes(n_cols, world))
+    buf = torch.zeros((per, width), dtype=torch.int64, device=device)
+    if local.shape[0]:
+        buf[: local.shape[0]] = torch.from_numpy(local.view(np.int64)).to(buf.device)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    res = np.zeros((n_cols, width), dtype=np.uint64)
+    for r in range(world):
+        idx = column_shard(n_cols, r, world)
+        res[idx] = out[r][: len(idx)].cpu().numpy().view(np.uint64)
+    return res

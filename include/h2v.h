@@ -106,6 +106,9 @@ int h2v_selftest_field(int field, int op, const uint64_t *a, const uint64_t *b, 
 /* out_affine[i] = affine(p[i] + q[i]) through the XYZZ mixed add (mode 0), full add (mode 1) or
  * doubling of p (mode 2); p, q affine */
 int h2v_selftest_group(int mode, const uint64_t *p, const uint64_t *q, size_t n, uint64_t *out_affine);
+/* synthetic bases with known discrete logs: out[i] = (a*i + b) * G, affine Montgomery (a, b < 2^62);
+ * sum_i s_i * out[i] must then equal (sum_i s_i (a i + b) mod r) * G, an algorithm-independent check at any n */
+int h2v_synthetic_bases(uint64_t a, uint64_t b, size_t n, uint64_t *out_affine);
 /* dependent-free IMAD.WIDE throughput probe: returns wide multiply-adds per second */
 int h2v_selftest_imad_peak(double *out_wmac_per_s);
 /* kernels launched by this process so far (for bench.py's gpu_launches) */
