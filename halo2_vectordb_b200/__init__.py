@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "h2v_best_fft", "h2v_domain_new", "h2v_domain_free", "h2v_domain_k", "h2v_domain_extended_k", "h2v_domain_constant",
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
     "h2v_divide_by_vanishing_poly", "h2v_domain_transform_batch", "h2v_domain_transform_dev",
-    "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_launch_count", "h2v_last_kernel_ms",
+    "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_op_rate", "h2v_launch_count", "h2v_last_kernel_ms",
 ]
 
 
@@ -80,6 +80,7 @@ def lib():
         L.h2v_selftest_group.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_synthetic_bases.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p]
         L.h2v_selftest_imad_peak.argtypes = [C.POINTER(C.c_double)]
+        L.h2v_selftest_op_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.h2v_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
         _lib = L
     return _lib
@@ -128,6 +129,13 @@ def imad_peak():
     return out.value
 
 
+def op_rate(which):
+    """0: Fq mul/s (1 chain per thread), 1: Fq mul/s (2 chains), 2: XYZZ mixed adds/s -- registers only."""
+    out = C.c_double()
+    _check(lib().h2v_selftest_op_rate(which, C.byref(out)))
+    return out.value
+
+
 # ----------------------------------------------------------------------------- arithmetic.rs
 def best_multiexp(coeffs, bases):
     """halo2-axiom arithmetic.rs `best_multiexp(coeffs, bases) -> C::Curve` (Jacobian, 12 limbs)."""
@@ -172,11 +180,15 @@ class ParamsKZG:
                                   None if ptrs[1] is None else _ptr(ptrs[1]), C.byref(self._h)))
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().h2v_srs_free(self._h)
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.h2v_srs_free(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
 
     def _commit(self, basis, poly):
         poly = _fr(poly)
@@ -232,11 +244,15 @@ class EvaluationDomain:
         return out
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().h2v_domain_free(self._h)
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.h2v_domain_free(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def get_quotient_poly_degree(self):
         return self.j - 1

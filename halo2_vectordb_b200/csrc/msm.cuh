@@ -9,12 +9,13 @@
 // Pipeline (one launch each, batched over `n_cols` scalar columns that share the bases):
 //   msm_digits     scalar: Montgomery -> canonical, + K, split into W signed c-bit digits
 //                  d in [-(2^(c-1)-1), 2^(c-1)]; per-bucket histogram
-//   msm_scan       exclusive prefix sum of the histogram -> bucket offsets
+//   msm_scan_*     exclusive prefix sum of the histogram -> bucket offsets (tiles / top / apply)
 //   msm_scatter    counting-sort the (point, sign) pairs by bucket
 //   msm_accumulate fixed-size chunks of the sorted list, one thread each, XYZZ mixed adds;
 //                  load balance is independent of the scalar distribution
-//   msm_finish     merge the partial sums of buckets that straddle chunk boundaries
-//   msm_reduce     sum_m (m+1) * bucket[m] by a radix-32 tree of running sums
+//   msm_finish     merge the partial sums of buckets that straddle chunk boundaries (thread per bucket;
+//                  a warp per bucket for the few that span many chunks)
+//   msm_reduce     sum_m (m+1) * bucket[m] by a radix-8..32 tree of running sums
 //   msm_final      fold window groups (Horner, c doublings each), normalise to affine
 // Two layouts of the same kernels:
 //   precomputed (SRS handles): tables T_j[i] = 2^(j c) B_i are built once per SRS, every digit
@@ -111,32 +112,82 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const fe *__restrict__ 
     }
 }
 
-// ------------------------------------------------------------------ exclusive scan (single CTA)
-// offsets[0..len] and cursor[0..len) from counts[0..len); offsets[len] = total
-__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ offsets,
-                                                        uint32_t *__restrict__ cursor, uint32_t len) {
-    __shared__ uint32_t part[1024];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t per = (len + 1023) / 1024;
-    const uint32_t lo = tid * per, hi = min(lo + per, len);
-    uint32_t s = 0;
-    for (uint32_t k = lo; k < hi; ++k) s += counts[k];
-    part[tid] = s;
+// ------------------------------------------------------------------ exclusive scan (three launches)
+// tile = 2048 counters per CTA (8 per thread).  (1) per-tile totals, (2) one CTA scans the totals,
+// (3) every tile rescans its counters on top of its base: offsets[0..len], cursor[0..len), offsets[len] = total
+#define H2V_SCAN_TILE 2048
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += t;
+    }
+    return v;
+}
+// exclusive prefix of `v` across a 256-thread CTA; *total receives the CTA sum
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t *total) {
+    __shared__ uint32_t wsum[8];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = warp_incl_scan(v);
+    if (lane == 31) wsum[wid] = inc;
     __syncthreads();
-    // Hillis-Steele inclusive scan over the 1024 partial sums
-    for (uint32_t off = 1; off < 1024; off <<= 1) {
-        uint32_t v = tid >= off ? part[tid - off] : 0;
-        __syncthreads();
-        part[tid] += v;
-        __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        uint32_t x = wsum[w];
+        if (w < (int)wid) base += x;
+        tot += x;
     }
-    uint32_t run = tid ? part[tid - 1] : 0;
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+__global__ void __launch_bounds__(256) msm_scan_tiles_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ tile_sums,
+                                                             uint32_t len) {
+    const uint32_t base = blockIdx.x * H2V_SCAN_TILE + threadIdx.x * 8;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (base + k < len) s += counts[base + k];
+    uint32_t tot;
+    block_excl_scan_256(s, &tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+// in-place exclusive scan of tile_sums[0..ntiles) by one CTA; offsets_total[0] = grand total
+__global__ void __launch_bounds__(256) msm_scan_top_kernel(uint32_t *__restrict__ tile_sums, uint32_t ntiles,
+                                                           uint32_t *__restrict__ offsets_total) {
+    const uint32_t per = (ntiles + 255) / 256;
+    const uint32_t lo = threadIdx.x * per, hi = min(lo + per, ntiles);
+    uint32_t s = 0;
+    for (uint32_t k = lo; k < hi; ++k) s += tile_sums[k];
+    uint32_t tot;
+    uint32_t run = block_excl_scan_256(s, &tot);
     for (uint32_t k = lo; k < hi; ++k) {
-        offsets[k] = run;
-        cursor[k] = run;
-        run += counts[k];
+        uint32_t v = tile_sums[k];
+        tile_sums[k] = run;
+        run += v;
     }
-    if (tid == 1023) offsets[len] = part[1023];
+    if (threadIdx.x == 0) offsets_total[0] = tot;
+}
+__global__ void __launch_bounds__(256) msm_scan_apply_kernel(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ tile_offs,
+                                                             uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor, uint32_t len) {
+    const uint32_t base = blockIdx.x * H2V_SCAN_TILE + threadIdx.x * 8;
+    uint32_t c[8], s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        c[k] = (base + k < len) ? counts[base + k] : 0u;
+        s += c[k];
+    }
+    uint32_t tot;
+    uint32_t run = block_excl_scan_256(s, &tot) + tile_offs[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (base + k < len) {
+            offsets[base + k] = run;
+            cursor[base + k] = run;
+        }
+        run += c[k];
+    }
 }
 
 // ------------------------------------------------------------------ scatter
@@ -198,10 +249,14 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const uint2 *__r
     }
 }
 
-// one thread per bucket: empty -> identity; straddling -> tail(t0) + heads(t0+1..t1)
+// one thread per bucket: empty -> identity; straddling -> tail(t0) + heads(t0+1..t1).  Buckets that span
+// more than `long_span` chunks (skewed witness columns put a large share of a column into a few buckets:
+// scalar 1, the shared high digits of r - small) are queued for msm_finish_long_kernel instead.
+#define H2V_LONG_SPAN 16
 __global__ void __launch_bounds__(128) msm_finish_kernel(const uint32_t *__restrict__ offsets, uint32_t n_buckets,
                                                          const xyzz *__restrict__ edges, xyzz *__restrict__ buckets,
-                                                         uint32_t chunk) {
+                                                         uint32_t chunk, uint32_t *__restrict__ long_list,
+                                                         uint32_t *__restrict__ long_count) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_buckets) return;
     uint32_t s = offsets[b], e = offsets[b + 1];
@@ -211,6 +266,10 @@ __global__ void __launch_bounds__(128) msm_finish_kernel(const uint32_t *__restr
     }
     uint32_t t0 = s / chunk, t1 = (e - 1) / chunk;
     if (t0 == t1) return;
+    if (t1 - t0 > H2V_LONG_SPAN) {
+        long_list[atomicAdd(long_count, 1u)] = b;
+        return;
+    }
     xyzz acc = xyzz_ld(edges + 2 * (size_t)t0 + 1);
     for (uint32_t t = t0 + 1; t <= t1; ++t) {
         xyzz h = xyzz_ld(edges + 2 * (size_t)t);
@@ -218,20 +277,59 @@ __global__ void __launch_bounds__(128) msm_finish_kernel(const uint32_t *__restr
     }
     xyzz_st(buckets + b, acc);
 }
+__device__ __forceinline__ xyzz xyzz_shfl_down(const xyzz &v, int off) {
+    xyzz r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        r.x.v[k] = __shfl_down_sync(0xffffffffu, v.x.v[k], off);
+        r.y.v[k] = __shfl_down_sync(0xffffffffu, v.y.v[k], off);
+        r.zz.v[k] = __shfl_down_sync(0xffffffffu, v.zz.v[k], off);
+        r.zzz.v[k] = __shfl_down_sync(0xffffffffu, v.zzz.v[k], off);
+    }
+    return r;
+}
+// one warp per queued bucket: the lanes stride over the chunk heads, then a shuffle tree folds the 32 partials
+__global__ void __launch_bounds__(128) msm_finish_long_kernel(const uint32_t *__restrict__ offsets, const xyzz *__restrict__ edges,
+                                                              xyzz *__restrict__ buckets, uint32_t chunk,
+                                                              const uint32_t *__restrict__ long_list,
+                                                              const uint32_t *__restrict__ long_count) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t count = *long_count;
+    for (uint32_t i = warp; i < count; i += n_warps) {
+        const uint32_t b = long_list[i];
+        const uint32_t t0 = offsets[b] / chunk, t1 = (offsets[b + 1] - 1) / chunk;
+        xyzz acc = xyzz_identity();
+        if (lane == 0) acc = xyzz_ld(edges + 2 * (size_t)t0 + 1);
+        for (uint32_t t = t0 + 1 + lane; t <= t1; t += 32) {
+            xyzz h = xyzz_ld(edges + 2 * (size_t)t);
+            xyzz_add(acc, h);
+        }
+#pragma unroll 1
+        for (int off = 16; off >= 1; off >>= 1) {
+            xyzz o = xyzz_shfl_down(acc, off);
+            xyzz_add(acc, o);
+        }
+        if (lane == 0) xyzz_st(buckets + b, acc);
+    }
+}
 
 // ------------------------------------------------------------------ bucket reduction tree
-// For each of `n_inst` instances: S_in[inst][0..cnt_in) (and optional A_in) -> cnt_out = ceil(cnt_in/32)
-//   S_out[s] = sum_{r} S_in[32 s + r]
-//   A_out[s] = sum_{r} A_in[32 s + r] + 2^shift * sum_r r * S_in[32 s + r]
+// For each of `n_inst` instances: S_in[inst][0..cnt_in) (and optional A_in) -> cnt_out = ceil(cnt_in / seg),
+// seg = 2^log_seg (8..32, chosen per level so that every level still fills the GPU):
+//   S_out[s] = sum_{r} S_in[seg s + r]
+//   A_out[s] = sum_{r} A_in[seg s + r] + 2^shift * sum_r r * S_in[seg s + r]     (shift = sum of earlier log_seg)
 // Iterating until cnt == 1 gives  A = sum_m m * S0[m],  S = sum_m S0[m];  the group result is A + S
 // (bucket m holds the points of digit magnitude m + 1).
-__global__ void __launch_bounds__(128) msm_reduce_kernel(const xyzz *__restrict__ S_in, const xyzz *__restrict__ A_in,
-                                                         xyzz *__restrict__ S_out, xyzz *__restrict__ A_out,
-                                                         uint32_t cnt_in, uint32_t cnt_out, uint32_t n_inst, uint32_t shift) {
+__global__ void __launch_bounds__(128, 3) msm_reduce_kernel(const xyzz *__restrict__ S_in, const xyzz *__restrict__ A_in,
+                                                            xyzz *__restrict__ S_out, xyzz *__restrict__ A_out,
+                                                            uint32_t cnt_in, uint32_t cnt_out, uint32_t n_inst, uint32_t shift,
+                                                            uint32_t log_seg) {
     uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n_inst * cnt_out) return;
     uint32_t inst = gid / cnt_out, s = gid % cnt_out;
-    uint32_t lo = s * 32, hi = min(lo + 32, cnt_in);
+    uint32_t lo = s << log_seg, hi = min(lo + (1u << log_seg), cnt_in);
     const xyzz *Sin = S_in + (size_t)inst * cnt_in;
     xyzz run = xyzz_identity(), tz = xyzz_identity();
     for (uint32_t r = hi; r-- > lo + 1;) {

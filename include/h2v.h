@@ -109,8 +109,12 @@ int h2v_selftest_group(int mode, const uint64_t *p, const uint64_t *q, size_t n,
 /* synthetic bases with known discrete logs: out[i] = (a*i + b) * G, affine Montgomery (a, b < 2^62);
  * sum_i s_i * out[i] must then equal (sum_i s_i (a i + b) mod r) * G, an algorithm-independent check at any n */
 int h2v_synthetic_bases(uint64_t a, uint64_t b, size_t n, uint64_t *out_affine);
-/* dependent-free IMAD.WIDE throughput probe: returns wide multiply-adds per second */
+/* IMAD.WIDE.U32 (32x32+64 -> 64) issue-rate probe with loop-variant operands: wide multiply-adds per second.
+ * This is the integer-pipe roofline denominator (MEASURED_PEAKS.json carries no integer peak). */
 int h2v_selftest_imad_peak(double *out_wmac_per_s);
+/* register-only throughput of the kernels' building blocks, operations per second over the whole GPU:
+ * which 0: Fq Montgomery product, one dependent chain per thread; 1: two chains; 2: XYZZ mixed-add chain */
+int h2v_selftest_op_rate(int which, double *out_ops_per_s);
 /* kernels launched by this process so far (for bench.py's gpu_launches) */
 uint64_t h2v_launch_count(void);
 /* device-side timing of the last commit_batch_dev / transform_dev call, in milliseconds per kernel class:

@@ -130,7 +130,7 @@ def windows_for(c):
     return (255 + c - 1) // c
 
 
-def msm_model(scalars, points, c, precomp, chunk, n_cols=1):
+def msm_model(scalars, points, c, precomp, chunk, n_cols=1, log_seg=5):
     """scalars: list of columns of canonical ints; points: ints k_i (point = k_i * G).
     Returns per-column result as an int (multiple of G), following msm.cuh kernel by kernel."""
     n = len(points)
@@ -225,12 +225,12 @@ def msm_model(scalars, points, c, precomp, chunk, n_cols=1):
     n_inst = n_cols * G
     S_in, A_in, cnt, shift = buckets, None, nb, 0
     while True:
-        cnt_out = (cnt + 31) // 32
+        cnt_out = (cnt + (1 << log_seg) - 1) >> log_seg
         S_out = [0] * (n_inst * cnt_out)
         A_out = [0] * (n_inst * cnt_out)
         for inst in range(n_inst):
             for s in range(cnt_out):
-                lo, hi = s * 32, min(s * 32 + 32, cnt)
+                lo, hi = s << log_seg, min((s << log_seg) + (1 << log_seg), cnt)
                 run = tz = 0
                 r = hi
                 while r > lo + 1:
@@ -244,7 +244,7 @@ def msm_model(scalars, points, c, precomp, chunk, n_cols=1):
                         tz = (tz + A_in[inst * cnt + r]) % R
                 S_out[inst * cnt_out + s] = run
                 A_out[inst * cnt_out + s] = tz
-        S_in, A_in, cnt, shift = S_out, A_out, cnt_out, shift + 5
+        S_in, A_in, cnt, shift = S_out, A_out, cnt_out, shift + log_seg
         if cnt <= 1:
             break
     out = []

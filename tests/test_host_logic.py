@@ -157,4 +157,6 @@ def test_msm_pipeline_model(n, c, pre, chunk, ncols, dist):
         else:
             s = [rnd.choice([0, P.R - 1, 1, P.R - 2, 1 << 253]) for _ in range(n)]
         cols.append(s)
-    assert KM.msm_model(cols, pts, c, pre, chunk, ncols) == [sum(a * b for a, b in zip(s, pts)) % P.R for s in cols]
+    exp = [sum(a * b for a, b in zip(s, pts)) % P.R for s in cols]
+    for log_seg in (3, 5):
+        assert KM.msm_model(cols, pts, c, pre, chunk, ncols, log_seg) == exp
