@@ -1,0 +1,139 @@
+//! h2v-sys -- Rust binding of `include/h2v.h` plus safe wrappers with the exact halo2-axiom signatures the
+//! reference reaches through `src/scaffold/mod.rs:273` (create_pk) and `:296` (gen_snark_shplonk):
+//! `best_multiexp`, `best_fft`, `ParamsKZG::{commit, commit_lagrange}` and
+//! `EvaluationDomain::{lagrange_to_coeff, coeff_to_extended, extended_to_coeff, divide_by_vanishing_poly}`.
+//!
+//! SOURCE ONLY: not compiled in this repository's image (no cargo).  `Fr`, `G1Affine`, `G1` of halo2curves
+//! are `#[repr(C)]`-compatible `[u64; 4]` Montgomery limbs (identity affine = (0,0)), which is exactly the
+//! ABI's layout, so slices are passed by pointer with no conversion.
+//!
+//! Error behaviour: upstream panics (`assert_eq!(a.len(), 1 << log_n)`, length mismatch) stay panics;
+//! any CUDA failure is also a panic -- there is no CPU fallback.
+use halo2curves::bn256::{Fr, G1Affine, G1};
+use std::ffi::CStr;
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct H2vSrs(c_void);
+#[repr(C)]
+pub struct H2vDomain(c_void);
+
+pub const H2V_BASIS_MONOMIAL: c_int = 0;
+pub const H2V_BASIS_LAGRANGE: c_int = 1;
+pub const H2V_OP_LAGRANGE_TO_COEFF: c_int = 0;
+pub const H2V_OP_COEFF_TO_LAGRANGE: c_int = 1;
+pub const H2V_OP_COEFF_TO_EXTENDED: c_int = 2;
+pub const H2V_OP_EXTENDED_TO_COEFF: c_int = 3;
+pub const H2V_OP_DIVIDE_BY_VANISHING: c_int = 4;
+
+extern "C" {
+    pub fn h2v_init(device: c_int) -> c_int;
+    pub fn h2v_device_count() -> c_int;
+    pub fn h2v_last_error() -> *const c_char;
+    pub fn h2v_srs_load(k: u32, g: *const u64, g_lagrange: *const u64, out: *mut *mut H2vSrs) -> c_int;
+    pub fn h2v_srs_free(srs: *mut H2vSrs);
+    pub fn h2v_commit(srs: *mut H2vSrs, basis: c_int, poly: *const u64, len: usize, out_affine: *mut u64) -> c_int;
+    pub fn h2v_commit_batch(srs: *mut H2vSrs, basis: c_int, polys: *const *const u64, n_polys: usize, len: usize,
+                            out_affine: *mut u64) -> c_int;
+    pub fn h2v_best_multiexp(coeffs: *const u64, bases: *const u64, n: usize, out_jacobian: *mut u64) -> c_int;
+    pub fn h2v_best_fft(a: *mut u64, omega: *const u64, log_n: u32) -> c_int;
+    pub fn h2v_domain_new(j: u32, k: u32, out: *mut *mut H2vDomain) -> c_int;
+    pub fn h2v_domain_free(dom: *mut H2vDomain);
+    pub fn h2v_domain_extended_k(dom: *mut H2vDomain) -> u32;
+    pub fn h2v_lagrange_to_coeff(dom: *mut H2vDomain, a: *mut u64) -> c_int;
+    pub fn h2v_coeff_to_lagrange(dom: *mut H2vDomain, a: *mut u64) -> c_int;
+    pub fn h2v_coeff_to_extended(dom: *mut H2vDomain, inp: *const u64, out: *mut u64) -> c_int;
+    pub fn h2v_extended_to_coeff(dom: *mut H2vDomain, inp: *const u64, out: *mut u64) -> c_int;
+    pub fn h2v_divide_by_vanishing_poly(dom: *mut H2vDomain, a: *mut u64) -> c_int;
+    pub fn h2v_domain_transform_batch(dom: *mut H2vDomain, op: c_int, inp: *const *const u64, out: *const *mut u64,
+                                      n_cols: usize) -> c_int;
+}
+
+fn ok(rc: c_int) {
+    if rc != 0 {
+        let msg = unsafe { CStr::from_ptr(h2v_last_error()) }.to_string_lossy().into_owned();
+        panic!("libh2v: {msg}");
+    }
+}
+
+/// `halo2_proofs::arithmetic::best_multiexp`
+pub fn best_multiexp(coeffs: &[Fr], bases: &[G1Affine]) -> G1 {
+    assert_eq!(coeffs.len(), bases.len());
+    let mut out = G1::default();
+    ok(unsafe { h2v_best_multiexp(coeffs.as_ptr() as *const u64, bases.as_ptr() as *const u64, coeffs.len(),
+                                  &mut out as *mut G1 as *mut u64) });
+    out
+}
+
+/// `halo2_proofs::arithmetic::best_fft` for `G = Fr` (the G1 instantiation is only used by `ParamsKZG::setup`)
+pub fn best_fft(a: &mut [Fr], omega: Fr, log_n: u32) {
+    assert_eq!(a.len(), 1 << log_n);
+    ok(unsafe { h2v_best_fft(a.as_mut_ptr() as *mut u64, &omega as *const Fr as *const u64, log_n) });
+}
+
+/// Device-resident bases of a `ParamsKZG<Bn256>`; create once next to the params (`gen_srs`, scaffold mod.rs:260).
+pub struct DeviceSrs(*mut H2vSrs);
+unsafe impl Send for DeviceSrs {}
+unsafe impl Sync for DeviceSrs {}
+impl DeviceSrs {
+    pub fn new(k: u32, g: &[G1Affine], g_lagrange: &[G1Affine]) -> Self {
+        assert_eq!(g.len(), 1 << k);
+        assert_eq!(g_lagrange.len(), 1 << k);
+        let mut h = std::ptr::null_mut();
+        ok(unsafe { h2v_srs_load(k, g.as_ptr() as *const u64, g_lagrange.as_ptr() as *const u64, &mut h) });
+        DeviceSrs(h)
+    }
+    fn commit_basis(&self, basis: c_int, poly: &[Fr]) -> G1 {
+        let mut aff = G1Affine::default();
+        ok(unsafe { h2v_commit(self.0, basis, poly.as_ptr() as *const u64, poly.len(), &mut aff as *mut G1Affine as *mut u64) });
+        aff.into()
+    }
+    /// `ParamsKZG::commit(&self, poly: &Polynomial<Fr, Coeff>, _: Blind<Fr>) -> G1`
+    pub fn commit(&self, poly: &[Fr]) -> G1 { self.commit_basis(H2V_BASIS_MONOMIAL, poly) }
+    /// `ParamsKZG::commit_lagrange(&self, poly: &Polynomial<Fr, LagrangeCoeff>, _: Blind<Fr>) -> G1`
+    pub fn commit_lagrange(&self, poly: &[Fr]) -> G1 { self.commit_basis(H2V_BASIS_LAGRANGE, poly) }
+    /// all columns of one prover phase in a single call (preferred: one launch, shared bases)
+    pub fn commit_lagrange_batch(&self, polys: &[&[Fr]]) -> Vec<G1Affine> {
+        let len = polys.first().map_or(0, |p| p.len());
+        assert!(polys.iter().all(|p| p.len() == len));
+        let ptrs: Vec<*const u64> = polys.iter().map(|p| p.as_ptr() as *const u64).collect();
+        let mut out = vec![G1Affine::default(); polys.len()];
+        ok(unsafe { h2v_commit_batch(self.0, H2V_BASIS_LAGRANGE, ptrs.as_ptr(), polys.len(), len, out.as_mut_ptr() as *mut u64) });
+        out
+    }
+}
+impl Drop for DeviceSrs {
+    fn drop(&mut self) { unsafe { h2v_srs_free(self.0) } }
+}
+
+/// Device twiddles/constants of an `EvaluationDomain<Fr>`; create inside `EvaluationDomain::new(j, k)`.
+pub struct DeviceDomain(*mut H2vDomain);
+unsafe impl Send for DeviceDomain {}
+unsafe impl Sync for DeviceDomain {}
+impl DeviceDomain {
+    pub fn new(j: u32, k: u32) -> Self {
+        let mut h = std::ptr::null_mut();
+        ok(unsafe { h2v_domain_new(j, k, &mut h) });
+        DeviceDomain(h)
+    }
+    pub fn extended_k(&self) -> u32 { unsafe { h2v_domain_extended_k(self.0) } }
+    /// `EvaluationDomain::lagrange_to_coeff` (values in place)
+    pub fn lagrange_to_coeff(&self, a: &mut [Fr]) { ok(unsafe { h2v_lagrange_to_coeff(self.0, a.as_mut_ptr() as *mut u64) }) }
+    pub fn coeff_to_lagrange(&self, a: &mut [Fr]) { ok(unsafe { h2v_coeff_to_lagrange(self.0, a.as_mut_ptr() as *mut u64) }) }
+    /// `EvaluationDomain::coeff_to_extended`: `a.len() == 2^k`, result `2^extended_k`
+    pub fn coeff_to_extended(&self, a: &[Fr]) -> Vec<Fr> {
+        let mut out = vec![Fr::zero(); 1 << self.extended_k()];
+        ok(unsafe { h2v_coeff_to_extended(self.0, a.as_ptr() as *const u64, out.as_mut_ptr() as *mut u64) });
+        out
+    }
+    /// `EvaluationDomain::extended_to_coeff`: result `2^k * (j - 1)`
+    pub fn extended_to_coeff(&self, a: &[Fr], out_len: usize) -> Vec<Fr> {
+        let mut out = vec![Fr::zero(); out_len];
+        ok(unsafe { h2v_extended_to_coeff(self.0, a.as_ptr() as *const u64, out.as_mut_ptr() as *mut u64) });
+        out
+    }
+    pub fn divide_by_vanishing_poly(&self, a: &mut [Fr]) { ok(unsafe { h2v_divide_by_vanishing_poly(self.0, a.as_mut_ptr() as *mut u64) }) }
+}
+impl Drop for DeviceDomain {
+    fn drop(&mut self) { unsafe { h2v_domain_free(self.0) } }
+}

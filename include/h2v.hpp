@@ -1,0 +1,123 @@
+// h2v.hpp -- header-only C++ mirror of the upstream Rust interface on top of the C ABI (h2v.h).
+//
+// Same names, argument meaning and error behaviour as halo2-axiom:
+//   arithmetic.rs            best_multiexp, best_fft
+//   poly/kzg/commitment.rs   ParamsKZG::{commit, commit_lagrange}
+//   poly/domain.rs           EvaluationDomain::{new, lagrange_to_coeff, coeff_to_extended, extended_to_coeff, ...}
+// Upstream panics (assert!) become std::invalid_argument; CUDA failures std::runtime_error (no CPU fallback).
+// The reference reaches these through src/scaffold/mod.rs:273 (create_pk) and :296 (gen_snark_shplonk).
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "h2v.h"
+
+namespace h2v_host {
+
+struct Fr { uint64_t l[4]; };          // Montgomery limbs, = halo2curves bn256::Fr
+struct G1Affine { uint64_t x[4], y[4]; };
+struct G1 { uint64_t x[4], y[4], z[4]; };
+
+inline void check(int rc) {
+    if (rc == H2V_OK) return;
+    std::string msg = h2v_last_error();
+    if (rc == H2V_EINVAL) throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);
+}
+inline void init(int device = 0) { check(h2v_init(device)); }
+
+inline G1 best_multiexp(const std::vector<Fr> &coeffs, const std::vector<G1Affine> &bases) {
+    if (coeffs.size() != bases.size()) throw std::invalid_argument("assertion failed: coeffs.len() == bases.len()");
+    G1 out{};
+    check(h2v_best_multiexp(reinterpret_cast<const uint64_t *>(coeffs.data()), reinterpret_cast<const uint64_t *>(bases.data()),
+                            coeffs.size(), reinterpret_cast<uint64_t *>(&out)));
+    return out;
+}
+inline void best_fft(std::vector<Fr> &a, const Fr &omega, uint32_t log_n) {
+    if (a.size() != (size_t(1) << log_n)) throw std::invalid_argument("assertion failed: a.len() == 1 << log_n");
+    check(h2v_best_fft(reinterpret_cast<uint64_t *>(a.data()), omega.l, log_n));
+}
+
+class ParamsKZG {
+  public:
+    ParamsKZG(uint32_t k, const std::vector<G1Affine> &g, const std::vector<G1Affine> &g_lagrange) : k_(k), n_(size_t(1) << k) {
+        if ((!g.empty() && g.size() != n_) || (!g_lagrange.empty() && g_lagrange.size() != n_))
+            throw std::invalid_argument("ParamsKZG: bases must have 2^k points");
+        check(h2v_srs_load(k, g.empty() ? nullptr : reinterpret_cast<const uint64_t *>(g.data()),
+                           g_lagrange.empty() ? nullptr : reinterpret_cast<const uint64_t *>(g_lagrange.data()), &h_));
+    }
+    ~ParamsKZG() { h2v_srs_free(h_); }
+    ParamsKZG(const ParamsKZG &) = delete;
+    ParamsKZG &operator=(const ParamsKZG &) = delete;
+    uint32_t k() const { return k_; }
+    size_t n() const { return n_; }
+    // commit(&poly, _blind): the blind is ignored by KZG upstream
+    G1Affine commit(const std::vector<Fr> &poly) const { return one(H2V_BASIS_MONOMIAL, poly); }
+    G1Affine commit_lagrange(const std::vector<Fr> &poly) const { return one(H2V_BASIS_LAGRANGE, poly); }
+    std::vector<G1Affine> commit_batch(int basis, const std::vector<const Fr *> &polys, size_t len) const {
+        std::vector<G1Affine> out(polys.size());
+        check(h2v_commit_batch(h_, basis, reinterpret_cast<const uint64_t *const *>(polys.data()), polys.size(), len,
+                               reinterpret_cast<uint64_t *>(out.data())));
+        return out;
+    }
+    h2v_srs_t handle() const { return h_; }
+
+  private:
+    G1Affine one(int basis, const std::vector<Fr> &poly) const {
+        G1Affine out{};
+        check(h2v_commit(h_, basis, reinterpret_cast<const uint64_t *>(poly.data()), poly.size(), reinterpret_cast<uint64_t *>(&out)));
+        return out;
+    }
+    uint32_t k_;
+    size_t n_;
+    h2v_srs_t h_ = nullptr;
+};
+
+class EvaluationDomain {
+  public:
+    EvaluationDomain(uint32_t j, uint32_t k) : j_(j), k_(k) { check(h2v_domain_new(j, k, &h_)); }
+    ~EvaluationDomain() { h2v_domain_free(h_); }
+    EvaluationDomain(const EvaluationDomain &) = delete;
+    EvaluationDomain &operator=(const EvaluationDomain &) = delete;
+    uint32_t k() const { return k_; }
+    uint32_t extended_k() const { return h2v_domain_extended_k(h_); }
+    size_t extended_len() const { return size_t(1) << extended_k(); }
+    uint32_t get_quotient_poly_degree() const { return j_ - 1; }
+    Fr get_omega() const { return constant(0); }
+    Fr get_omega_inv() const { return constant(1); }
+    Fr get_extended_omega() const { return constant(2); }
+    Fr constant(int which) const {
+        Fr f{};
+        check(h2v_domain_constant(h_, which, f.l));
+        return f;
+    }
+    void lagrange_to_coeff(std::vector<Fr> &a) const { need(a.size(), size_t(1) << k_); check(h2v_lagrange_to_coeff(h_, u(a))); }
+    void coeff_to_lagrange(std::vector<Fr> &a) const { need(a.size(), size_t(1) << k_); check(h2v_coeff_to_lagrange(h_, u(a))); }
+    std::vector<Fr> coeff_to_extended(const std::vector<Fr> &a) const {
+        need(a.size(), size_t(1) << k_);
+        std::vector<Fr> out(extended_len());
+        check(h2v_coeff_to_extended(h_, reinterpret_cast<const uint64_t *>(a.data()), u(out)));
+        return out;
+    }
+    std::vector<Fr> extended_to_coeff(const std::vector<Fr> &a) const {
+        need(a.size(), extended_len());
+        std::vector<Fr> out((size_t(1) << k_) * (j_ - 1));
+        check(h2v_extended_to_coeff(h_, reinterpret_cast<const uint64_t *>(a.data()), u(out)));
+        return out;
+    }
+    void divide_by_vanishing_poly(std::vector<Fr> &a) const { need(a.size(), extended_len()); check(h2v_divide_by_vanishing_poly(h_, u(a))); }
+    h2v_domain_t handle() const { return h_; }
+
+  private:
+    static uint64_t *u(std::vector<Fr> &v) { return reinterpret_cast<uint64_t *>(v.data()); }
+    static void need(size_t got, size_t want) {
+        if (got != want) throw std::invalid_argument("assertion failed: polynomial length does not match the domain");
+    }
+    uint32_t j_, k_;
+    h2v_domain_t h_ = nullptr;
+};
+
+}  // namespace h2v_host
