@@ -187,7 +187,9 @@ def main():
     def step_e2e():
         h._check(h.lib().h2v_commit_batch(srs._h, h.H2V_BASIS_LAGRANGE, col_ptrs, cols, N, out_host.ctypes.data_as(C.c_void_p)))
 
-    peak = h.imad_peak()                               # measured IMAD.WIDE rate on this GPU, wide-MAC/s
+    # integer-pipe peak, measured live (MEASURED_PEAKS.json has none): the better of a loop-variant mad.wide.u32
+    # stream and a register-resident Fq Montgomery-product chain (136 wide-MACs per product)
+    peak = max(h.imad_peak(), h.op_rate(1) * FQ_MUL_MACS)
 
     # ---- device-resident timing
     for _ in range(args.warmup):
@@ -244,12 +246,14 @@ def main():
         "roofline": {"bound": "int32-pipe (IMAD.WIDE)", "kernel": "msm_accumulate_kernel", "achieved": achieved,
                      "peak": peak / 1e12, "unit": "T wide-MAC/s", "frac": (achieved / (peak / 1e12)) if achieved else None,
                      "traffic": None,
-                     "peak_source": "measured live: h2v_selftest_imad_peak (MEASURED_PEAKS.json has no integer peak)",
+                     "peak_source": "measured live: max(h2v_selftest_imad_peak, h2v_selftest_op_rate(Fq mul) x 136); MEASURED_PEAKS.json has no integer peak; nominal 148 SM x 32 IMAD.WIDE/clk x 1.965 GHz = 9.31",
+                     "executed": (cols * N * 16 * 1360) / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None,
                      "algorithmic": f"{MSM_MACS_PER_POINT[K]} wide-MAC/pt x {cols * N} pts per launch (SURVEY.md 8d)"},
     }
 
     if not args.no_extras and rank == 0:
         line["ntt"] = bench_ntt(h, torch, dev, peak)
+        line["witness_like"] = bench_witness(h, torch, dev, srs)
         if world == 1:
             threads = os.cpu_count() or 1
             v, secs = cpu_msm_sample(8, threads)
@@ -262,6 +266,23 @@ def main():
     srs.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_witness(h, torch, dev, srs):
+    """Same commit batch on witness-shaped scalars (60% {0,1}, 30% < 2^15, 10% full width / r - small): the
+    distribution FixedPointChip columns really have (/root/reference/src/gadget/fixed_point.rs:68-119)."""
+    import numpy as np
+    from halo2_vectordb_b200.synthetic import witness_like
+    cols = 96
+    a = torch.from_numpy(witness_like(cols, N, 15, 7).view(np.int64)).to(dev)
+    out = torch.zeros((cols, 8), dtype=torch.int64, device=dev)
+    ms = []
+    for i in range(6):
+        srs.commit_batch_dev(a.data_ptr(), N, cols, N, out.data_ptr())
+        if i >= 2:
+            ms.append(sum(h.last_kernel_ms().values()))
+    t = statistics.median(ms) * 1e-3
+    return {"msm_mpts_per_s": cols * N / t / 1e6, "ms_per_step": t * 1e3, "cols_per_step": cols, "lookup_bits": 15}
 
 
 def bench_ntt(h, torch, dev, peak):

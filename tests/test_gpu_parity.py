@@ -284,3 +284,52 @@ def test_commit_k20_closed_form(h2v):
     for i, c in enumerate(cols):
         assert (got[i] == O.msm_closed_form(c)).all(), i
     srs.close()
+
+
+@pytest.mark.parametrize("log_n,mode", [(22, 0), (24, 1)])
+def test_best_multiexp_sweep_sizes_closed_form(h2v, log_n, mode):
+    """config 5 sweep sizes: device-generated bases (a*i+b)*G, closed-form check on the host (O(n) field ops)."""
+    n = 1 << log_n
+    bases = h2v.synthetic_bases(n)
+    chk = O.gen_bases(64)
+    assert (bases[:64] == chk).all() and O.g1_is_on_curve(bases[n - 1])
+    s = O.fr_fill(n, 77 + log_n, mode=mode, lookup_bits=20)
+    got = O.g1_to_affine(h2v.best_multiexp(s, bases))
+    assert (got == O.msm_closed_form(s)).all()
+
+
+def test_synthetic_bases_match_oracle(h2v):
+    for n in (1, 5, 300):
+        assert (h2v.synthetic_bases(n) == O.gen_bases(n)).all()
+    assert (h2v.synthetic_bases(17, 12345677, 987654321) == O.gen_bases(17, a=12345677, b=987654321)).all()
+
+
+def test_witness_columns_with_giant_buckets(h2v):
+    """A column that is 90% ones and small values puts most points into a handful of buckets: exercises the
+    chunk-straddling merge and the warp-per-bucket path for long spans."""
+    k, n = 14, 1 << 14
+    b = O.gen_bases(n)
+    srs = h2v.ParamsKZG(k, None, b)
+    rnd = random.Random(5)
+    vals = [1 if rnd.random() < 0.9 else rnd.choice([0, 2, P.R - 1, P.R - 5, rnd.randrange(P.R)]) for _ in range(n)]
+    col = fr_arr(vals)
+    ones = fr_arr([1] * n)
+    neg = fr_arr([P.R - 3] * n)
+    got = srs.commit_batch([col, ones, neg])
+    for g, c in zip(got, (col, ones, neg)):
+        assert (g == O.msm_closed_form(c)).all()
+    srs.close()
+
+
+def test_cpp_mirror(h2v, tmp_path):
+    """include/h2v.hpp: compile, link against libh2v.so and run the round-trip check on the GPU."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cpp_mirror_check")
+    libdir = os.path.join(root, "halo2_vectordb_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(root, "include"), "-o", exe,
+                           os.path.join(root, "tests", "cpp_mirror_check.cpp"), "-L" + libdir, "-lh2v", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "cpp mirror ok" in out.stdout, out.stdout + out.stderr

@@ -160,3 +160,17 @@ def test_msm_pipeline_model(n, c, pre, chunk, ncols, dist):
     exp = [sum(a * b for a, b in zip(s, pts)) % P.R for s in cols]
     for log_seg in (3, 5):
         assert KM.msm_model(cols, pts, c, pre, chunk, ncols, log_seg) == exp
+
+
+def test_cpp_mirror_compiles_and_fails_loudly_without_gpu(built, tmp_path):
+    import subprocess
+
+    import halo2_vectordb_b200 as h
+
+    exe = str(tmp_path / "cpp_mirror_check")
+    libdir = os.path.join(ROOT, "halo2_vectordb_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp_mirror_check.cpp"), "-L" + libdir, "-lh2v", "-Wl,-rpath," + libdir])
+    if h.device_count() == 0:
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 0 and "no device" in out.stdout
