@@ -256,3 +256,215 @@ def msm_model(scalars, points, c, precomp, chunk, n_cols=1, log_seg=5):
             acc = (acc + S_in[col * G + g] + A_in[col * G + g]) % R
         out.append(acc)
     return out
+
+
+# ----------------------------------------------------------------------------- batch-affine pair rounds
+def _upper_bound(arr, n, v):
+    """first index i in [0, n] with arr[i] > v (arr non-decreasing, arr has n+1 entries)"""
+    lo, hi = 0, n + 1
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if arr[mid] > v:
+            hi = mid
+        else:
+            lo = mid + 1
+    return lo
+
+
+def batch_inverse_tree(X, G):
+    """mirror of binv_up / binv_top / binv_down: inverses of all X (non-zero) with ONE modular inversion"""
+    levels = [list(X)]
+    prefixes = []
+    while len(levels[-1]) > 1:
+        cur = levels[-1]
+        nxt, pre = [], [0] * len(cur)
+        for g in range(0, len(cur), G):
+            run = 1
+            for i in range(g, min(g + G, len(cur))):
+                pre[i] = run
+                run = run * cur[i] % R
+            nxt.append(run)
+        prefixes.append(pre)
+        levels.append(nxt)
+    inv = [pow(levels[-1][0], -1, R)]          # the only true inversion (binv_top)
+    for lvl in range(len(levels) - 2, -1, -1):
+        cur, pre = levels[lvl], prefixes[lvl]
+        out = [0] * len(cur)
+        for g in range(0, len(cur), G):
+            I = inv[g // G]
+            for i in range(min(g + G, len(cur)) - 1, g - 1, -1):
+                out[i] = I * pre[i] % R
+                I = I * cur[i] % R
+        inv = out
+    return inv
+
+
+def pair_round(points_in, off_in, n_buckets, K, G, first_entries=None, table=None):
+    """One batch-affine round.  points_in: list of ints (None = identity) or, for the first round, entries
+    (pref, neg, b) into `table`.  Returns (points_out, off_out, bid_out).  'Affine add' of k1*G and k2*G is
+    modelled as (k1 + k2) mod R, with the x-coordinate stand-in x(k) = k*k+7 mod R (so that x(k) == x(-k),
+    as on the curve) driving the same case analysis and the same batch-inversion tree as the kernels."""
+    def load(idx):
+        if first_entries is not None:
+            pref, neg, _ = first_entries[idx]
+            v = table[pref]
+            return None if v is None else ((-v) % R if neg else v)
+        return points_in[idx]
+
+    def xcoord(v):
+        return (v * v + 7) % R
+
+    def classify(a, b):
+        # returns (kind, d): kinds ADD, DOUBLE, CANCEL, TAKE_A, TAKE_B
+        if a is None and b is None:
+            return "CANCEL", 1
+        if a is None:
+            return "TAKE_B", 1
+        if b is None:
+            return "TAKE_A", 1
+        if xcoord(a) != xcoord(b):
+            return "ADD", (xcoord(b) - xcoord(a)) % R
+        if a == b and a != 0:
+            return "DOUBLE", (2 * a) % R or 1
+        return "CANCEL", 1
+
+    cnt = [(off_in[b + 1] - off_in[b] + 1) // 2 for b in range(n_buckets)]
+    off_out = [0]
+    for c in cnt:
+        off_out.append(off_out[-1] + c)
+    S = off_out[-1]
+    n_thr = (S + K - 1) // K
+    P0 = [None] * S
+    X1 = [1] * n_thr
+    # forward
+    for t in range(n_thr):
+        o0 = t * K
+        b = _upper_bound(off_out, n_buckets, o0) - 1
+        run = 1
+        for k in range(K):
+            o = o0 + k
+            if o >= S:
+                break
+            while o >= off_out[b + 1]:
+                b += 1
+            i = o - off_out[b]
+            in0 = off_in[b] + 2 * i
+            P0[o] = run
+            if in0 + 1 < off_in[b + 1]:
+                _, d = classify(load(in0), load(in0 + 1))
+                run = run * d % R
+        X1[t] = run
+    I1 = batch_inverse_tree(X1, G)
+    out = [None] * S
+    bid = [None] * S
+    # backward
+    for t in range(n_thr):
+        o_last = min(t * K + K, S) - 1
+        b = _upper_bound(off_out, n_buckets, o_last) - 1
+        I = I1[t]
+        for o in range(o_last, t * K - 1, -1):
+            while o < off_out[b]:
+                b -= 1
+            i = o - off_out[b]
+            in0 = off_in[b] + 2 * i
+            bid[o] = b
+            if in0 + 1 < off_in[b + 1]:
+                a, c = load(in0), load(in0 + 1)
+                kind, d = classify(a, c)
+                inv_d = I * P0[o] % R
+                I = I * d % R
+                assert inv_d * d % R == 1
+                if kind in ("ADD", "DOUBLE"):
+                    out[o] = (a + c) % R
+                elif kind == "TAKE_A":
+                    out[o] = a
+                elif kind == "TAKE_B":
+                    out[o] = c
+                else:
+                    out[o] = None
+            else:
+                out[o] = load(in0)
+    return out, off_out, bid
+
+
+def msm_model_affine(scalars, points, c, precomp, chunk, n_cols=1, rounds=3, K=4, G=4):
+    """msm_model with `rounds` batch-affine pair rounds in front of the chunked XYZZ accumulation."""
+    n = len(points)
+    W = windows_for(c)
+    Gw = 1 if precomp else W
+    nb = 1 << (c - 1)
+    half = nb - 1
+    Kadd = sum(half << (j * c) for j in range(W))
+    table = [(k << (j * c)) % R for j in range(W) for k in points] if precomp else list(points)
+    n_buckets = n_cols * Gw * nb
+    lists = [[] for _ in range(n_buckets)]
+    for col in range(n_cols):
+        for j in range(W):
+            for i in range(n):
+                t = scalars[col][i] + Kadd
+                sd = ((t >> (j * c)) & ((1 << c) - 1)) - half
+                if sd:
+                    g = j if Gw > 1 else 0
+                    lists[(col * Gw + g) * nb + abs(sd) - 1].append((i if Gw > 1 else j * n + i, sd < 0))
+    entries, off = [], [0]
+    for b, l in enumerate(lists):
+        entries += [(p, s, b) for p, s in l]
+        off.append(len(entries))
+    pts, first = None, entries
+    for r in range(rounds):
+        pts, off, bid = pair_round(pts, off, n_buckets, K, G, first_entries=first, table=table)
+        first = None
+    if rounds:
+        entries = [(o, False, bid[o]) for o in range(len(pts))]
+        table = pts
+    # chunked accumulation + finish + reduction exactly as msm_model (identity points are skipped)
+    M = len(entries)
+    buckets = [None] * n_buckets
+    nthreads = max((M + chunk - 1) // chunk, 1)
+    edges = [None] * (2 * nthreads)
+    for t in range(nthreads):
+        start = t * chunk
+        if start >= M:
+            continue
+        end = min(start + chunk, M)
+        prev_b = entries[start - 1][2] if start > 0 else -1
+        next_b = entries[end][2] if end < M else -1
+        acc, cur_b, first_run = 0, entries[start][2], True
+        for e in range(start, end):
+            nxt_b = entries[e + 1][2] if e + 1 < end else -1
+            pref, neg, _ = entries[e]
+            v = table[pref]
+            if v is not None:
+                acc = (acc + (-v if neg else v)) % R
+            if nxt_b != cur_b:
+                last_run = e + 1 == end
+                sb, ca = first_run and prev_b == cur_b, last_run and next_b == cur_b
+                if not sb and not ca:
+                    buckets[cur_b] = acc
+                elif sb:
+                    edges[2 * t] = acc
+                else:
+                    edges[2 * t + 1] = acc
+                acc, cur_b, first_run = 0, nxt_b, False
+    for b in range(n_buckets):
+        s, e = off[b], off[b + 1]
+        if s == e:
+            buckets[b] = 0
+            continue
+        t0, t1 = s // chunk, (e - 1) // chunk
+        if t0 == t1:
+            continue
+        acc = edges[2 * t0 + 1]
+        for t in range(t0 + 1, t1 + 1):
+            acc = (acc + edges[2 * t]) % R
+        buckets[b] = acc
+    out = []
+    for col in range(n_cols):
+        acc = 0
+        for g in reversed(range(Gw)):
+            if g + 1 != Gw:
+                acc = (acc << c) % R
+            base = (col * Gw + g) * nb
+            acc = (acc + sum((m + 1) * buckets[base + m] for m in range(nb))) % R
+        out.append(acc)
+    return out
