@@ -254,6 +254,7 @@ def main():
     if not args.no_extras and rank == 0:
         line["ntt"] = bench_ntt(h, torch, dev, peak)
         line["witness_like"] = bench_witness(h, torch, dev, srs)
+        line["prove_shaped"] = bench_prove_shaped(h, torch, dev, srs, d_cols, cols)
         if world == 1:
             threads = os.cpu_count() or 1
             v, secs = cpu_msm_sample(8, threads)
@@ -266,6 +267,51 @@ def main():
     srs.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_prove_shaped(h, torch, dev, srs, d_cols, cols):
+    """The hot-path call schedule of ONE kmeans k=16 proof (~1150 commit_lagrange,
+    ~1140 lagrange_to_coeff, ~1140 coeff_to_extended, 1 fused divide_by_vanishing + extended_to_coeff) on
+    device-resident synthetic columns.  A PROXY for create_proof: witness generation, lookup sorting,
+    evaluate_h, evaluations and the transcript are not part of the path and not included."""
+    n_msm, n_intt, n_cntt = 1150, 1140, 1140
+    dom = h.EvaluationDomain(4, K)
+    d_out = torch.zeros((cols, 8), dtype=torch.int64, device=dev)
+    d_coef = torch.empty_like(d_cols)
+    ext_cols = 32
+    d_ext = torch.empty((ext_cols, 4 * N, 4), dtype=torch.int64, device=dev)
+    d_h = torch.empty((1, 4 * N, 4), dtype=torch.int64, device=dev)
+
+    def run():
+        left = n_msm
+        while left > 0:
+            c = min(cols, left)
+            srs.commit_batch_dev(d_cols.data_ptr(), N, c, N, d_out.data_ptr())
+            left -= c
+        left = n_intt
+        while left > 0:
+            c = min(cols, left)
+            dom.transform_dev(h.OP_LAGRANGE_TO_COEFF, d_cols.data_ptr(), N, d_coef.data_ptr(), N, c)
+            left -= c
+        left = n_cntt
+        while left > 0:
+            c = min(ext_cols, left)
+            dom.transform_dev(h.OP_COEFF_TO_EXTENDED, d_coef.data_ptr(), N, d_ext.data_ptr(), 4 * N, c)
+            left -= c
+        dom.transform_dev(h.OP_DIVIDE_BY_VANISHING, d_ext.data_ptr(), 4 * N, d_h.data_ptr(), 4 * N, 1)
+
+    run()
+    ts = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        run()
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t)
+    dom.close()
+    return {"latency_s": statistics.median(ts), "schedule": {"commit_lagrange": n_msm, "lagrange_to_coeff": n_intt,
+            "coeff_to_extended": n_cntt, "divide_by_vanishing+extended_to_coeff": 1}, "k": K,
+            "note": "hot-path proxy for one kmeans k=16 create_proof, uniform scalars, device-resident"}
 
 
 def bench_witness(h, torch, dev, srs):

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "h2v_best_fft", "h2v_domain_new", "h2v_domain_free", "h2v_domain_k", "h2v_domain_extended_k", "h2v_domain_constant",
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
     "h2v_divide_by_vanishing_poly", "h2v_domain_transform_batch", "h2v_domain_transform_dev",
-    "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_op_rate", "h2v_launch_count", "h2v_last_kernel_ms",
+    "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_op_rate", "h2v_set_tuning", "h2v_launch_count", "h2v_last_kernel_ms",
 ]
 
 
@@ -81,6 +81,7 @@ def lib():
         L.h2v_synthetic_bases.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p]
         L.h2v_selftest_imad_peak.argtypes = [C.POINTER(C.c_double)]
         L.h2v_selftest_op_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.h2v_set_tuning.argtypes = [C.c_int, C.c_int]
         L.h2v_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
         _lib = L
     return _lib
@@ -127,6 +128,11 @@ def imad_peak():
     out = C.c_double()
     _check(lib().h2v_selftest_imad_peak(C.byref(out)))
     return out.value
+
+
+def set_tuning(chunk=-1, ba_rounds=-1):
+    """MSM tuning knobs (-1 = automatic): results never depend on them."""
+    _check(lib().h2v_set_tuning(chunk, ba_rounds))
 
 
 def op_rate(which):

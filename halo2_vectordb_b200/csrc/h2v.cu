@@ -18,6 +18,7 @@
 
 #include "h2v.h"
 #include "msm.cuh"
+#include "msm_affine.cuh"
 #include "ntt.cuh"
 
 using namespace h2v;
@@ -332,30 +333,71 @@ struct Carver {
 };
 // sorted entries per accumulate thread: long enough that the per-chunk edge merge (one full add) is
 // amortised, short enough that a single small MSM still fills the GPU.  H2V_CHUNK overrides (tuning).
+std::atomic<int> g_tune_chunk{-2}, g_tune_ba{-2};   // -2: read the environment on first use; -1: automatic
+int tuning(std::atomic<int> &slot, const char *env) {
+    int v = slot.load();
+    if (v == -2) {
+        const char *e = getenv(env);
+        v = e ? atoi(e) : -1;
+        slot.store(v);
+    }
+    return v;
+}
 uint32_t pick_chunk(uint64_t max_entries) {
-    static const uint32_t forced = [] {
-        const char *e = getenv("H2V_CHUNK");
-        return e ? (uint32_t)atoi(e) : 0u;
-    }();
-    if (forced) return forced;
+    const int forced = tuning(g_tune_chunk, "H2V_CHUNK");
+    if (forced > 0) return (uint32_t)forced;
     uint64_t c = max_entries / (148ull * 2048ull);
     if (c < 4) c = 4;
     if (c > 64) c = 64;
     return (uint32_t)c;
 }
+#define H2V_BA_MAX_ROUNDS 8
+#define H2V_BA_MAX_LEVELS 12
 struct MsmLayout {
     size_t bytes;
     uint32_t *keys, *counts, *offsets, *cursor, *tile_sums, *long_list, *long_count;
     uint2 *entries;
     xyzz *buckets, *edges, *S[2], *A[2];
     uint32_t nthreads, n_buckets, l1;
+    // batch-affine rounds (ba_rounds > 0)
+    uint32_t ba_rounds, ba_K, ba_G;
+    uint64_t ba_slots[H2V_BA_MAX_ROUNDS];      // upper bound of the output slots of round r
+    uint32_t ba_chunk;                         // chunk of the final XYZZ pass over the surviving list
+    uint32_t *ba_off[2];
+    affine *ba_list[2];
+    fe *ba_P0;
+    uint2 *ba_entries;
+    uint32_t ba_levels;                        // inversion tree: level sizes n[0] = threads of round 0, ...
+    uint32_t ba_n[H2V_BA_MAX_LEVELS];
+    fe *ba_X[H2V_BA_MAX_LEVELS], *ba_P[H2V_BA_MAX_LEVELS], *ba_I[H2V_BA_MAX_LEVELS];
 };
+// Batch-affine pair rounds in front of the XYZZ accumulation (msm_affine.cuh).  OFF by default: measured on
+// B200 (profiles/r01_msm_batch_affine_launches.txt) the 6-product additions are paid for with ~350 B of
+// list / prefix-product traffic per pair and ~0.5 ms of serial inversion-tree latency per round, so
+// 96 columns x 2^16 take 17.0 ms with 5 rounds vs 17.0 ms for the pure XYZZ path (best: 3 rounds, 16.2 ms).
+// h2v_set_tuning / H2V_BA_ROUNDS switch them on (tests run them for the tuning-invariance check).
+uint32_t pick_ba_rounds(const MsmShape &, uint32_t) {
+    const int forced = tuning(g_tune_ba, "H2V_BA_ROUNDS");
+    if (forced >= 0) return std::min<uint32_t>((uint32_t)forced, H2V_BA_MAX_ROUNDS);
+    return 0;
+}
 MsmLayout msm_layout(void *base, const MsmShape &sh, uint32_t cols) {
     MsmLayout L;
+    memset(&L, 0, sizeof L);
     Carver cv(base);
     uint64_t ent = (uint64_t)cols * sh.W * sh.n;
     L.n_buckets = cols * sh.G * sh.nb;
-    L.nthreads = (uint32_t)((ent + sh.chunk - 1) / sh.chunk);
+    L.ba_rounds = pick_ba_rounds(sh, cols);
+    L.ba_K = 16;
+    L.ba_G = 16;
+    uint64_t final_len = ent;
+    for (uint32_t r = 0; r < L.ba_rounds; ++r) {
+        final_len = (final_len + L.n_buckets + 1) / 2;
+        L.ba_slots[r] = final_len;
+    }
+    L.ba_chunk = L.ba_rounds ? pick_chunk(final_len) : sh.chunk;
+    L.nthreads = (uint32_t)std::max<uint64_t>((ent + sh.chunk - 1) / sh.chunk, (final_len + L.ba_chunk - 1) / L.ba_chunk);
+    if (!L.ba_rounds) L.nthreads = (uint32_t)((ent + sh.chunk - 1) / sh.chunk);
     L.l1 = (sh.nb + 7) / 8;            // the reduction tree uses segments of 8..32: size for the worst case
     size_t l2 = (L.l1 + 7) / 8;
     L.keys = cv.take<uint32_t>(ent);
@@ -372,11 +414,31 @@ MsmLayout msm_layout(void *base, const MsmShape &sh, uint32_t cols) {
     L.A[0] = cv.take<xyzz>((size_t)cols * sh.G * L.l1);
     L.S[1] = cv.take<xyzz>((size_t)cols * sh.G * l2);
     L.A[1] = cv.take<xyzz>((size_t)cols * sh.G * l2);
+    if (L.ba_rounds) {
+        L.ba_off[0] = cv.take<uint32_t>((size_t)L.n_buckets + 1);
+        L.ba_off[1] = cv.take<uint32_t>((size_t)L.n_buckets + 1);
+        L.ba_list[0] = cv.take<affine>(L.ba_slots[0]);
+        L.ba_list[1] = cv.take<affine>(L.ba_rounds > 1 ? L.ba_slots[1] : 1);
+        L.ba_P0 = cv.take<fe>(L.ba_slots[0]);
+        L.ba_entries = cv.take<uint2>(L.ba_slots[L.ba_rounds - 1]);
+        // inversion tree sized for round 0 (the largest)
+        uint64_t nlev = (L.ba_slots[0] + L.ba_K - 1) / L.ba_K;
+        L.ba_levels = 0;
+        for (;;) {
+            L.ba_n[L.ba_levels] = (uint32_t)nlev;
+            L.ba_X[L.ba_levels] = cv.take<fe>(nlev);
+            L.ba_P[L.ba_levels] = cv.take<fe>(nlev);
+            L.ba_I[L.ba_levels] = cv.take<fe>(nlev);
+            ++L.ba_levels;
+            if (nlev <= 1 || L.ba_levels >= H2V_BA_MAX_LEVELS) break;
+            nlev = (nlev + L.ba_G - 1) / L.ba_G;
+        }
+    }
     L.bytes = cv.off + 256;
     return L;
 }
 
-const size_t MSM_WS_BUDGET = (size_t)6 << 30;   // per handle; columns per launch are sized to fit
+const size_t MSM_WS_BUDGET = (size_t)16 << 30;   // per handle; columns per launch are sized to fit
 
 // d_scalars: n_cols columns of `len` Fr (Montgomery), col_stride apart.  points: bases (raw) or
 // window tables (precomputed, level stride `pstride`).  Results: affine and/or Jacobian per column.
@@ -440,14 +502,85 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
         msm_scatter_kernel<<<dim3(gx, sh.W, cols), 256, 0, st>>>(L.keys, L.cursor, L.entries, sh);
         LAUNCHED();
         if (tm) { tm->end(); tm->begin(3); }
-        msm_accumulate_kernel<<<(L.nthreads + 127) / 128, 128, 0, st>>>(L.entries, L.offsets, L.n_buckets, points, L.buckets,
-                                                                        L.edges, sh.chunk);
+        const uint2 *acc_entries = L.entries;
+        const uint32_t *acc_offsets = L.offsets;
+        const affine *acc_points = points;
+        uint32_t acc_chunk = sh.chunk, acc_threads = (uint32_t)(((uint64_t)cols * sh.W * sh.n + sh.chunk - 1) / sh.chunk);
+        if (L.ba_rounds) {
+            // batch-affine pair rounds: every round halves each bucket with 6 products per addition
+            const uint32_t ntiles = (L.n_buckets + H2V_SCAN_TILE - 1) / H2V_SCAN_TILE;
+            const uint32_t *off_in = L.offsets;
+            const affine *list_in = nullptr;
+            for (uint32_t r = 0; r < L.ba_rounds; ++r) {
+                uint32_t *off_out = L.ba_off[r & 1];
+                affine *list_out = L.ba_list[r & 1];
+                ba_count_kernel<<<(L.n_buckets + 255) / 256, 256, 0, st>>>(off_in, L.counts, L.n_buckets);
+                LAUNCHED();
+                msm_scan_tiles_kernel<<<ntiles, 256, 0, st>>>(L.counts, L.tile_sums, L.n_buckets);
+                LAUNCHED();
+                msm_scan_top_kernel<<<1, 256, 0, st>>>(L.tile_sums, ntiles, off_out + L.n_buckets);
+                LAUNCHED();
+                msm_scan_apply_kernel<<<ntiles, 256, 0, st>>>(L.counts, L.tile_sums, off_out, L.cursor, L.n_buckets);
+                LAUNCHED();
+                BaRound br;
+                memset(&br, 0, sizeof br);
+                br.entries = L.entries;
+                br.table = points;
+                br.list_in = list_in;
+                br.off_in = off_in;
+                br.off_out = off_out;
+                br.n_buckets = L.n_buckets;
+                br.K = L.ba_K;
+                br.P0 = L.ba_P0;
+                br.X1 = L.ba_X[0];
+                br.I1 = L.ba_I[0];
+                br.list_out = list_out;
+                br.entries_out = (r + 1 == L.ba_rounds) ? L.ba_entries : nullptr;
+                br.n_threads = (uint32_t)((L.ba_slots[r] + L.ba_K - 1) / L.ba_K);
+                // inversion tree levels for this round's thread count
+                uint32_t nlev[H2V_BA_MAX_LEVELS], levels = 0;
+                for (uint64_t v = br.n_threads;;) {
+                    nlev[levels++] = (uint32_t)v;
+                    if (v <= 1 || levels >= H2V_BA_MAX_LEVELS) break;
+                    v = (v + L.ba_G - 1) / L.ba_G;
+                }
+                if (nlev[levels - 1] != 1) return fail(H2V_EINVAL, "MSM too large for the inversion tree");
+                const unsigned gb = (br.n_threads + 127) / 128;
+                if (r == 0) ba_forward_kernel<true><<<gb, 128, 0, st>>>(br);
+                else ba_forward_kernel<false><<<gb, 128, 0, st>>>(br);
+                LAUNCHED();
+                for (uint32_t l = 0; l + 1 < levels; ++l) {
+                    binv_up_kernel<<<(nlev[l + 1] + 127) / 128, 128, 0, st>>>(L.ba_X[l], L.ba_P[l], L.ba_X[l + 1], nlev[l], L.ba_G);
+                    LAUNCHED();
+                }
+                binv_top_kernel<<<1, 32, 0, st>>>(L.ba_X[levels - 1], L.ba_I[levels - 1]);
+                LAUNCHED();
+                for (uint32_t l = levels - 1; l-- > 0;) {
+                    binv_down_kernel<<<(nlev[l + 1] + 127) / 128, 128, 0, st>>>(L.ba_X[l], L.ba_P[l], L.ba_I[l + 1], L.ba_I[l], nlev[l], L.ba_G);
+                    LAUNCHED();
+                }
+                if (r == 0) ba_backward_kernel<true><<<gb, 128, 0, st>>>(br);
+                else ba_backward_kernel<false><<<gb, 128, 0, st>>>(br);
+                LAUNCHED();
+                off_in = off_out;
+                list_in = list_out;
+            }
+            acc_entries = L.ba_entries;
+            acc_offsets = off_in;
+            acc_points = list_in;
+            acc_chunk = L.ba_chunk;
+            acc_threads = (uint32_t)((L.ba_slots[L.ba_rounds - 1] + acc_chunk - 1) / acc_chunk);
+        }
+        msm_accumulate_kernel<<<(acc_threads + 127) / 128, 128, 0, st>>>(acc_entries, acc_offsets, L.n_buckets, acc_points, L.buckets,
+                                                                        L.edges, acc_chunk);
         LAUNCHED();
         if (tm) { tm->end(); tm->begin(4); }
-        msm_finish_kernel<<<(L.n_buckets + 127) / 128, 128, 0, st>>>(L.offsets, L.n_buckets, L.edges, L.buckets, sh.chunk, L.long_list,
+        // long_count shares the histogram buffer, which the rounds reuse: clear it again
+        CU(cudaMemsetAsync(L.long_count, 0, sizeof(uint32_t), st));
+        msm_finish_kernel<<<(L.n_buckets + 127) / 128, 128, 0, st>>>(acc_offsets, L.n_buckets, L.edges, L.buckets, acc_chunk, L.long_list,
                                                                      L.long_count);
         LAUNCHED();
-        msm_finish_long_kernel<<<148 * 4, 128, 0, st>>>(L.offsets, L.edges, L.buckets, sh.chunk, L.long_list, L.long_count);
+        msm_finish_long_kernel<<<148 * 4, 128, 0, st>>>(acc_offsets, L.edges, L.buckets, acc_chunk, L.long_list, L.long_count);
         LAUNCHED();
         if (tm) { tm->end(); tm->begin(5); }
         // reduction tree over each (column, group)
@@ -515,6 +648,11 @@ int h2v_init(int device) {
     g_device = device;
     CU(cudaSetDevice(device));
     CU(cudaFree(0));
+    return H2V_OK;
+}
+int h2v_set_tuning(int chunk, int ba_rounds) {
+    g_tune_chunk.store(chunk > 0 ? chunk : -1);
+    g_tune_ba.store(ba_rounds >= 0 ? ba_rounds : -1);
     return H2V_OK;
 }
 int h2v_last_kernel_ms(float out[8]) {

@@ -115,6 +115,10 @@ int h2v_selftest_imad_peak(double *out_wmac_per_s);
 /* register-only throughput of the kernels' building blocks, operations per second over the whole GPU:
  * which 0: Fq Montgomery product, one dependent chain per thread; 1: two chains; 2: XYZZ mixed-add chain */
 int h2v_selftest_op_rate(int which, double *out_ops_per_s);
+/* MSM tuning knobs (tests / tuning; -1 = automatic, the default; also H2V_CHUNK / H2V_BA_ROUNDS in the
+ * environment): `chunk` = sorted entries per accumulate thread, `ba_rounds` = batch-affine pair rounds in
+ * front of the XYZZ accumulation (0 disables them).  Results do not depend on either. */
+int h2v_set_tuning(int chunk, int ba_rounds);
 /* kernels launched by this process so far (for bench.py's gpu_launches) */
 uint64_t h2v_launch_count(void);
 /* device-side timing of the last commit_batch_dev / transform_dev call, in milliseconds per kernel class:

@@ -333,3 +333,35 @@ def test_cpp_mirror(h2v, tmp_path):
                            os.path.join(root, "tests", "cpp_mirror_check.cpp"), "-L" + libdir, "-lh2v", "-Wl,-rpath," + libdir])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "cpp mirror ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("ba_rounds,chunk", [(1, 4), (3, 7), (6, 64), (0, 5)])
+def test_msm_tuning_invariance(h2v, ba_rounds, chunk):
+    """Batch-affine pair rounds and the chunk length change the schedule, never the result: force them on
+    small inputs (uniform, witness-like with giant buckets, duplicate / opposite / identity bases)."""
+    try:
+        h2v.set_tuning(chunk, ba_rounds)
+        k, n = 11, 1 << 11
+        b = O.gen_bases(n)
+        srs = h2v.ParamsKZG(k, None, b)
+        rnd = random.Random(ba_rounds * 100 + chunk)
+        cols = [O.fr_fill(n, 1, mode=0), O.fr_fill(n, 2, mode=1), fr_arr([1] * n),
+                fr_arr([rnd.choice([0, 1, 2, P.R - 1]) for _ in range(n)])]
+        got = srs.commit_batch(cols)
+        for g, c in zip(got, cols):
+            assert (g == O.msm_closed_form(c)).all()
+        srs.close()
+        # raw path with pathological bases
+        m = 700
+        g7 = O.g1_mul(O.g1_generator(), 7)
+        x, y = O.g1_affine_to_ints(g7)
+        neg7 = O.g1_affine_from_ints((x, (-y) % P.P))
+        bases = np.stack([rnd.choice([g7, g7, neg7, np.zeros(8, dtype=np.uint64), b[3]]) for _ in range(m)])
+        s = O.fr_fill(m, 9, mode=1)
+        assert (O.g1_to_affine(h2v.best_multiexp(s, bases)) == O.best_multiexp_affine(s, bases)).all()
+        for v in golden()["msm"]:
+            sc = fr_arr([ival(x) for x in v["scalars"]])
+            bs = g1_arr([ipt(p) for p in v["bases"]])
+            assert O.g1_affine_to_ints(O.g1_to_affine(h2v.best_multiexp(sc, bs))) == ipt(v["result"])
+    finally:
+        h2v.set_tuning(-1, -1)
