@@ -35,6 +35,7 @@ N = 1 << K
 COLS = 96                      # 96 x 2 MiB of scalars = 192 MiB per step (> 126 MB L2), tables 64 MiB more
 MSM_MACS_PER_POINT = {16: 27200, 13: 27200, 20: 20400}   # W(n) * 1360 wide-MACs
 FQ_MUL_MACS = 136
+ACC_DRAM_BYTES_PER_LAUNCH = 3.82e9   # msm_accumulate_kernel, 96 columns x 2^16: 3.223 GB read + 0.592 GB written (ncu, r01)
 SYN_A, SYN_B = 0x9E3779B97F4A7C15 >> 2, 0x632BE59BD9B4E019 >> 2
 
 
@@ -107,7 +108,7 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     from oracle import oracle as O
-    sample_cols = 4
+    sample_cols = 8
     bases = O.gen_bases(N, threads=threads)
     cols = [O.fr_fill(N, 7000 + i) for i in range(sample_cols)]
     for _ in range(min(args.warmup, 1)):
@@ -192,12 +193,14 @@ def main():
     peak = max(h.imad_peak(), h.op_rate(1) * FQ_MUL_MACS)
 
     # ---- device-resident timing
+    # the clock sampler starts before the warm-up (nvidia-smi needs a few hundred ms to deliver its first
+    # line); warm-up and timed steps are the same load, so every sample is taken under load
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_dev()
-    sampler = ClockSampler(local_rank)
     kernel_ms = {k: 0.0 for k in h.KERNEL_CLASSES}
     barrier()
-    sampler.start()
     l0 = h.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -245,7 +248,8 @@ def main():
         "kernel_ms_per_step": {k: round(v / args.steps, 4) for k, v in kernel_ms.items() if v},
         "roofline": {"bound": "int32-pipe (IMAD.WIDE)", "kernel": "msm_accumulate_kernel", "achieved": achieved,
                      "peak": peak / 1e12, "unit": "T wide-MAC/s", "frac": (achieved / (peak / 1e12)) if achieved else None,
-                     "traffic": None,
+                     "traffic": ACC_DRAM_BYTES_PER_LAUNCH if cols == COLS else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full of this command (profiles/r01_bench_launches_ncu.txt)",
                      "peak_source": "measured live: max(h2v_selftest_imad_peak, h2v_selftest_op_rate(Fq mul) x 136); MEASURED_PEAKS.json has no integer peak; nominal 148 SM x 32 IMAD.WIDE/clk x 1.965 GHz = 9.31",
                      "executed": (cols * N * 16 * 1360) / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None,
                      "algorithmic": f"{MSM_MACS_PER_POINT[K]} wide-MAC/pt x {cols * N} pts per launch (SURVEY.md 8d)"},
@@ -257,9 +261,9 @@ def main():
         line["prove_shaped"] = bench_prove_shaped(h, torch, dev, srs, d_cols, cols)
         if world == 1:
             threads = os.cpu_count() or 1
-            v, secs = cpu_msm_sample(8, threads)
+            v, secs = cpu_msm_sample(24, threads)
             line["cpu_baseline"] = {"value": v, "unit": "Mpts/s", "cores": threads, "kind": "port",
-                                    "sample": f"8 of the {cols} columns (2^16 uniform Fr each), restated halo2-axiom best_multiexp, {secs:.1f} s"}
+                                    "sample": f"24 of the {cols} columns (2^16 uniform Fr each), restated halo2-axiom best_multiexp, {secs:.1f} s"}
     if world > 1:
         dist.barrier()
     if rank == 0:
