@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -103,7 +103,7 @@ def cpu_msm_sample(n_cols, threads):
     return n_cols * N / dt / 1e6, dt
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
@@ -120,7 +120,7 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t
     v = args.steps * sample_cols * N / dt / 1e6
     sample = f"{sample_cols} columns of 2^16 uniform Fr per step (of the {args.cols}-column batch), best_multiexp over {threads} threads"
-    print(json.dumps({
+    print(file=out, *[json.dumps({
         "impl": "reference", "metric": "msm_mpts_per_s", "value": v, "unit": "Mpts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 Montgomery (4x64 on the CPU)", "data": "synthetic",
@@ -128,17 +128,29 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": v, "unit": "Mpts/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated halo2-axiom CPU path (oracle/bn254_oracle.c); the Rust reference cannot be built here (no cargo, un-vendored deps)",
-    }))
+    })])
 
 
 # ----------------------------------------------------------------------------------- GPU arm
 def main():
     args = parse()
+    # rank 0 must print exactly ONE JSON line: park the real stdout and send everything else (NCCL's version
+    # banner, library chatter) to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    try:
+        _main(args, real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(args, real_stdout):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, real_stdout)
         return
 
     import numpy as np
@@ -267,7 +279,7 @@ def main():
     if world > 1:
         dist.barrier()
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout)
     srs.close()
     if world > 1:
         dist.destroy_process_group()

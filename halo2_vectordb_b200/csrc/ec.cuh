@@ -143,6 +143,18 @@ H2V_HD affine xyzz_to_affine(const xyzz &p) {
     r.y = fe_mul<Fq>(p.y, fe_mul<Fq>(i, p.zz));
     return r;
 }
+// the same with the binary-Euclid inversion: for single-thread, latency-bound callers
+H2V_HD affine xyzz_to_affine_fast(const xyzz &p) {
+    affine r;
+    if (xyzz_is_identity(p)) {
+        r.x = fe_zero(); r.y = fe_zero();
+        return r;
+    }
+    fe i = fe_inv_fast<Fq>(fe_mul<Fq>(p.zz, p.zzz));
+    r.x = fe_mul<Fq>(p.x, fe_mul<Fq>(i, p.zzz));
+    r.y = fe_mul<Fq>(p.y, fe_mul<Fq>(i, p.zz));
+    return r;
+}
 // a Jacobian representative of the same point, no inversion: Z = ZZZ  =>  X' = X*ZZ^2, Y' = Y*ZZZ^2
 H2V_HD jacobian xyzz_to_jacobian(const xyzz &p) {
     jacobian r;

@@ -45,6 +45,10 @@ struct FqP {
         return i == 0 ? 0x538afa89u : i == 1 ? 0xf32cfc5bu : i == 2 ? 0xd44501fbu : i == 3 ? 0xb5e71911u
              : i == 4 ? 0x0a417ff6u : i == 5 ? 0x47ab1effu : i == 6 ? 0xcab8351fu : 0x06d89f71u;
     }
+    static H2V_HD uint32_t r3(int i) {                      // R^3 mod p
+        return i == 0 ? 0xda1530dfu : i == 1 ? 0xb1cd6dafu : i == 2 ? 0xa7283db6u : i == 3 ? 0x62f210e6u
+             : i == 4 ? 0x0ada0afbu : i == 5 ? 0xef7f0b0cu : i == 6 ? 0x2d592544u : 0x20fd6e90u;
+    }
 };
 struct FrP {
     static H2V_HD uint32_t m(int i) {
@@ -59,6 +63,10 @@ struct FrP {
     static H2V_HD uint32_t r2(int i) {
         return i == 0 ? 0xae216da7u : i == 1 ? 0x1bb8e645u : i == 2 ? 0xe35c59e3u : i == 3 ? 0x53fe3ab1u
              : i == 4 ? 0x53bb8085u : i == 5 ? 0x8c49833du : i == 6 ? 0x7f4e44a5u : 0x0216d0b1u;
+    }
+    static H2V_HD uint32_t r3(int i) {
+        return i == 0 ? 0xb4bf0040u : i == 1 ? 0x5e94d8e1u : i == 2 ? 0x1cfbb6b8u : i == 3 ? 0x2a489cbeu
+             : i == 4 ? 0xa19fcfedu : i == 5 ? 0x893cc664u : i == 6 ? 0x7fcc657cu : 0x0cf8594bu;
     }
 };
 
@@ -343,6 +351,88 @@ template <class F> H2V_HD fe fe_inv(const fe &a) {
     for (int i = 0; i < 8; ++i) e[i] = F::m(i);
     e[0] -= 2;   // low limbs of p and r are >= 2
     return fe_pow<F>(a, e, 254);
+}
+
+// ------------------------------------------------------------------ fast inversion (binary extended Euclid)
+// Latency matters where ONE inversion sits on the critical path (affine normalisation of an MSM result,
+// the root of the batch-inversion tree): ~500 shift/subtract steps on the ALU pipe instead of the ~380
+// dependent Montgomery products of Fermat's a^(m-2).  Works on the stored integer a = x R and converts:
+// (xR)^-1 * R^3 * R^-1 = x^-1 R.   a == 0 -> 0.
+H2V_HD void raw_shr1(uint32_t *a, uint32_t top) {      // a = (top:a) >> 1
+#pragma unroll
+    for (int i = 0; i < 7; ++i) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+    a[7] = (a[7] >> 1) | (top << 31);
+}
+H2V_HD bool raw_is_one(const uint32_t *a) {
+    uint32_t o = a[0] ^ 1u;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) o |= a[i];
+    return o == 0;
+}
+template <class F> H2V_HD void half_mod(uint32_t *x, const uint32_t *mm) {   // x = x / 2 mod m, x < m
+    if (x[0] & 1u) {
+        uint32_t t[8];
+        raw_add(t, x, mm);            // x + m < 2^255: no carry out
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = t[i];
+    }
+    raw_shr1(x, 0);
+}
+template <class F> H2V_HD fe fe_inv_fast(const fe &a) {
+    if (fe_is_zero(a)) return a;
+    uint32_t mm[8], u[8], v[8], x1[8], x2[8], t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        mm[i] = F::m(i);
+        u[i] = a.v[i];
+        v[i] = mm[i];
+        x1[i] = 0;
+        x2[i] = 0;
+    }
+    x1[0] = 1;
+    while (!raw_is_one(u) && !raw_is_one(v)) {
+        while (!(u[0] & 1u)) {
+            raw_shr1(u, 0);
+            half_mod<F>(x1, mm);
+        }
+        while (!(v[0] & 1u)) {
+            raw_shr1(v, 0);
+            half_mod<F>(x2, mm);
+        }
+        uint32_t bw = raw_sub(t, u, v);
+        if (!bw) {                    // u >= v
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[i] = t[i];
+            bw = raw_sub(t, x1, x2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x1[i] = t[i];
+            if (bw) {
+                raw_add(t, x1, mm);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x1[i] = t[i];
+            }
+        } else {
+            raw_sub(t, v, u);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = t[i];
+            bw = raw_sub(t, x2, x1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x2[i] = t[i];
+            if (bw) {
+                raw_add(t, x2, mm);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x2[i] = t[i];
+            }
+        }
+    }
+    fe r, r3;
+    const bool uo = raw_is_one(u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.v[i] = uo ? x1[i] : x2[i];
+        r3.v[i] = F::r3(i);
+    }
+    return fe_mul<F>(r, r3);
 }
 
 }  // namespace h2v

@@ -603,7 +603,7 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
             shift += log_seg;
         } while (cnt > 1);
         if (tm) { tm->end(); tm->begin(6); }
-        msm_final_kernel<<<(cols + 31) / 32, 32, 0, st>>>(Sin, Ain, cols, sh.G, sh.c, d_out_aff ? d_out_aff + c0 : nullptr,
+        msm_final_kernel<<<cols, 32, 0, st>>>(Sin, Ain, cols, sh.G, sh.c, d_out_aff ? d_out_aff + c0 : nullptr,
                                                           d_out_jac ? d_out_jac + c0 : nullptr);
         LAUNCHED();
         if (tm) tm->end();
@@ -619,9 +619,9 @@ struct h2v_srs {
     DevBuf table[2];     // [basis]: W levels of n affine points (level 0 = the bases)
     bool have[2] = {false, false};
     MsmCfg cfg;
-    MsmWorkspace ws;
+    MsmWorkspace ws, ws2;
     DevBuf stage, out;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, computed[2] = {nullptr, nullptr};
     std::mutex mu;
 };
@@ -708,11 +708,13 @@ void h2v_srs_free(h2v_srs_t s) {
     s->table[0].release();
     s->table[1].release();
     s->ws.buf.release();
+    s->ws2.buf.release();
     s->stage.release();
     s->out.release();
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) {
         cudaStreamDestroy(s->copy_stream);
+        cudaStreamDestroy(s->stream2);
         for (int b = 0; b < 2; ++b) {
             cudaEventDestroy(s->copied[b]);
             cudaEventDestroy(s->computed[b]);
@@ -751,8 +753,10 @@ int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_
     int rc = use_device();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(s->mu);
-    // Double-buffered staging: while the kernels of sub-batch i run on `stream`, the columns of sub-batch
-    // i+1 cross PCIe on `copy_stream` (effective when the caller's buffers are pinned).
+    // Double-buffered staging: while the kernels of sub-batch i run, the columns of sub-batch i+1 cross PCIe
+    // on `copy_stream` (effective when the caller's buffers are pinned).  Sub-batches alternate between two
+    // compute streams with their own workspaces, so the latency-bound tail of one (bucket-reduction tree,
+    // affine normalisation) overlaps the bulk kernels of the next.
     const size_t stride = std::max<size_t>(len, 1);
     size_t sub = std::max<size_t>(1, ((size_t)48 << 20) / (stride * sizeof(fe)));
     sub = std::min(sub, n_polys);
@@ -760,6 +764,7 @@ int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_
     if ((rc = s->out.ensure(n_polys * sizeof(affine)))) return rc;
     if (!s->copy_stream) {
         CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
         for (int b = 0; b < 2; ++b) {
             CU(cudaEventCreateWithFlags(&s->copied[b], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s->computed[b], cudaEventDisableTiming));
@@ -780,16 +785,19 @@ int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_
             if (len) CU(cudaMemcpyAsync(stg + c * stride, polys[c0 + c], len * sizeof(fe), cudaMemcpyHostToDevice, s->copy_stream));
         }
         CU(cudaEventRecord(s->copied[b], s->copy_stream));
-        CU(cudaStreamWaitEvent(s->stream, s->copied[b], 0));
-        rc = run_msm(s->stream, s->ws, stg, stride, cols, len, s->table[basis].as<affine>(), s->cfg, s->n,
+        cudaStream_t cst = b ? s->stream2 : s->stream;
+        CU(cudaStreamWaitEvent(cst, s->copied[b], 0));
+        rc = run_msm(cst, b ? s->ws2 : s->ws, stg, stride, cols, len, s->table[basis].as<affine>(), s->cfg, s->n,
                      s->out.as<affine>() + c0, nullptr, nullptr);
         if (rc) {
             cudaStreamSynchronize(s->stream);
+            cudaStreamSynchronize(s->stream2);
             cudaStreamSynchronize(s->copy_stream);
             return rc;
         }
-        CU(cudaEventRecord(s->computed[b], s->stream));
+        CU(cudaEventRecord(s->computed[b], cst));
     }
+    if (it > 1) CU(cudaStreamWaitEvent(s->stream, s->computed[1], 0));
     CU(cudaMemcpyAsync(out_affine, s->out.p, n_polys * sizeof(affine), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return H2V_OK;
@@ -1036,7 +1044,8 @@ template <class F> __global__ void selftest_field_kernel(int op, const fe *a, co
     if (op == 0) r = fe_mul<F>(x, y);
     else if (op == 1) r = fe_add<F>(x, y);
     else if (op == 2) r = fe_sub<F>(x, y);
-    else r = fe_inv<F>(x);
+    else if (op == 3) r = fe_inv<F>(x);
+    else r = fe_inv_fast<F>(x);
     o[i] = r;
 }
 __global__ void selftest_group_kernel(int mode, const affine *p, const affine *q, affine *o, size_t n) {

@@ -10,8 +10,8 @@ void h2v_host_field(int field, int op, const uint64_t *a, const uint64_t *b, uin
     fe x, y, r;
     memcpy(x.v, a, 32);
     if (b) memcpy(y.v, b, 32); else y = fe_zero();
-    if (field == 0) r = op == 0 ? fe_mul<FrP>(x, y) : op == 1 ? fe_add<FrP>(x, y) : op == 2 ? fe_sub<FrP>(x, y) : op == 3 ? fe_inv<FrP>(x) : op == 4 ? fe_to_mont<FrP>(x) : fe_from_mont<FrP>(x);
-    else r = op == 0 ? fe_mul<FqP>(x, y) : op == 1 ? fe_add<FqP>(x, y) : op == 2 ? fe_sub<FqP>(x, y) : op == 3 ? fe_inv<FqP>(x) : op == 4 ? fe_to_mont<FqP>(x) : fe_from_mont<FqP>(x);
+    if (field == 0) r = op == 0 ? fe_mul<FrP>(x, y) : op == 1 ? fe_add<FrP>(x, y) : op == 2 ? fe_sub<FrP>(x, y) : op == 3 ? fe_inv<FrP>(x) : op == 4 ? fe_to_mont<FrP>(x) : op == 5 ? fe_from_mont<FrP>(x) : fe_inv_fast<FrP>(x);
+    else r = op == 0 ? fe_mul<FqP>(x, y) : op == 1 ? fe_add<FqP>(x, y) : op == 2 ? fe_sub<FqP>(x, y) : op == 3 ? fe_inv<FqP>(x) : op == 4 ? fe_to_mont<FqP>(x) : op == 5 ? fe_from_mont<FqP>(x) : fe_inv_fast<FqP>(x);
     memcpy(o, r.v, 32);
 }
 // mode 0: mixed add p + q; 1: full add with q given a non-trivial ZZ; 2: double p; 3: p + q returned as Jacobian (12 limbs)

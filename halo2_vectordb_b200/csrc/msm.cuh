@@ -353,11 +353,12 @@ __global__ void __launch_bounds__(128, 3) msm_reduce_kernel(const xyzz *__restri
     xyzz_st(A_out + (size_t)inst * cnt_out + s, tz);
 }
 
-// one thread per column: group results R_g = A[g] + S[g]; fold sum_g 2^(g c) R_g; write affine or Jacobian
+// one warp per column (lane 0 works: the data-dependent inversion would diverge across columns): group results
+// R_g = A[g] + S[g]; fold sum_g 2^(g c) R_g; write affine or Jacobian
 __global__ void msm_final_kernel(const xyzz *__restrict__ S, const xyzz *__restrict__ A, uint32_t n_cols, uint32_t G,
                                  uint32_t c, affine *__restrict__ out_affine, jacobian *__restrict__ out_jac) {
-    uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= n_cols) return;
+    uint32_t col = blockIdx.x;
+    if (col >= n_cols || threadIdx.x != 0) return;
     xyzz acc = xyzz_identity();
     for (uint32_t g = G; g-- > 0;) {
         if (g + 1 != G)
@@ -368,7 +369,7 @@ __global__ void msm_final_kernel(const xyzz *__restrict__ S, const xyzz *__restr
         xyzz_add(acc, r);
     }
     if (out_affine) {
-        affine o = xyzz_to_affine(acc);
+        affine o = xyzz_to_affine_fast(acc);
         fe_st(&out_affine[col].x, o.x);
         fe_st(&out_affine[col].y, o.y);
     }

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(128) binv_up_kernel(const fe *__restrict__ X, 
     fe_st(Xn + g, run);
 }
 __global__ void binv_top_kernel(const fe *__restrict__ X, fe *__restrict__ I) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) fe_st(I, fe_inv<Fq>(fe_ld(X)));
+    if (blockIdx.x == 0 && threadIdx.x == 0) fe_st(I, fe_inv_fast<Fq>(fe_ld(X)));
 }
 // I[i] = 1 / X[i] from In[g] = 1 / (product of group g)
 __global__ void __launch_bounds__(128) binv_down_kernel(const fe *__restrict__ X, const fe *__restrict__ P, const fe *__restrict__ In,

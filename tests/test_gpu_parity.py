@@ -31,9 +31,10 @@ def test_device_field_ops(h2v, field, nm):
         got = h2v.selftest_field(field, op, a, b)
         exp = np.stack([O.field_op(f"{nm}_{opn}", a[i], b[i]) for i in range(len(a))])
         assert (got == exp).all(), opn
-    got = h2v.selftest_field(field, 3, a[1:65])
     exp = np.stack([O.field_op(f"{nm}_inv", a[i]) for i in range(1, 65)])
-    assert (got == exp).all()
+    for op in (3, 4):           # Fermat and binary-Euclid inversions
+        assert (h2v.selftest_field(field, op, a[1:65]) == exp).all(), op
+    assert not h2v.selftest_field(field, 4, a[0:1]).any()      # 0 -> 0
 
 
 def test_device_group_law(h2v):
