@@ -165,7 +165,13 @@ int run_ntt(cudaStream_t st, const fe *src, size_t src_stride, fe *dst, size_t d
             p.t0 = t0;
             p.first = (i == 0);
             p.last = (i == pl.P - 1);
-            p.logT = p.first ? std::min(11 - S, L - S) : std::min(11 - S, t0);
+            static const int loge = [] {   // log2 of the elements per CTA tile (H2V_NTT_LOGE: tuning)
+                const char *e = getenv("H2V_NTT_LOGE");
+                int v = e ? atoi(e) : 10;
+                return v < 9 ? 9 : v > 11 ? 11 : v;
+            }();
+            p.logT = p.first ? std::min(loge - S, L - S) : std::min(loge - S, t0);
+            if (p.logT < 0) p.logT = 0;
             unsigned threads = 1u << (S + p.logT - 3);
             unsigned tiles = 1u << (L - S - p.logT);
             size_t smem = ((size_t)2 * (1u << (S + p.logT)) + H2V_NTT_PLANE_PAD) * 16;
@@ -357,7 +363,7 @@ struct MsmLayout {
     size_t bytes;
     uint32_t *keys, *counts, *offsets, *cursor, *tile_sums, *long_list, *long_count;
     uint2 *entries;
-    xyzz *buckets, *edges, *S[2], *A[2];
+    xyzz *buckets, *edges, *S[2], *A[2], *T;
     uint32_t nthreads, n_buckets, l1;
     // batch-affine rounds (ba_rounds > 0)
     uint32_t ba_rounds, ba_K, ba_G;
@@ -414,6 +420,7 @@ MsmLayout msm_layout(void *base, const MsmShape &sh, uint32_t cols) {
     L.A[0] = cv.take<xyzz>((size_t)cols * sh.G * L.l1);
     L.S[1] = cv.take<xyzz>((size_t)cols * sh.G * l2);
     L.A[1] = cv.take<xyzz>((size_t)cols * sh.G * l2);
+    L.T = cv.take<xyzz>((size_t)cols * sh.G * 16);      // bit sums of the reduction tail: <= 13 + 2 per instance
     if (L.ba_rounds) {
         L.ba_off[0] = cv.take<uint32_t>((size_t)L.n_buckets + 1);
         L.ba_off[1] = cv.take<uint32_t>((size_t)L.n_buckets + 1);
@@ -580,7 +587,7 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
         msm_finish_kernel<<<(L.n_buckets + 127) / 128, 128, 0, st>>>(acc_offsets, L.n_buckets, L.edges, L.buckets, acc_chunk, L.long_list,
                                                                      L.long_count);
         LAUNCHED();
-        msm_finish_long_kernel<<<148 * 4, 128, 0, st>>>(acc_offsets, L.edges, L.buckets, acc_chunk, L.long_list, L.long_count);
+        msm_finish_long_kernel<<<148 * 2, 256, 0, st>>>(acc_offsets, L.edges, L.buckets, acc_chunk, L.long_list, L.long_count);
         LAUNCHED();
         if (tm) { tm->end(); tm->begin(5); }
         // reduction tree over each (column, group)
@@ -588,7 +595,21 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
         const xyzz *Sin = L.buckets, *Ain = nullptr;
         uint32_t cnt = sh.nb, shift = 0;
         int pp = 0;
-        do {
+        while (cnt > 1) {
+            if (cnt <= 8192 && Ain && (uint64_t)n_inst * cnt <= (1u << 16)) {
+                // few partials left: bit-decomposed tree sums instead of latency-bound serial levels
+                uint32_t nbits = 0;
+                while ((1u << nbits) < cnt) ++nbits;
+                unsigned threads = std::min(256u, std::max(32u, ((cnt / 4 + 31) / 32) * 32));
+                msm_reduce_bits_kernel<<<dim3(nbits + 2, n_inst), threads, 0, st>>>(Sin, Ain, cnt, nbits, L.T);
+                LAUNCHED();
+                msm_reduce_combine_kernel<<<n_inst, 32, 0, st>>>(L.T, nbits, shift, n_inst, L.S[pp], L.A[pp]);
+                LAUNCHED();
+                Sin = L.S[pp];
+                Ain = L.A[pp];
+                cnt = 1;
+                break;
+            }
             // shorter segments while the level would otherwise leave SMs idle (each thread is a serial chain)
             uint32_t log_seg = 5;
             while (log_seg > 3 && (uint64_t)n_inst * (cnt >> log_seg) < 148ull * 1024) --log_seg;
@@ -601,7 +622,13 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
             pp ^= 1;
             cnt = cnt_out;
             shift += log_seg;
-        } while (cnt > 1);
+        }
+        if (!Ain) {   // nb == 1: a single bucket per group, its weight is 1 and there is no weighted part
+            msm_reduce_kernel<<<(n_inst + 127) / 128, 128, 0, st>>>(Sin, nullptr, L.S[pp], L.A[pp], 1, 1, n_inst, 0, 3);
+            LAUNCHED();
+            Sin = L.S[pp];
+            Ain = L.A[pp];
+        }
         if (tm) { tm->end(); tm->begin(6); }
         msm_final_kernel<<<cols, 32, 0, st>>>(Sin, Ain, cols, sh.G, sh.c, d_out_aff ? d_out_aff + c0 : nullptr,
                                                           d_out_jac ? d_out_jac + c0 : nullptr);

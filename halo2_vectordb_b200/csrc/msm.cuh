@@ -288,30 +288,73 @@ __device__ __forceinline__ xyzz xyzz_shfl_down(const xyzz &v, int off) {
     }
     return r;
 }
-// one warp per queued bucket: the lanes stride over the chunk heads, then a shuffle tree folds the 32 partials
-__global__ void __launch_bounds__(128) msm_finish_long_kernel(const uint32_t *__restrict__ offsets, const xyzz *__restrict__ edges,
+__device__ __forceinline__ xyzz xyzz_warp_sum(xyzz v) {      // total in lane 0
+#pragma unroll 1
+    for (int off = 16; off >= 1; off >>= 1) {
+        xyzz o = xyzz_shfl_down(v, off);
+        xyzz_add(v, o);
+    }
+    return v;
+}
+// sum of `v` over the threads of a CTA of up to 8 warps (shuffle tree inside each warp, the warp partials
+// through shared memory); the total is returned by thread 0 only
+__device__ __forceinline__ xyzz xyzz_block_sum_256(xyzz v, xyzz *sm8) {
+#pragma unroll 1
+    for (int off = 16; off >= 1; off >>= 1) {
+        xyzz o = xyzz_shfl_down(v, off);
+        xyzz_add(v, o);
+    }
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();                       // sm8 may still be read from a previous call
+    if (lane == 0) sm8[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        v = lane < (blockDim.x >> 5) ? sm8[lane] : xyzz_identity();
+#pragma unroll 1
+        for (int off = 4; off >= 1; off >>= 1) {
+            xyzz o = xyzz_shfl_down(v, off);
+            xyzz_add(v, o);
+        }
+    }
+    return v;
+}
+// Queued long buckets.  Few of them (a single witness column): one CTA per bucket, 256 threads stride over the
+// chunk heads and a tree folds the partials -- shortest critical path.  Many of them (a batch of columns):
+// one warp per bucket -- same work with fewer redundant tree steps.
+__global__ void __launch_bounds__(256) msm_finish_long_kernel(const uint32_t *__restrict__ offsets, const xyzz *__restrict__ edges,
                                                               xyzz *__restrict__ buckets, uint32_t chunk,
                                                               const uint32_t *__restrict__ long_list,
                                                               const uint32_t *__restrict__ long_count) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    __shared__ xyzz sm8[8];
     const uint32_t count = *long_count;
-    for (uint32_t i = warp; i < count; i += n_warps) {
-        const uint32_t b = long_list[i];
-        const uint32_t t0 = offsets[b] / chunk, t1 = (offsets[b + 1] - 1) / chunk;
-        xyzz acc = xyzz_identity();
-        if (lane == 0) acc = xyzz_ld(edges + 2 * (size_t)t0 + 1);
-        for (uint32_t t = t0 + 1 + lane; t <= t1; t += 32) {
-            xyzz h = xyzz_ld(edges + 2 * (size_t)t);
-            xyzz_add(acc, h);
+    if (count <= 2 * gridDim.x) {
+        for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
+            const uint32_t b = long_list[i];
+            const uint32_t t0 = offsets[b] / chunk, t1 = (offsets[b + 1] - 1) / chunk;
+            xyzz acc = xyzz_identity();
+            if (threadIdx.x == 0) acc = xyzz_ld(edges + 2 * (size_t)t0 + 1);
+            for (uint32_t t = t0 + 1 + threadIdx.x; t <= t1; t += 256) {
+                xyzz h = xyzz_ld(edges + 2 * (size_t)t);
+                xyzz_add(acc, h);
+            }
+            acc = xyzz_block_sum_256(acc, sm8);
+            if (threadIdx.x == 0) xyzz_st(buckets + b, acc);
         }
-#pragma unroll 1
-        for (int off = 16; off >= 1; off >>= 1) {
-            xyzz o = xyzz_shfl_down(acc, off);
-            xyzz_add(acc, o);
+    } else {
+        const uint32_t lane = threadIdx.x & 31;
+        const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+        for (uint32_t i = warp; i < count; i += n_warps) {
+            const uint32_t b = long_list[i];
+            const uint32_t t0 = offsets[b] / chunk, t1 = (offsets[b + 1] - 1) / chunk;
+            xyzz acc = xyzz_identity();
+            if (lane == 0) acc = xyzz_ld(edges + 2 * (size_t)t0 + 1);
+            for (uint32_t t = t0 + 1 + lane; t <= t1; t += 32) {
+                xyzz h = xyzz_ld(edges + 2 * (size_t)t);
+                xyzz_add(acc, h);
+            }
+            acc = xyzz_warp_sum(acc);
+            if (lane == 0) xyzz_st(buckets + b, acc);
         }
-        if (lane == 0) xyzz_st(buckets + b, acc);
     }
 }
 
@@ -351,6 +394,45 @@ __global__ void __launch_bounds__(128, 3) msm_reduce_kernel(const xyzz *__restri
     }
     xyzz_st(S_out + (size_t)inst * cnt_out + s, run);
     xyzz_st(A_out + (size_t)inst * cnt_out + s, tz);
+}
+
+// Tail of the reduction once a few thousand partials per instance are left: the serial radix levels would be
+// latency-bound there, so the weighted sum is taken bit by bit with parallel tree sums instead:
+//   sum_i i * S[i] = sum_b 2^b * T_b,   T_b = sum over { i : bit b of i set } of S[i].
+// grid (nbits + 2, n_inst): CTA `which` < nbits computes T_which, nbits the plain sum of A, nbits + 1 that of S.
+__global__ void __launch_bounds__(256) msm_reduce_bits_kernel(const xyzz *__restrict__ S_in, const xyzz *__restrict__ A_in,
+                                                              uint32_t cnt, uint32_t nbits, xyzz *__restrict__ T) {
+    __shared__ xyzz sm8[8];
+    const uint32_t which = blockIdx.x, inst = blockIdx.y;
+    const xyzz *src = (which == nbits ? A_in : S_in) + (size_t)inst * cnt;
+    xyzz acc = xyzz_identity();
+    if (which != nbits || A_in) {
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+            if (which < nbits && !((i >> which) & 1u)) continue;
+            xyzz v = xyzz_ld(src + i);
+            xyzz_add(acc, v);
+        }
+    }
+    acc = xyzz_block_sum_256(acc, sm8);
+    if (threadIdx.x == 0) xyzz_st(T + (size_t)inst * (nbits + 2) + which, acc);
+}
+// one warp per instance (lane 0 works): Horner over the bit sums, weight 2^shift, plus the plain sum of A
+__global__ void msm_reduce_combine_kernel(const xyzz *__restrict__ T, uint32_t nbits, uint32_t shift, uint32_t n_inst,
+                                          xyzz *__restrict__ S_out, xyzz *__restrict__ A_out) {
+    const uint32_t inst = blockIdx.x;
+    if (inst >= n_inst || threadIdx.x != 0) return;
+    const xyzz *t = T + (size_t)inst * (nbits + 2);
+    xyzz acc = xyzz_identity();
+    for (uint32_t b = nbits; b-- > 0;) {
+        acc = xyzz_double(acc);
+        xyzz v = xyzz_ld(t + b);
+        xyzz_add(acc, v);
+    }
+    for (uint32_t k = 0; k < shift; ++k) acc = xyzz_double(acc);
+    xyzz a = xyzz_ld(t + nbits);
+    xyzz_add(acc, a);
+    xyzz_st(S_out + inst, xyzz_ld(t + nbits + 1));
+    xyzz_st(A_out + inst, acc);
 }
 
 // one warp per column (lane 0 works: the data-dependent inversion would diverge across columns): group results
