@@ -30,6 +30,8 @@ extern "C" {
     pub fn h2v_init(device: c_int) -> c_int;
     pub fn h2v_device_count() -> c_int;
     pub fn h2v_last_error() -> *const c_char;
+    pub fn h2v_host_register(ptr: *mut c_void, bytes: usize) -> c_int;
+    pub fn h2v_host_unregister(ptr: *mut c_void) -> c_int;
     pub fn h2v_srs_load(k: u32, g: *const u64, g_lagrange: *const u64, out: *mut *mut H2vSrs) -> c_int;
     pub fn h2v_srs_free(srs: *mut H2vSrs);
     pub fn h2v_commit(srs: *mut H2vSrs, basis: c_int, poly: *const u64, len: usize, out_affine: *mut u64) -> c_int;

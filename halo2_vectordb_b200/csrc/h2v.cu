@@ -677,6 +677,19 @@ int h2v_init(int device) {
     CU(cudaFree(0));
     return H2V_OK;
 }
+int h2v_host_register(void *ptr, size_t bytes) {
+    int rc = use_device();
+    if (rc) return rc;
+    if (!ptr || !bytes) return fail(H2V_EINVAL, "host_register: bad argument");
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return H2V_OK;
+}
+int h2v_host_unregister(void *ptr) {
+    int rc = use_device();
+    if (rc) return rc;
+    CU(cudaHostUnregister(ptr));
+    return H2V_OK;
+}
 int h2v_set_tuning(int chunk, int ba_rounds) {
     g_tune_chunk.store(chunk > 0 ? chunk : -1);
     g_tune_ba.store(ba_rounds >= 0 ? ba_rounds : -1);

@@ -46,6 +46,11 @@ int h2v_device_count(void);
 const char *h2v_last_error(void);
 const char *h2v_version(void);
 
+/* Page-lock a caller-owned buffer (a Rust Vec<Fr>, a numpy array) so that the library's asynchronous,
+ * double-buffered H2D / D2H copies really overlap with the kernels; pageable memory works too, only slower. */
+int h2v_host_register(void *ptr, size_t bytes);
+int h2v_host_unregister(void *ptr);
+
 /* ---- KZG commit path ---------------------------------------------------------------------- */
 /* halo2-axiom poly/kzg/commitment.rs ParamsKZG {k, n, g, g_lagrange}: upload both bases
  * (n = 2^k G1Affine each) and build the per-window tables 2^(jc) * B_i once.

@@ -366,3 +366,27 @@ def test_msm_tuning_invariance(h2v, ba_rounds, chunk):
             assert O.g1_affine_to_ints(O.g1_to_affine(h2v.best_multiexp(sc, bs))) == ipt(v["result"])
     finally:
         h2v.set_tuning(-1, -1)
+
+
+def test_tiny_srs_and_pinned_buffers(h2v):
+    """k = 0, 1, 2 (degenerate SRS sizes) and page-locked caller buffers."""
+    for k in (0, 1, 2):
+        n = 1 << k
+        b = O.gen_bases(n)
+        srs = h2v.ParamsKZG(k, b, b)
+        s = O.fr_fill(n, 40 + k)
+        assert (srs.commit(s) == O.best_multiexp_affine(s, b)).all()
+        assert (srs.commit_lagrange(s) == O.msm_closed_form(s)).all()
+        srs.close()
+    k, n = 12, 1 << 12
+    d, od = h2v.EvaluationDomain(4, k), O.EvaluationDomain(4, k)
+    a = O.fr_fill(n, 3)
+    h2v.host_register(a)
+    try:
+        assert (d.lagrange_to_coeff(a) == od.lagrange_to_coeff(a)).all()
+        srs = h2v.ParamsKZG(k, None, O.gen_bases(n))
+        assert (srs.commit_batch([a] * 30)[29] == O.msm_closed_form(a)).all()
+        srs.close()
+    finally:
+        h2v.host_unregister(a)
+    d.close()
