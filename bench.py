@@ -271,6 +271,7 @@ def _main(args, real_stdout):
         line["ntt"] = bench_ntt(h, torch, dev, peak)
         line["witness_like"] = bench_witness(h, torch, dev, srs)
         line["prove_shaped"] = bench_prove_shaped(h, torch, dev, srs, d_cols, cols)
+        line["next_row2"] = bench_row2(h, torch, dev, d_cols, cols)
         if world == 1:
             threads = os.cpu_count() or 1
             v, secs = cpu_msm_sample(24, threads)
@@ -328,6 +329,30 @@ def bench_prove_shaped(h, torch, dev, srs, d_cols, cols):
     return {"latency_s": statistics.median(ts), "schedule": {"commit_lagrange": n_msm, "lagrange_to_coeff": n_intt,
             "coeff_to_extended": n_cntt, "divide_by_vanishing+extended_to_coeff": 1}, "k": K,
             "note": "hot-path proxy for one kmeans k=16 create_proof, uniform scalars, device-resident"}
+
+
+def bench_row2(h, torch, dev, d_cols, cols):
+    """eval_polynomial (SURVEY.md 8(f) row 2) on the same columns: every column at 3 points, device-resident;
+    beside it the oracle's single-threaded Horner on one column (kind "port")."""
+    import numpy as np
+    from oracle import oracle as O
+    pts = d_cols[0, :3].contiguous()
+    out = torch.zeros((cols, 3, 4), dtype=torch.int64, device=dev)
+    ms = []
+    for i in range(6):
+        h._check(h.lib().h2v_eval_polynomial_dev(d_cols.data_ptr(), N, cols, N, pts.data_ptr(), 3, out.data_ptr()))
+        if i >= 2:
+            ms.append(h.last_kernel_ms()["ntt"])       # the polynomial kernels report under class 7
+    t = statistics.median(ms) * 1e-3
+    col0 = d_cols[0].cpu().numpy().view(np.uint64)
+    x0 = pts[0].cpu().numpy().view(np.uint64)
+    assert (O.fr_eval_poly(col0, x0) == out[0, 0].cpu().numpy().view(np.uint64)).all()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        O.fr_eval_poly(col0, x0)
+    cpu = 4 * N / (time.perf_counter() - t0)
+    return {"eval_polynomial_gcoeff_per_s": cols * 3 * N / t / 1e9, "ms": t * 1e3, "polys": cols, "points": 3,
+            "cpu_port_gcoeff_per_s": cpu / 1e9, "cpu_cores": 1}
 
 
 def bench_witness(h, torch, dev, srs):

@@ -30,6 +30,7 @@ ABI_SYMBOLS = [
     "h2v_best_fft", "h2v_domain_new", "h2v_domain_free", "h2v_domain_k", "h2v_domain_extended_k", "h2v_domain_constant",
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
     "h2v_divide_by_vanishing_poly", "h2v_domain_transform_batch", "h2v_domain_transform_dev",
+    "h2v_eval_polynomial_batch", "h2v_eval_polynomial_dev", "h2v_batch_invert", "h2v_grand_product", "h2v_kate_division",
     "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_op_rate", "h2v_set_tuning", "h2v_launch_count", "h2v_last_kernel_ms",
 ]
 
@@ -78,6 +79,11 @@ def lib():
             getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.h2v_domain_transform_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t]
         L.h2v_domain_transform_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]
+        L.h2v_eval_polynomial_batch.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.h2v_eval_polynomial_dev.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.h2v_batch_invert.argtypes = [C.c_void_p, C.c_size_t]
+        L.h2v_grand_product.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.h2v_kate_division.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.h2v_selftest_field.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_selftest_group.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_synthetic_bases.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p]
@@ -175,6 +181,51 @@ def best_fft(a, omega, log_n):
     omega = np.ascontiguousarray(omega, dtype=np.uint64).reshape(4)
     _check(lib().h2v_best_fft(_ptr(a), _ptr(omega), log_n))
     return a
+
+
+def eval_polynomial(poly, point):
+    """halo2-axiom arithmetic.rs `eval_polynomial(poly, point)` (Horner) -> (4,)"""
+    return eval_polynomial_batch([poly], np.ascontiguousarray(point, dtype=np.uint64).reshape(1, 4))[0, 0]
+
+
+def eval_polynomial_batch(polys, points):
+    """every polynomial at every point -> (n_polys, n_points, 4)"""
+    cols = [_fr(p) for p in polys]
+    points = _fr(points)
+    out = np.zeros((len(cols), points.shape[0], 4), dtype=np.uint64)
+    if cols and points.shape[0]:
+        ln = cols[0].shape[0]
+        if any(c.shape[0] != ln for c in cols):
+            raise ValueError("eval_polynomial_batch: polynomials must have equal length")
+        arr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        _check(lib().h2v_eval_polynomial_batch(arr, len(cols), ln, _ptr(points), points.shape[0], _ptr(out)))
+    return out
+
+
+def batch_invert(a):
+    """ff `BatchInvert::batch_invert`: non-zero elements inverted, zeros untouched (returns a copy)."""
+    a = np.array(_fr(a), copy=True)
+    _check(lib().h2v_batch_invert(_ptr(a), a.shape[0]))
+    return a
+
+
+def grand_product(num, den):
+    """z[0] = 1, z[i+1] = z[i] * num[i] / den[i]: the running product of the permutation / lookup arguments."""
+    num, den = _fr(num), _fr(den)
+    if num.shape != den.shape:
+        raise ValueError("grand_product: num and den must have equal length")
+    out = np.zeros_like(num)
+    _check(lib().h2v_grand_product(_ptr(num), _ptr(den), num.shape[0], _ptr(out)))
+    return out
+
+
+def kate_division(a, b):
+    """halo2-axiom arithmetic.rs `kate_division(a, b)`: quotient of a(X) by (X - b)."""
+    a = _fr(a)
+    out = np.zeros((max(a.shape[0] - 1, 0), 4), dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(4)
+    _check(lib().h2v_kate_division(_ptr(a), a.shape[0], _ptr(b), _ptr(out)))
+    return out
 
 
 # ----------------------------------------------------------------------------- poly/kzg/commitment.rs

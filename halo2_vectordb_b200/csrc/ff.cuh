@@ -340,6 +340,17 @@ template <class F> H2V_HD fe fe_pow(const fe &a, const uint32_t *e, int nbits = 
     }
     return acc;
 }
+// a^e scanning only the significant bits of a small exponent
+template <class F> H2V_HD fe fe_pow_small(const fe &a, uint32_t e) {
+    fe acc = fe_one<F>();
+    int top = 31;
+    while (top >= 0 && !((e >> top) & 1u)) --top;
+    for (int i = top; i >= 0; --i) {
+        acc = fe_sqr<F>(acc);
+        if ((e >> i) & 1u) acc = fe_mul<F>(acc, a);
+    }
+    return acc;
+}
 template <class F> H2V_HD fe fe_pow_u64(const fe &a, uint64_t e) {
     uint32_t ee[8] = {(uint32_t)e, (uint32_t)(e >> 32), 0, 0, 0, 0, 0, 0};
     return fe_pow<F>(a, ee, 64);

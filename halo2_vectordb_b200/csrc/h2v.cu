@@ -20,6 +20,7 @@
 #include "msm.cuh"
 #include "msm_affine.cuh"
 #include "ntt.cuh"
+#include "poly.cuh"
 
 using namespace h2v;
 
@@ -557,13 +558,13 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
                 else ba_forward_kernel<false><<<gb, 128, 0, st>>>(br);
                 LAUNCHED();
                 for (uint32_t l = 0; l + 1 < levels; ++l) {
-                    binv_up_kernel<<<(nlev[l + 1] + 127) / 128, 128, 0, st>>>(L.ba_X[l], L.ba_P[l], L.ba_X[l + 1], nlev[l], L.ba_G);
+                    binv_up_kernel<Fq><<<(nlev[l + 1] + 127) / 128, 128, 0, st>>>(L.ba_X[l], L.ba_P[l], L.ba_X[l + 1], nlev[l], L.ba_G);
                     LAUNCHED();
                 }
-                binv_top_kernel<<<1, 32, 0, st>>>(L.ba_X[levels - 1], L.ba_I[levels - 1]);
+                binv_top_kernel<Fq><<<1, 32, 0, st>>>(L.ba_X[levels - 1], L.ba_I[levels - 1]);
                 LAUNCHED();
                 for (uint32_t l = levels - 1; l-- > 0;) {
-                    binv_down_kernel<<<(nlev[l + 1] + 127) / 128, 128, 0, st>>>(L.ba_X[l], L.ba_P[l], L.ba_I[l + 1], L.ba_I[l], nlev[l], L.ba_G);
+                    binv_down_kernel<Fq><<<(nlev[l + 1] + 127) / 128, 128, 0, st>>>(L.ba_X[l], L.ba_P[l], L.ba_I[l + 1], L.ba_I[l], nlev[l], L.ba_G);
                     LAUNCHED();
                 }
                 if (r == 0) ba_backward_kernel<true><<<gb, 128, 0, st>>>(br);
@@ -1073,6 +1074,197 @@ int h2v_divide_by_vanishing_poly(h2v_domain_t d, uint64_t *a) {
     return H2V_OK;
 }
 
+}  // extern "C"
+
+// ================================================================== polynomial primitives ("next" row 2)
+namespace {
+struct PolyCtx {
+    std::mutex mu;
+    cudaStream_t st = nullptr;
+    DevBuf a, b, c, d, tree;
+};
+PolyCtx g_poly;
+int poly_ctx_ready() {
+    if (!g_poly.st) CU(cudaStreamCreateWithFlags(&g_poly.st, cudaStreamNonBlocking));
+    return H2V_OK;
+}
+// I[i] = 1 / X[i] for n non-zero elements (one inversion in total); X and I are device arrays
+template <class F> int run_batch_invert(cudaStream_t st, const fe *X, fe *I, uint32_t n, DevBuf &scratch) {
+    const uint32_t G = 16;
+    uint32_t sizes[16], levels = 0;
+    size_t total = 0;
+    for (uint64_t v = n;;) {
+        sizes[levels++] = (uint32_t)v;
+        if (v <= 1 || levels >= 16) break;
+        v = (v + G - 1) / G;
+        total += v;
+    }
+    if (sizes[levels - 1] != 1) return fail(H2V_EINVAL, "batch_invert: n = %u unsupported", n);
+    // scratch: X_l (levels >= 1), P_l (all levels), I_l (levels >= 1)
+    int rc = scratch.ensure((2 * total + n + total + 16) * sizeof(fe));
+    if (rc) return rc;
+    fe *base = scratch.as<fe>();
+    const fe *Xl[16];
+    fe *Xw[16], *Pl[16], *Il[16];
+    Xl[0] = X;
+    Il[0] = I;
+    fe *cur = base;
+    Pl[0] = cur;
+    cur += n;
+    for (uint32_t l = 1; l < levels; ++l) {
+        Xw[l] = cur; cur += sizes[l];
+        Pl[l] = cur; cur += sizes[l];
+        Il[l] = cur; cur += sizes[l];
+        Xl[l] = Xw[l];
+    }
+    for (uint32_t l = 0; l + 1 < levels; ++l) {
+        binv_up_kernel<F><<<(sizes[l + 1] + 127) / 128, 128, 0, st>>>(Xl[l], Pl[l], Xw[l + 1], sizes[l], G);
+        LAUNCHED();
+    }
+    binv_top_kernel<F><<<1, 32, 0, st>>>(Xl[levels - 1], Il[levels - 1]);
+    LAUNCHED();
+    for (uint32_t l = levels - 1; l-- > 0;) {
+        binv_down_kernel<F><<<(sizes[l + 1] + 127) / 128, 128, 0, st>>>(Xl[l], Pl[l], Il[l + 1], Il[l], sizes[l], G);
+        LAUNCHED();
+    }
+    return H2V_OK;
+}
+}  // namespace
+
+extern "C" {
+int h2v_eval_polynomial_dev(const void *d_polys, size_t stride, size_t n_polys, size_t len, const void *d_points, size_t n_points,
+                            void *d_out) {
+    if (!n_polys || !n_points) return H2V_OK;
+    if (!d_polys || !d_points || !d_out) return fail(H2V_EINVAL, "eval_polynomial: NULL buffer");
+    if (n_polys > 65535 || n_points > (1u << 20) || len >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "eval_polynomial: batch too large");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_poly.mu);
+    if ((rc = poly_ctx_ready())) return rc;
+    Timer tm(g_poly.st);
+    tm.begin(7);
+    poly_eval_kernel<<<dim3((unsigned)n_points, (unsigned)n_polys), 256, 0, g_poly.st>>>((const fe *)d_polys, stride, (uint32_t)len,
+                                                                                       (const fe *)d_points, (uint32_t)n_points, (fe *)d_out);
+    LAUNCHED();
+    tm.end();
+    CU(cudaStreamSynchronize(g_poly.st));
+    tm.collect(true);
+    return H2V_OK;
+}
+int h2v_eval_polynomial_batch(const uint64_t *const *polys, size_t n_polys, size_t len, const uint64_t *points, size_t n_points,
+                              uint64_t *out) {
+    if (!n_polys || !n_points) return H2V_OK;
+    if (!polys || !points || !out) return fail(H2V_EINVAL, "eval_polynomial: NULL buffer");
+    if (n_points > (1u << 20) || len >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "eval_polynomial: batch too large");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_poly.mu);
+    if ((rc = poly_ctx_ready())) return rc;
+    cudaStream_t st = g_poly.st;
+    const size_t stride = std::max<size_t>(len, 1);
+    size_t per = std::max<size_t>(1, ((size_t)1 << 30) / (stride * sizeof(fe)));
+    per = std::min<size_t>(std::min(per, n_polys), 65535);
+    if ((rc = g_poly.a.ensure(per * stride * sizeof(fe))) || (rc = g_poly.b.ensure(n_points * sizeof(fe))) ||
+        (rc = g_poly.c.ensure(per * n_points * sizeof(fe))))
+        return rc;
+    CU(cudaMemcpyAsync(g_poly.b.p, points, n_points * sizeof(fe), cudaMemcpyHostToDevice, st));
+    for (size_t c0 = 0; c0 < n_polys; c0 += per) {
+        size_t cols = std::min(per, n_polys - c0);
+        for (size_t c = 0; c < cols; ++c) {
+            if (!polys[c0 + c] && len) return fail(H2V_EINVAL, "eval_polynomial: polys[%zu] is NULL", c0 + c);
+            if (len) CU(cudaMemcpyAsync(g_poly.a.as<fe>() + c * stride, polys[c0 + c], len * sizeof(fe), cudaMemcpyHostToDevice, st));
+        }
+        poly_eval_kernel<<<dim3((unsigned)n_points, (unsigned)cols), 256, 0, st>>>(g_poly.a.as<fe>(), stride, (uint32_t)len, g_poly.b.as<fe>(),
+                                                                                  (uint32_t)n_points, g_poly.c.as<fe>());
+        LAUNCHED();
+        CU(cudaMemcpyAsync(out + 4 * c0 * n_points, g_poly.c.p, cols * n_points * sizeof(fe), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return H2V_OK;
+}
+int h2v_batch_invert(uint64_t *a, size_t n) {
+    if (!n) return H2V_OK;
+    if (!a) return fail(H2V_EINVAL, "batch_invert: NULL buffer");
+    if (n >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "batch_invert: n too large");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_poly.mu);
+    if ((rc = poly_ctx_ready())) return rc;
+    cudaStream_t st = g_poly.st;
+    if ((rc = g_poly.a.ensure(n * sizeof(fe))) || (rc = g_poly.b.ensure(n * sizeof(fe))) || (rc = g_poly.c.ensure(n * sizeof(fe)))) return rc;
+    CU(cudaMemcpyAsync(g_poly.a.p, a, n * sizeof(fe), cudaMemcpyHostToDevice, st));
+    const unsigned gb = (unsigned)((n + 255) / 256);
+    fr_zero_to_one_kernel<<<gb, 256, 0, st>>>(g_poly.a.as<fe>(), g_poly.b.as<fe>(), (uint32_t)n);
+    LAUNCHED();
+    if ((rc = run_batch_invert<FrP>(st, g_poly.b.as<fe>(), g_poly.c.as<fe>(), (uint32_t)n, g_poly.tree))) return rc;
+    fr_select_inverse_kernel<<<gb, 256, 0, st>>>(g_poly.a.as<fe>(), g_poly.c.as<fe>(), g_poly.b.as<fe>(), (uint32_t)n);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(a, g_poly.b.p, n * sizeof(fe), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return H2V_OK;
+}
+int h2v_grand_product(const uint64_t *num, const uint64_t *den, size_t n, uint64_t *out) {
+    if (!n) return H2V_OK;
+    if (!num || !den || !out) return fail(H2V_EINVAL, "grand_product: NULL buffer");
+    if (n >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "grand_product: n too large");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_poly.mu);
+    if ((rc = poly_ctx_ready())) return rc;
+    cudaStream_t st = g_poly.st;
+    const uint32_t ntiles = (uint32_t)((n + H2V_FR_TILE - 1) / H2V_FR_TILE);
+    if ((rc = g_poly.a.ensure(n * sizeof(fe))) || (rc = g_poly.b.ensure(n * sizeof(fe))) || (rc = g_poly.c.ensure(n * sizeof(fe))) ||
+        (rc = g_poly.d.ensure(((size_t)ntiles + 1) * sizeof(fe))))
+        return rc;
+    CU(cudaMemcpyAsync(g_poly.a.p, num, n * sizeof(fe), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(g_poly.b.p, den, n * sizeof(fe), cudaMemcpyHostToDevice, st));
+    // denominators must be non-zero (the reference would panic on invert().unwrap()); 1/den in c
+    if ((rc = run_batch_invert<FrP>(st, g_poly.b.as<fe>(), g_poly.c.as<fe>(), (uint32_t)n, g_poly.tree))) return rc;
+    fr_prod_tiles_kernel<<<ntiles, 256, 0, st>>>(g_poly.a.as<fe>(), g_poly.c.as<fe>(), (uint32_t)n, g_poly.d.as<fe>());
+    LAUNCHED();
+    fr_scan_top_kernel<OpMul><<<1, 256, 0, st>>>(g_poly.d.as<fe>(), ntiles);
+    LAUNCHED();
+    fr_prod_apply_kernel<<<ntiles, 256, 0, st>>>(g_poly.a.as<fe>(), g_poly.c.as<fe>(), (uint32_t)n, g_poly.d.as<fe>(), g_poly.b.as<fe>());
+    LAUNCHED();
+    CU(cudaMemcpyAsync(out, g_poly.b.p, n * sizeof(fe), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return H2V_OK;
+}
+int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t *out) {
+    if (n <= 1) return H2V_OK;
+    if (!a || !b || !out) return fail(H2V_EINVAL, "kate_division: NULL buffer");
+    if (n >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "kate_division: n too large");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_poly.mu);
+    if ((rc = poly_ctx_ready())) return rc;
+    cudaStream_t st = g_poly.st;
+    const uint32_t ntiles = (uint32_t)((n + H2V_FR_TILE - 1) / H2V_FR_TILE);
+    if ((rc = g_poly.a.ensure(n * sizeof(fe))) || (rc = g_poly.b.ensure(n * sizeof(fe))) || (rc = g_poly.d.ensure(((size_t)ntiles + 1) * sizeof(fe))))
+        return rc;
+    CU(cudaMemcpyAsync(g_poly.a.p, a, n * sizeof(fe), cudaMemcpyHostToDevice, st));
+    KateParams kp;
+    kp.a = g_poly.a.as<fe>();
+    kp.q = g_poly.b.as<fe>();
+    kp.n = (uint32_t)n;
+    kp.b = fe_from_u64x4(b);
+    kp.tile = g_poly.d.as<fe>();
+    if (fe_is_zero(kp.b)) {
+        kate_shift_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kp.a, kp.q, kp.n);
+        LAUNCHED();
+    } else {
+        kp.binv = fe_inv<Fr>(kp.b);      // one host-side inversion of the evaluation point
+        kate_tiles_kernel<<<ntiles, 256, 0, st>>>(kp);
+        LAUNCHED();
+        fr_scan_top_kernel<OpAdd><<<1, 256, 0, st>>>(kp.tile, ntiles);
+        LAUNCHED();
+        kate_apply_kernel<<<ntiles, 256, 0, st>>>(kp);
+        LAUNCHED();
+    }
+    CU(cudaMemcpyAsync(out, g_poly.b.p, (n - 1) * sizeof(fe), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return H2V_OK;
+}
 }  // extern "C"
 
 // ================================================================== self-tests

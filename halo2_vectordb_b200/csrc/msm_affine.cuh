@@ -177,23 +177,23 @@ template <bool FIRST> __global__ void __launch_bounds__(128) ba_backward_kernel(
 
 // ------------------------------------------------------------------ inversion tree (all elements non-zero)
 // P[i] = product of X[j] for j < i inside i's group of G;  Xn[g] = product of group g
-__global__ void __launch_bounds__(128) binv_up_kernel(const fe *__restrict__ X, fe *__restrict__ P, fe *__restrict__ Xn, uint32_t n, uint32_t G) {
+template <class F> __global__ void __launch_bounds__(128) binv_up_kernel(const fe *__restrict__ X, fe *__restrict__ P, fe *__restrict__ Xn, uint32_t n, uint32_t G) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t lo = (uint64_t)g * G;
     if (lo >= n) return;
     uint32_t hi = (uint32_t)min((uint64_t)n, lo + G);
-    fe run = fe_one<Fq>();
+    fe run = fe_one<F>();
     for (uint32_t i = (uint32_t)lo; i < hi; ++i) {
         fe_st(P + i, run);
-        run = fe_mul<Fq>(run, fe_ld(X + i));
+        run = fe_mul<F>(run, fe_ld(X + i));
     }
     fe_st(Xn + g, run);
 }
-__global__ void binv_top_kernel(const fe *__restrict__ X, fe *__restrict__ I) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) fe_st(I, fe_inv_fast<Fq>(fe_ld(X)));
+template <class F> __global__ void binv_top_kernel(const fe *__restrict__ X, fe *__restrict__ I) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) fe_st(I, fe_inv_fast<F>(fe_ld(X)));
 }
 // I[i] = 1 / X[i] from In[g] = 1 / (product of group g)
-__global__ void __launch_bounds__(128) binv_down_kernel(const fe *__restrict__ X, const fe *__restrict__ P, const fe *__restrict__ In,
+template <class F> __global__ void __launch_bounds__(128) binv_down_kernel(const fe *__restrict__ X, const fe *__restrict__ P, const fe *__restrict__ In,
                                                         fe *__restrict__ I, uint32_t n, uint32_t G) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t lo = (uint64_t)g * G;
@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(128) binv_down_kernel(const fe *__restrict__ X
     uint32_t hi = (uint32_t)min((uint64_t)n, lo + G);
     fe inv = fe_ld(In + g);
     for (uint32_t i = hi; i-- > (uint32_t)lo;) {
-        fe_st(I + i, fe_mul<Fq>(inv, fe_ld(P + i)));
-        inv = fe_mul<Fq>(inv, fe_ld(X + i));
+        fe_st(I + i, fe_mul<F>(inv, fe_ld(P + i)));
+        inv = fe_mul<F>(inv, fe_ld(X + i));
     }
 }
 

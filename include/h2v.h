@@ -104,6 +104,19 @@ int h2v_domain_transform_batch(h2v_domain_t dom, int op, const uint64_t *const *
 int h2v_domain_transform_dev(h2v_domain_t dom, int op, const void *d_in, size_t in_stride, void *d_out, size_t out_stride,
                              size_t n_cols);
 
+/* ---- polynomial primitives around the commits ("next": SURVEY.md 8(f) row 2) ------------------ */
+/* arithmetic.rs eval_polynomial(poly, point) for every (poly, point) pair: out[p * n_points + t] */
+int h2v_eval_polynomial_batch(const uint64_t *const *polys, size_t n_polys, size_t len, const uint64_t *points, size_t n_points,
+                              uint64_t *out);
+int h2v_eval_polynomial_dev(const void *d_polys, size_t stride, size_t n_polys, size_t len, const void *d_points, size_t n_points,
+                            void *d_out);
+/* ff BatchInvert::batch_invert: every non-zero element replaced by its inverse, zeros untouched; in place */
+int h2v_batch_invert(uint64_t *a, size_t n);
+/* running product of the permutation / lookup arguments: out[0] = 1, out[i+1] = out[i] * num[i] / den[i] (den != 0) */
+int h2v_grand_product(const uint64_t *num, const uint64_t *den, size_t n, uint64_t *out);
+/* arithmetic.rs kate_division(a, b): quotient of a(X) (n coefficients) by (X - b), n - 1 coefficients */
+int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t *out);
+
 /* ---- device self-tests (used by tests/ to localise failures; not part of the drop-in surface) */
 /* out[i] = a[i] (op) b[i] computed by the device field routines; field 0 = Fr, 1 = Fq;
  * op 0 mul, 1 add, 2 sub, 3 inverse by Fermat (b ignored), 4 inverse by binary Euclid (b ignored) */

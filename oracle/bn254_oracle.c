@@ -758,3 +758,58 @@ void orc_divide_by_vanishing_poly(const orc_domain *d, u64 *a) {
     fe *p = (fe *)a;
     for (size_t i = 0; i < en; ++i) f_mul(&FR, &p[i], &p[i], &d->t_evaluations[i % d->n_t]);
 }
+
+/* ------------------------------------------------------------------ "next" row 2: the callers
+ * on either side of every commit, restated from halo2-axiom arithmetic.rs / plonk/permutation/prover.rs:
+ *   eval_polynomial(poly, point)        Horner evaluation                          -> orc_fr_eval_poly (above)
+ *   BatchInvert::batch_invert           every non-zero element replaced by its inverse, zeros untouched
+ *   grand product z                      z[0] = 1, z[i+1] = z[i] * num[i] / den[i]   (the running product of
+ *                                        the permutation / lookup arguments, before blinding)
+ *   kate_division(a, b)                  quotient of a(X) by (X - b), remainder dropped                     */
+void orc_fr_batch_invert(u64 *a, size_t n) {
+    fe *p = (fe *)a;
+    fe *pre = malloc((n ? n : 1) * sizeof(fe));
+    fe acc;
+    memcpy(acc.l, FR.r1, 32);
+    for (size_t i = 0; i < n; ++i) {
+        pre[i] = acc;
+        if (!f_is_zero(&p[i])) f_mul(&FR, &acc, &acc, &p[i]);
+    }
+    fe inv;
+    f_inv(&FR, &inv, &acc);
+    for (size_t i = n; i-- > 0;) {
+        if (f_is_zero(&p[i])) continue;
+        fe t;
+        f_mul(&FR, &t, &inv, &pre[i]);
+        f_mul(&FR, &inv, &inv, &p[i]);
+        p[i] = t;
+    }
+    free(pre);
+}
+/* out[0] = 1, out[i+1] = out[i] * num[i] / den[i], i < n - 1   (den[i] != 0) */
+void orc_fr_grand_product(const u64 *num, const u64 *den, size_t n, u64 *out) {
+    if (!n) return;
+    fe *d = malloc(n * sizeof(fe));
+    memcpy(d, den, n * 32);
+    orc_fr_batch_invert((u64 *)d, n);
+    fe *o = (fe *)out;
+    memcpy(o[0].l, FR.r1, 32);
+    for (size_t i = 0; i + 1 < n; ++i) {
+        fe t;
+        f_mul(&FR, &t, (const fe *)(num + 4 * i), &d[i]);
+        f_mul(&FR, &o[i + 1], &o[i], &t);
+    }
+    free(d);
+}
+/* a has n coefficients (n >= 1); out has n - 1:  q[n-2] = a[n-1], q[i-1] = a[i] + b * q[i] */
+void orc_fr_kate_division(const u64 *a, size_t n, const u64 b[4], u64 *out) {
+    const fe *p = (const fe *)a;
+    fe *q = (fe *)out;
+    fe tmp = {{0, 0, 0, 0}};
+    for (size_t i = n; i-- > 1;) {
+        fe t;
+        f_mul(&FR, &t, &tmp, (const fe *)b);
+        f_add(&FR, &tmp, &p[i], &t);
+        q[i - 1] = tmp;
+    }
+}

@@ -59,6 +59,9 @@ _to_mont = _sig("orc_to_mont", C.c_int, _u64p, C.c_size_t, _u64p)
 _from_mont = _sig("orc_from_mont", C.c_int, _u64p, C.c_size_t, _u64p)
 _dot = _sig("orc_fr_dot_affine_index", _u64p, C.c_size_t, C.c_uint64, C.c_uint64, _u64p)
 _eval_poly = _sig("orc_fr_eval_poly", _u64p, C.c_size_t, _u64p, _u64p)
+_batch_invert = _sig("orc_fr_batch_invert", _u64p, C.c_size_t)
+_grand_product = _sig("orc_fr_grand_product", _u64p, _u64p, C.c_size_t, _u64p)
+_kate = _sig("orc_fr_kate_division", _u64p, C.c_size_t, _u64p, _u64p)
 _best_fft = _sig("orc_best_fft", _u64p, _u64p, C.c_uint32, C.c_int)
 _domain_new = _sig("orc_domain_new", C.c_uint32, C.c_uint32, C.c_void_p, res=C.c_int)
 _domain_sizeof = _sig("orc_domain_sizeof", res=C.c_size_t)
@@ -243,6 +246,31 @@ def fr_eval_poly(a, x):
     o = np.empty(4, dtype=np.uint64)
     _eval_poly(_p(a), len(a), _p(np.ascontiguousarray(x, dtype=np.uint64)), _p(o))
     return o
+
+
+def fr_batch_invert(a):
+    """ff::BatchInvert::batch_invert: non-zero elements inverted, zeros untouched."""
+    a = np.array(a, dtype=np.uint64, copy=True).reshape(-1, 4)
+    _batch_invert(_p(a), len(a))
+    return a
+
+
+def fr_grand_product(num, den):
+    """z[0] = 1, z[i+1] = z[i] * num[i] / den[i] (permutation / lookup running product)."""
+    num = np.ascontiguousarray(num, dtype=np.uint64).reshape(-1, 4)
+    den = np.ascontiguousarray(den, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros_like(num)
+    _grand_product(_p(num), _p(den), len(num), _p(out))
+    return out
+
+
+def fr_kate_division(a, b):
+    """arithmetic.rs kate_division: quotient of a(X) by (X - b)."""
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros((max(len(a) - 1, 0), 4), dtype=np.uint64)
+    if len(a) > 1:
+        _kate(_p(a), len(a), _p(np.ascontiguousarray(b, dtype=np.uint64)), _p(out))
+    return out
 
 
 class EvaluationDomain:

@@ -390,3 +390,49 @@ def test_tiny_srs_and_pinned_buffers(h2v):
     finally:
         h2v.host_unregister(a)
     d.close()
+
+
+# ----------------------------------------------------------------------------- "next" row 2 primitives
+@pytest.mark.parametrize("n,n_polys,n_points", [(1, 1, 1), (7, 2, 3), (256, 3, 2), (1000, 2, 2), (1 << 13, 5, 3), (1 << 16, 2, 4)])
+def test_eval_polynomial_vs_oracle(h2v, n, n_polys, n_points):
+    polys = [O.fr_fill(n, 60 + i + n, mode=i % 2) for i in range(n_polys)]
+    pts = O.fr_fill(n_points, 5 + n)
+    pts[0] = 0 if n_points > 1 else pts[0]          # x = 0 -> constant term
+    got = h2v.eval_polynomial_batch(polys, pts)
+    for i, p in enumerate(polys):
+        for j in range(n_points):
+            assert (got[i, j] == O.fr_eval_poly(p, pts[j])).all(), (i, j)
+    assert (h2v.eval_polynomial(polys[0], pts[-1]) == O.fr_eval_poly(polys[0], pts[-1])).all()
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 300, 4097, 1 << 16])
+def test_batch_invert_and_grand_product_vs_oracle(h2v, n):
+    a = O.fr_fill(n, 800 + n, mode=1)              # witness-like: contains zeros and ones
+    assert (h2v.batch_invert(a) == O.fr_batch_invert(a)).all()
+    num, den = O.fr_fill(n, 900 + n), O.fr_fill(n, 901 + n)
+    assert (h2v.grand_product(num, den) == O.fr_grand_product(num, den)).all()
+
+
+@pytest.mark.parametrize("n", [2, 3, 9, 2048, 2049, 5000, 1 << 16])
+def test_kate_division_vs_oracle(h2v, n):
+    a = O.fr_fill(n, 700 + n)
+    for b in (O.fr_fill(1, n)[0], np.zeros(4, dtype=np.uint64), O.fr_from_ints([1])[0]):
+        assert (h2v.kate_division(a, b) == O.fr_kate_division(a, b)).all()
+
+
+def test_row2_properties_k20(h2v):
+    """config-4 size: z[n-1] * r[n-1] telescopes, a(x) = (x - b) q(x) + a(b) at a random x."""
+    n = 1 << 20
+    a = O.fr_fill(n, 2024)
+    b, x = O.fr_fill(2, 99)
+    q = h2v.kate_division(a, b)
+    ax, ab, qx = (h2v.eval_polynomial(a, x), h2v.eval_polynomial(a, b), h2v.eval_polynomial(q, x))
+    lhs = O.field_op("fr_add", O.field_op("fr_mul", O.field_op("fr_sub", x, b), qx), ab)
+    assert (lhs == ax).all() and (ax == O.fr_eval_poly(a, x)).all()
+    num = O.fr_fill(n, 1)
+    z = h2v.grand_product(num, num)                 # num / num = 1 everywhere
+    one = O.fr_from_ints([1])[0]
+    assert (z == one).all()
+    inv = h2v.batch_invert(a)
+    for i in (0, 12345, n - 1):
+        assert (O.field_op("fr_mul", inv[i], a[i]) == one).all()

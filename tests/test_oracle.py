@@ -148,3 +148,26 @@ def test_oracle_domain_roundtrip_k13():
     assert (d.coeff_to_lagrange(d.lagrange_to_coeff(a)) == a).all()
     back = d.extended_to_coeff(d.coeff_to_extended(a))
     assert (back[: d.n] == a).all() and not back[d.n:].any()
+
+
+def test_oracle_row2_primitives():
+    """batch_invert / grand product / kate_division restatements against first principles."""
+    rnd = random.Random(21)
+    n = 70
+    a = [rnd.randrange(P.R) for _ in range(n)]
+    a[3] = a[40] = 0
+    assert O.fr_to_ints(O.fr_batch_invert(fr_arr(a))) == [pow(x, -1, P.R) if x else 0 for x in a]
+    num = [rnd.randrange(1, P.R) for _ in range(n)]
+    den = [rnd.randrange(1, P.R) for _ in range(n)]
+    exp = [1]
+    for i in range(n - 1):
+        exp.append(exp[-1] * num[i] * pow(den[i], -1, P.R) % P.R)
+    assert O.fr_to_ints(O.fr_grand_product(fr_arr(num), fr_arr(den))) == exp
+    for b in (rnd.randrange(P.R), 0, 1):
+        q = O.fr_to_ints(O.fr_kate_division(fr_arr(a), fr_arr([b])[0]))
+        back = [0] * n                      # (X - b) q(X) + a(b) == a(X)
+        for i, c in enumerate(q):
+            back[i + 1] = (back[i + 1] + c) % P.R
+            back[i] = (back[i] - b * c) % P.R
+        back[0] = (back[0] + P.eval_poly(a, b)) % P.R
+        assert back == a
