@@ -232,16 +232,27 @@ struct h2v_domain {
     bool tw_ready[4] = {false, false, false, false};
     DevBuf stage_a, stage_b;
     cudaStream_t stream = nullptr;
-    std::mutex mu;
+    std::mutex mu, tw_mu;
+    struct Lane {            // small host-facing transforms from concurrent caller threads (see h2v_srs::Lane)
+        std::mutex mu;
+        cudaStream_t st = nullptr;
+        DevBuf stage_a, stage_b;
+    };
+    static const int H2V_LANES = 4;
+    Lane lanes[H2V_LANES];
+    std::atomic<unsigned> next_lane{0};
 };
 
 namespace {
 
+// twiddle tables are built once per domain and direction, synchronously, so that any stream may use them
 int domain_twiddles(h2v_domain *d, int which, const fe **out) {
+    std::lock_guard<std::mutex> lk(d->tw_mu);
     if (!d->tw_ready[which]) {
         const fe &w = which == 0 ? d->omega : which == 1 ? d->omega_inv : which == 2 ? d->ext_omega : d->ext_omega_inv;
         int rc = build_twiddles(d->stream, d->tw[which], w, which < 2 ? (int)d->k : (int)d->ek);
         if (rc) return rc;
+        CU(cudaStreamSynchronize(d->stream));
         d->tw_ready[which] = true;
     }
     *out = d->tw[which].as<fe>();
@@ -249,7 +260,7 @@ int domain_twiddles(h2v_domain *d, int which, const fe **out) {
 }
 
 // enqueue one EvaluationDomain transform on device-resident columns
-int domain_op_dev(h2v_domain *d, int op, const fe *in, size_t in_stride, fe *out, size_t out_stride, size_t n_cols) {
+int domain_op_dev(h2v_domain *d, cudaStream_t st, int op, const fe *in, size_t in_stride, fe *out, size_t out_stride, size_t n_cols) {
     const fe *tw;
     const fe *dc = d->dconst.as<fe>();
     const uint32_t n = 1u << d->k, en = 1u << d->ek;
@@ -257,19 +268,19 @@ int domain_op_dev(h2v_domain *d, int op, const fe *in, size_t in_stride, fe *out
     switch (op) {
     case H2V_OP_LAGRANGE_TO_COEFF:
         if ((rc = domain_twiddles(d, 1, &tw))) return rc;
-        return run_ntt(d->stream, in, in_stride, out, out_stride, d->k, tw, nullptr, 1, n, dc + 3, 1, n, n_cols);
+        return run_ntt(st, in, in_stride, out, out_stride, d->k, tw, nullptr, 1, n, dc + 3, 1, n, n_cols);
     case H2V_OP_COEFF_TO_LAGRANGE:
         if ((rc = domain_twiddles(d, 0, &tw))) return rc;
-        return run_ntt(d->stream, in, in_stride, out, out_stride, d->k, tw, nullptr, 1, n, nullptr, 1, n, n_cols);
+        return run_ntt(st, in, in_stride, out, out_stride, d->k, tw, nullptr, 1, n, nullptr, 1, n, n_cols);
     case H2V_OP_COEFF_TO_EXTENDED:
         if ((rc = domain_twiddles(d, 2, &tw))) return rc;
-        return run_ntt(d->stream, in, in_stride, out, out_stride, d->ek, tw, dc, 3, n, nullptr, 1, en, n_cols);
+        return run_ntt(st, in, in_stride, out, out_stride, d->ek, tw, dc, 3, n, nullptr, 1, en, n_cols);
     case H2V_OP_EXTENDED_TO_COEFF:
         if ((rc = domain_twiddles(d, 3, &tw))) return rc;
-        return run_ntt(d->stream, in, in_stride, out, out_stride, d->ek, tw, nullptr, 1, en, dc + 4, 3, n * (d->j - 1), n_cols);
+        return run_ntt(st, in, in_stride, out, out_stride, d->ek, tw, nullptr, 1, en, dc + 4, 3, n * (d->j - 1), n_cols);
     case H2V_OP_DIVIDE_BY_VANISHING:
         if ((rc = domain_twiddles(d, 3, &tw))) return rc;
-        return run_ntt(d->stream, in, in_stride, out, out_stride, d->ek, tw, dc + 8, d->nt, en, dc + 4, 3, n * (d->j - 1), n_cols);
+        return run_ntt(st, in, in_stride, out, out_stride, d->ek, tw, dc + 8, d->nt, en, dc + 4, 3, n * (d->j - 1), n_cols);
     default:
         return fail(H2V_EINVAL, "unknown domain op %d", op);
     }
@@ -652,6 +663,18 @@ struct h2v_srs {
     cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, computed[2] = {nullptr, nullptr};
     std::mutex mu;
+    // Small calls (a single commit_lagrange from one of the caller's worker threads -- stock create_proof
+    // commits column by column from a rayon pool) run on one of H2V_LANES independent lanes, each with its
+    // own stream, workspace and staging, so concurrent callers overlap instead of queueing on one mutex.
+    struct Lane {
+        std::mutex mu;
+        cudaStream_t st = nullptr;
+        MsmWorkspace ws;
+        DevBuf stage, out;
+    };
+    static const int H2V_LANES = 4;
+    Lane lanes[H2V_LANES];
+    std::atomic<unsigned> next_lane{0};
 };
 
 // ================================================================== C ABI
@@ -750,6 +773,12 @@ void h2v_srs_free(h2v_srs_t s) {
     s->table[1].release();
     s->ws.buf.release();
     s->ws2.buf.release();
+    for (auto &ln : s->lanes) {
+        ln.ws.buf.release();
+        ln.stage.release();
+        ln.out.release();
+        if (ln.st) cudaStreamDestroy(ln.st);
+    }
     s->stage.release();
     s->out.release();
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -793,6 +822,40 @@ int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_
     if (!polys || !out_affine) return fail(H2V_EINVAL, "commit: NULL buffer");
     int rc = use_device();
     if (rc) return rc;
+    const size_t stride_small = std::max<size_t>(len, 1);
+    if (n_polys * stride_small * sizeof(fe) <= ((size_t)48 << 20)) {
+        // one sub-batch: take a free lane (or wait for the next one in round-robin order)
+        const unsigned first = s->next_lane.fetch_add(1) % h2v_srs::H2V_LANES;
+        h2v_srs::Lane *ln = nullptr;
+        for (int i = 0; i < h2v_srs::H2V_LANES && !ln; ++i) {
+            h2v_srs::Lane &c = s->lanes[(first + i) % h2v_srs::H2V_LANES];
+            if (c.mu.try_lock()) ln = &c;
+        }
+        if (!ln) {
+            ln = &s->lanes[first];
+            ln->mu.lock();
+        }
+        std::lock_guard<std::mutex> lk(ln->mu, std::adopt_lock);
+        if (!ln->st) CU(cudaStreamCreateWithFlags(&ln->st, cudaStreamNonBlocking));
+        if ((rc = ln->stage.ensure(n_polys * stride_small * sizeof(fe)))) return rc;
+        if ((rc = ln->out.ensure(n_polys * sizeof(affine)))) return rc;
+        for (size_t c = 0; c < n_polys; ++c) {
+            if (!polys[c] && len) {
+                cudaStreamSynchronize(ln->st);
+                return fail(H2V_EINVAL, "commit: polys[%zu] is NULL", c);
+            }
+            if (len) CU(cudaMemcpyAsync(ln->stage.as<fe>() + c * stride_small, polys[c], len * sizeof(fe), cudaMemcpyHostToDevice, ln->st));
+        }
+        rc = run_msm(ln->st, ln->ws, ln->stage.as<fe>(), stride_small, n_polys, len, s->table[basis].as<affine>(), s->cfg, s->n,
+                     ln->out.as<affine>(), nullptr, nullptr);
+        if (rc) {
+            cudaStreamSynchronize(ln->st);
+            return rc;
+        }
+        CU(cudaMemcpyAsync(out_affine, ln->out.p, n_polys * sizeof(affine), cudaMemcpyDeviceToHost, ln->st));
+        CU(cudaStreamSynchronize(ln->st));
+        return H2V_OK;
+    }
     std::lock_guard<std::mutex> lk(s->mu);
     // Double-buffered staging: while the kernels of sub-batch i run, the columns of sub-batch i+1 cross PCIe
     // on `copy_stream` (effective when the caller's buffers are pinned).  Sub-batches alternate between two
@@ -972,6 +1035,11 @@ void h2v_domain_free(h2v_domain_t d) {
     for (auto &t : d->tw) t.release();
     d->stage_a.release();
     d->stage_b.release();
+    for (auto &ln : d->lanes) {
+        ln.stage_a.release();
+        ln.stage_b.release();
+        if (ln.st) cudaStreamDestroy(ln.st);
+    }
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }
@@ -1012,7 +1080,7 @@ int h2v_domain_transform_dev(h2v_domain_t d, int op, const void *d_in, size_t in
     std::lock_guard<std::mutex> lk(d->mu);
     Timer tm(d->stream);
     tm.begin(7);
-    rc = domain_op_dev(d, op, (const fe *)d_in, in_stride, (fe *)d_out, out_stride, n_cols);
+    rc = domain_op_dev(d, d->stream, op, (const fe *)d_in, in_stride, (fe *)d_out, out_stride, n_cols);
     tm.end();
     cudaError_t e = cudaStreamSynchronize(d->stream);
     tm.collect(true);
@@ -1028,9 +1096,41 @@ int h2v_domain_transform_batch(h2v_domain_t d, int op, const uint64_t *const *in
     if (!in || !out) return fail(H2V_EINVAL, "transform: NULL buffer");
     int rc = use_device();
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(d->mu);
     const size_t nin = op_in_len(d, op), nout = op_out_len(d, op);
     const size_t out_stride = std::max(nout, (size_t)1 << (op >= H2V_OP_COEFF_TO_EXTENDED ? d->ek : d->k));
+    if (n_cols * out_stride * sizeof(fe) <= ((size_t)64 << 20)) {
+        const unsigned first = d->next_lane.fetch_add(1) % h2v_domain::H2V_LANES;
+        h2v_domain::Lane *ln = nullptr;
+        for (int i = 0; i < h2v_domain::H2V_LANES && !ln; ++i) {
+            h2v_domain::Lane &c = d->lanes[(first + i) % h2v_domain::H2V_LANES];
+            if (c.mu.try_lock()) ln = &c;
+        }
+        if (!ln) {
+            ln = &d->lanes[first];
+            ln->mu.lock();
+        }
+        std::lock_guard<std::mutex> lk(ln->mu, std::adopt_lock);
+        if (!ln->st) CU(cudaStreamCreateWithFlags(&ln->st, cudaStreamNonBlocking));
+        if ((rc = ln->stage_a.ensure(n_cols * nin * sizeof(fe)))) return rc;
+        if ((rc = ln->stage_b.ensure(n_cols * out_stride * sizeof(fe)))) return rc;
+        for (size_t c = 0; c < n_cols; ++c) {
+            if (!in[c] || !out[c]) {
+                cudaStreamSynchronize(ln->st);
+                return fail(H2V_EINVAL, "transform: column %zu is NULL", c);
+            }
+            CU(cudaMemcpyAsync(ln->stage_a.as<fe>() + c * nin, in[c], nin * sizeof(fe), cudaMemcpyHostToDevice, ln->st));
+        }
+        rc = domain_op_dev(d, ln->st, op, ln->stage_a.as<fe>(), nin, ln->stage_b.as<fe>(), out_stride, n_cols);
+        if (rc) {
+            cudaStreamSynchronize(ln->st);
+            return rc;
+        }
+        for (size_t c = 0; c < n_cols; ++c)
+            CU(cudaMemcpyAsync(out[c], ln->stage_b.as<fe>() + c * out_stride, nout * sizeof(fe), cudaMemcpyDeviceToHost, ln->st));
+        CU(cudaStreamSynchronize(ln->st));
+        return H2V_OK;
+    }
+    std::lock_guard<std::mutex> lk(d->mu);
     size_t per = std::max<size_t>(1, ((size_t)1 << 30) / (out_stride * sizeof(fe)));
     per = std::min(per, n_cols);
     if ((rc = d->stage_a.ensure(per * nin * sizeof(fe)))) return rc;
@@ -1041,7 +1141,7 @@ int h2v_domain_transform_batch(h2v_domain_t d, int op, const uint64_t *const *in
             if (!in[c0 + c] || !out[c0 + c]) return fail(H2V_EINVAL, "transform: column %zu is NULL", c0 + c);
             CU(cudaMemcpyAsync(d->stage_a.as<fe>() + c * nin, in[c0 + c], nin * sizeof(fe), cudaMemcpyHostToDevice, d->stream));
         }
-        rc = domain_op_dev(d, op, d->stage_a.as<fe>(), nin, d->stage_b.as<fe>(), out_stride, cols);
+        rc = domain_op_dev(d, d->stream, op, d->stage_a.as<fe>(), nin, d->stage_b.as<fe>(), out_stride, cols);
         if (rc) { cudaStreamSynchronize(d->stream); return rc; }
         for (size_t c = 0; c < cols; ++c)
             CU(cudaMemcpyAsync(out[c0 + c], d->stage_b.as<fe>() + c * out_stride, nout * sizeof(fe), cudaMemcpyDeviceToHost, d->stream));

@@ -38,3 +38,21 @@ for k in (13, 16, 20):
         ms = h.last_kernel_ms()
         print(k, nm, "sum %.3f" % sum(ms.values()), {a: round(b, 3) for a, b in ms.items() if b}, flush=True)
     srs.close()
+print("--- concurrent per-column callers (k=16, uniform), commits per second")
+import threading
+k = 16; n = 1 << k
+srs = h.ParamsKZG(k, None, h.synthetic_bases(n))
+cols = [torch.from_numpy(uniform_scalars(1, n, 10 + i).view(np.int64)).pin_memory().numpy().view(np.uint64)[0] for i in range(16)]
+for nthreads in (1, 2, 4, 8):
+    per = 64 // nthreads
+    def work(t):
+        for i in range(per):
+            srs.commit_lagrange(cols[(t * per + i) % 16])
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    work(0)
+    t0 = time.perf_counter()
+    for t in ths: t.start()
+    for t in ths: t.join()
+    dt = time.perf_counter() - t0
+    print(f"{nthreads} threads: {nthreads * per / dt:.0f} commits/s", flush=True)
+srs.close()

@@ -436,3 +436,37 @@ def test_row2_properties_k20(h2v):
     inv = h2v.batch_invert(a)
     for i in (0, 12345, n - 1):
         assert (O.field_op("fr_mul", inv[i], a[i]) == one).all()
+
+
+def test_concurrent_callers(h2v):
+    """Entry points are thread-safe: worker threads commit / transform column by column at the same time
+    (what stock create_proof does from its rayon pool); every result must still be exact."""
+    import threading
+
+    k, n = 12, 1 << 12
+    b = O.gen_bases(n)
+    srs = h2v.ParamsKZG(k, None, b)
+    dom, od = h2v.EvaluationDomain(4, k), O.EvaluationDomain(4, k)
+    cols = [O.fr_fill(n, 3000 + i, mode=i % 2) for i in range(24)]
+    exp_c = [O.msm_closed_form(c) for c in cols]
+    exp_t = [od.lagrange_to_coeff(c) for c in cols]
+    errors = []
+
+    def worker(tid):
+        try:
+            for i in range(tid, len(cols), 8):
+                if not (srs.commit_lagrange(cols[i]) == exp_c[i]).all():
+                    errors.append(("commit", i))
+                if not (dom.lagrange_to_coeff(cols[i]) == exp_t[i]).all():
+                    errors.append(("l2c", i))
+        except Exception as e:      # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    srs.close()
+    dom.close()
