@@ -407,6 +407,22 @@ def bench_ntt(h, torch, dev, peak):
                                   "frac": alg_bytes / t / 1e9 / hbm, "peak_source": hbm_src, "traffic": None},
                      "roofline_int": {"achieved": alg_macs / t / 1e12, "peak": peak / 1e12, "unit": "T wide-MAC/s",
                                       "frac": alg_macs / t / peak}}
+    # end to end through the host-facing batch entry point: pinned host columns in, pinned host columns out
+    import ctypes as C
+    import numpy as np
+    hin = a[:32].contiguous().pin_memory()
+    hout = torch.empty((32, 4 * N, 4), dtype=torch.int64).pin_memory()
+    ia = (C.c_void_p * 32)(*[hin[i].data_ptr() for i in range(32)])
+    for name, op, rows in (("lagrange_to_coeff", h.OP_LAGRANGE_TO_COEFF, N), ("coeff_to_extended", h.OP_COEFF_TO_EXTENDED, 4 * N)):
+        oa = (C.c_void_p * 32)(*[hout[i].data_ptr() for i in range(32)])
+        ts = []
+        for i in range(8):
+            t0 = time.perf_counter()
+            h._check(h.lib().h2v_domain_transform_batch(dom._h, op, ia, oa, 32))
+            ts.append(time.perf_counter() - t0)
+        t = statistics.median(ts[3:])
+        res[name]["e2e"] = {"gelem_per_s": 32 * rows / t / 1e9, "ms": t * 1e3, "cols": 32,
+                            "h2d_bytes": 32 * N * 32, "d2h_bytes": 32 * rows * 32}
     dom.close()
     return res
 

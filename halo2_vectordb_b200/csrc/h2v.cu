@@ -230,8 +230,8 @@ struct h2v_domain {
     DevBuf dconst;
     DevBuf tw[4];   // 0: omega, 1: omega_inv, 2: ext_omega, 3: ext_omega_inv
     bool tw_ready[4] = {false, false, false, false};
-    DevBuf stage_a, stage_b;
-    cudaStream_t stream = nullptr;
+    DevBuf stage_a, stage_b, pipe_a, pipe_b;
+    cudaStream_t stream = nullptr, pipe_stream = nullptr;
     std::mutex mu, tw_mu;
     struct Lane {            // small host-facing transforms from concurrent caller threads (see h2v_srs::Lane)
         std::mutex mu;
@@ -825,14 +825,12 @@ int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_
     const size_t stride_small = std::max<size_t>(len, 1);
     if (n_polys * stride_small * sizeof(fe) <= ((size_t)48 << 20)) {
         // one sub-batch: take a free lane (or wait for the next one in round-robin order)
-        const unsigned first = s->next_lane.fetch_add(1) % h2v_srs::H2V_LANES;
+        // lowest free lane first (a single-threaded caller keeps reusing lane 0 and its buffers)
         h2v_srs::Lane *ln = nullptr;
-        for (int i = 0; i < h2v_srs::H2V_LANES && !ln; ++i) {
-            h2v_srs::Lane &c = s->lanes[(first + i) % h2v_srs::H2V_LANES];
-            if (c.mu.try_lock()) ln = &c;
-        }
+        for (int i = 0; i < h2v_srs::H2V_LANES && !ln; ++i)
+            if (s->lanes[i].mu.try_lock()) ln = &s->lanes[i];
         if (!ln) {
-            ln = &s->lanes[first];
+            ln = &s->lanes[s->next_lane.fetch_add(1) % h2v_srs::H2V_LANES];
             ln->mu.lock();
         }
         std::lock_guard<std::mutex> lk(ln->mu, std::adopt_lock);
@@ -1035,6 +1033,9 @@ void h2v_domain_free(h2v_domain_t d) {
     for (auto &t : d->tw) t.release();
     d->stage_a.release();
     d->stage_b.release();
+    d->pipe_a.release();
+    d->pipe_b.release();
+    if (d->pipe_stream) cudaStreamDestroy(d->pipe_stream);
     for (auto &ln : d->lanes) {
         ln.stage_a.release();
         ln.stage_b.release();
@@ -1099,14 +1100,11 @@ int h2v_domain_transform_batch(h2v_domain_t d, int op, const uint64_t *const *in
     const size_t nin = op_in_len(d, op), nout = op_out_len(d, op);
     const size_t out_stride = std::max(nout, (size_t)1 << (op >= H2V_OP_COEFF_TO_EXTENDED ? d->ek : d->k));
     if (n_cols * out_stride * sizeof(fe) <= ((size_t)64 << 20)) {
-        const unsigned first = d->next_lane.fetch_add(1) % h2v_domain::H2V_LANES;
         h2v_domain::Lane *ln = nullptr;
-        for (int i = 0; i < h2v_domain::H2V_LANES && !ln; ++i) {
-            h2v_domain::Lane &c = d->lanes[(first + i) % h2v_domain::H2V_LANES];
-            if (c.mu.try_lock()) ln = &c;
-        }
+        for (int i = 0; i < h2v_domain::H2V_LANES && !ln; ++i)
+            if (d->lanes[i].mu.try_lock()) ln = &d->lanes[i];
         if (!ln) {
-            ln = &d->lanes[first];
+            ln = &d->lanes[d->next_lane.fetch_add(1) % h2v_domain::H2V_LANES];
             ln->mu.lock();
         }
         std::lock_guard<std::mutex> lk(ln->mu, std::adopt_lock);
@@ -1130,23 +1128,44 @@ int h2v_domain_transform_batch(h2v_domain_t d, int op, const uint64_t *const *in
         CU(cudaStreamSynchronize(ln->st));
         return H2V_OK;
     }
+    // Large batch: sub-batches of ~64 MB alternate between two pipelines (stream + staging each) with no sync
+    // in between, so the upload of sub-batch i+1, the kernels of sub-batch i and the download of sub-batch i-1
+    // overlap (PCIe is full duplex; the transforms themselves are ~4x faster than the link).
     std::lock_guard<std::mutex> lk(d->mu);
-    size_t per = std::max<size_t>(1, ((size_t)1 << 30) / (out_stride * sizeof(fe)));
+    size_t per = std::max<size_t>(1, ((size_t)64 << 20) / (out_stride * sizeof(fe)));
     per = std::min(per, n_cols);
-    if ((rc = d->stage_a.ensure(per * nin * sizeof(fe)))) return rc;
-    if ((rc = d->stage_b.ensure(per * out_stride * sizeof(fe)))) return rc;
-    for (size_t c0 = 0; c0 < n_cols; c0 += per) {
-        size_t cols = std::min(per, n_cols - c0);
-        for (size_t c = 0; c < cols; ++c) {
-            if (!in[c0 + c] || !out[c0 + c]) return fail(H2V_EINVAL, "transform: column %zu is NULL", c0 + c);
-            CU(cudaMemcpyAsync(d->stage_a.as<fe>() + c * nin, in[c0 + c], nin * sizeof(fe), cudaMemcpyHostToDevice, d->stream));
-        }
-        rc = domain_op_dev(d, d->stream, op, d->stage_a.as<fe>(), nin, d->stage_b.as<fe>(), out_stride, cols);
-        if (rc) { cudaStreamSynchronize(d->stream); return rc; }
-        for (size_t c = 0; c < cols; ++c)
-            CU(cudaMemcpyAsync(out[c0 + c], d->stage_b.as<fe>() + c * out_stride, nout * sizeof(fe), cudaMemcpyDeviceToHost, d->stream));
-        CU(cudaStreamSynchronize(d->stream));
+    cudaStream_t pst[2];
+    DevBuf *pa[2] = {&d->stage_a, &d->pipe_a}, *pb[2] = {&d->stage_b, &d->pipe_b};
+    if (!d->pipe_stream) CU(cudaStreamCreateWithFlags(&d->pipe_stream, cudaStreamNonBlocking));
+    pst[0] = d->stream;
+    pst[1] = d->pipe_stream;
+    for (int b = 0; b < 2; ++b) {
+        if ((rc = pa[b]->ensure(per * nin * sizeof(fe)))) return rc;
+        if ((rc = pb[b]->ensure(per * out_stride * sizeof(fe)))) return rc;
     }
+    size_t it = 0;
+    for (size_t c0 = 0; c0 < n_cols; c0 += per, ++it) {
+        const size_t cols = std::min(per, n_cols - c0);
+        const int b = (int)(it & 1);
+        for (size_t c = 0; c < cols; ++c) {
+            if (!in[c0 + c] || !out[c0 + c]) {
+                cudaStreamSynchronize(pst[0]);
+                cudaStreamSynchronize(pst[1]);
+                return fail(H2V_EINVAL, "transform: column %zu is NULL", c0 + c);
+            }
+            CU(cudaMemcpyAsync(pa[b]->as<fe>() + c * nin, in[c0 + c], nin * sizeof(fe), cudaMemcpyHostToDevice, pst[b]));
+        }
+        rc = domain_op_dev(d, pst[b], op, pa[b]->as<fe>(), nin, pb[b]->as<fe>(), out_stride, cols);
+        if (rc) {
+            cudaStreamSynchronize(pst[0]);
+            cudaStreamSynchronize(pst[1]);
+            return rc;
+        }
+        for (size_t c = 0; c < cols; ++c)
+            CU(cudaMemcpyAsync(out[c0 + c], pb[b]->as<fe>() + c * out_stride, nout * sizeof(fe), cudaMemcpyDeviceToHost, pst[b]));
+    }
+    CU(cudaStreamSynchronize(pst[0]));
+    CU(cudaStreamSynchronize(pst[1]));
     return H2V_OK;
 }
 static int one_col(h2v_domain_t d, int op, const uint64_t *in, uint64_t *out) {
