@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
     __syncthreads();
 
     // ------------------------------------------------------------------ rounds of up to 3 stages
+    const bool pad4 = p.first && (((uint64_t)p.n_in << 2) <= ((uint64_t)1 << L));
     for (int b = 0; b < S; b += 3) {
         const int bp = (b + 3 <= S) ? b : S - 3;   // the thread's 3 index bits are [bp, bp+3)
         const int u0 = b - bp;                     // stages below u0 were done in the previous round
@@ -153,13 +154,20 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
             //   lo + ((low + (k mod 2^u) << bp) << t0)
             const uint32_t lo = p.first ? 0u : (lo_tile * T + q);
             const uint32_t jlow = lo + (low << t0);
-            if (u0 <= 0) {
-                int t = t0 + bp;
-                ntt_stage<0>(x, p.tw, jlow << (L - 1 - t), L, t == 0);
-            }
-            if (u0 <= 1) {
-                int t = t0 + bp + 1;
-                ntt_stage<1>(x, p.tw, jlow << (L - 1 - t), L, false);
+            if (pad4 && b == 0) {
+                // zero-padded input (coeff_to_extended: n_in <= N/4): after the bit reversal only every 4th
+                // element is non-zero, so the first two stages just broadcast it -- no products with zero
+                x[1] = x[0]; x[2] = x[0]; x[3] = x[0];
+                x[5] = x[4]; x[6] = x[4]; x[7] = x[4];
+            } else {
+                if (u0 <= 0) {
+                    int t = t0 + bp;
+                    ntt_stage<0>(x, p.tw, jlow << (L - 1 - t), L, t == 0);
+                }
+                if (u0 <= 1) {
+                    int t = t0 + bp + 1;
+                    ntt_stage<1>(x, p.tw, jlow << (L - 1 - t), L, false);
+                }
             }
             {
                 int t = t0 + bp + 2;

@@ -66,8 +66,13 @@ def ntt_pass(src, dst, tw, L, t0, S, logT, first, last, n_in, n_out, pre, post):
                 x = [sm[swz(((mid_base + (k << bp)) << logT) | q)] for k in range(8)]
                 lo = 0 if first else lo_tile * T + q
                 jlow = lo + (low << t0)
+                pad4 = first and 4 * n_in <= (1 << L) and b == 0
+                if pad4:
+                    assert all(x[k] == 0 for k in (1, 2, 3, 5, 6, 7))
+                    x[1] = x[2] = x[3] = x[0]
+                    x[5] = x[6] = x[7] = x[4]
                 for U in range(3):
-                    if U < u0:
+                    if U < u0 or (pad4 and U < 2):
                         continue
                     t = t0 + bp + U
                     e_base = jlow << (L - 1 - t)
