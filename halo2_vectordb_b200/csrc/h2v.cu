@@ -860,7 +860,12 @@ int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_
     // compute streams with their own workspaces, so the latency-bound tail of one (bucket-reduction tree,
     // affine normalisation) overlaps the bulk kernels of the next.
     const size_t stride = std::max<size_t>(len, 1);
-    size_t sub = std::max<size_t>(1, ((size_t)48 << 20) / (stride * sizeof(fe)));
+    static const size_t sub_mb = [] {   // scalars per sub-batch in MiB (H2V_SUB_MB: tuning; 48 measured best)
+        const char *e = getenv("H2V_SUB_MB");
+        int v = e ? atoi(e) : 48;
+        return (size_t)(v < 1 ? 1 : v);
+    }();
+    size_t sub = std::max<size_t>(1, (sub_mb << 20) / (stride * sizeof(fe)));
     sub = std::min(sub, n_polys);
     if ((rc = s->stage.ensure(2 * sub * stride * sizeof(fe)))) return rc;
     if ((rc = s->out.ensure(n_polys * sizeof(affine)))) return rc;
