@@ -26,7 +26,7 @@ KERNEL_CLASSES = ["msm_digits", "msm_scan", "msm_scatter", "msm_accumulate", "ms
 # every symbol include/h2v.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "h2v_init", "h2v_device_count", "h2v_last_error", "h2v_version", "h2v_host_register", "h2v_host_unregister",
-    "h2v_srs_load", "h2v_srs_free", "h2v_commit", "h2v_commit_batch", "h2v_commit_batch_dev", "h2v_best_multiexp",
+    "h2v_srs_load", "h2v_srs_setup", "h2v_srs_free", "h2v_commit", "h2v_commit_batch", "h2v_commit_batch_dev", "h2v_best_multiexp",
     "h2v_best_fft", "h2v_domain_new", "h2v_domain_free", "h2v_domain_k", "h2v_domain_extended_k", "h2v_domain_constant",
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
     "h2v_divide_by_vanishing_poly", "h2v_domain_transform_batch", "h2v_domain_transform_dev",
@@ -62,6 +62,7 @@ def lib():
         L.h2v_host_register.argtypes = [C.c_void_p, C.c_size_t]
         L.h2v_host_unregister.argtypes = [C.c_void_p]
         L.h2v_srs_load.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.h2v_srs_setup.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.h2v_srs_free.argtypes = [C.c_void_p]
         L.h2v_srs_free.restype = None
         L.h2v_commit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -229,6 +230,16 @@ def kate_division(a, b):
 
 
 # ----------------------------------------------------------------------------- poly/kzg/commitment.rs
+def srs_setup(k, s):
+    """`ParamsKZG::setup(k, rng)` with the secret s (Montgomery Fr, (4,)) given: returns (g, g_lagrange)."""
+    n = 1 << k
+    s = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
+    g = np.zeros((n, 8), dtype=np.uint64)
+    gl = np.zeros((n, 8), dtype=np.uint64)
+    _check(lib().h2v_srs_setup(k, _ptr(s), _ptr(g), _ptr(gl)))
+    return g, gl
+
+
 class ParamsKZG:
     """halo2-axiom `ParamsKZG<Bn256>` restricted to the commit path: {k, n, g, g_lagrange}."""
 
@@ -246,6 +257,14 @@ class ParamsKZG:
             ptrs.append(b)
         _check(lib().h2v_srs_load(k, None if ptrs[0] is None else _ptr(ptrs[0]),
                                   None if ptrs[1] is None else _ptr(ptrs[1]), C.byref(self._h)))
+
+    @classmethod
+    def setup(cls, k, s):
+        """`ParamsKZG::setup`: build both bases on the device from the secret s and load them."""
+        g, gl = srs_setup(k, s)
+        p = cls(k, g, gl)
+        p.g, p.g_lagrange = g, gl
+        return p
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value and _lib is not None:

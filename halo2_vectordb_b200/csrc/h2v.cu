@@ -1530,6 +1530,36 @@ int h2v_selftest_group(int mode, const uint64_t *p, const uint64_t *q, size_t n,
     A.release(); B.release(); O.release();
     return H2V_OK;
 }
+int h2v_srs_setup(uint32_t k, const uint64_t s_mont[4], uint64_t *g_out, uint64_t *g_lagrange_out) {
+    int rc = use_device();
+    if (rc) return rc;
+    if (!s_mont || (!g_out && !g_lagrange_out)) return fail(H2V_EINVAL, "srs_setup: NULL argument");
+    if (k > 26) return fail(H2V_EINVAL, "srs_setup: k = %u unsupported", k);
+    const size_t n = (size_t)1 << k;
+    SetupParams sp;
+    sp.s = fe_from_u64x4(s_mont);
+    sp.n = (uint32_t)n;
+    fe root;
+    memcpy(root.v, FR_ROOT, 32);
+    sp.omega = fe_to_mont<Fr>(root);
+    for (uint32_t i = k; i < (uint32_t)FR_S; ++i) sp.omega = fe_sqr<Fr>(sp.omega);
+    fe sn = sp.s;
+    for (uint32_t i = 0; i < k; ++i) sn = fe_sqr<Fr>(sn);                       // s^(2^k)
+    sp.mult = fe_mul<Fr>(fe_sub<Fr>(sn, fe_one<Fr>()), fe_inv<Fr>(fr_from_small((uint64_t)n)));
+    if (fe_is_zero(fe_sub<Fr>(sn, fe_one<Fr>()))) return fail(H2V_EINVAL, "srs_setup: s is a 2^k-th root of unity");
+    DevBuf O;
+    if ((rc = O.ensure(n * sizeof(affine)))) return rc;
+    uint64_t *dst[2] = {g_out, g_lagrange_out};
+    for (int b = 0; b < 2; ++b) {
+        if (!dst[b]) continue;
+        srs_setup_kernel<<<(unsigned)((n + 127) / 128), 128>>>(sp, b, O.as<affine>());
+        LAUNCHED();
+        CU(cudaDeviceSynchronize());
+        CU(cudaMemcpy(dst[b], O.p, n * sizeof(affine), cudaMemcpyDeviceToHost));
+    }
+    O.release();
+    return H2V_OK;
+}
 int h2v_synthetic_bases(uint64_t a, uint64_t b, size_t n, uint64_t *out_affine) {
     int rc = use_device();
     if (rc) return rc;

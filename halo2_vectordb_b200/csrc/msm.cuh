@@ -481,4 +481,41 @@ __global__ void __launch_bounds__(128) msm_precompute_kernel(affine *__restrict_
     fe_st(&table[(size_t)level * n + i].y, o.y);
 }
 
+// ------------------------------------------------------------------ ParamsKZG::setup
+// halo2-axiom poly/kzg/commitment.rs `ParamsKZG::setup`: g[i] = s^i G and, directly from s,
+// g_lagrange[i] = ((s^n - 1)/n) w^i / (s - w^i) G.  One thread per point: the Fr scalar, then a 254-bit
+// double-and-add from the generator and the affine normalisation.  One-time work, not on the prove path.
+struct SetupParams {
+    fe s;        // the secret, Montgomery Fr
+    fe omega;    // 2^k-th root of unity
+    fe mult;     // (s^n - 1) / n
+    uint32_t n;
+};
+__global__ void __launch_bounds__(128) srs_setup_kernel(SetupParams p, int lagrange, affine *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    fe sc;
+    if (!lagrange) {
+        sc = fe_pow_small<Fr>(p.s, i);
+    } else {
+        fe w = fe_pow_small<Fr>(p.omega, i);
+        sc = fe_mul<Fr>(fe_mul<Fr>(p.mult, w), fe_inv<Fr>(fe_sub<Fr>(p.s, w)));
+    }
+    sc = fe_from_mont<Fr>(sc);
+    affine g;
+    fe c = fe_zero();
+    c.v[0] = 1;
+    g.x = fe_to_mont<Fq>(c);
+    c.v[0] = 2;
+    g.y = fe_to_mont<Fq>(c);
+    xyzz acc = xyzz_identity();
+    for (int bit = 253; bit >= 0; --bit) {
+        acc = xyzz_double(acc);
+        if ((sc.v[bit >> 5] >> (bit & 31)) & 1u) xyzz_add_mixed(acc, g);
+    }
+    affine o = xyzz_to_affine(acc);
+    fe_st(&out[i].x, o.x);
+    fe_st(&out[i].y, o.y);
+}
+
 }  // namespace h2v

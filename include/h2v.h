@@ -56,6 +56,10 @@ int h2v_host_unregister(void *ptr);
  * (n = 2^k G1Affine each) and build the per-window tables 2^(jc) * B_i once.
  * `g` or `g_lagrange` may be NULL if that basis is never used.  (scaffold: gen_srs, mod.rs:260) */
 int h2v_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, h2v_srs_t *out);
+/* ParamsKZG::setup(k, rng) with the secret supplied by the caller (upstream draws s = Fr::random(rng); gen_srs
+ * seeds ChaCha20 with zeros -- "unsafe" by design): g[i] = s^i G and g_lagrange[i] = L_i(s) G, each 2^k affine
+ * points (either output may be NULL).  One-time work; g2 / s_g2 are verifier-side and not produced. */
+int h2v_srs_setup(uint32_t k, const uint64_t s_mont[4], uint64_t *g_out, uint64_t *g_lagrange_out);
 void h2v_srs_free(h2v_srs_t srs);
 /* ParamsKZG::commit(poly, _blind) / commit_lagrange(poly, _blind) = best_multiexp(poly, bases[..len]);
  * the Blind argument is ignored by KZG upstream, so it is not part of the ABI.  len <= 2^k.

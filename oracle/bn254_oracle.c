@@ -813,3 +813,68 @@ void orc_fr_kate_division(const u64 *a, size_t n, const u64 b[4], u64 *out) {
         q[i - 1] = tmp;
     }
 }
+
+/* ------------------------------------------------------------------ ParamsKZG::setup
+ * halo2-axiom poly/kzg/commitment.rs `ParamsKZG::setup(k, rng)`: s = Fr::random(rng) (here: supplied by the
+ * caller, Montgomery form), g[i] = s^i * G, and the Lagrange basis directly from s:
+ *   g_lagrange[i] = ((s^n - 1) / n) * w^i / (s - w^i) * G,   w = the 2^k-th root of unity of EvaluationDomain.
+ * (g2 / s_g2 belong to the verifier and are not on the commit path.) */
+typedef struct { const fe *sc; size_t lo, hi; g1a *out; } fixmul_job;
+static void *fixmul_worker(void *p) {
+    fixmul_job *j = p;
+    g1a g;
+    orc_g1_generator((u64 *)&g);
+    for (size_t i = j->lo; i < j->hi; ++i) {
+        u64 c[4];
+        f_from_mont(&FR, c, &j->sc[i]);
+        g1j t;
+        j_mul_canon(&t, &g, c);
+        j_to_affine(&j->out[i], &t);
+    }
+    return NULL;
+}
+static void fixed_base_mul(const fe *sc, size_t n, int threads, g1a *out) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t th[256]; fixmul_job jobs[256];
+    size_t per = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        size_t lo = (size_t)t * per, hi = lo + per > n ? n : lo + per;
+        if (lo > n) lo = n;
+        jobs[t] = (fixmul_job){sc, lo, hi, out};
+        pthread_create(&th[t], NULL, fixmul_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+}
+int orc_srs_setup(uint32_t k, const u64 s_mont[4], int threads, u64 *g_out, u64 *g_lagrange_out) {
+    if (k > FR_S) return -1;
+    size_t n = (size_t)1 << k;
+    const fe *s = (const fe *)s_mont;
+    fe *sc = malloc(n * sizeof(fe));
+    fe one, cur;
+    memcpy(one.l, FR.r1, 32);
+    cur = one;
+    for (size_t i = 0; i < n; ++i) { sc[i] = cur; f_mul(&FR, &cur, &cur, s); }
+    fixed_base_mul(sc, n, threads, (g1a *)g_out);
+    /* cur == s^n now */
+    fe omega, nf, ninv, mult, w;
+    f_to_mont(&FR, &omega, FR_ROOT_OF_UNITY);
+    for (uint32_t i = k; i < FR_S; ++i) f_sqr(&FR, &omega, &omega);
+    u64 c[4] = {(u64)n, 0, 0, 0};
+    f_to_mont(&FR, &nf, c);
+    f_inv(&FR, &ninv, &nf);
+    f_sub(&FR, &mult, &cur, &one);
+    f_mul(&FR, &mult, &mult, &ninv);
+    w = one;
+    for (size_t i = 0; i < n; ++i) {
+        fe d, di;
+        f_sub(&FR, &d, s, &w);
+        f_inv(&FR, &di, &d);            /* s is not a root of unity for any honest setup */
+        f_mul(&FR, &sc[i], &mult, &w);
+        f_mul(&FR, &sc[i], &sc[i], &di);
+        f_mul(&FR, &w, &w, &omega);
+    }
+    fixed_base_mul(sc, n, threads, (g1a *)g_lagrange_out);
+    free(sc);
+    return 0;
+}

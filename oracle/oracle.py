@@ -62,6 +62,7 @@ _eval_poly = _sig("orc_fr_eval_poly", _u64p, C.c_size_t, _u64p, _u64p)
 _batch_invert = _sig("orc_fr_batch_invert", _u64p, C.c_size_t)
 _grand_product = _sig("orc_fr_grand_product", _u64p, _u64p, C.c_size_t, _u64p)
 _kate = _sig("orc_fr_kate_division", _u64p, C.c_size_t, _u64p, _u64p)
+_srs_setup = _sig("orc_srs_setup", C.c_uint32, _u64p, C.c_int, _u64p, _u64p, res=C.c_int)
 _best_fft = _sig("orc_best_fft", _u64p, _u64p, C.c_uint32, C.c_int)
 _domain_new = _sig("orc_domain_new", C.c_uint32, C.c_uint32, C.c_void_p, res=C.c_int)
 _domain_sizeof = _sig("orc_domain_sizeof", res=C.c_size_t)
@@ -246,6 +247,16 @@ def fr_eval_poly(a, x):
     o = np.empty(4, dtype=np.uint64)
     _eval_poly(_p(a), len(a), _p(np.ascontiguousarray(x, dtype=np.uint64)), _p(o))
     return o
+
+
+def srs_setup(k, s_mont, threads=NCPU):
+    """ParamsKZG::setup(k, rng) with the secret s given: returns (g, g_lagrange), each (2^k, 8)."""
+    n = 1 << k
+    g = np.zeros((n, 8), dtype=np.uint64)
+    gl = np.zeros((n, 8), dtype=np.uint64)
+    if _srs_setup(k, _p(np.ascontiguousarray(s_mont, dtype=np.uint64)), threads, _p(g), _p(gl)) != 0:
+        raise ValueError("unsupported k")
+    return g, gl
 
 
 def fr_batch_invert(a):

@@ -470,3 +470,45 @@ def test_concurrent_callers(h2v):
     assert not errors, errors
     srs.close()
     dom.close()
+
+
+# ----------------------------------------------------------------------------- ParamsKZG::setup + KZG consistency
+def test_srs_setup_vs_oracle(h2v):
+    s = O.fr_from_ints([0x1234567890ABCDEF1234567890ABCDEF % P.R])[0]
+    for k in (0, 1, 4, 7):
+        g, gl = h2v.srs_setup(k, s)
+        og, ogl = O.srs_setup(k, s)
+        assert (g == og).all() and (gl == ogl).all(), k
+    with pytest.raises(ValueError):
+        h2v.srs_setup(3, O.fr_from_ints([P.omega_for(3)])[0])       # s must not be a root of unity
+
+
+@pytest.mark.parametrize("k", [6, 12, 16])
+def test_kzg_consistency_monomial_vs_lagrange(h2v, k):
+    """With a real SRS the two bases describe the same commitment scheme: for any polynomial,
+    commit(coefficients) == commit_lagrange(evaluations).  This ties MSM (both bases, window tables),
+    the NTT (lagrange_to_coeff / coeff_to_lagrange) and the setup together at the kmeans size."""
+    n = 1 << k
+    s = O.fr_fill(1, 4242 + k)[0]
+    srs = h2v.ParamsKZG.setup(k, s)
+    dom = h2v.EvaluationDomain(4, k)
+    one = O.fr_from_ints([1])[0]
+    G = O.g1_generator()
+    # sum_i L_i(s) = 1  =>  commit_lagrange(1, 1, ..., 1) = G ;  commit(X) = s G = g[1]
+    assert (srs.commit_lagrange(np.tile(one, (n, 1))) == G).all()
+    xpoly = np.zeros((n, 4), dtype=np.uint64)
+    xpoly[1] = one
+    assert (srs.commit(xpoly) == srs.g[1]).all()
+    assert (srs.g[0] == G).all()
+    for mode in (0, 1):
+        evals = O.fr_fill(n, 77 + mode, mode=mode, lookup_bits=max(k - 1, 2))
+        coeffs = dom.lagrange_to_coeff(evals)
+        c_l = srs.commit_lagrange(evals)
+        c_m = srs.commit(coeffs)
+        assert (c_l == c_m).all(), mode
+        assert O.g1_is_on_curve(c_l)
+        # and the commitment is p(s) G
+        ps = O.fr_to_ints(O.fr_eval_poly(coeffs, s))[0]
+        assert (c_m == O.g1_mul(G, ps)).all()
+    srs.close()
+    dom.close()

@@ -171,3 +171,23 @@ def test_oracle_row2_primitives():
             back[i] = (back[i] - b * c) % P.R
         back[0] = (back[0] + P.eval_poly(a, b)) % P.R
         assert back == a
+
+
+def test_oracle_srs_setup_is_lagrange_basis():
+    """ParamsKZG::setup restatement: g[i] = s^i G and g_lagrange[i] = L_i(s) G (Lagrange polynomials of the
+    2^k-th roots of unity), checked against the product formula."""
+    k, n, s = 3, 8, 123456789123456789
+    g, gl = O.srs_setup(k, fr_arr([s])[0])
+    w = P.omega_for(k)
+    for i in range(n):
+        assert O.g1_affine_to_ints(g[i]) == P.g1_mul(P.G1_GEN, pow(s, i, P.R))
+        num = den = 1
+        for j in range(n):
+            if j != i:
+                num = num * (s - pow(w, j, P.R)) % P.R
+                den = den * (pow(w, i, P.R) - pow(w, j, P.R)) % P.R
+        assert O.g1_affine_to_ints(gl[i]) == P.g1_mul(P.G1_GEN, num * pow(den, -1, P.R) % P.R)
+    # KZG consistency on the CPU path: commit(coeffs) == commit_lagrange(evals)
+    d = O.EvaluationDomain(4, k)
+    ev = O.fr_fill(n, 9)
+    assert (O.best_multiexp_affine(ev, gl) == O.best_multiexp_affine(d.lagrange_to_coeff(ev), g)).all()
