@@ -512,3 +512,24 @@ def test_kzg_consistency_monomial_vs_lagrange(h2v, k):
         assert (c_m == O.g1_mul(G, ps)).all()
     srs.close()
     dom.close()
+
+
+def test_kzg_opening_identity(h2v):
+    """A KZG opening assembled from the library's own pieces: q = kate_division(p, z), then
+    commit(q) * (s - z) == commit(p) - p(z) G, checked through the known secret."""
+    k, n = 12, 1 << 12
+    s = O.fr_fill(1, 31337)[0]
+    srs = h2v.ParamsKZG.setup(k, s)
+    p = O.fr_fill(n, 5)
+    z = O.fr_fill(1, 6)[0]
+    q = h2v.kate_division(p, z)
+    qpad = np.zeros((n, 4), dtype=np.uint64)
+    qpad[: n - 1] = q
+    pz = h2v.eval_polynomial(p, z)
+    cq = srs.commit(qpad)
+    si, zi = O.fr_to_ints(s)[0], O.fr_to_ints(z)[0]
+    ps, pzi = O.fr_to_ints(O.fr_eval_poly(p, s))[0], O.fr_to_ints(pz)[0]
+    G = O.g1_generator()
+    assert (cq == O.g1_mul(G, (ps - pzi) * pow(si - zi, -1, P.R) % P.R)).all()
+    assert (srs.commit(p) == O.g1_mul(G, ps)).all()
+    srs.close()
