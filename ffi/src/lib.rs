@@ -49,7 +49,40 @@ extern "C" {
     pub fn h2v_divide_by_vanishing_poly(dom: *mut H2vDomain, a: *mut u64) -> c_int;
     pub fn h2v_domain_transform_batch(dom: *mut H2vDomain, op: c_int, inp: *const *const u64, out: *const *mut u64,
                                       n_cols: usize) -> c_int;
+    pub fn h2v_srs_setup(k: u32, s_mont: *const u64, g_out: *mut u64, g_lagrange_out: *mut u64) -> c_int;
+    // polynomial primitives around the commits
+    pub fn h2v_eval_polynomial_batch(polys: *const *const u64, n_polys: usize, len: usize, points: *const u64,
+                                     n_points: usize, out: *mut u64) -> c_int;
+    pub fn h2v_batch_invert(a: *mut u64, n: usize) -> c_int;
+    pub fn h2v_grand_product(num: *const u64, den: *const u64, n: usize, out: *mut u64) -> c_int;
+    pub fn h2v_kate_division(a: *const u64, n: usize, b: *const u64, out: *mut u64) -> c_int;
+    // device-resident columns
+    pub fn h2v_dev_alloc(bytes: usize, d_out: *mut *mut c_void) -> c_int;
+    pub fn h2v_dev_free(d_ptr: *mut c_void) -> c_int;
+    pub fn h2v_dev_upload(d_dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
+    pub fn h2v_dev_download(dst: *mut c_void, d_src: *const c_void, bytes: usize) -> c_int;
+    pub fn h2v_commit_batch_dev(srs: *mut H2vSrs, basis: c_int, d_polys: *const c_void, col_stride: usize, n_polys: usize,
+                                len: usize, d_out_affine: *mut c_void) -> c_int;
+    pub fn h2v_domain_transform_dev(dom: *mut H2vDomain, op: c_int, d_in: *const c_void, in_stride: usize,
+                                    d_out: *mut c_void, out_stride: usize, n_cols: usize) -> c_int;
 }
+
+/// `halo2_proofs::arithmetic::eval_polynomial`
+pub fn eval_polynomial(poly: &[Fr], point: Fr) -> Fr {
+    let ptr = [poly.as_ptr() as *const u64];
+    let mut out = Fr::zero();
+    ok(unsafe { h2v_eval_polynomial_batch(ptr.as_ptr(), 1, poly.len(), &point as *const Fr as *const u64, 1,
+                                          &mut out as *mut Fr as *mut u64) });
+    out
+}
+/// `halo2_proofs::arithmetic::kate_division(a, b)`
+pub fn kate_division(a: &[Fr], b: Fr) -> Vec<Fr> {
+    let mut out = vec![Fr::zero(); a.len().saturating_sub(1)];
+    ok(unsafe { h2v_kate_division(a.as_ptr() as *const u64, a.len(), &b as *const Fr as *const u64, out.as_mut_ptr() as *mut u64) });
+    out
+}
+/// `ff::BatchInvert::batch_invert` on a slice
+pub fn batch_invert(a: &mut [Fr]) { ok(unsafe { h2v_batch_invert(a.as_mut_ptr() as *mut u64, a.len()) }) }
 
 fn ok(rc: c_int) {
     if rc != 0 {

@@ -25,7 +25,7 @@ KERNEL_CLASSES = ["msm_digits", "msm_scan", "msm_scatter", "msm_accumulate", "ms
 
 # every symbol include/h2v.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
-    "h2v_init", "h2v_device_count", "h2v_last_error", "h2v_version", "h2v_host_register", "h2v_host_unregister",
+    "h2v_init", "h2v_device_count", "h2v_last_error", "h2v_version", "h2v_host_register", "h2v_host_unregister", "h2v_dev_alloc", "h2v_dev_free", "h2v_dev_upload", "h2v_dev_download",
     "h2v_srs_load", "h2v_srs_setup", "h2v_srs_free", "h2v_commit", "h2v_commit_batch", "h2v_commit_batch_dev", "h2v_best_multiexp",
     "h2v_best_fft", "h2v_domain_new", "h2v_domain_free", "h2v_domain_k", "h2v_domain_extended_k", "h2v_domain_constant",
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
@@ -59,6 +59,10 @@ def lib():
         L.h2v_domain_k.argtypes = [C.c_void_p]
         L.h2v_domain_extended_k.argtypes = [C.c_void_p]
         L.h2v_init.argtypes = [C.c_int]
+        L.h2v_dev_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        L.h2v_dev_free.argtypes = [C.c_void_p]
+        L.h2v_dev_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.h2v_dev_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.h2v_host_register.argtypes = [C.c_void_p, C.c_size_t]
         L.h2v_host_unregister.argtypes = [C.c_void_p]
         L.h2v_srs_load.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
@@ -117,6 +121,43 @@ def _ptr(a):
 
 def init(device=0):
     _check(lib().h2v_init(device))
+
+
+class DeviceBuffer:
+    """A device allocation for the `_dev` entry points (columns resident in HBM across several steps)."""
+
+    def __init__(self, nbytes):
+        self.nbytes = nbytes
+        self._p = C.c_void_p()
+        _check(lib().h2v_dev_alloc(nbytes, C.byref(self._p)))
+
+    @property
+    def ptr(self):
+        return self._p.value
+
+    def upload(self, arr, offset=0):
+        arr = np.ascontiguousarray(arr)
+        if offset + arr.nbytes > self.nbytes:
+            raise ValueError("upload out of range")
+        _check(lib().h2v_dev_upload(self._p.value + offset, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+
+    def download(self, shape, dtype=np.uint64, offset=0):
+        out = np.zeros(shape, dtype=dtype)
+        if offset + out.nbytes > self.nbytes:
+            raise ValueError("download out of range")
+        _check(lib().h2v_dev_download(out.ctypes.data_as(C.c_void_p), self._p.value + offset, out.nbytes))
+        return out
+
+    def free(self):
+        if self._p.value and _lib is not None:
+            _lib.h2v_dev_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def host_register(arr):

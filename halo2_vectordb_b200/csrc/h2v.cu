@@ -701,6 +701,37 @@ int h2v_init(int device) {
     CU(cudaFree(0));
     return H2V_OK;
 }
+int h2v_dev_alloc(size_t bytes, void **d_out) {
+    int rc = use_device();
+    if (rc) return rc;
+    if (!d_out || !bytes) return fail(H2V_EINVAL, "dev_alloc: bad argument");
+    cudaError_t e = cudaMalloc(d_out, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(H2V_ENOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+    return H2V_OK;
+}
+int h2v_dev_free(void *d_ptr) {
+    int rc = use_device();
+    if (rc) return rc;
+    if (d_ptr) CU(cudaFree(d_ptr));
+    return H2V_OK;
+}
+int h2v_dev_upload(void *d_dst, const void *src, size_t bytes) {
+    int rc = use_device();
+    if (rc) return rc;
+    if (bytes && (!d_dst || !src)) return fail(H2V_EINVAL, "dev_upload: NULL buffer");
+    CU(cudaMemcpy(d_dst, src, bytes, cudaMemcpyHostToDevice));
+    return H2V_OK;
+}
+int h2v_dev_download(void *dst, const void *d_src, size_t bytes) {
+    int rc = use_device();
+    if (rc) return rc;
+    if (bytes && (!dst || !d_src)) return fail(H2V_EINVAL, "dev_download: NULL buffer");
+    CU(cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return H2V_OK;
+}
 int h2v_host_register(void *ptr, size_t bytes) {
     int rc = use_device();
     if (rc) return rc;

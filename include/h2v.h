@@ -46,6 +46,12 @@ int h2v_device_count(void);
 const char *h2v_last_error(void);
 const char *h2v_version(void);
 
+/* Device buffers for the `_dev` entry points (columns that stay in HBM between commit / transform / evaluation
+ * steps of one prover phase); plain synchronous copies. */
+int h2v_dev_alloc(size_t bytes, void **d_out);
+int h2v_dev_free(void *d_ptr);
+int h2v_dev_upload(void *d_dst, const void *src, size_t bytes);
+int h2v_dev_download(void *dst, const void *d_src, size_t bytes);
 /* Page-lock a caller-owned buffer (a Rust Vec<Fr>, a numpy array) so that the library's asynchronous,
  * double-buffered H2D / D2H copies really overlap with the kernels; pageable memory works too, only slower. */
 int h2v_host_register(void *ptr, size_t bytes);

@@ -41,6 +41,27 @@ inline void best_fft(std::vector<Fr> &a, const Fr &omega, uint32_t log_n) {
     check(h2v_best_fft(reinterpret_cast<uint64_t *>(a.data()), omega.l, log_n));
 }
 
+// arithmetic.rs eval_polynomial / kate_division, ff BatchInvert, the running product of the permutation argument
+inline Fr eval_polynomial(const std::vector<Fr> &poly, const Fr &point) {
+    const uint64_t *p[1] = {reinterpret_cast<const uint64_t *>(poly.data())};
+    Fr out{};
+    check(h2v_eval_polynomial_batch(p, 1, poly.size(), point.l, 1, out.l));
+    return out;
+}
+inline std::vector<Fr> kate_division(const std::vector<Fr> &a, const Fr &b) {
+    std::vector<Fr> out(a.empty() ? 0 : a.size() - 1);
+    check(h2v_kate_division(reinterpret_cast<const uint64_t *>(a.data()), a.size(), b.l, reinterpret_cast<uint64_t *>(out.data())));
+    return out;
+}
+inline void batch_invert(std::vector<Fr> &a) { check(h2v_batch_invert(reinterpret_cast<uint64_t *>(a.data()), a.size())); }
+inline std::vector<Fr> grand_product(const std::vector<Fr> &num, const std::vector<Fr> &den) {
+    if (num.size() != den.size()) throw std::invalid_argument("grand_product: length mismatch");
+    std::vector<Fr> out(num.size());
+    check(h2v_grand_product(reinterpret_cast<const uint64_t *>(num.data()), reinterpret_cast<const uint64_t *>(den.data()), num.size(),
+                            reinterpret_cast<uint64_t *>(out.data())));
+    return out;
+}
+
 class ParamsKZG {
   public:
     ParamsKZG(uint32_t k, const std::vector<G1Affine> &g, const std::vector<G1Affine> &g_lagrange) : k_(k), n_(size_t(1) << k) {

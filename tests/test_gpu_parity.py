@@ -533,3 +533,42 @@ def test_kzg_opening_identity(h2v):
     assert (cq == O.g1_mul(G, (ps - pzi) * pow(si - zi, -1, P.R) % P.R)).all()
     assert (srs.commit(p) == O.g1_mul(G, ps)).all()
     srs.close()
+
+
+def test_device_resident_phase_through_the_abi(h2v):
+    """One prover phase with the columns uploaded once and kept in HBM: commit_lagrange, lagrange_to_coeff,
+    coeff_to_extended and evaluations, all through `_dev` entry points and h2v_dev_* buffers (no torch)."""
+    k, n, cols = 10, 1 << 10, 5
+    srs = h2v.ParamsKZG(k, None, O.gen_bases(n))
+    dom, od = h2v.EvaluationDomain(4, k), O.EvaluationDomain(4, k)
+    data = np.stack([O.fr_fill(n, 50 + i, mode=i % 2) for i in range(cols)])
+    d_cols = h2v.DeviceBuffer(cols * n * 32)
+    d_coef = h2v.DeviceBuffer(cols * n * 32)
+    d_ext = h2v.DeviceBuffer(cols * 4 * n * 32)
+    d_commit = h2v.DeviceBuffer(cols * 64)
+    pts = O.fr_fill(2, 8)
+    d_pts = h2v.DeviceBuffer(2 * 32)
+    d_ev = h2v.DeviceBuffer(cols * 2 * 32)
+    d_cols.upload(data)
+    d_pts.upload(pts)
+    srs.commit_batch_dev(d_cols.ptr, n, cols, n, d_commit.ptr)
+    dom.transform_dev(h2v.OP_LAGRANGE_TO_COEFF, d_cols.ptr, n, d_coef.ptr, n, cols)
+    dom.transform_dev(h2v.OP_COEFF_TO_EXTENDED, d_coef.ptr, n, d_ext.ptr, 4 * n, cols)
+    h2v._check(h2v.lib().h2v_eval_polynomial_dev(d_coef.ptr, n, cols, n, d_pts.ptr, 2, d_ev.ptr))
+    commits = d_commit.download((cols, 8))
+    coefs = d_coef.download((cols, n, 4))
+    exts = d_ext.download((cols, 4 * n, 4))
+    evs = d_ev.download((cols, 2, 4))
+    for i in range(cols):
+        assert (commits[i] == O.msm_closed_form(data[i])).all()
+        oc = od.lagrange_to_coeff(data[i])
+        assert (coefs[i] == oc).all()
+        assert (exts[i] == od.coeff_to_extended(oc)).all()
+        for j in range(2):
+            assert (evs[i, j] == O.fr_eval_poly(oc, pts[j])).all()
+    with pytest.raises(ValueError):
+        dom.transform_dev(h2v.OP_COEFF_TO_EXTENDED, d_coef.ptr, n, d_ext.ptr, n, cols)   # out stride too short
+    for b in (d_cols, d_coef, d_ext, d_commit, d_pts, d_ev):
+        b.free()
+    srs.close()
+    dom.close()
