@@ -572,3 +572,34 @@ def test_device_resident_phase_through_the_abi(h2v):
         b.free()
     srs.close()
     dom.close()
+
+
+def test_large_batches_take_the_pipelined_paths(h2v):
+    """Batches larger than one staging buffer: double-buffered commit (two streams), pipelined transforms, and
+    more columns than one MSM launch holds (workspace-sized sub-batches)."""
+    k, n = 16, 1 << 16
+    b = h2v.synthetic_bases(n)
+    srs = h2v.ParamsKZG(k, None, b)
+    base_cols = [O.fr_fill(n, 600 + i, mode=i % 2, lookup_bits=15) for i in range(5)]
+    exp = [O.msm_closed_form(c) for c in base_cols]
+    cols = [base_cols[i % 5] for i in range(40)]                 # 80 MiB of scalars -> 2 sub-batches
+    got = srs.commit_batch(cols)
+    for i in range(40):
+        assert (got[i] == exp[i % 5]).all(), i
+    # 700 identical device-resident columns (stride 0): exceeds the columns one launch holds
+    d_col = h2v.DeviceBuffer(n * 32)
+    d_col.upload(base_cols[0])
+    d_out = h2v.DeviceBuffer(700 * 64)
+    srs.commit_batch_dev(d_col.ptr, 0, 700, n, d_out.ptr)
+    outs = d_out.download((700, 8))
+    assert (outs == exp[0]).all()
+    d_col.free()
+    d_out.free()
+    srs.close()
+    dom, od = h2v.EvaluationDomain(4, k), O.EvaluationDomain(4, k)
+    tcols = [base_cols[i % 5] for i in range(12)]                # 96 MiB of extended output -> pipelined path
+    ext = dom.transform_batch(h2v.OP_COEFF_TO_EXTENDED, tcols)
+    oext = [od.coeff_to_extended(c) for c in base_cols]
+    for i in range(12):
+        assert (ext[i] == oext[i % 5]).all(), i
+    dom.close()
