@@ -174,3 +174,32 @@ def test_cpp_mirror_compiles_and_fails_loudly_without_gpu(built, tmp_path):
     if h.device_count() == 0:
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 0 and "no device" in out.stdout
+
+
+def test_batch_inverse_tree_model():
+    rnd = random.Random(11)
+    for n, g in ((1, 4), (5, 4), (17, 4), (64, 4), (100, 8), (33, 32), (257, 16)):
+        xs = [rnd.randrange(1, P.R) for _ in range(n)]
+        inv = KM.batch_inverse_tree(xs, g)
+        assert all(a * b % P.R == 1 for a, b in zip(xs, inv)), (n, g)
+
+
+@pytest.mark.parametrize("n,c,pre,chunk,ncols,dist,rounds,K,G", [
+    (64, 4, True, 4, 1, "u", 3, 4, 4), (64, 4, False, 4, 2, "u", 2, 3, 2), (100, 5, True, 7, 2, "skew", 4, 5, 4),
+    (200, 6, False, 5, 1, "skew", 6, 8, 4), (33, 3, True, 32, 3, "u", 1, 2, 8), (40, 2, False, 6, 1, "dup", 5, 4, 3)])
+def test_msm_batch_affine_rounds_model(n, c, pre, chunk, ncols, dist, rounds, K, G):
+    """pair rounds (msm_affine.cuh): slot <-> bucket walking in both directions, the inversion tree, and the
+    identity / doubling / cancelling cases, on the integer model of the group."""
+    rnd = random.Random(n * 7 + rounds)
+    pts = [rnd.randrange(1, P.R) for _ in range(n)]
+    if dist == "dup":
+        pts = [rnd.choice([5, 5, (-5) % P.R, None, 10, (-10) % P.R, 7]) for _ in range(n)]
+    cols = []
+    for _ in range(ncols):
+        if dist in ("u", "dup"):
+            s = [rnd.randrange(P.R) for _ in range(n)]
+        else:
+            s = [rnd.choice([0, 1, 1, 1, rnd.randrange(4096), P.R - rnd.randrange(1, 1000), rnd.randrange(P.R)]) for _ in range(n)]
+        cols.append(s)
+    exp = [sum(a * (b or 0) for a, b in zip(s, pts)) % P.R for s in cols]
+    assert KM.msm_model_affine(cols, pts, c, pre, chunk, ncols, rounds, K, G) == exp
