@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
     "h2v_divide_by_vanishing_poly", "h2v_domain_transform_batch", "h2v_domain_transform_dev",
     "h2v_eval_polynomial_batch", "h2v_eval_polynomial_dev", "h2v_batch_invert", "h2v_grand_product", "h2v_kate_division",
+    "h2v_g1_to_bytes", "h2v_fr_to_repr",
     "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_op_rate", "h2v_set_tuning", "h2v_launch_count", "h2v_last_kernel_ms",
 ]
 
@@ -89,6 +90,8 @@ def lib():
         L.h2v_batch_invert.argtypes = [C.c_void_p, C.c_size_t]
         L.h2v_grand_product.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_kate_division.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.h2v_g1_to_bytes.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.h2v_fr_to_repr.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_selftest_field.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_selftest_group.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_synthetic_bases.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p]
@@ -268,6 +271,22 @@ def kate_division(a, b):
     b = np.ascontiguousarray(b, dtype=np.uint64).reshape(4)
     _check(lib().h2v_kate_division(_ptr(a), a.shape[0], _ptr(b), _ptr(out)))
     return out
+
+
+def g1_to_bytes(points):
+    """halo2curves `G1Affine::to_bytes()` for (n, 8) affine points -> list of 32-byte strings (host-side)."""
+    pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros((pts.shape[0], 32), dtype=np.uint8)
+    _check(lib().h2v_g1_to_bytes(_ptr(pts), pts.shape[0], _ptr(out)))
+    return [bytes(r) for r in out]
+
+
+def fr_to_repr(scalars):
+    """`Fr::to_repr()` for (n, 4) Montgomery scalars -> list of 32-byte little-endian strings (host-side)."""
+    a = _fr(scalars)
+    out = np.zeros((a.shape[0], 32), dtype=np.uint8)
+    _check(lib().h2v_fr_to_repr(_ptr(a), a.shape[0], _ptr(out)))
+    return [bytes(r) for r in out]
 
 
 # ----------------------------------------------------------------------------- poly/kzg/commitment.rs

@@ -701,6 +701,36 @@ int h2v_init(int device) {
     CU(cudaFree(0));
     return H2V_OK;
 }
+// Proof wire format of a commitment: halo2curves 0.3.x `G1Affine::to_bytes()` =
+// canonical x, little-endian, with the parity of canonical y in bit 6 of byte 31; identity = 32 zero bytes.
+// Host-side (a proof holds ~10^3 commitments); uses the host instantiation of the field code.
+int h2v_g1_to_bytes(const uint64_t *affine_pts, size_t n, uint8_t *out) {
+    if (n && (!affine_pts || !out)) return fail(H2V_EINVAL, "g1_to_bytes: NULL buffer");
+    for (size_t i = 0; i < n; ++i) {
+        affine p;
+        memcpy(&p, affine_pts + 8 * i, sizeof p);
+        uint8_t *o = out + 32 * i;
+        if (affine_is_identity(p)) {
+            memset(o, 0, 32);
+            continue;
+        }
+        fe x = fe_from_mont<Fq>(p.x), y = fe_from_mont<Fq>(p.y);
+        memcpy(o, x.v, 32);
+        o[31] |= (uint8_t)((y.v[0] & 1u) << 6);
+    }
+    return H2V_OK;
+}
+// `Fr::to_repr()`: canonical little-endian bytes of Montgomery-form scalars
+int h2v_fr_to_repr(const uint64_t *fr_mont, size_t n, uint8_t *out) {
+    if (n && (!fr_mont || !out)) return fail(H2V_EINVAL, "fr_to_repr: NULL buffer");
+    for (size_t i = 0; i < n; ++i) {
+        fe a;
+        memcpy(a.v, fr_mont + 4 * i, 32);
+        fe c = fe_from_mont<Fr>(a);
+        memcpy(out + 32 * i, c.v, 32);
+    }
+    return H2V_OK;
+}
 int h2v_dev_alloc(size_t bytes, void **d_out) {
     int rc = use_device();
     if (rc) return rc;

@@ -127,6 +127,13 @@ int h2v_grand_product(const uint64_t *num, const uint64_t *den, size_t n, uint64
 /* arithmetic.rs kate_division(a, b): quotient of a(X) (n coefficients) by (X - b), n - 1 coefficients */
 int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t *out);
 
+/* ---- wire format of commitments and evaluations ("next": SURVEY.md 8(f) row 3; host-side) --------------- */
+/* halo2curves 0.3.x G1Affine::to_bytes(): 32 bytes = canonical x little-endian, bit 6 of byte 31 = parity of
+ * canonical y, identity = zeros (the flag convention is recalled, not verified against the crate) */
+int h2v_g1_to_bytes(const uint64_t *affine_pts, size_t n, uint8_t *out);
+/* Fr::to_repr(): canonical little-endian 32 bytes per scalar */
+int h2v_fr_to_repr(const uint64_t *fr_mont, size_t n, uint8_t *out);
+
 /* ---- device self-tests (used by tests/ to localise failures; not part of the drop-in surface) */
 /* out[i] = a[i] (op) b[i] computed by the device field routines; field 0 = Fr, 1 = Fq;
  * op 0 mul, 1 add, 2 sub, 3 inverse by Fermat (b ignored), 4 inverse by binary Euclid (b ignored) */

@@ -203,3 +203,18 @@ def test_msm_batch_affine_rounds_model(n, c, pre, chunk, ncols, dist, rounds, K,
         cols.append(s)
     exp = [sum(a * (b or 0) for a, b in zip(s, pts)) % P.R for s in cols]
     assert KM.msm_model_affine(cols, pts, c, pre, chunk, ncols, rounds, K, G) == exp
+
+
+def test_wire_format_helpers(built):
+    """h2v_g1_to_bytes / h2v_fr_to_repr run on the host (no GPU needed): against the oracle and first principles."""
+    import halo2_vectordb_b200 as h
+
+    G = O.g1_generator()
+    pts = [O.g1_mul(G, k) for k in (1, 2, 3, 0xDEADBEEF, P.R - 1)] + [np.zeros(8, dtype=np.uint64)]
+    got = h.g1_to_bytes(np.stack(pts))
+    for g, p in zip(got, pts):
+        assert g == O.g1_compress(p) == P.g1_compress(O.g1_affine_to_ints(p))
+    assert got[0] == (1).to_bytes(32, "little")                      # G = (1, 2): y even, no flag
+    assert got[-1] == bytes(32)
+    vals = [0, 1, P.R - 1, 0x1234567890ABCDEF << 100]
+    assert h.fr_to_repr(O.fr_from_ints(vals)) == [v.to_bytes(32, "little") for v in vals]
