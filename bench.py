@@ -123,7 +123,7 @@ def run_reference(args, rank, world, out):
     print(file=out, *[json.dumps({
         "impl": "reference", "metric": "msm_mpts_per_s", "value": v, "unit": "Mpts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 Montgomery (4x64 on the CPU)", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "dtype_note": "4 x 64-bit limbs, Montgomery form (CPU restatement)", "data": "synthetic",
         "config": {"workload": "kmeans k=16 commit_lagrange batch (BASELINE configs[2])", "k": K, "cols_per_step": sample_cols},
         "cpu_baseline": {"value": v, "unit": "Mpts/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -249,7 +249,7 @@ def _main(args, real_stdout):
     line = {
         "metric": "msm_mpts_per_s", "value": value, "unit": "Mpts/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32x8 Montgomery (BN254 Fq/Fr)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u32", "dtype_note": "8 x 32-bit limbs, Montgomery form, BN254 Fq/Fr (IMAD.WIDE 32x32+64)", "data": "synthetic",
         "config": {"workload": "kmeans k=16 commit_lagrange batch (BASELINE configs[2])", "k": K, "cols_per_step": cols,
                    "scalars": "uniform", "l2": "inputs larger than L2 (192 MiB scalars + 64 MiB tables per step)",
                    "parallelism": f"columns x{world}"},

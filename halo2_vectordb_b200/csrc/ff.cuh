@@ -17,10 +17,8 @@
 
 #if defined(__CUDACC__)
 #define H2V_HD __host__ __device__ __forceinline__
-#define H2V_D __device__ __forceinline__
 #else
 #define H2V_HD inline
-#define H2V_D inline
 #endif
 
 namespace h2v {
