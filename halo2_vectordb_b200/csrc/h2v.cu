@@ -364,8 +364,10 @@ int tuning(std::atomic<int> &slot, const char *env) {
 uint32_t pick_chunk(uint64_t max_entries) {
     const int forced = tuning(g_tune_chunk, "H2V_CHUNK");
     if (forced > 0) return (uint32_t)forced;
+    // small inputs are latency-bound: chunk * t(mixed add) in the accumulate thread against
+    // (bucket load / chunk) * t(full add) in the finish thread is flattest around 12..24 (measured)
     uint64_t c = max_entries / (148ull * 2048ull);
-    if (c < 4) c = 4;
+    if (c < 12) c = 12;
     if (c > 64) c = 64;
     return (uint32_t)c;
 }
