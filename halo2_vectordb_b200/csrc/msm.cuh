@@ -416,18 +416,18 @@ __global__ void __launch_bounds__(256) msm_reduce_bits_kernel(const xyzz *__rest
     acc = xyzz_block_sum_256(acc, sm8);
     if (threadIdx.x == 0) xyzz_st(T + (size_t)inst * (nbits + 2) + which, acc);
 }
-// one warp per instance (lane 0 works): Horner over the bit sums, weight 2^shift, plus the plain sum of A
+// one warp per instance: lane b scales its bit sum by 2^b (b doublings, all lanes in lockstep), a shuffle tree
+// adds them, then the common weight 2^shift and the plain sum of A
 __global__ void msm_reduce_combine_kernel(const xyzz *__restrict__ T, uint32_t nbits, uint32_t shift, uint32_t n_inst,
                                           xyzz *__restrict__ S_out, xyzz *__restrict__ A_out) {
-    const uint32_t inst = blockIdx.x;
-    if (inst >= n_inst || threadIdx.x != 0) return;
+    const uint32_t inst = blockIdx.x, lane = threadIdx.x;
+    if (inst >= n_inst) return;
     const xyzz *t = T + (size_t)inst * (nbits + 2);
-    xyzz acc = xyzz_identity();
-    for (uint32_t b = nbits; b-- > 0;) {
-        acc = xyzz_double(acc);
-        xyzz v = xyzz_ld(t + b);
-        xyzz_add(acc, v);
-    }
+    xyzz acc = lane < nbits ? xyzz_ld(t + lane) : xyzz_identity();
+    for (uint32_t k = 0; k + 1 < nbits; ++k)
+        if (k < lane && lane < nbits) acc = xyzz_double(acc);
+    acc = xyzz_warp_sum(acc);
+    if (lane != 0) return;
     for (uint32_t k = 0; k < shift; ++k) acc = xyzz_double(acc);
     xyzz a = xyzz_ld(t + nbits);
     xyzz_add(acc, a);
