@@ -192,14 +192,18 @@ __global__ void __launch_bounds__(256) msm_scan_apply_kernel(const uint32_t *__r
 
 // ------------------------------------------------------------------ scatter
 // entries[pos] = (point_ref | sign<<31, global bucket)
+// Only digits with magnitude in [mag_lo, mag_hi) are placed: for a very large MSM the host sweeps the bucket
+// space in slices so that the randomly written part of `entries` stays L2-resident (the keys are re-read per
+// slice, which is sequential and cheap).
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t *__restrict__ keys, uint32_t *__restrict__ cursor,
-                                                          uint2 *__restrict__ entries, MsmShape sh) {
+                                                          uint2 *__restrict__ entries, MsmShape sh, uint32_t mag_lo, uint32_t mag_hi) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t j = blockIdx.y, col = blockIdx.z;
     if (i >= sh.n) return;
     uint32_t key = keys[((size_t)col * sh.W + j) * sh.n + i];
     if (key == H2V_KEY_INVALID) return;
     uint32_t mag = key & 0x7fffffffu;
+    if (mag < mag_lo || mag >= mag_hi) return;
     uint32_t g = sh.G > 1 ? j : 0;
     uint32_t b = (col * sh.G + g) * sh.nb + mag;
     uint32_t pref = (sh.G > 1 ? i : j * sh.pstride + i) | (key & 0x80000000u);
