@@ -939,12 +939,20 @@ int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_
     // compute streams with their own workspaces, so the latency-bound tail of one (bucket-reduction tree,
     // affine normalisation) overlaps the bulk kernels of the next.
     const size_t stride = std::max<size_t>(len, 1);
-    static const size_t sub_mb = [] {   // scalars per sub-batch in MiB (H2V_SUB_MB: tuning; 48 measured best)
+    // Sub-batch schedule: a small first sub-batch (its upload is the only one nothing can hide) and large ones
+    // after it (big launches are the efficient ones; their uploads hide behind the previous launch).
+    static const size_t sub_mb = [] {   // scalars per large sub-batch in MiB (H2V_SUB_MB / H2V_FIRST_MB: tuning; 96 / 16 measured best)
         const char *e = getenv("H2V_SUB_MB");
-        int v = e ? atoi(e) : 48;
+        int v = e ? atoi(e) : 96;
+        return (size_t)(v < 1 ? 1 : v);
+    }();
+    static const size_t first_mb = [] {
+        const char *e = getenv("H2V_FIRST_MB");
+        int v = e ? atoi(e) : 16;
         return (size_t)(v < 1 ? 1 : v);
     }();
     size_t sub = std::max<size_t>(1, (sub_mb << 20) / (stride * sizeof(fe)));
+    const size_t first = std::max<size_t>(1, std::min(sub, (first_mb << 20) / (stride * sizeof(fe))));
     sub = std::min(sub, n_polys);
     if ((rc = s->stage.ensure(2 * sub * stride * sizeof(fe)))) return rc;
     if ((rc = s->out.ensure(n_polys * sizeof(affine)))) return rc;
@@ -957,8 +965,9 @@ int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_
         }
     }
     size_t it = 0;
-    for (size_t c0 = 0; c0 < n_polys; c0 += sub, ++it) {
-        const size_t cols = std::min(sub, n_polys - c0);
+    for (size_t c0 = 0, step = 0; c0 < n_polys; c0 += step, ++it) {
+        step = it == 0 ? first : sub;
+        const size_t cols = std::min(step, n_polys - c0);
         const int b = (int)(it & 1);
         fe *stg = s->stage.as<fe>() + (size_t)b * sub * stride;
         if (it >= 2) CU(cudaStreamWaitEvent(s->copy_stream, s->computed[b], 0));

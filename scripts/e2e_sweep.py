@@ -15,4 +15,4 @@ for i in range(8):
     h._check(h.lib().h2v_commit_batch(srs._h, 1, ptrs, cols, N, out.ctypes.data_as(C.c_void_p)))
     ts.append(time.perf_counter() - t0)
 t = sorted(ts[2:])[len(ts[2:]) // 2]
-print(os.environ.get("H2V_SUB_MB", "48"), "MiB sub-batches: %.2f ms -> %.1f Mpts/s" % (t * 1e3, cols * N / t / 1e6))
+print(os.environ.get("H2V_FIRST_MB", "32"), os.environ.get("H2V_SUB_MB", "160"), "MiB first/sub: %.2f ms -> %.1f Mpts/s" % (t * 1e3, cols * N / t / 1e6))
