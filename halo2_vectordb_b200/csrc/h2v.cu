@@ -412,8 +412,10 @@ MsmLayout msm_layout(void *base, const MsmShape &sh, uint32_t cols) {
     L.ba_G = 16;
     uint64_t final_len = ent;
     for (uint32_t r = 0; r < L.ba_rounds; ++r) {
-        final_len = (final_len + L.n_buckets + 1) / 2;
-        L.ba_slots[r] = final_len;
+        // a round maps each bucket of length l to ceil(l/2): at most (len + non-empty buckets)/2 slots and never
+        // more than it had (the bound must not grow: every later round reuses the buffers sized for round 0)
+        final_len = std::min<uint64_t>(final_len, (final_len + L.n_buckets + 1) / 2);
+        L.ba_slots[r] = std::max<uint64_t>(final_len, 1);
     }
     L.ba_chunk = L.ba_rounds ? pick_chunk(final_len) : sh.chunk;
     L.nthreads = (uint32_t)std::max<uint64_t>((ent + sh.chunk - 1) / sh.chunk, (final_len + L.ba_chunk - 1) / L.ba_chunk);

@@ -1,0 +1,95 @@
+"""Randomised differential test: the CUDA path (through the C ABI) against the oracle on random sizes,
+distributions, tuning knobs and entry points.  Not part of pytest (minutes); run on a GPU box:
+    python scripts/fuzz.py [seconds] [seed]"""
+import os, sys, time, random
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import halo2_vectordb_b200 as h
+from oracle import oracle as O, pyref as P
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+rnd = random.Random(seed)
+h.init(0)
+t_end = time.time() + budget
+stats = {}
+
+def scalars(n, mode):
+    if mode == 2:   # pathological: few distinct values
+        vals = [rnd.choice([0, 1, 2, P.R - 1, P.R - 2, 1 << 253, rnd.randrange(P.R)]) for _ in range(8)]
+        return O.fr_from_ints([rnd.choice(vals) for _ in range(n)])
+    return O.fr_fill(n, rnd.randrange(1 << 30), mode=mode, lookup_bits=rnd.randrange(1, 20))
+
+def bases_for(n):
+    b = O.gen_bases(n, a=rnd.randrange(1, 1 << 40), b=rnd.randrange(1, 1 << 40))
+    if rnd.random() < 0.3:      # duplicates, opposites, identities
+        for _ in range(max(1, n // 8)):
+            i, j = rnd.randrange(n), rnd.randrange(n)
+            r = rnd.random()
+            if r < 0.4: b[i] = b[j]
+            elif r < 0.7:
+                xy = O.g1_affine_to_ints(b[j])
+                b[i] = O.g1_affine_from_ints(None if xy is None else (xy[0], (-xy[1]) % P.P))
+            else: b[i] = 0
+    return b
+
+it = 0
+while time.time() < t_end:
+    it += 1
+    kind = rnd.choice(["commit", "commit", "multiexp", "ntt", "domain", "row2"])
+    stats[kind] = stats.get(kind, 0) + 1
+    tune = (rnd.choice([-1, -1, 1, 3, 5, 17, 64]), rnd.choice([-1, -1, 0, 1, 2, 4, 7]))
+    h.set_tuning(*tune)
+    case = None
+    try:
+        if kind == "commit":
+            k = rnd.randrange(0, 13); n = 1 << k
+            b = bases_for(n)
+            srs = h.ParamsKZG(k, b if rnd.random() < 0.5 else None, b)
+            cols = rnd.randrange(1, 7); ln = rnd.choice([n, n, rnd.randrange(0, n + 1)])
+            data = [scalars(n, rnd.randrange(3))[:ln] for _ in range(cols)]
+            case = ("commit", k, ln, cols, tune)
+            got = srs.commit_batch(data)
+            for g, c in zip(got, data):
+                exp = O.best_multiexp_affine(c, b[:ln]) if ln else np.zeros(8, dtype=np.uint64)
+                assert (g == exp).all(), ("commit", k, ln, cols)
+            srs.close()
+        elif kind == "multiexp":
+            n = rnd.choice([rnd.randrange(1, 64), rnd.randrange(1, 3000), rnd.randrange(1, 20000)])
+            b = bases_for(n); s = scalars(n, rnd.randrange(3))
+            case = ("multiexp", n, tune)
+            assert (O.g1_to_affine(h.best_multiexp(s, b)) == O.best_multiexp_affine(s, b)).all(), ("multiexp", n)
+        elif kind == "ntt":
+            L = rnd.randrange(0, 17); a = scalars(1 << L, rnd.randrange(3))
+            w = O.fr_from_ints([pow(P.omega_for(L), rnd.randrange(1, 1 << (L + 1), 2), P.R)])[0]   # any primitive root
+            assert (h.best_fft(a, w, L) == O.best_fft(a, w, L)).all(), ("ntt", L)
+        elif kind == "domain":
+            k = rnd.randrange(1, 13); j = rnd.choice([2, 3, 4, 4, 4, 5, 6, 9])
+            d, od = h.EvaluationDomain(j, k), O.EvaluationDomain(j, k)
+            a = scalars(1 << k, rnd.randrange(3)); ext = scalars(1 << d.extended_k, rnd.randrange(3))
+            ncol = rnd.randrange(1, 5)
+            outs = d.transform_batch(h.OP_LAGRANGE_TO_COEFF, [a] * ncol)
+            assert all((o == od.lagrange_to_coeff(a)).all() for o in outs)
+            assert (d.coeff_to_extended(a) == od.coeff_to_extended(a)).all(), ("c2e", j, k)
+            assert (d.extended_to_coeff(ext) == od.extended_to_coeff(ext)).all(), ("e2c", j, k)
+            f = d.transform_batch(h.OP_DIVIDE_BY_VANISHING, [ext])[0]
+            assert (f == od.extended_to_coeff(od.divide_by_vanishing_poly(ext))).all(), ("dvp", j, k)
+            d.close()
+        else:
+            n = rnd.choice([rnd.randrange(1, 40), rnd.randrange(1, 5000), rnd.randrange(1, 70000)])
+            a = scalars(n, rnd.randrange(3))
+            x = scalars(2, 0)
+            assert (h.eval_polynomial_batch([a], x)[0, 1] == O.fr_eval_poly(a, x[1])).all(), ("eval", n)
+            assert (h.batch_invert(a) == O.fr_batch_invert(a)).all(), ("binv", n)
+            num, den = scalars(n, 0), scalars(n, 0)
+            assert (h.grand_product(num, den) == O.fr_grand_product(num, den)).all(), ("gp", n)
+            bb = rnd.choice([x[0], np.zeros(4, dtype=np.uint64)])
+            assert (h.kate_division(a, bb) == O.fr_kate_division(a, bb)).all(), ("kate", n)
+    except AssertionError as e:
+        print("MISMATCH at iteration", it, e, "seed", seed, flush=True)
+        sys.exit(1)
+    except Exception as e:
+        print("ERROR at iteration", it, kind, case, "seed", seed, repr(e)[:300], flush=True)
+        sys.exit(2)
+h.set_tuning(-1, -1)
+print(f"fuzz ok: {it} iterations in {budget:.0f} s, seed {seed}: {stats}")

@@ -603,3 +603,20 @@ def test_large_batches_take_the_pipelined_paths(h2v):
     for i in range(12):
         assert (ext[i] == oext[i % 5]).all(), i
     dom.close()
+
+
+def test_forced_pair_rounds_on_sparse_input_regression(h2v):
+    """Found by scripts/fuzz.py: 7 forced batch-affine rounds on 6 columns of 14 scalars against a 2^10 SRS --
+    far fewer entries than buckets.  The per-round slot bound must never grow past the round-0 buffers."""
+    try:
+        h2v.set_tuning(1, 7)
+        k, n, ln = 10, 1 << 10, 14
+        b = O.gen_bases(n)
+        srs = h2v.ParamsKZG(k, None, b)
+        cols = [O.fr_fill(ln, 70 + i, mode=i % 2) for i in range(6)]
+        got = srs.commit_batch(cols)
+        for g, c in zip(got, cols):
+            assert (g == O.best_multiexp_affine(c, b[:ln])).all()
+        srs.close()
+    finally:
+        h2v.set_tuning(-1, -1)
