@@ -7,6 +7,8 @@ import numpy as np
 import halo2_vectordb_b200 as h
 from oracle import oracle as O, pyref as P
 
+BIG = "--big" in sys.argv
+sys.argv = [a for a in sys.argv if a != "--big"]
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 rnd = random.Random(seed)
@@ -33,10 +35,11 @@ def bases_for(n):
             else: b[i] = 0
     return b
 
+BIG_SRS = {}
 it = 0
 while time.time() < t_end:
     it += 1
-    kind = rnd.choice(["commit", "commit", "multiexp", "ntt", "domain", "row2"])
+    kind = rnd.choice(["commit", "commit", "multiexp", "ntt", "domain", "row2"] if not BIG else ["commit_big", "domain_big", "dev_big"])
     stats[kind] = stats.get(kind, 0) + 1
     tune = (rnd.choice([-1, -1, 1, 3, 5, 17, 64]), rnd.choice([-1, -1, 0, 1, 2, 4, 7]))
     h.set_tuning(*tune)
@@ -54,6 +57,50 @@ while time.time() < t_end:
                 exp = O.best_multiexp_affine(c, b[:ln]) if ln else np.zeros(8, dtype=np.uint64)
                 assert (g == exp).all(), ("commit", k, ln, cols)
             srs.close()
+        elif kind == "commit_big":      # staged / double-buffered host path, closed-form check on a few columns
+            k = rnd.randrange(12, 17); n = 1 << k
+            if k not in BIG_SRS:
+                BIG_SRS[k] = h.ParamsKZG(k, None, h.synthetic_bases(n))
+            cols = rnd.randrange(1, 60)
+            distinct = [scalars(n, rnd.randrange(3)) for _ in range(min(cols, 4))]
+            data = [distinct[i % len(distinct)] for i in range(cols)]
+            case = ("commit_big", k, cols, tune)
+            got = BIG_SRS[k].commit_batch(data)
+            exp = [O.msm_closed_form(c) for c in distinct]
+            for i in range(cols):
+                assert (got[i] == exp[i % len(distinct)]).all(), case
+        elif kind == "domain_big":
+            k = rnd.randrange(12, 17); cols = rnd.randrange(1, 24)
+            d, od = h.EvaluationDomain(4, k), O.EvaluationDomain(4, k)
+            distinct = [scalars(1 << k, rnd.randrange(3)) for _ in range(min(cols, 2))]
+            data = [distinct[i % len(distinct)] for i in range(cols)]
+            op = rnd.choice([h.OP_LAGRANGE_TO_COEFF, h.OP_COEFF_TO_EXTENDED, h.OP_COEFF_TO_LAGRANGE])
+            case = ("domain_big", k, cols, op)
+            outs = d.transform_batch(op, data)
+            f = {h.OP_LAGRANGE_TO_COEFF: od.lagrange_to_coeff, h.OP_COEFF_TO_EXTENDED: od.coeff_to_extended,
+                 h.OP_COEFF_TO_LAGRANGE: od.coeff_to_lagrange}[op]
+            exp = [f(c) for c in distinct]
+            for i in range(cols):
+                assert (outs[i] == exp[i % len(distinct)]).all(), case
+            d.close()
+        elif kind == "dev_big":         # device-resident entry points with strides
+            k = rnd.randrange(10, 15); n = 1 << k; cols = rnd.randrange(1, 12)
+            if k not in BIG_SRS:
+                BIG_SRS[k] = h.ParamsKZG(k, None, h.synthetic_bases(n))
+            stride = n + rnd.choice([0, 0, 4, 64])
+            data = [scalars(n, rnd.randrange(3)) for _ in range(cols)]
+            buf = np.zeros((cols, stride, 4), dtype=np.uint64)
+            for i, c in enumerate(data):
+                buf[i, :n] = c
+            d_in = h.DeviceBuffer(buf.nbytes); d_in.upload(buf)
+            d_out = h.DeviceBuffer(cols * 64)
+            ln = rnd.choice([n, rnd.randrange(1, n + 1)])
+            case = ("dev_big", k, cols, stride, ln, tune)
+            BIG_SRS[k].commit_batch_dev(d_in.ptr, stride, cols, ln, d_out.ptr)
+            got = d_out.download((cols, 8))
+            for i in range(cols):
+                assert (got[i] == O.msm_closed_form(data[i][:ln])).all(), case
+            d_in.free(); d_out.free()
         elif kind == "multiexp":
             n = rnd.choice([rnd.randrange(1, 64), rnd.randrange(1, 3000), rnd.randrange(1, 20000)])
             b = bases_for(n); s = scalars(n, rnd.randrange(3))
