@@ -620,3 +620,17 @@ def test_forced_pair_rounds_on_sparse_input_regression(h2v):
         srs.close()
     finally:
         h2v.set_tuning(-1, -1)
+
+
+def test_plain_c_example(h2v, tmp_path):
+    """examples/commit_example.c: the ABI from plain C99 -- setup, both commits agree, wire format."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "commit_example")
+    libdir = os.path.join(root, "halo2_vectordb_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "commit_example.c"),
+                           "-L" + libdir, "-lh2v", "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "== commit(coeffs)" in out.stdout, out.stdout + out.stderr
