@@ -535,7 +535,7 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
             slices = std::max(1u, std::min(slices, sh.nb));
             const uint32_t per = (sh.nb + slices - 1) / slices;
             for (uint32_t sl = 0; sl < slices; ++sl) {
-                msm_scatter_kernel<<<dim3(gx, sh.W, cols), 256, 0, st>>>(L.keys, L.cursor, L.entries, sh, sl * per,
+                msm_scatter_kernel<<<dim3(gx, cols), 256, 0, st>>>(L.keys, L.cursor, L.entries, sh, sl * per,
                                                                          std::min(sh.nb, (sl + 1) * per));
                 LAUNCHED();
             }

@@ -197,18 +197,33 @@ __global__ void __launch_bounds__(256) msm_scan_apply_kernel(const uint32_t *__r
 // slice, which is sequential and cheap).
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t *__restrict__ keys, uint32_t *__restrict__ cursor,
                                                           uint2 *__restrict__ entries, MsmShape sh, uint32_t mag_lo, uint32_t mag_hi) {
+    // one thread per scalar, looping over its W digits four at a time: four independent atomics in flight
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t j = blockIdx.y, col = blockIdx.z;
+    uint32_t col = blockIdx.y;
     if (i >= sh.n) return;
-    uint32_t key = keys[((size_t)col * sh.W + j) * sh.n + i];
-    if (key == H2V_KEY_INVALID) return;
-    uint32_t mag = key & 0x7fffffffu;
-    if (mag < mag_lo || mag >= mag_hi) return;
-    uint32_t g = sh.G > 1 ? j : 0;
-    uint32_t b = (col * sh.G + g) * sh.nb + mag;
-    uint32_t pref = (sh.G > 1 ? i : j * sh.pstride + i) | (key & 0x80000000u);
-    uint32_t pos = atomicAdd(&cursor[b], 1u);
-    entries[pos] = make_uint2(pref, b);
+    const uint32_t *kp = keys + (size_t)col * sh.W * sh.n + i;
+    for (uint32_t j0 = 0; j0 < sh.W; j0 += 4) {
+        uint32_t key[4], b[4], pos[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) key[u] = (j0 + u < sh.W) ? kp[(size_t)(j0 + u) * sh.n] : H2V_KEY_INVALID;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            uint32_t mag = key[u] & 0x7fffffffu;
+            if (key[u] == H2V_KEY_INVALID || mag < mag_lo || mag >= mag_hi) {
+                key[u] = H2V_KEY_INVALID;
+                continue;
+            }
+            uint32_t g = sh.G > 1 ? j0 + u : 0;
+            b[u] = (col * sh.G + g) * sh.nb + mag;
+            pos[u] = atomicAdd(&cursor[b[u]], 1u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (key[u] == H2V_KEY_INVALID) continue;
+            uint32_t pref = (sh.G > 1 ? i : (j0 + u) * sh.pstride + i) | (key[u] & 0x80000000u);
+            entries[pos[u]] = make_uint2(pref, b[u]);
+        }
+    }
 }
 
 // ------------------------------------------------------------------ chunked accumulation
