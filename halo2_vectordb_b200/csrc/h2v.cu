@@ -306,7 +306,15 @@ MsmCfg choose_cfg(size_t n, bool precomp) {
     for (uint32_t c = 2; c <= 22; ++c) {
         uint32_t W = windows_for(c);
         double nb = (double)(1u << (c - 1));
-        double cost = precomp ? (double)W * n + 3.0 * nb : (double)W * (n + 3.0 * nb) + 10.0 * c * W;
+        // cost of one bucket in the reduction, in bucket additions.  Measured: 3 fits large n; at 2^16 the value 5
+        // (c = 15 instead of 16) costs uniform columns 1 % and saves witness-shaped columns 10 % and single-column
+        // latency 5 %; at 2^20 it loses (c = 19: 14.2 vs 12.9 ms per 4 columns).  H2V_RED_WEIGHT: tuning.
+        static const double forced_w = [] {
+            const char *e = getenv("H2V_RED_WEIGHT");
+            return e ? atof(e) : 0.0;
+        }();
+        const double wred = forced_w > 0 ? forced_w : (n < ((size_t)1 << 18) ? 5.0 : 3.0);
+        double cost = precomp ? (double)W * n + wred * nb : (double)W * (n + wred * nb) + 10.0 * c * W;
         if (cost < best_cost) {
             best_cost = cost;
             best = {c, W, precomp ? 1u : W};
