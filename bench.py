@@ -281,7 +281,8 @@ def _main(args, real_stdout):
                      "traffic": ACC_DRAM_BYTES_PER_LAUNCH if cols == COLS else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full of this command (profiles/r01_bench_launches_ncu.txt)",
                      "peak_source": "measured live: max(h2v_selftest_imad_peak, h2v_selftest_op_rate(Fq mul) x 136); MEASURED_PEAKS.json has no integer peak; nominal 148 SM x 32 IMAD.WIDE/clk x 1.965 GHz = 9.31",
-                     "executed": (cols * N * 16 * 1360) / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None,
+                     "executed": (cols * N * srs.info()[1] * 1360) / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None,
+                     "window_bits": srs.info()[0], "windows": srs.info()[1],
                      "algorithmic": f"{MSM_MACS_PER_POINT[K]} wide-MAC/pt x {cols * N} pts per launch (SURVEY.md 8d)"},
     }
 

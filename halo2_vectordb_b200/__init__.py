@@ -26,7 +26,7 @@ KERNEL_CLASSES = ["msm_digits", "msm_scan", "msm_scatter", "msm_accumulate", "ms
 # every symbol include/h2v.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "h2v_init", "h2v_device_count", "h2v_last_error", "h2v_version", "h2v_host_register", "h2v_host_unregister", "h2v_dev_alloc", "h2v_dev_free", "h2v_dev_upload", "h2v_dev_download",
-    "h2v_srs_load", "h2v_srs_setup", "h2v_srs_free", "h2v_commit", "h2v_commit_batch", "h2v_commit_batch_dev", "h2v_best_multiexp",
+    "h2v_srs_load", "h2v_srs_setup", "h2v_srs_free", "h2v_srs_info", "h2v_commit", "h2v_commit_batch", "h2v_commit_batch_dev", "h2v_best_multiexp",
     "h2v_best_fft", "h2v_domain_new", "h2v_domain_free", "h2v_domain_k", "h2v_domain_extended_k", "h2v_domain_constant",
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
     "h2v_divide_by_vanishing_poly", "h2v_domain_transform_batch", "h2v_domain_transform_dev",
@@ -69,6 +69,7 @@ def lib():
         L.h2v_srs_load.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.h2v_srs_setup.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.h2v_srs_free.argtypes = [C.c_void_p]
+        L.h2v_srs_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.h2v_srs_free.restype = None
         L.h2v_commit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_commit_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t, C.c_void_p]
@@ -336,6 +337,12 @@ class ParamsKZG:
             self.close()
         except Exception:      # interpreter shutdown: module globals may already be gone
             pass
+
+    def info(self):
+        """(window bits c, windows W) of the precomputed tables."""
+        c, w = C.c_uint32(), C.c_uint32()
+        _check(lib().h2v_srs_info(self._h, C.byref(c), C.byref(w)))
+        return c.value, w.value
 
     def _commit(self, basis, poly):
         poly = _fr(poly)

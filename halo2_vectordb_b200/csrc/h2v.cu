@@ -855,6 +855,12 @@ int h2v_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, h2v_
     *out = s;
     return H2V_OK;
 }
+int h2v_srs_info(h2v_srs_t s, uint32_t *window_bits, uint32_t *windows) {
+    if (!s) return fail(H2V_EINVAL, "srs_info: NULL srs");
+    if (window_bits) *window_bits = s->cfg.c;
+    if (windows) *windows = s->cfg.W;
+    return H2V_OK;
+}
 void h2v_srs_free(h2v_srs_t s) {
     if (!s) return;
     cudaSetDevice(g_device);

@@ -67,6 +67,8 @@ int h2v_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, h2v_
  * points (either output may be NULL).  One-time work; g2 / s_g2 are verifier-side and not produced. */
 int h2v_srs_setup(uint32_t k, const uint64_t s_mont[4], uint64_t *g_out, uint64_t *g_lagrange_out);
 void h2v_srs_free(h2v_srs_t srs);
+/* window size c and number of windows W = ceil(255 / c) the handle's tables were built for (diagnostics) */
+int h2v_srs_info(h2v_srs_t srs, uint32_t *window_bits, uint32_t *windows);
 /* ParamsKZG::commit(poly, _blind) / commit_lagrange(poly, _blind) = best_multiexp(poly, bases[..len]);
  * the Blind argument is ignored by KZG upstream, so it is not part of the ABI.  len <= 2^k.
  * Output: the unique affine representative (G1::to_affine()). */
