@@ -376,7 +376,56 @@ def bench_prove_shaped(h, torch, dev, srs16, d_cols16, cols16):
         del d_ext, d_h, d_coef
     res["note"] = "hot-path proxy for one create_proof per circuit (call counts: SURVEY.md App. C estimates), uniform scalars, device-resident"
     res["latency_s"] = res["kmeans_k16"]["latency_s"]
+    res["kmeans_k16_host_facing_s"] = prove_shaped_host(h, torch, srs16)
     return res
+
+
+def prove_shaped_host(h, torch, srs):
+    """The kmeans k=16 schedule again, but every column crosses PCIe the way a drop-in under today's create_proof
+    would move it (columns live in pinned host memory, evaluate_h stays on the CPU): commit_lagrange batches upload
+    the columns, lagrange_to_coeff uploads and downloads them, coeff_to_extended downloads 4x the data."""
+    import ctypes as C
+    import numpy as np
+    k, n_msm, n_intt, n_cntt, _ = PROVE_SHAPES["kmeans_k16"]
+    bc = 32
+    g = torch.Generator(device="cpu").manual_seed(5)
+    hin = torch.randint(-(1 << 63), (1 << 63) - 1, (bc, N, 4), dtype=torch.int64, generator=g)
+    hin[..., 3] &= (1 << 60) - 1
+    hin = hin.pin_memory()
+    hcoef = torch.empty((bc, N, 4), dtype=torch.int64).pin_memory()
+    hext = torch.empty((bc, 4 * N, 4), dtype=torch.int64).pin_memory()
+    hout = np.zeros((bc, 8), dtype=np.uint64)
+    ia = (C.c_void_p * bc)(*[hin[i].data_ptr() for i in range(bc)])
+    ca = (C.c_void_p * bc)(*[hcoef[i].data_ptr() for i in range(bc)])
+    ea = (C.c_void_p * bc)(*[hext[i].data_ptr() for i in range(bc)])
+    dom = h.EvaluationDomain(4, k)
+    L = h.lib()
+
+    def run():
+        left = n_msm
+        while left > 0:
+            c = min(bc, left)
+            h._check(L.h2v_commit_batch(srs._h, h.H2V_BASIS_LAGRANGE, ia, c, N, hout.ctypes.data_as(C.c_void_p)))
+            left -= c
+        left = n_intt
+        while left > 0:
+            c = min(bc, left)
+            h._check(L.h2v_domain_transform_batch(dom._h, h.OP_LAGRANGE_TO_COEFF, ia, ca, c))
+            left -= c
+        left = n_cntt
+        while left > 0:
+            c = min(bc, left)
+            h._check(L.h2v_domain_transform_batch(dom._h, h.OP_COEFF_TO_EXTENDED, ca, ea, c))
+            left -= c
+
+    run()
+    ts = []
+    for _ in range(2):
+        t = time.perf_counter()
+        run()
+        ts.append(time.perf_counter() - t)
+    dom.close()
+    return min(ts)
 
 
 def bench_row2(h, torch, dev, d_cols, cols):
