@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
     "h2v_divide_by_vanishing_poly", "h2v_domain_transform_batch", "h2v_domain_transform_dev",
     "h2v_eval_polynomial_batch", "h2v_eval_polynomial_dev", "h2v_batch_invert", "h2v_grand_product", "h2v_kate_division",
+    "h2v_quotient_gates_dev", "h2v_quotient_permutation_dev", "h2v_quotient_lookup_dev",
     "h2v_g1_to_bytes", "h2v_fr_to_repr",
     "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_op_rate", "h2v_set_tuning", "h2v_launch_count", "h2v_last_kernel_ms",
 ]
@@ -91,6 +92,10 @@ def lib():
         L.h2v_batch_invert.argtypes = [C.c_void_p, C.c_size_t]
         L.h2v_grand_product.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_kate_division.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.h2v_quotient_gates_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.h2v_quotient_permutation_dev.argtypes = ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+                                                   + [C.c_void_p, C.c_size_t] * 3 + [C.c_void_p] * 3 + [C.c_uint32])
+        L.h2v_quotient_lookup_dev.argtypes = [C.c_void_p] * 13
         L.h2v_g1_to_bytes.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_fr_to_repr.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_selftest_field.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -117,6 +122,10 @@ def _fr(a, n=None):
     if a.ndim != 2 or a.shape[1] != 4 or (n is not None and a.shape[0] != n):
         raise ValueError(f"expected Fr array of shape ({'n' if n is None else n}, 4), got {a.shape}")
     return a
+
+
+def _fr1(x):
+    return _fr(np.asarray(x, dtype=np.uint64).reshape(1, 4), 1)
 
 
 def _ptr(a):
@@ -453,6 +462,21 @@ class EvaluationDomain:
 
     def transform_dev(self, op, d_in_ptr, in_stride, d_out_ptr, out_stride, n_cols):
         _check(lib().h2v_domain_transform_dev(self._h, op, d_in_ptr, in_stride, d_out_ptr, out_stride, n_cols))
+
+    # --- evaluate_h row loops on device-resident extended columns (halo2-axiom plonk/evaluation.rs [UPSTREAM])
+    def quotient_gates(self, d_h, y, n_gates, d_q, q_stride, d_a, a_stride):
+        """h <- h*y + q_j*(a_j + a_j(wX)*a_j(w^2X) - a_j(w^3X)) for every halo2-base vertical gate j, in order."""
+        _check(lib().h2v_quotient_gates_dev(self._h, d_h, _ptr(_fr1(y)), n_gates, d_q, q_stride, d_a, a_stride))
+
+    def quotient_permutation(self, d_h, y, beta, gamma, n_cols, chunk_len, d_cols, cols_stride, d_sigma, sigma_stride,
+                             d_z, z_stride, d_l0, d_l_last, d_l_active, blinding_factors):
+        _check(lib().h2v_quotient_permutation_dev(self._h, d_h, _ptr(_fr1(y)), _ptr(_fr1(beta)), _ptr(_fr1(gamma)),
+                                                  n_cols, chunk_len, d_cols, cols_stride, d_sigma, sigma_stride, d_z, z_stride,
+                                                  d_l0, d_l_last, d_l_active, blinding_factors))
+
+    def quotient_lookup(self, d_h, y, beta, gamma, d_input, d_table, d_perm_input, d_perm_table, d_z, d_l0, d_l_last, d_l_active):
+        _check(lib().h2v_quotient_lookup_dev(self._h, d_h, _ptr(_fr1(y)), _ptr(_fr1(beta)), _ptr(_fr1(gamma)),
+                                             d_input, d_table, d_perm_input, d_perm_table, d_z, d_l0, d_l_last, d_l_active))
 
 
 # ----------------------------------------------------------------------------- device self-tests

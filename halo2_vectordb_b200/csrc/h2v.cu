@@ -21,6 +21,7 @@
 #include "msm_affine.cuh"
 #include "ntt.cuh"
 #include "poly.cuh"
+#include "quotient.cuh"
 
 using namespace h2v;
 
@@ -1492,6 +1493,101 @@ int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t
     CU(cudaMemcpyAsync(out, g_poly.b.p, (n - 1) * sizeof(fe), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return H2V_OK;
+}
+}  // extern "C"
+
+// ================================================================== quotient evaluation ("next" row 1)
+namespace {
+int quotient_common(h2v_domain_t d, const void *d_h, const uint64_t *y, QuotientCommon *c) {
+    if (!d) return fail(H2V_EINVAL, "quotient: NULL domain");
+    if (!d_h || !y) return fail(H2V_EINVAL, "quotient: NULL buffer");
+    c->y = fe_from_u64x4(y);
+    c->n_ext = 1u << d->ek;
+    c->rot = 1u << (d->ek - d->k);
+    return use_device();
+}
+int quotient_finish(h2v_domain_t d, Timer &tm) {
+    tm.end();
+    cudaError_t e = cudaStreamSynchronize(d->stream);
+    tm.collect(true);
+    if (e != cudaSuccess) return fail(H2V_ECUDA, "quotient: %s", cudaGetErrorString(e));
+    return H2V_OK;
+}
+}  // namespace
+
+extern "C" {
+int h2v_quotient_gates_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], size_t n_gates, const void *d_q, size_t q_stride,
+                           const void *d_a, size_t a_stride) {
+    QuotientCommon c;
+    int rc = quotient_common(d, d_h, y, &c);
+    if (rc) return rc;
+    if (!n_gates) return H2V_OK;
+    if (!d_q || !d_a) return fail(H2V_EINVAL, "quotient_gates: NULL buffer");
+    if (q_stride < c.n_ext || a_stride < c.n_ext || n_gates > (1u << 20))
+        return fail(H2V_EINVAL, "quotient_gates: stride shorter than 2^extended_k, or too many gates");
+    std::lock_guard<std::mutex> lk(d->mu);
+    Timer tm(d->stream);
+    tm.begin(7);
+    quotient_gates_kernel<<<(c.n_ext + 255) / 256, 256, 0, d->stream>>>((fe *)d_h, c, (uint32_t)n_gates, (const fe *)d_q, q_stride,
+                                                                        (const fe *)d_a, a_stride);
+    LAUNCHED();
+    return quotient_finish(d, tm);
+}
+int h2v_quotient_permutation_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                                 size_t n_cols, size_t chunk_len, const void *d_cols, size_t cols_stride, const void *d_sigma,
+                                 size_t sigma_stride, const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last,
+                                 const void *d_l_active, uint32_t blinding_factors) {
+    QuotientCommon c;
+    int rc = quotient_common(d, d_h, y, &c);
+    if (rc) return rc;
+    if (!n_cols) return H2V_OK;   // upstream: `if !sets.is_empty()`
+    if (!beta || !gamma || !d_cols || !d_sigma || !d_z || !d_l0 || !d_l_last || !d_l_active)
+        return fail(H2V_EINVAL, "quotient_permutation: NULL buffer");
+    if (!chunk_len || n_cols > (1u << 20) || blinding_factors + 1 >= (1u << d->k))
+        return fail(H2V_EINVAL, "quotient_permutation: chunk_len = 0, too many columns, or blinding_factors >= n - 1");
+    if (cols_stride < c.n_ext || sigma_stride < c.n_ext || z_stride < c.n_ext)
+        return fail(H2V_EINVAL, "quotient_permutation: stride shorter than 2^extended_k");
+    QuotientPerm p;
+    p.beta = fe_from_u64x4(beta);
+    p.gamma = fe_from_u64x4(gamma);
+    p.delta = fe_pow_u64<Fr>(fr_from_small(7), (uint64_t)1 << 28);   // Fr::DELTA = MULTIPLICATIVE_GENERATOR^(2^S)
+    p.beta_zeta = fe_mul<Fr>(p.beta, d->g_coset);
+    p.n_cols = (uint32_t)n_cols;
+    p.chunk_len = (uint32_t)std::min<size_t>(chunk_len, n_cols);
+    p.n_sets = (p.n_cols + p.chunk_len - 1) / p.chunk_len;
+    p.last_rot = -(int)(blinding_factors + 1);
+    p.cols = (const fe *)d_cols; p.sigma = (const fe *)d_sigma; p.z = (const fe *)d_z;
+    p.cols_stride = cols_stride; p.sigma_stride = sigma_stride; p.z_stride = z_stride;
+    p.l0 = (const fe *)d_l0; p.l_last = (const fe *)d_l_last; p.l_active = (const fe *)d_l_active;
+    if ((rc = domain_twiddles(d, 2, &p.tw))) return rc;
+    std::lock_guard<std::mutex> lk(d->mu);
+    Timer tm(d->stream);
+    tm.begin(7);
+    quotient_permutation_kernel<<<(c.n_ext + 255) / 256, 256, 0, d->stream>>>((fe *)d_h, c, p);
+    LAUNCHED();
+    return quotient_finish(d, tm);
+}
+int h2v_quotient_lookup_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                            const void *d_input, const void *d_table, const void *d_perm_input, const void *d_perm_table,
+                            const void *d_z, const void *d_l0, const void *d_l_last, const void *d_l_active) {
+    QuotientCommon c;
+    int rc = quotient_common(d, d_h, y, &c);
+    if (rc) return rc;
+    if (!beta || !gamma || !d_input || !d_table || !d_perm_input || !d_perm_table || !d_z || !d_l0 || !d_l_last || !d_l_active)
+        return fail(H2V_EINVAL, "quotient_lookup: NULL buffer");
+    QuotientLookup p;
+    p.beta = fe_from_u64x4(beta);
+    p.gamma = fe_from_u64x4(gamma);
+    p.input = (const fe *)d_input; p.table = (const fe *)d_table;
+    p.perm_input = (const fe *)d_perm_input; p.perm_table = (const fe *)d_perm_table;
+    p.z = (const fe *)d_z;
+    p.l0 = (const fe *)d_l0; p.l_last = (const fe *)d_l_last; p.l_active = (const fe *)d_l_active;
+    std::lock_guard<std::mutex> lk(d->mu);
+    Timer tm(d->stream);
+    tm.begin(7);
+    quotient_lookup_kernel<<<(c.n_ext + 255) / 256, 256, 0, d->stream>>>((fe *)d_h, c, p);
+    LAUNCHED();
+    return quotient_finish(d, tm);
 }
 }  // extern "C"
 

@@ -129,6 +129,29 @@ int h2v_grand_product(const uint64_t *num, const uint64_t *den, size_t n, uint64
 /* arithmetic.rs kate_division(a, b): quotient of a(X) (n coefficients) by (X - b), n - 1 coefficients */
 int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t *out);
 
+/* ---- quotient evaluation on the extended coset ("next": SURVEY.md 8(f) row 1) ------------------------------
+ * The per-row loops of halo2-axiom plonk/evaluation.rs Evaluator::evaluate_h [UPSTREAM; reached from
+ * src/scaffold/mod.rs:296] for the constraint system halo2-base builds.  Every polynomial is a device-resident
+ * column of 2^extended_k Fr values (h2v_dev_alloc; produced by h2v_domain_transform_dev COEFF_TO_EXTENDED), so the
+ * 4n-sized columns never cross PCIe; `d_h` is the running value, updated in place as  h <- h * y + term  for each
+ * term in upstream's order (custom gates, then permutation, then each lookup).  Start from a zeroed column and
+ * finish with h2v_domain_transform_dev(H2V_OP_DIVIDE_BY_VANISHING).  Rotation r reads row i + r * 2^(extended_k-k). */
+/* custom gates: halo2-base's vertical gate on advice column j,  q_j * (a_j + a_j(wX) * a_j(w^2 X) - a_j(w^3 X)) */
+int h2v_quotient_gates_dev(h2v_domain_t dom, void *d_h, const uint64_t y[4], size_t n_gates, const void *d_q, size_t q_stride,
+                           const void *d_a, size_t a_stride);
+/* permutation argument: `n_cols` permuted columns (advice / fixed / instance values, in permutation-column order) with
+ * their sigma polynomials, ceil(n_cols / chunk_len) grand products z (chunk_len = cs.degree() - 2), l_0, l_last and
+ * l_active_row; X = g_coset * extended_omega^i and Fr::DELTA come from the domain. */
+int h2v_quotient_permutation_dev(h2v_domain_t dom, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                                 size_t n_cols, size_t chunk_len, const void *d_cols, size_t cols_stride, const void *d_sigma,
+                                 size_t sigma_stride, const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last,
+                                 const void *d_l_active, uint32_t blinding_factors);
+/* one lookup argument: compressed input / table expressions (theta-folded by the caller; for halo2-base's range
+ * lookup they are the lookup advice column and the fixed table column), permuted A' / S', grand product z */
+int h2v_quotient_lookup_dev(h2v_domain_t dom, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                            const void *d_input, const void *d_table, const void *d_perm_input, const void *d_perm_table,
+                            const void *d_z, const void *d_l0, const void *d_l_last, const void *d_l_active);
+
 /* ---- wire format of commitments and evaluations ("next": SURVEY.md 8(f) row 3; host-side) --------------- */
 /* halo2curves 0.3.x G1Affine::to_bytes(): 32 bytes = canonical x little-endian, bit 6 of byte 31 = parity of
  * canonical y, identity = zeros (the flag convention is recalled, not verified against the crate) */

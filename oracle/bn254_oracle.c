@@ -878,3 +878,149 @@ int orc_srs_setup(uint32_t k, const u64 s_mont[4], int threads, u64 *g_out, u64 
     free(sc);
     return 0;
 }
+
+/* ---- quotient evaluation row loops ("next" row 1) ----------------------------------------------------------------
+ * Restates halo2-axiom plonk/evaluation.rs Evaluator::evaluate_h [UPSTREAM, absent from /root/reference; reached from
+ * src/scaffold/mod.rs:296], for the constraint system halo2-base builds.  Written from the published PLONKish argument
+ * (halo2 book: permutation and lookup arguments) and the recalled structure of that function: `values[idx] = values[idx]
+ * * y + term` per term, custom gates first, then the permutation argument, then each lookup; rotation r at row idx reads
+ * row (idx + r * 2^(extended_k - k)) mod 2^extended_k (get_rotation_idx).  PARITY UNPINNED like the rest of this file;
+ * tests additionally check the defining property (the folded expression vanishes on the 2^k domain for a satisfied
+ * circuit, and h(x) * (x^n - 1) equals the expression re-evaluated at a random point with big integers). */
+static inline size_t rot_idx(size_t idx, int r, size_t rot_scale, size_t n_ext) {
+    return (idx + (size_t)((long)r * (long)rot_scale + (long)n_ext * 64)) & (n_ext - 1);
+}
+static inline void fold(fe *v, const fe *y, const fe *term) {
+    f_mul(&FR, v, v, y);
+    f_add(&FR, v, v, term);
+}
+/* custom gates of halo2-base's FlexGateConfig: for advice column j,  q_j * (a + b * c - d)  with a, b, c, d = the
+ * column at rotations 0, 1, 2, 3 */
+void orc_quotient_gates(const orc_domain *d, u64 *h_, const u64 y_[4], size_t n_gates, const u64 *q_, size_t q_stride,
+                        const u64 *a_, size_t a_stride) {
+    const size_t n_ext = (size_t)1 << d->extended_k, rs = (size_t)1 << (d->extended_k - d->k);
+    fe *h = (fe *)h_;
+    const fe *y = (const fe *)y_, *q = (const fe *)q_, *a = (const fe *)a_;
+    for (size_t idx = 0; idx < n_ext; ++idx)
+        for (size_t j = 0; j < n_gates; ++j) {
+            const fe *col = a + j * a_stride;
+            fe t;
+            f_mul(&FR, &t, &col[rot_idx(idx, 1, rs, n_ext)], &col[rot_idx(idx, 2, rs, n_ext)]);
+            f_add(&FR, &t, &col[idx], &t);
+            f_sub(&FR, &t, &t, &col[rot_idx(idx, 3, rs, n_ext)]);
+            f_mul(&FR, &t, &q[j * q_stride + idx], &t);
+            fold(&h[idx], y, &t);
+        }
+}
+void orc_fr_delta(u64 out[4]) {     /* Fr::DELTA = MULTIPLICATIVE_GENERATOR^(2^S) = 7^(2^28) */
+    u64 seven[4] = {7, 0, 0, 0};
+    fe g;
+    f_to_mont(&FR, &g, seven);
+    f_pow_u64(&FR, (fe *)out, &g, (u64)1 << FR_S);
+}
+void orc_quotient_permutation(const orc_domain *d, u64 *h_, const u64 y_[4], const u64 beta_[4], const u64 gamma_[4],
+                              size_t n_cols, size_t chunk_len, const u64 *cols_, size_t cols_stride, const u64 *sigma_,
+                              size_t sigma_stride, const u64 *z_, size_t z_stride, const u64 *l0_, const u64 *l_last_,
+                              const u64 *l_active_, uint32_t blinding_factors) {
+    if (!n_cols) return;
+    const size_t n_ext = (size_t)1 << d->extended_k, rs = (size_t)1 << (d->extended_k - d->k);
+    const size_t n_sets = (n_cols + chunk_len - 1) / chunk_len;
+    const int last_rotation = -(int)(blinding_factors + 1);
+    fe *h = (fe *)h_;
+    const fe *y = (const fe *)y_, *beta = (const fe *)beta_, *gamma = (const fe *)gamma_;
+    const fe *cols = (const fe *)cols_, *sigma = (const fe *)sigma_, *z = (const fe *)z_;
+    const fe *l0 = (const fe *)l0_, *l_last = (const fe *)l_last_, *l_active = (const fe *)l_active_;
+    fe one, delta, delta_start, beta_term;
+    memcpy(one.l, FR.r1, 32);
+    orc_fr_delta(delta.l);
+    f_mul(&FR, &delta_start, beta, &d->g_coset);
+    beta_term = one;                                    /* extended_omega^idx */
+    for (size_t idx = 0; idx < n_ext; ++idx) {
+        const size_t r_next = rot_idx(idx, 1, rs, n_ext), r_last = rot_idx(idx, last_rotation, rs, n_ext);
+        fe t, u;
+        /* l_0(X) * (1 - z_0(X)) */
+        f_sub(&FR, &t, &one, &z[idx]);
+        f_mul(&FR, &t, &t, &l0[idx]);
+        fold(&h[idx], y, &t);
+        /* l_last(X) * (z_l(X)^2 - z_l(X)) */
+        const fe *zl = z + (n_sets - 1) * z_stride;
+        f_sqr(&FR, &t, &zl[idx]);
+        f_sub(&FR, &t, &t, &zl[idx]);
+        f_mul(&FR, &t, &t, &l_last[idx]);
+        fold(&h[idx], y, &t);
+        /* l_0(X) * (z_i(X) - z_{i-1}(omega^last X)) */
+        for (size_t s = 1; s < n_sets; ++s) {
+            f_sub(&FR, &t, &z[s * z_stride + idx], &z[(s - 1) * z_stride + r_last]);
+            f_mul(&FR, &t, &t, &l0[idx]);
+            fold(&h[idx], y, &t);
+        }
+        /* l_active(X) * (z_i(omega X) prod (p + beta s_j + gamma) - z_i(X) prod (p + delta^j beta X + gamma)) */
+        fe current_delta;
+        f_mul(&FR, &current_delta, &delta_start, &beta_term);
+        for (size_t s = 0; s < n_sets; ++s) {
+            const size_t c0 = s * chunk_len, c1 = c0 + chunk_len < n_cols ? c0 + chunk_len : n_cols;
+            fe left = z[s * z_stride + r_next], right = z[s * z_stride + idx];
+            for (size_t j = c0; j < c1; ++j) {
+                f_mul(&FR, &t, beta, &sigma[j * sigma_stride + idx]);
+                f_add(&FR, &t, &cols[j * cols_stride + idx], &t);
+                f_add(&FR, &t, &t, gamma);
+                f_mul(&FR, &left, &left, &t);
+            }
+            for (size_t j = c0; j < c1; ++j) {
+                f_add(&FR, &u, &cols[j * cols_stride + idx], &current_delta);
+                f_add(&FR, &u, &u, gamma);
+                f_mul(&FR, &right, &right, &u);
+                f_mul(&FR, &current_delta, &current_delta, &delta);
+            }
+            f_sub(&FR, &t, &left, &right);
+            f_mul(&FR, &t, &t, &l_active[idx]);
+            fold(&h[idx], y, &t);
+        }
+        f_mul(&FR, &beta_term, &beta_term, &d->ext_omega);
+    }
+}
+void orc_quotient_lookup(const orc_domain *d, u64 *h_, const u64 y_[4], const u64 beta_[4], const u64 gamma_[4],
+                         const u64 *input_, const u64 *table_, const u64 *perm_input_, const u64 *perm_table_, const u64 *z_,
+                         const u64 *l0_, const u64 *l_last_, const u64 *l_active_) {
+    const size_t n_ext = (size_t)1 << d->extended_k, rs = (size_t)1 << (d->extended_k - d->k);
+    fe *h = (fe *)h_;
+    const fe *y = (const fe *)y_, *beta = (const fe *)beta_, *gamma = (const fe *)gamma_;
+    const fe *input = (const fe *)input_, *table = (const fe *)table_, *pa = (const fe *)perm_input_, *ps = (const fe *)perm_table_;
+    const fe *z = (const fe *)z_, *l0 = (const fe *)l0_, *l_last = (const fe *)l_last_, *l_active = (const fe *)l_active_;
+    fe one;
+    memcpy(one.l, FR.r1, 32);
+    for (size_t idx = 0; idx < n_ext; ++idx) {
+        const size_t r_next = rot_idx(idx, 1, rs, n_ext), r_prev = rot_idx(idx, -1, rs, n_ext);
+        fe t, u, w, a_minus_s;
+        f_sub(&FR, &a_minus_s, &pa[idx], &ps[idx]);
+        /* l_0(X) * (1 - z(X)) */
+        f_sub(&FR, &t, &one, &z[idx]);
+        f_mul(&FR, &t, &t, &l0[idx]);
+        fold(&h[idx], y, &t);
+        /* l_last(X) * (z(X)^2 - z(X)) */
+        f_sqr(&FR, &t, &z[idx]);
+        f_sub(&FR, &t, &t, &z[idx]);
+        f_mul(&FR, &t, &t, &l_last[idx]);
+        fold(&h[idx], y, &t);
+        /* l_active(X) * (z(omega X) (a'(X) + beta) (s'(X) + gamma) - z(X) (a(X) + beta) (s(X) + gamma)) */
+        f_add(&FR, &t, &pa[idx], beta);
+        f_mul(&FR, &t, &z[r_next], &t);
+        f_add(&FR, &u, &ps[idx], gamma);
+        f_mul(&FR, &t, &t, &u);
+        f_add(&FR, &u, &input[idx], beta);
+        f_add(&FR, &w, &table[idx], gamma);
+        f_mul(&FR, &u, &u, &w);
+        f_mul(&FR, &u, &z[idx], &u);
+        f_sub(&FR, &t, &t, &u);
+        f_mul(&FR, &t, &t, &l_active[idx]);
+        fold(&h[idx], y, &t);
+        /* l_0(X) * (a'(X) - s'(X)) */
+        f_mul(&FR, &t, &a_minus_s, &l0[idx]);
+        fold(&h[idx], y, &t);
+        /* l_active(X) * (a'(X) - s'(X)) (a'(X) - a'(omega^-1 X)) */
+        f_sub(&FR, &t, &pa[idx], &pa[r_prev]);
+        f_mul(&FR, &t, &a_minus_s, &t);
+        f_mul(&FR, &t, &t, &l_active[idx]);
+        fold(&h[idx], y, &t);
+    }
+}

@@ -73,6 +73,11 @@ _c2l = _sig("orc_coeff_to_lagrange", C.c_void_p, _u64p, C.c_int)
 _c2e = _sig("orc_coeff_to_extended", C.c_void_p, _u64p, _u64p, C.c_int)
 _e2c = _sig("orc_extended_to_coeff", C.c_void_p, _u64p, _u64p, C.c_int)
 _dvp = _sig("orc_divide_by_vanishing_poly", C.c_void_p, _u64p)
+_q_gates = _sig("orc_quotient_gates", C.c_void_p, _u64p, _u64p, C.c_size_t, _u64p, C.c_size_t, _u64p, C.c_size_t)
+_q_perm = _sig("orc_quotient_permutation", C.c_void_p, _u64p, _u64p, _u64p, _u64p, C.c_size_t, C.c_size_t, _u64p, C.c_size_t,
+               _u64p, C.c_size_t, _u64p, C.c_size_t, _u64p, _u64p, _u64p, C.c_uint32)
+_q_lookup = _sig("orc_quotient_lookup", C.c_void_p, *([_u64p] * 12))
+_fr_delta = _sig("orc_fr_delta", _u64p)
 for _n in ("fr_mul", "fr_add", "fr_sub", "fq_mul", "fq_add", "fq_sub"):
     _sig("orc_" + _n, _u64p, _u64p, _u64p)
 for _n in ("fr_inv", "fq_inv"):
@@ -335,3 +340,48 @@ class EvaluationDomain:
         a = np.array(a, dtype=np.uint64, copy=True).reshape(1 << self.extended_k, 4)
         _dvp(self._d, _p(a))
         return a
+
+    # --- evaluate_h row loops (plonk/evaluation.rs [UPSTREAM]); h is updated and returned, columns are (n_cols, 2^extended_k, 4)
+    def _ext(self, a, cols=None):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        shape = (1 << self.extended_k, 4) if cols is None else (cols, 1 << self.extended_k, 4)
+        if a.shape != shape:
+            raise ValueError(f"expected {shape}, got {a.shape}")
+        return a
+
+    def quotient_gates(self, h, y, q, a):
+        h = np.array(self._ext(h), copy=True)
+        n_gates = len(q)
+        if n_gates:
+            q, a = self._ext(q, n_gates), self._ext(a, n_gates)
+            _q_gates(self._d, _p(h), _p(_one(y)), n_gates, _p(q), 1 << self.extended_k, _p(a), 1 << self.extended_k)
+        return h
+
+    def quotient_permutation(self, h, y, beta, gamma, chunk_len, cols, sigma, z, l0, l_last, l_active, blinding_factors):
+        h = np.array(self._ext(h), copy=True)
+        n_cols = len(cols)
+        if n_cols:
+            n_sets = (n_cols + chunk_len - 1) // chunk_len
+            e = 1 << self.extended_k
+            _q_perm(self._d, _p(h), _p(_one(y)), _p(_one(beta)), _p(_one(gamma)), n_cols, chunk_len, _p(self._ext(cols, n_cols)), e,
+                    _p(self._ext(sigma, n_cols)), e, _p(self._ext(z, n_sets)), e, _p(self._ext(l0)), _p(self._ext(l_last)),
+                    _p(self._ext(l_active)), blinding_factors)
+        return h
+
+    def quotient_lookup(self, h, y, beta, gamma, inp, table, perm_input, perm_table, z, l0, l_last, l_active):
+        h = np.array(self._ext(h), copy=True)
+        _q_lookup(self._d, _p(h), _p(_one(y)), _p(_one(beta)), _p(_one(gamma)), _p(self._ext(inp)), _p(self._ext(table)),
+                  _p(self._ext(perm_input)), _p(self._ext(perm_table)), _p(self._ext(z)), _p(self._ext(l0)), _p(self._ext(l_last)),
+                  _p(self._ext(l_active)))
+        return h
+
+
+def _one(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.uint64).reshape(4))
+
+
+def fr_delta():
+    """Fr::DELTA (Montgomery limbs)."""
+    o = np.empty(4, dtype=np.uint64)
+    _fr_delta(_p(o))
+    return o
