@@ -291,6 +291,7 @@ def _main(args, real_stdout):
         line["witness_like"] = bench_witness(h, torch, dev, srs)
         line["prove_shaped"] = bench_prove_shaped(h, torch, dev, srs, d_cols, cols)
         line["next_row2"] = bench_row2(h, torch, dev, d_cols, cols)
+        line["next_row1"] = bench_row1(h, torch, dev)
         if world == 1:
             threads = os.cpu_count() or 1
             v, secs = cpu_msm_sample(24, threads)
@@ -377,7 +378,60 @@ def bench_prove_shaped(h, torch, dev, srs16, d_cols16, cols16):
     res["note"] = "hot-path proxy for one create_proof per circuit (call counts: SURVEY.md App. C estimates), uniform scalars, device-resident"
     res["latency_s"] = res["kmeans_k16"]["latency_s"]
     res["kmeans_k16_host_facing_s"] = prove_shaped_host(h, torch, srs16)
+    res["kmeans_k16_host_in_quotient_on_device_s"] = prove_shaped_resident(h, torch, dev, srs16)
     return res
+
+
+def prove_shaped_resident(h, torch, dev, srs):
+    """The kmeans k=16 schedule with the quotient evaluation on the device as well: every
+    column is uploaded ONCE from pinned host memory (2 MiB), committed, brought to coefficient form, extended and
+    folded into h by the gate / permutation kernels without leaving HBM; only the commitments and the divided
+    quotient (3n coefficients) come back.  Selector / sigma / z columns reuse the extended buffers (timing only)."""
+    import numpy as np
+    k, n_msm, n_intt, n_cntt, _ = PROVE_SHAPES["kmeans_k16"]
+    bc = 32
+    g = torch.Generator(device="cpu").manual_seed(6)
+    hin = torch.randint(-(1 << 63), (1 << 63) - 1, (bc, N, 4), dtype=torch.int64, generator=g)
+    hin[..., 3] &= (1 << 60) - 1
+    hin = hin.pin_memory()
+    hq = torch.empty((3 * N, 4), dtype=torch.int64).pin_memory()
+    dom = h.EvaluationDomain(4, k)
+    ne = 4 * N
+    d_in = torch.empty((bc, N, 4), dtype=torch.int64, device=dev)
+    d_coef = torch.empty_like(d_in)
+    d_ext = torch.empty((bc, ne, 4), dtype=torch.int64, device=dev)
+    d_h = torch.zeros((ne, 4), dtype=torch.int64, device=dev)
+    d_hq = torch.empty((ne, 4), dtype=torch.int64, device=dev)
+    d_out = torch.zeros((bc, 8), dtype=torch.int64, device=dev)
+    hout = torch.empty((bc, 8), dtype=torch.int64).pin_memory()
+    y = hin[0, :3].numpy().view(np.uint64)
+    L = h.lib()
+
+    def run():
+        left = n_msm
+        while left > 0:
+            c = min(bc, left)
+            h._check(L.h2v_dev_upload(d_in.data_ptr(), hin.data_ptr(), c * N * 32))
+            srs.commit_batch_dev(d_in.data_ptr(), N, c, N, d_out.data_ptr())
+            h._check(L.h2v_dev_download(hout.data_ptr(), d_out.data_ptr(), c * 64))
+            dom.transform_dev(h.OP_LAGRANGE_TO_COEFF, d_in.data_ptr(), N, d_coef.data_ptr(), N, c)
+            dom.transform_dev(h.OP_COEFF_TO_EXTENDED, d_coef.data_ptr(), N, d_ext.data_ptr(), ne, c)
+            dom.quotient_gates(d_h.data_ptr(), y[0], c, d_ext.data_ptr(), ne, d_ext.data_ptr(), ne)
+            dom.quotient_permutation(d_h.data_ptr(), y[0], y[1], y[2], c, 2, d_ext.data_ptr(), ne, d_ext.data_ptr(), ne,
+                                     d_ext.data_ptr(), ne, d_ext[0].data_ptr(), d_ext[1].data_ptr(), d_ext[2].data_ptr(), 5)
+            left -= c
+        dom.transform_dev(h.OP_DIVIDE_BY_VANISHING, d_h.data_ptr(), ne, d_hq.data_ptr(), ne, 1)
+        h._check(L.h2v_dev_download(hq.data_ptr(), d_hq.data_ptr(), 3 * N * 32))
+
+    run()
+    ts = []
+    for _ in range(2):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        run()
+        ts.append(time.perf_counter() - t)
+    dom.close()
+    return min(ts)
 
 
 def prove_shaped_host(h, torch, srs):
@@ -450,6 +504,63 @@ def bench_row2(h, torch, dev, d_cols, cols):
     cpu = 4 * N / (time.perf_counter() - t0)
     return {"eval_polynomial_gcoeff_per_s": cols * 3 * N / t / 1e9, "ms": t * 1e3, "polys": cols, "points": 3,
             "cpu_port_gcoeff_per_s": cpu / 1e9, "cpu_cores": 1}
+
+
+def bench_row1(h, torch, dev):
+    """evaluate_h's row loops at k = 16, extended_k = 18, device-resident: 128 vertical gates,
+    a permutation argument over 128 columns (chunk_len 2) and one lookup, on uniform synthetic extended columns;
+    beside them the oracle's scalar loops on a k = 10 domain (kind "port", one core)."""
+    import numpy as np
+    from oracle import oracle as O
+    k, gates = K, 128
+    dom = h.EvaluationDomain(4, k)
+    ne = 1 << dom.extended_k
+    g = torch.Generator(device=dev).manual_seed(11)
+
+    def cols_dev(c):
+        a = torch.randint(-(1 << 63), (1 << 63) - 1, (c, ne, 4), dtype=torch.int64, generator=g, device=dev)
+        a[..., 3] &= (1 << 60) - 1
+        return a
+
+    d_q, d_a, d_sig, d_z, d_misc = cols_dev(gates), cols_dev(gates), cols_dev(gates), cols_dev(gates // 2), cols_dev(9)
+    d_h = torch.zeros((ne, 4), dtype=torch.int64, device=dev)
+    y = d_misc[0, :3].cpu().numpy().view(np.uint64)
+    m = lambda i: d_misc[i].data_ptr()
+
+    def timed(fn):
+        ms = []
+        for i in range(6):
+            fn()
+            if i >= 2:
+                ms.append(h.last_kernel_ms()["ntt"])       # the quotient kernels report under class 7
+        return statistics.median(ms) * 1e-3
+
+    t_g = timed(lambda: dom.quotient_gates(d_h.data_ptr(), y[0], gates, d_q.data_ptr(), ne, d_a.data_ptr(), ne))
+    t_p = timed(lambda: dom.quotient_permutation(d_h.data_ptr(), y[0], y[1], y[2], gates, 2, d_a.data_ptr(), ne, d_sig.data_ptr(), ne,
+                                                 d_z.data_ptr(), ne, m(1), m(2), m(3), 5))
+    t_l = timed(lambda: dom.quotient_lookup(d_h.data_ptr(), y[0], y[1], y[2], m(4), m(5), m(6), m(7), m(8), m(1), m(2), m(3)))
+    dom.close()
+    # CPU port on a small domain, one core
+    ck, cg = 10, 8
+    od = O.EvaluationDomain(4, ck)
+    cne = 1 << od.extended_k
+    ca = O.fr_fill(cg * cne, 3).reshape(cg, cne, 4)
+    cz = O.fr_fill((cg // 2) * cne, 4).reshape(cg // 2, cne, 4)
+    ch = np.zeros((cne, 4), dtype=np.uint64)
+    t0 = time.perf_counter()
+    od.quotient_gates(ch, y[0], ca, ca)
+    c_g = cg * cne / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    od.quotient_permutation(ch, y[0], y[1], y[2], 2, ca, ca, cz, ca[0], ca[1], ca[2], 5)
+    c_p = cg * cne / (time.perf_counter() - t0)
+    # products per row: 3 per gate, 4 per permuted column + 2.5 per grand product, 13 per lookup
+    n_adv = PROVE_SHAPES["kmeans_k16"][4]
+    return {"gate_rows_per_s": gates * ne / t_g, "perm_col_rows_per_s": gates * ne / t_p, "lookup_rows_per_s": ne / t_l,
+            "ms": {"gates_128": t_g * 1e3, "permutation_128": t_p * 1e3, "lookup_1": t_l * 1e3},
+            "fr_mul_per_s": {"gates": 3 * gates * ne / t_g, "permutation": (4 * gates + 2.5 * gates / 2 + 4) * ne / t_p},
+            "dram_gb_per_s": {"gates": (2 * gates + 2) * ne * 32 / t_g / 1e9, "permutation": (2.5 * gates + 5) * ne * 32 / t_p / 1e9},
+            "cpu_port": {"gate_rows_per_s": c_g, "perm_col_rows_per_s": c_p, "cores": 1, "sample": f"k={ck}, {cg} columns, oracle scalar loops"},
+            "note": f"k={k}, extended_k={dom.extended_k}, uniform synthetic extended columns resident in HBM; per-term rates, {n_adv} advice columns in the kmeans batch"}
 
 
 def bench_witness(h, torch, dev, srs):

@@ -65,6 +65,17 @@ extern "C" {
                                 len: usize, d_out_affine: *mut c_void) -> c_int;
     pub fn h2v_domain_transform_dev(dom: *mut H2vDomain, op: c_int, d_in: *const c_void, in_stride: usize,
                                     d_out: *mut c_void, out_stride: usize, n_cols: usize) -> c_int;
+    pub fn h2v_quotient_gates_dev(dom: *mut H2vDomain, d_h: *mut c_void, y: *const u64, n_gates: usize, d_q: *const c_void,
+                                  q_stride: usize, d_a: *const c_void, a_stride: usize) -> c_int;
+    pub fn h2v_quotient_permutation_dev(dom: *mut H2vDomain, d_h: *mut c_void, y: *const u64, beta: *const u64, gamma: *const u64,
+                                        n_cols: usize, chunk_len: usize, d_cols: *const c_void, cols_stride: usize,
+                                        d_sigma: *const c_void, sigma_stride: usize, d_z: *const c_void, z_stride: usize,
+                                        d_l0: *const c_void, d_l_last: *const c_void, d_l_active: *const c_void,
+                                        blinding_factors: u32) -> c_int;
+    pub fn h2v_quotient_lookup_dev(dom: *mut H2vDomain, d_h: *mut c_void, y: *const u64, beta: *const u64, gamma: *const u64,
+                                   d_input: *const c_void, d_table: *const c_void, d_perm_input: *const c_void,
+                                   d_perm_table: *const c_void, d_z: *const c_void, d_l0: *const c_void, d_l_last: *const c_void,
+                                   d_l_active: *const c_void) -> c_int;
 }
 
 /// `halo2_proofs::arithmetic::eval_polynomial`
@@ -168,6 +179,12 @@ impl DeviceDomain {
         out
     }
     pub fn divide_by_vanishing_poly(&self, a: &mut [Fr]) { ok(unsafe { h2v_divide_by_vanishing_poly(self.0, a.as_mut_ptr() as *mut u64) }) }
+    /// `Evaluator::evaluate_h`, custom-gate loop for halo2-base's vertical gates, on device-resident extended columns
+    /// (`d_q`, `d_a`: `n_gates` columns `stride` elements apart, from `h2v_domain_transform_dev(COEFF_TO_EXTENDED)`)
+    pub fn quotient_gates(&self, d_h: *mut c_void, y: &Fr, n_gates: usize, d_q: *const c_void, d_a: *const c_void, stride: usize) {
+        ok(unsafe { h2v_quotient_gates_dev(self.0, d_h, y as *const Fr as *const u64, n_gates, d_q, stride, d_a, stride) })
+    }
+    pub fn raw(&self) -> *mut H2vDomain { self.0 }
 }
 impl Drop for DeviceDomain {
     fn drop(&mut self) { unsafe { h2v_domain_free(self.0) } }

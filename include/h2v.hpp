@@ -132,6 +132,24 @@ class EvaluationDomain {
     void divide_by_vanishing_poly(std::vector<Fr> &a) const { need(a.size(), extended_len()); check(h2v_divide_by_vanishing_poly(h_, u(a))); }
     h2v_domain_t handle() const { return h_; }
 
+    // evaluate_h's row loops on device-resident extended columns (plonk/evaluation.rs [UPSTREAM]); pointers are
+    // device pointers from h2v_dev_alloc, columns `stride` Fr elements apart; h <- h * y + term, in upstream's order
+    void quotient_gates(void *d_h, const Fr &y, size_t n_gates, const void *d_q, size_t q_stride, const void *d_a, size_t a_stride) const {
+        check(h2v_quotient_gates_dev(h_, d_h, y.l, n_gates, d_q, q_stride, d_a, a_stride));
+    }
+    void quotient_permutation(void *d_h, const Fr &y, const Fr &beta, const Fr &gamma, size_t n_cols, size_t chunk_len, const void *d_cols,
+                              size_t cols_stride, const void *d_sigma, size_t sigma_stride, const void *d_z, size_t z_stride,
+                              const void *d_l0, const void *d_l_last, const void *d_l_active, uint32_t blinding_factors) const {
+        check(h2v_quotient_permutation_dev(h_, d_h, y.l, beta.l, gamma.l, n_cols, chunk_len, d_cols, cols_stride, d_sigma, sigma_stride,
+                                           d_z, z_stride, d_l0, d_l_last, d_l_active, blinding_factors));
+    }
+    void quotient_lookup(void *d_h, const Fr &y, const Fr &beta, const Fr &gamma, const void *d_input, const void *d_table,
+                         const void *d_perm_input, const void *d_perm_table, const void *d_z, const void *d_l0, const void *d_l_last,
+                         const void *d_l_active) const {
+        check(h2v_quotient_lookup_dev(h_, d_h, y.l, beta.l, gamma.l, d_input, d_table, d_perm_input, d_perm_table, d_z, d_l0, d_l_last,
+                                      d_l_active));
+    }
+
   private:
     static uint64_t *u(std::vector<Fr> &v) { return reinterpret_cast<uint64_t *>(v.data()); }
     static void need(size_t got, size_t want) {
