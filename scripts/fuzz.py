@@ -39,7 +39,7 @@ BIG_SRS = {}
 it = 0
 while time.time() < t_end:
     it += 1
-    kind = rnd.choice(["commit", "commit", "multiexp", "ntt", "domain", "row2"] if not BIG else ["commit_big", "domain_big", "dev_big"])
+    kind = rnd.choice(["commit", "commit", "multiexp", "ntt", "domain", "row2", "quotient"] if not BIG else ["commit_big", "domain_big", "dev_big"])
     stats[kind] = stats.get(kind, 0) + 1
     tune = (rnd.choice([-1, -1, 1, 3, 5, 17, 64]), rnd.choice([-1, -1, 0, 1, 2, 4, 7]))
     h.set_tuning(*tune)
@@ -121,6 +121,39 @@ while time.time() < t_end:
             assert (d.extended_to_coeff(ext) == od.extended_to_coeff(ext)).all(), ("e2c", j, k)
             f = d.transform_batch(h.OP_DIVIDE_BY_VANISHING, [ext])[0]
             assert (f == od.extended_to_coeff(od.divide_by_vanishing_poly(ext))).all(), ("dvp", j, k)
+            d.close()
+        elif kind == "quotient":        # evaluate_h row loops, random shapes / strides / pathological values
+            k = rnd.randrange(1, 11); j = rnd.choice([3, 4, 4, 4, 5, 6, 9])
+            d, od = h.EvaluationDomain(j, k), O.EvaluationDomain(j, k)
+            ne = 1 << d.extended_k
+            ng = rnd.randrange(0, 6); nc = rnd.randrange(0, 8); chunk = max(1, j - 2)
+            bf = rnd.randrange(0, max(1, min(8, (1 << k) - 2)))
+            ns = (nc + chunk - 1) // chunk if nc else 0
+            stride = ne + rnd.choice([0, 0, 2, 32])
+            mk = lambda c: [scalars(ne, rnd.randrange(3)) for _ in range(c)]
+            q, a, sg, z, misc = mk(ng), mk(max(ng, nc)), mk(nc), mk(ns), mk(9)
+            yv = scalars(3, 0)
+            case = ("quotient", j, k, ng, nc, bf, stride)
+            def dev(arrs):
+                buf = h.DeviceBuffer(max(1, len(arrs)) * stride * 32)
+                for i, c in enumerate(arrs):
+                    buf.upload(c, offset=i * stride * 32)
+                return buf
+            dq, da, ds, dz, dm, dh = dev(q), dev(a), dev(sg), dev(z), dev(misc[1:]), dev(misc[:1])
+            m = lambda i: dm.ptr + (i - 1) * stride * 32
+            want = misc[0]
+            d.quotient_gates(dh.ptr, yv[0], ng, dq.ptr, stride, da.ptr, stride)
+            want = od.quotient_gates(want, yv[0], np.stack(q) if ng else [], np.stack(a[:ng]) if ng else [])
+            if nc:
+                d.quotient_permutation(dh.ptr, yv[0], yv[1], yv[2], nc, chunk, da.ptr, stride, ds.ptr, stride, dz.ptr, stride,
+                                       m(1), m(2), m(3), bf)
+                want = od.quotient_permutation(want, yv[0], yv[1], yv[2], chunk, np.stack(a[:nc]), np.stack(sg), np.stack(z),
+                                               misc[1], misc[2], misc[3], bf)
+            d.quotient_lookup(dh.ptr, yv[0], yv[1], yv[2], m(4), m(5), m(6), m(7), m(8), m(1), m(2), m(3))
+            want = od.quotient_lookup(want, yv[0], yv[1], yv[2], misc[4], misc[5], misc[6], misc[7], misc[8], misc[1], misc[2], misc[3])
+            assert (dh.download((ne, 4)) == want).all(), case
+            for b_ in (dq, da, ds, dz, dm, dh):
+                b_.free()
             d.close()
         else:
             n = rnd.choice([rnd.randrange(1, 40), rnd.randrange(1, 5000), rnd.randrange(1, 70000)])
