@@ -26,7 +26,7 @@ KERNEL_CLASSES = ["msm_digits", "msm_scan", "msm_scatter", "msm_accumulate", "ms
 # every symbol include/h2v.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "h2v_init", "h2v_device_count", "h2v_last_error", "h2v_version", "h2v_host_register", "h2v_host_unregister", "h2v_dev_alloc", "h2v_dev_free", "h2v_dev_upload", "h2v_dev_download",
-    "h2v_srs_load", "h2v_srs_setup", "h2v_srs_free", "h2v_srs_info", "h2v_commit", "h2v_commit_batch", "h2v_commit_batch_dev", "h2v_best_multiexp",
+    "h2v_srs_load", "h2v_srs_setup", "h2v_srs_free", "h2v_srs_info", "h2v_commit", "h2v_commit_batch", "h2v_commit_batch_dev", "h2v_best_multiexp", "h2v_g1_sum",
     "h2v_best_fft", "h2v_domain_new", "h2v_domain_free", "h2v_domain_k", "h2v_domain_extended_k", "h2v_domain_constant",
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
     "h2v_divide_by_vanishing_poly", "h2v_domain_transform_batch", "h2v_domain_transform_dev",
@@ -76,6 +76,7 @@ def lib():
         L.h2v_commit_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t, C.c_void_p]
         L.h2v_commit_batch_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
         L.h2v_best_multiexp.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.h2v_g1_sum.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_best_fft.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.h2v_domain_new.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
         L.h2v_domain_free.argtypes = [C.c_void_p]
@@ -225,6 +226,14 @@ def best_multiexp(coeffs, bases):
         raise ValueError("best_multiexp: assertion failed: coeffs.len() == bases.len()")
     out = np.zeros(12, dtype=np.uint64)
     _check(lib().h2v_best_multiexp(_ptr(coeffs), _ptr(bases), coeffs.shape[0], _ptr(out)))
+    return out
+
+
+def g1_sum(points):
+    """Sum of affine points -> affine (combines the per-GPU partial sums of a multiexp split by index range)."""
+    pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros(8, dtype=np.uint64)
+    _check(lib().h2v_g1_sum(_ptr(pts), pts.shape[0], _ptr(out)))
     return out
 
 

@@ -88,6 +88,14 @@ struct Timer {   // CUDA-event stopwatch on one stream, accumulating per kernel 
     cudaStream_t st;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
     explicit Timer(cudaStream_t s) : st(s) {}
+    Timer(const Timer &) = delete;
+    Timer &operator=(const Timer &) = delete;
+    ~Timer() {   // error paths return before collect(): do not leak the events
+        for (auto &s : spans) {
+            cudaEventDestroy(s.second.first);
+            cudaEventDestroy(s.second.second);
+        }
+    }
     void begin(int cls) {
         cudaEvent_t a, b;
         cudaEventCreate(&a);
@@ -1019,16 +1027,10 @@ int h2v_commit(h2v_srs_t s, int basis, const uint64_t *poly, size_t len, uint64_
     return h2v_commit_batch(s, basis, cols, 1, len, out_affine);
 }
 
-int h2v_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t out_jacobian[12]) {
-    if (!out_jacobian) return fail(H2V_EINVAL, "best_multiexp: NULL output");
-    if (n && (!coeffs || !bases)) return fail(H2V_EINVAL, "best_multiexp: NULL input");
-    if (n >= ((size_t)1 << 27)) return fail(H2V_EINVAL, "best_multiexp: n = %zu unsupported", n);
+// one MSM over caller-supplied bases (no handle, no tables): Jacobian and / or affine result
+static int multiexp_raw(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t *out_jacobian, uint64_t *out_affine) {
     int rc = use_device();
     if (rc) return rc;
-    if (n == 0) {
-        memset(out_jacobian, 0, 96);
-        return H2V_OK;
-    }
     static std::mutex mu;
     static MsmWorkspace ws;
     static DevBuf sc, pts, outb;
@@ -1037,15 +1039,43 @@ int h2v_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, u
     if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if ((rc = sc.ensure(n * sizeof(fe)))) return rc;
     if ((rc = pts.ensure(n * sizeof(affine)))) return rc;
-    if ((rc = outb.ensure(sizeof(jacobian)))) return rc;
+    if ((rc = outb.ensure(sizeof(jacobian) + sizeof(affine)))) return rc;
     CU(cudaMemcpyAsync(sc.p, coeffs, n * sizeof(fe), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(pts.p, bases, n * sizeof(affine), cudaMemcpyHostToDevice, st));
     MsmCfg cfg = choose_cfg(n, false);
-    rc = run_msm(st, ws, sc.as<fe>(), n, 1, n, pts.as<affine>(), cfg, n, nullptr, outb.as<jacobian>(), nullptr);
+    jacobian *dj = outb.as<jacobian>();
+    affine *da = reinterpret_cast<affine *>(dj + 1);
+    rc = run_msm(st, ws, sc.as<fe>(), n, 1, n, pts.as<affine>(), cfg, n, out_affine ? da : nullptr, out_jacobian ? dj : nullptr, nullptr);
     if (rc) { cudaStreamSynchronize(st); return rc; }
-    CU(cudaMemcpyAsync(out_jacobian, outb.p, sizeof(jacobian), cudaMemcpyDeviceToHost, st));
+    if (out_jacobian) CU(cudaMemcpyAsync(out_jacobian, dj, sizeof(jacobian), cudaMemcpyDeviceToHost, st));
+    if (out_affine) CU(cudaMemcpyAsync(out_affine, da, sizeof(affine), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return H2V_OK;
+}
+int h2v_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t out_jacobian[12]) {
+    if (!out_jacobian) return fail(H2V_EINVAL, "best_multiexp: NULL output");
+    if (n && (!coeffs || !bases)) return fail(H2V_EINVAL, "best_multiexp: NULL input");
+    if (n >= ((size_t)1 << 27)) return fail(H2V_EINVAL, "best_multiexp: n = %zu unsupported", n);
+    if (n == 0) {
+        int rc = use_device();
+        if (rc) return rc;
+        memset(out_jacobian, 0, 96);
+        return H2V_OK;
+    }
+    return multiexp_raw(coeffs, bases, n, out_jacobian, nullptr);
+}
+int h2v_g1_sum(const uint64_t *affine_pts, size_t n, uint64_t out_affine[8]) {
+    if (!out_affine) return fail(H2V_EINVAL, "g1_sum: NULL output");
+    if (n && !affine_pts) return fail(H2V_EINVAL, "g1_sum: NULL input");
+    if (n >= ((size_t)1 << 27)) return fail(H2V_EINVAL, "g1_sum: n = %zu unsupported", n);
+    if (n == 0) {
+        int rc = use_device();
+        if (rc) return rc;
+        memset(out_affine, 0, 64);
+        return H2V_OK;
+    }
+    std::vector<fe> ones(n, fe_one<Fr>());
+    return multiexp_raw(reinterpret_cast<const uint64_t *>(ones.data()), affine_pts, n, nullptr, out_affine);
 }
 
 // ---------------------------------------------------------------- FFT / domain

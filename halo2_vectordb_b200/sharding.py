@@ -42,3 +42,40 @@ def gather_in_column_order(local, n_cols, rank, world, width=8, device=None):
         idx = column_shard(n_cols, r, world)
         res[idx] = out[r][: len(idx)].cpu().numpy().view(np.uint64)
     return res
+
+
+# ---- one standalone multiexp split over the GPUs by index range (SURVEY.md 8(e), config 5) -----------------------
+def index_slice(n, rank, world):
+    """[lo, hi) of the scalar / base index range rank `rank` owns: contiguous, near-equal slices."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    per = -(-n // world) if n else 0
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def gather_partials(partial_affine, rank, world, device=None):
+    """The one exchange step of a sliced multiexp: all-gather of the `world` affine partial sums (64 B each).
+    Returns a (world, 8) uint64 array, identical on every rank."""
+    partial_affine = np.ascontiguousarray(partial_affine, dtype=np.uint64).reshape(8)
+    if world == 1:
+        return partial_affine.reshape(1, 8).copy()
+    import torch
+    import torch.distributed as dist
+
+    mine = torch.from_numpy(partial_affine.view(np.int64).copy())
+    if device is not None:
+        mine = mine.to(device)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    return np.stack([o.cpu().numpy().view(np.uint64) for o in out])
+
+
+def sliced_multiexp(local_msm, combine, n, rank, world, device=None):
+    """sum_i s_i B_i with the index range split over `world` ranks.  `local_msm(lo, hi)` returns this rank's affine
+    partial sum over [lo, hi) (on a GPU: ParamsKZG.commit on a handle holding bases[lo:hi], or best_multiexp);
+    `combine(partials)` adds the gathered partial sums (on a GPU: halo2_vectordb_b200.g1_sum).  Every rank returns
+    the same affine point."""
+    lo, hi = index_slice(n, rank, world)
+    part = local_msm(lo, hi)
+    return combine(gather_partials(part, rank, world, device))

@@ -84,6 +84,10 @@ int h2v_commit_batch_dev(h2v_srs_t srs, int basis, const void *d_polys, size_t c
 /* halo2-axiom arithmetic.rs best_multiexp(coeffs, bases) -> C::Curve, exact shape: arbitrary bases,
  * no handle, Jacobian result (any representative; compare after to_affine). */
 int h2v_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t out_jacobian[12]);
+/* sum of n affine points, affine result: the fold of the per-thread partial sums at the end of best_multiexp
+ * (arithmetic.rs: `results.iter().fold(C::Curve::identity(), |a, b| a + b)`), used here to combine the per-GPU
+ * partial sums of ONE multiexp whose index range was split across GPUs. */
+int h2v_g1_sum(const uint64_t *affine_pts, size_t n, uint64_t out_affine[8]);
 
 /* ---- EvaluationDomain --------------------------------------------------------------------- */
 /* arithmetic.rs best_fft(a, omega, log_n): in place, natural order in and out. */

@@ -634,3 +634,44 @@ def test_plain_c_example(h2v, tmp_path):
                            "-L" + libdir, "-lh2v", "-Wl,-rpath," + libdir, "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "== commit(coeffs)" in out.stdout, out.stdout + out.stderr
+
+
+# ---- one multiexp split over GPUs by index range: slices + g1_sum --------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 8, 100, 1000])
+def test_g1_sum_vs_oracle(h2v, n):
+    rng = random.Random(n)
+    pts = O.gen_bases(max(n, 1), a=rng.randrange(1, 1 << 30), b=rng.randrange(1, 1 << 30))[:n]
+    if n >= 3:      # identity, a duplicate and an opposite pair
+        pts[0] = 0
+        pts[1] = pts[2]
+        xy = O.g1_affine_to_ints(pts[n - 1])
+        pts[n - 2] = O.g1_affine_from_ints((xy[0], (-xy[1]) % P.P))
+    acc = np.zeros(12, dtype=np.uint64)
+    for p in pts:
+        acc = O.g1_add_mixed(acc, p)
+    assert np.array_equal(h2v.g1_sum(pts), O.g1_to_affine(acc))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,world", [(4, 2), (10, 2), (12, 4), (14, 8), (12, 3)])
+def test_sliced_multiexp_equals_whole(h2v, k, world):
+    """every 'rank' holds only its slice of the bases; the partial sums add up to the unsliced commitment"""
+    from halo2_vectordb_b200 import sharding
+    n = 1 << k
+    bases = h2v.synthetic_bases(n)
+    s = O.fr_fill(n, 900 + k, mode=k & 1)
+    parts = []
+    for r in range(world):
+        lo, hi = sharding.index_slice(n, r, world)
+        if world & (world - 1):         # uneven slices: the handle-free entry point
+            parts.append(O.g1_to_affine(h2v.best_multiexp(s[lo:hi], bases[lo:hi])))
+        else:                           # power-of-two slices: a handle over the slice's bases
+            srs = h2v.ParamsKZG(k - (world.bit_length() - 1), None, bases[lo:hi])
+            parts.append(srs.commit_lagrange(s[lo:hi]))
+            srs.close()
+    got = h2v.g1_sum(np.stack(parts))
+    whole = h2v.ParamsKZG(k, None, bases)
+    assert np.array_equal(got, whole.commit_lagrange(s))
+    assert np.array_equal(got, O.msm_closed_form(s))
+    whole.close()
