@@ -389,7 +389,7 @@ def prove_shaped_resident(h, torch, dev, srs):
     quotient (3n coefficients) come back.  Selector / sigma / z columns reuse the extended buffers (timing only)."""
     import numpy as np
     k, n_msm, n_intt, n_cntt, _ = PROVE_SHAPES["kmeans_k16"]
-    bc = 32
+    bc = int(os.environ.get("H2V_BENCH_BC", "96"))
     g = torch.Generator(device="cpu").manual_seed(6)
     hin = torch.randint(-(1 << 63), (1 << 63) - 1, (bc, N, 4), dtype=torch.int64, generator=g)
     hin[..., 3] &= (1 << 60) - 1
@@ -397,8 +397,8 @@ def prove_shaped_resident(h, torch, dev, srs):
     hq = torch.empty((3 * N, 4), dtype=torch.int64).pin_memory()
     dom = h.EvaluationDomain(4, k)
     ne = 4 * N
-    d_in = torch.empty((bc, N, 4), dtype=torch.int64, device=dev)
-    d_coef = torch.empty_like(d_in)
+    d_in2 = torch.empty((2, bc, N, 4), dtype=torch.int64, device=dev)     # double-buffered uploads
+    d_coef = torch.empty((bc, N, 4), dtype=torch.int64, device=dev)
     d_ext = torch.empty((bc, ne, 4), dtype=torch.int64, device=dev)
     d_h = torch.zeros((ne, 4), dtype=torch.int64, device=dev)
     d_hq = torch.empty((ne, 4), dtype=torch.int64, device=dev)
@@ -406,12 +406,20 @@ def prove_shaped_resident(h, torch, dev, srs):
     hout = torch.empty((bc, 8), dtype=torch.int64).pin_memory()
     y = hin[0, :3].numpy().view(np.uint64)
     L = h.lib()
+    import threading
+
+    def upload(slot, c):
+        h._check(L.h2v_dev_upload(d_in2[slot].data_ptr(), hin.data_ptr(), c * N * 32))
 
     def run():
-        left = n_msm
-        while left > 0:
-            c = min(bc, left)
-            h._check(L.h2v_dev_upload(d_in.data_ptr(), hin.data_ptr(), c * N * 32))
+        batches = [min(bc, n_msm - i) for i in range(0, n_msm, bc)]
+        upload(0, batches[0])
+        for i, c in enumerate(batches):
+            nxt = None
+            if i + 1 < len(batches):        # the next batch crosses PCIe while this one is being processed
+                nxt = threading.Thread(target=upload, args=((i + 1) & 1, batches[i + 1]))
+                nxt.start()
+            d_in = d_in2[i & 1]
             srs.commit_batch_dev(d_in.data_ptr(), N, c, N, d_out.data_ptr())
             h._check(L.h2v_dev_download(hout.data_ptr(), d_out.data_ptr(), c * 64))
             dom.transform_dev(h.OP_LAGRANGE_TO_COEFF, d_in.data_ptr(), N, d_coef.data_ptr(), N, c)
@@ -419,7 +427,8 @@ def prove_shaped_resident(h, torch, dev, srs):
             dom.quotient_gates(d_h.data_ptr(), y[0], c, d_ext.data_ptr(), ne, d_ext.data_ptr(), ne)
             dom.quotient_permutation(d_h.data_ptr(), y[0], y[1], y[2], c, 2, d_ext.data_ptr(), ne, d_ext.data_ptr(), ne,
                                      d_ext.data_ptr(), ne, d_ext[0].data_ptr(), d_ext[1].data_ptr(), d_ext[2].data_ptr(), 5)
-            left -= c
+            if nxt is not None:
+                nxt.join()
         dom.transform_dev(h.OP_DIVIDE_BY_VANISHING, d_h.data_ptr(), ne, d_hq.data_ptr(), ne, 1)
         h._check(L.h2v_dev_download(hq.data_ptr(), d_hq.data_ptr(), 3 * N * 32))
 
