@@ -511,8 +511,32 @@ def bench_row2(h, torch, dev, d_cols, cols):
     for _ in range(4):
         O.fr_eval_poly(col0, x0)
     cpu = 4 * N / (time.perf_counter() - t0)
+    # permute_expression_pair (lookup argument, create_proof step 5): 2^16 - 6 usable rows of a LOOKUP_BITS = 15 range lookup
+    u, bits = N - 6, 15
+    g = torch.Generator(device=dev).manual_seed(17)
+    vals = torch.zeros((u, 4), dtype=torch.int64, device=dev)
+    vals[:, 0] = torch.randint(0, 1 << bits, (u,), dtype=torch.int64, generator=g, device=dev)
+    tab = torch.zeros((u, 4), dtype=torch.int64, device=dev)
+    tab[: 1 << bits, 0] = torch.arange(1 << bits, dtype=torch.int64, device=dev)
+    # inputs must be Montgomery: convert the small canonical values through the oracle once (setup, untimed)
+    m_in = torch.from_numpy(O.to_mont(vals.cpu().numpy().view(np.uint64)).view(np.int64)).to(dev)
+    m_tab = torch.from_numpy(O.to_mont(tab.cpu().numpy().view(np.uint64)).view(np.int64)).to(dev)
+    o_a, o_s = torch.empty_like(m_in), torch.empty_like(m_in)
+    pm = []
+    for i in range(6):
+        h.permute_expression_pair_dev(m_in.data_ptr(), m_tab.data_ptr(), u, o_a.data_ptr(), o_s.data_ptr())
+        if i >= 2:
+            pm.append(h.last_kernel_ms()["ntt"])
+    t_p = statistics.median(pm) * 1e-3
+    hi, ht = m_in.cpu().numpy().view(np.uint64), m_tab.cpu().numpy().view(np.uint64)
+    t0 = time.perf_counter()
+    ea, es = O.permute_expression_pair(hi, ht)
+    cpu_p = time.perf_counter() - t0
+    assert (ea == o_a.cpu().numpy().view(np.uint64)).all() and (es == o_s.cpu().numpy().view(np.uint64)).all()
     return {"eval_polynomial_gcoeff_per_s": cols * 3 * N / t / 1e9, "ms": t * 1e3, "polys": cols, "points": 3,
-            "cpu_port_gcoeff_per_s": cpu / 1e9, "cpu_cores": 1}
+            "cpu_port_gcoeff_per_s": cpu / 1e9, "cpu_cores": 1,
+            "permute_expression_pair": {"rows": u, "ms": t_p * 1e3, "mrows_per_s": u / t_p / 1e6, "cpu_port_ms": cpu_p * 1e3,
+                                        "note": "LOOKUP_BITS = 15 range lookup, device-resident; CPU port = oracle qsort, one core"}}
 
 
 def bench_row1(h, torch, dev):

@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
     "h2v_divide_by_vanishing_poly", "h2v_domain_transform_batch", "h2v_domain_transform_dev",
     "h2v_eval_polynomial_batch", "h2v_eval_polynomial_dev", "h2v_batch_invert", "h2v_grand_product", "h2v_kate_division",
+    "h2v_permute_expression_pair", "h2v_permute_expression_pair_dev",
     "h2v_quotient_gates_dev", "h2v_quotient_permutation_dev", "h2v_quotient_lookup_dev",
     "h2v_g1_to_bytes", "h2v_fr_to_repr",
     "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_op_rate", "h2v_set_tuning", "h2v_launch_count", "h2v_last_kernel_ms",
@@ -93,6 +94,8 @@ def lib():
         L.h2v_batch_invert.argtypes = [C.c_void_p, C.c_size_t]
         L.h2v_grand_product.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_kate_division.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.h2v_permute_expression_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.h2v_permute_expression_pair_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.h2v_quotient_gates_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.h2v_quotient_permutation_dev.argtypes = ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
                                                    + [C.c_void_p, C.c_size_t] * 3 + [C.c_void_p] * 3 + [C.c_uint32])
@@ -290,6 +293,20 @@ def kate_division(a, b):
     b = np.ascontiguousarray(b, dtype=np.uint64).reshape(4)
     _check(lib().h2v_kate_division(_ptr(a), a.shape[0], _ptr(b), _ptr(out)))
     return out
+
+
+def permute_expression_pair(inp, table):
+    """plonk/lookup/prover.rs permute_expression_pair on the usable rows -> (permuted_input, permuted_table)."""
+    inp, table = _fr(inp), _fr(table)
+    if inp.shape != table.shape:
+        raise ValueError("input and table must have the same number of usable rows")
+    a, s = np.zeros_like(inp), np.zeros_like(inp)
+    _check(lib().h2v_permute_expression_pair(_ptr(inp), _ptr(table), inp.shape[0], _ptr(a), _ptr(s)))
+    return a, s
+
+
+def permute_expression_pair_dev(d_input, d_table, usable_rows, d_permuted_input, d_permuted_table):
+    _check(lib().h2v_permute_expression_pair_dev(d_input, d_table, usable_rows, d_permuted_input, d_permuted_table))
 
 
 def g1_to_bytes(points):

@@ -22,6 +22,7 @@
 #include "ntt.cuh"
 #include "poly.cuh"
 #include "quotient.cuh"
+#include "lookup.cuh"
 
 using namespace h2v;
 
@@ -1521,6 +1522,113 @@ int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t
         LAUNCHED();
     }
     CU(cudaMemcpyAsync(out, g_poly.b.p, (n - 1) * sizeof(fe), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return H2V_OK;
+}
+}  // extern "C"
+
+// ================================================================== lookup argument: permuted columns
+namespace {
+// A', S' of `u` usable rows from device-resident input / table expressions (Montgomery); g_poly.mu held by the caller
+int run_permute_pair(cudaStream_t st, const fe *d_in_a, const fe *d_in_t, uint32_t u, fe *d_out_a, fe *d_out_s) {
+    int rc;
+    uint32_t n_pad = 1;
+    while (n_pad < u) n_pad <<= 1;
+    const uint32_t ntiles = (u + H2V_SCAN_TILE - 1) / H2V_SCAN_TILE;
+    if ((rc = g_poly.a.ensure((size_t)n_pad * sizeof(fe))) || (rc = g_poly.b.ensure((size_t)n_pad * sizeof(fe))) ||
+        (rc = g_poly.tree.ensure(((size_t)6 * u + 2 * ntiles + 8) * sizeof(uint32_t))))
+        return rc;
+    fe *As = g_poly.a.as<fe>(), *Ts = g_poly.b.as<fe>();
+    uint32_t *rep = g_poly.tree.as<uint32_t>(), *free_ = rep + u, *rep_offs = free_ + u, *free_offs = rep_offs + u;
+    uint32_t *scratch = free_offs + u, *rep_rows = scratch + u, *tiles = rep_rows + u, *totals = tiles + 2 * ntiles;
+    int *err = reinterpret_cast<int *>(totals + 2);
+    const unsigned gp = (n_pad + 255) / 256, gu = (u + 255) / 256;
+    CU(cudaMemsetAsync(err, 0, sizeof(int), st));
+    for (int which = 0; which < 2; ++which) {
+        fe *keys = which ? Ts : As;
+        lookup_canon_pad_kernel<<<gp, 256, 0, st>>>(which ? d_in_t : d_in_a, keys, u, n_pad);
+        LAUNCHED();
+        const uint32_t tile = std::min<uint32_t>(H2V_SORT_TILE, n_pad);
+        const unsigned tiles_n = n_pad / tile;
+        const size_t smem = (size_t)tile * sizeof(fe);
+        bitonic_tile_kernel<<<tiles_n, H2V_SORT_TILE / 2, smem, st>>>(keys, n_pad, 0, 1);
+        LAUNCHED();
+        for (uint32_t k = 2 * tile; k <= n_pad && k; k <<= 1) {
+            for (uint32_t j = k >> 1; j >= tile; j >>= 1) {
+                bitonic_global_kernel<<<(n_pad / 2 + 255) / 256, 256, 0, st>>>(keys, n_pad, k, j);
+                LAUNCHED();
+            }
+            bitonic_tile_kernel<<<tiles_n, H2V_SORT_TILE / 2, smem, st>>>(keys, n_pad, k, 0);
+            LAUNCHED();
+        }
+    }
+    lookup_fill_kernel<<<gu, 256, 0, st>>>(free_, 1u, u);
+    LAUNCHED();
+    lookup_flags_kernel<<<gu, 256, 0, st>>>(As, Ts, u, rep, free_, err);
+    LAUNCHED();
+    for (int which = 0; which < 2; ++which) {
+        const uint32_t *cnt = which ? free_ : rep;
+        uint32_t *offs = which ? free_offs : rep_offs, *tl = tiles + which * ntiles;
+        msm_scan_tiles_kernel<<<ntiles, 256, 0, st>>>(cnt, tl, u);
+        LAUNCHED();
+        msm_scan_top_kernel<<<1, 256, 0, st>>>(tl, ntiles, totals + which);
+        LAUNCHED();
+        msm_scan_apply_kernel<<<ntiles, 256, 0, st>>>(cnt, tl, offs, scratch, u);
+        LAUNCHED();
+    }
+    lookup_emit_input_kernel<<<gu, 256, 0, st>>>(As, u, rep, rep_offs, rep_rows, d_out_a, d_out_s);
+    LAUNCHED();
+    lookup_emit_table_kernel<<<gu, 256, 0, st>>>(Ts, u, free_, free_offs, totals, rep_rows, d_out_s, err);
+    LAUNCHED();
+    int herr = 0;
+    CU(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (herr == 1) return fail(H2V_EINVAL, "permute_expression_pair: an input value is not in the table (ConstraintSystemFailure)");
+    if (herr) return fail(H2V_ECUDA, "permute_expression_pair: leftover count mismatch");
+    return H2V_OK;
+}
+}  // namespace
+
+extern "C" {
+int h2v_permute_expression_pair_dev(const void *d_input, const void *d_table, size_t usable_rows, void *d_permuted_input,
+                                    void *d_permuted_table) {
+    if (!usable_rows) return H2V_OK;
+    if (!d_input || !d_table || !d_permuted_input || !d_permuted_table) return fail(H2V_EINVAL, "permute_expression_pair: NULL buffer");
+    if (usable_rows > ((size_t)1 << 28)) return fail(H2V_EINVAL, "permute_expression_pair: too many rows");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_poly.mu);
+    if ((rc = poly_ctx_ready())) return rc;
+    Timer tm(g_poly.st);
+    tm.begin(7);
+    rc = run_permute_pair(g_poly.st, (const fe *)d_input, (const fe *)d_table, (uint32_t)usable_rows, (fe *)d_permuted_input,
+                          (fe *)d_permuted_table);
+    tm.end();
+    cudaStreamSynchronize(g_poly.st);
+    tm.collect(true);
+    return rc;
+}
+int h2v_permute_expression_pair(const uint64_t *input, const uint64_t *table, size_t usable_rows, uint64_t *permuted_input,
+                                uint64_t *permuted_table) {
+    if (!usable_rows) return H2V_OK;
+    if (!input || !table || !permuted_input || !permuted_table) return fail(H2V_EINVAL, "permute_expression_pair: NULL buffer");
+    if (usable_rows > ((size_t)1 << 28)) return fail(H2V_EINVAL, "permute_expression_pair: too many rows");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_poly.mu);
+    if ((rc = poly_ctx_ready())) return rc;
+    cudaStream_t st = g_poly.st;
+    const size_t bytes = usable_rows * sizeof(fe);
+    if ((rc = g_poly.c.ensure(bytes)) || (rc = g_poly.d.ensure(bytes))) return rc;
+    CU(cudaMemcpyAsync(g_poly.c.p, input, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(g_poly.d.p, table, bytes, cudaMemcpyHostToDevice, st));
+    // the canonical copies are taken first, so the staging buffers double as the outputs
+    if ((rc = run_permute_pair(st, g_poly.c.as<fe>(), g_poly.d.as<fe>(), (uint32_t)usable_rows, g_poly.c.as<fe>(), g_poly.d.as<fe>()))) {
+        cudaStreamSynchronize(st);
+        return rc;
+    }
+    CU(cudaMemcpyAsync(permuted_input, g_poly.c.p, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(permuted_table, g_poly.d.p, bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return H2V_OK;
 }

@@ -133,6 +133,17 @@ int h2v_grand_product(const uint64_t *num, const uint64_t *den, size_t n, uint64
 /* arithmetic.rs kate_division(a, b): quotient of a(X) (n coefficients) by (X - b), n - 1 coefficients */
 int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t *out);
 
+/* halo2-axiom plonk/lookup/prover.rs permute_expression_pair [UPSTREAM] (create_proof step 5): from the first
+ * `usable_rows` values of the compressed input and table expressions, permuted_input = the input sorted ascending
+ * (canonical integers) and permuted_table = the table rearranged so that permuted_table[i] == permuted_input[i] on every
+ * row where permuted_input changes, the leftover table values filling the repeated rows (ascending values onto the
+ * repeated rows taken from the last one backwards, as upstream's `pop()` does).  H2V_EINVAL when an input value is
+ * not in the table (upstream: Error::ConstraintSystemFailure).  The caller appends the blinding rows. */
+int h2v_permute_expression_pair(const uint64_t *input, const uint64_t *table, size_t usable_rows, uint64_t *permuted_input,
+                                uint64_t *permuted_table);
+int h2v_permute_expression_pair_dev(const void *d_input, const void *d_table, size_t usable_rows, void *d_permuted_input,
+                                    void *d_permuted_table);
+
 /* ---- quotient evaluation on the extended coset ("next": SURVEY.md 8(f) row 1) ------------------------------
  * The per-row loops of halo2-axiom plonk/evaluation.rs Evaluator::evaluate_h [UPSTREAM; reached from
  * src/scaffold/mod.rs:296] for the constraint system halo2-base builds.  Every polynomial is a device-resident

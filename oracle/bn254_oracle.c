@@ -1024,3 +1024,56 @@ void orc_quotient_lookup(const orc_domain *d, u64 *h_, const u64 y_[4], const u6
         fold(&h[idx], y, &t);
     }
 }
+
+/* ---- lookup argument: permuted input / table columns ----------------------------------------------------------------
+ * Restates halo2-axiom plonk/lookup/prover.rs permute_expression_pair [UPSTREAM, absent from /root/reference; create_proof
+ * step 5, reached from src/scaffold/mod.rs:296], as recalled from the zcash/PSE lineage: sort the usable input rows (Ord on
+ * Fr = canonical value); count the table values in an ordered map; walking the sorted input, a row that starts a new value
+ * takes that value and removes one copy from the map (missing -> ConstraintSystemFailure), every other row is remembered as
+ * "repeated"; finally the map's leftovers, in ascending key order, are written to the repeated rows popped from the END of
+ * the list.  Returns 0, or -1 when an input value is not in the table.  PARITY UNPINNED (the pop order is the recalled one). */
+static int canon_cmp(const void *a, const void *b) {
+    const u64 *x = a, *y = b;
+    for (int i = 3; i >= 0; --i)
+        if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
+    return 0;
+}
+int orc_permute_expression_pair(const u64 *input, const u64 *table, size_t usable_rows, u64 *perm_input, u64 *perm_table) {
+    const size_t u = usable_rows;
+    if (!u) return 0;
+    u64 *a = malloc(u * 32), *t = malloc(u * 32);
+    size_t *repeated = malloc(u * sizeof(size_t));
+    unsigned char *taken = calloc(u, 1);
+    for (size_t i = 0; i < u; ++i) {
+        f_from_mont(&FR, a + 4 * i, (const fe *)(input + 4 * i));
+        f_from_mont(&FR, t + 4 * i, (const fe *)(table + 4 * i));
+    }
+    qsort(a, u, 32, canon_cmp);
+    qsort(t, u, 32, canon_cmp);      /* the ordered map: sorted table values, `taken` marks removed copies */
+    size_t n_rep = 0, tp = 0;
+    int rc = 0;
+    u64 *pa = malloc(u * 32), *ps = malloc(u * 32);
+    memcpy(pa, a, u * 32);
+    for (size_t row = 0; row < u && rc == 0; ++row) {
+        if (row == 0 || canon_cmp(a + 4 * row, a + 4 * (row - 1)) != 0) {
+            memcpy(ps + 4 * row, a + 4 * row, 32);
+            while (tp < u && canon_cmp(t + 4 * tp, a + 4 * row) < 0) ++tp;      /* both sequences ascend */
+            if (tp < u && canon_cmp(t + 4 * tp, a + 4 * row) == 0) taken[tp++] = 1;
+            else rc = -1;
+        } else {
+            repeated[n_rep++] = row;
+        }
+    }
+    if (rc == 0) {
+        for (size_t p = 0; p < u; ++p) {
+            if (taken[p]) continue;
+            memcpy(ps + 4 * repeated[--n_rep], t + 4 * p, 32);      /* repeated_input_rows.pop() */
+        }
+        for (size_t i = 0; i < u; ++i) {
+            f_to_mont(&FR, (fe *)(perm_input + 4 * i), pa + 4 * i);
+            f_to_mont(&FR, (fe *)(perm_table + 4 * i), ps + 4 * i);
+        }
+    }
+    free(a); free(t); free(repeated); free(taken); free(pa); free(ps);
+    return rc;
+}

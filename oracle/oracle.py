@@ -78,6 +78,7 @@ _q_perm = _sig("orc_quotient_permutation", C.c_void_p, _u64p, _u64p, _u64p, _u64
                _u64p, C.c_size_t, _u64p, C.c_size_t, _u64p, _u64p, _u64p, C.c_uint32)
 _q_lookup = _sig("orc_quotient_lookup", C.c_void_p, *([_u64p] * 12))
 _fr_delta = _sig("orc_fr_delta", _u64p)
+_permute_pair = _sig("orc_permute_expression_pair", _u64p, _u64p, C.c_size_t, _u64p, _u64p, res=C.c_int)
 for _n in ("fr_mul", "fr_add", "fr_sub", "fq_mul", "fq_add", "fq_sub"):
     _sig("orc_" + _n, _u64p, _u64p, _u64p)
 for _n in ("fr_inv", "fq_inv"):
@@ -385,3 +386,16 @@ def fr_delta():
     o = np.empty(4, dtype=np.uint64)
     _fr_delta(_p(o))
     return o
+
+
+def permute_expression_pair(inp, table):
+    """plonk/lookup/prover.rs permute_expression_pair on the usable rows -> (permuted_input, permuted_table);
+    ValueError when an input value is missing from the table (upstream: Error::ConstraintSystemFailure)."""
+    inp = np.ascontiguousarray(inp, dtype=np.uint64).reshape(-1, 4)
+    table = np.ascontiguousarray(table, dtype=np.uint64).reshape(-1, 4)
+    if inp.shape != table.shape:
+        raise ValueError("input and table must have the same number of usable rows")
+    a, s_ = np.zeros_like(inp), np.zeros_like(inp)
+    if len(inp) and _permute_pair(_p(inp), _p(table), len(inp), _p(a), _p(s_)) != 0:
+        raise ValueError("input value not in table")
+    return a, s_
