@@ -65,6 +65,9 @@ extern "C" {
                                 len: usize, d_out_affine: *mut c_void) -> c_int;
     pub fn h2v_domain_transform_dev(dom: *mut H2vDomain, op: c_int, d_in: *const c_void, in_stride: usize,
                                     d_out: *mut c_void, out_stride: usize, n_cols: usize) -> c_int;
+    pub fn h2v_permute_expression_pair(input: *const u64, table: *const u64, usable_rows: usize, permuted_input: *mut u64,
+                                       permuted_table: *mut u64) -> c_int;
+    pub fn h2v_g1_sum(affine_pts: *const u64, n: usize, out_affine: *mut u64) -> c_int;
     pub fn h2v_quotient_gates_dev(dom: *mut H2vDomain, d_h: *mut c_void, y: *const u64, n_gates: usize, d_q: *const c_void,
                                   q_stride: usize, d_a: *const c_void, a_stride: usize) -> c_int;
     pub fn h2v_quotient_permutation_dev(dom: *mut H2vDomain, d_h: *mut c_void, y: *const u64, beta: *const u64, gamma: *const u64,
@@ -76,6 +79,17 @@ extern "C" {
                                    d_input: *const c_void, d_table: *const c_void, d_perm_input: *const c_void,
                                    d_perm_table: *const c_void, d_z: *const c_void, d_l0: *const c_void, d_l_last: *const c_void,
                                    d_l_active: *const c_void) -> c_int;
+}
+
+/// `plonk::lookup::prover::permute_expression_pair` on the usable rows; `Err(())` = `Error::ConstraintSystemFailure`
+pub fn permute_expression_pair(input: &[Fr], table: &[Fr]) -> Result<(Vec<Fr>, Vec<Fr>), ()> {
+    assert_eq!(input.len(), table.len());
+    let (mut a, mut s) = (vec![Fr::zero(); input.len()], vec![Fr::zero(); input.len()]);
+    let rc = unsafe {
+        h2v_permute_expression_pair(input.as_ptr() as *const u64, table.as_ptr() as *const u64, input.len(),
+                                    a.as_mut_ptr() as *mut u64, s.as_mut_ptr() as *mut u64)
+    };
+    match rc { 0 => Ok((a, s)), -1 => Err(()), _ => { ok(rc); unreachable!() } }
 }
 
 /// `halo2_proofs::arithmetic::eval_polynomial`

@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "h2v.h"
@@ -158,5 +159,15 @@ class EvaluationDomain {
     uint32_t j_, k_;
     h2v_domain_t h_ = nullptr;
 };
+
+// plonk/lookup/prover.rs permute_expression_pair [UPSTREAM]: (permuted_input, permuted_table) of the usable rows;
+// throws std::invalid_argument when an input value is missing from the table (upstream: ConstraintSystemFailure)
+inline std::pair<std::vector<Fr>, std::vector<Fr>> permute_expression_pair(const std::vector<Fr> &input, const std::vector<Fr> &table) {
+    if (input.size() != table.size()) throw std::invalid_argument("input and table must have the same number of usable rows");
+    std::vector<Fr> a(input.size()), s(input.size());
+    check(h2v_permute_expression_pair(reinterpret_cast<const uint64_t *>(input.data()), reinterpret_cast<const uint64_t *>(table.data()),
+                                      input.size(), reinterpret_cast<uint64_t *>(a.data()), reinterpret_cast<uint64_t *>(s.data())));
+    return {std::move(a), std::move(s)};
+}
 
 }  // namespace h2v_host

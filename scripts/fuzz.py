@@ -39,7 +39,7 @@ BIG_SRS = {}
 it = 0
 while time.time() < t_end:
     it += 1
-    kind = rnd.choice(["commit", "commit", "multiexp", "ntt", "domain", "row2", "quotient"] if not BIG else ["commit_big", "domain_big", "dev_big"])
+    kind = rnd.choice(["commit", "commit", "multiexp", "ntt", "domain", "row2", "quotient", "permute"] if not BIG else ["commit_big", "domain_big", "dev_big"])
     stats[kind] = stats.get(kind, 0) + 1
     tune = (rnd.choice([-1, -1, 1, 3, 5, 17, 64]), rnd.choice([-1, -1, 0, 1, 2, 4, 7]))
     h.set_tuning(*tune)
@@ -122,6 +122,26 @@ while time.time() < t_end:
             f = d.transform_batch(h.OP_DIVIDE_BY_VANISHING, [ext])[0]
             assert (f == od.extended_to_coeff(od.divide_by_vanishing_poly(ext))).all(), ("dvp", j, k)
             d.close()
+        elif kind == "permute":         # lookup argument A', S': random sizes, heavy repetition, full-width values
+            u = rnd.choice([rnd.randrange(1, 40), rnd.randrange(1, 3000), rnd.randrange(1, 40000)])
+            pool = [rnd.choice([0, 1, P.R - 1, rnd.randrange(P.R), rnd.randrange(1 << 16)]) for _ in range(rnd.randrange(1, max(2, u)))]
+            inp = [rnd.choice(pool) for _ in range(u)]
+            distinct = list(set(inp))
+            table = distinct + [rnd.choice(pool + [rnd.randrange(P.R)]) for _ in range(u - len(distinct))]
+            rnd.shuffle(table)
+            bad = rnd.random() < 0.1 and u > 1
+            if bad:
+                table = [v for v in table if v != inp[0]] ; table += [(inp[0] + 1) % P.R] * (u - len(table))
+                bad = inp[0] not in table
+            fi, ft = O.fr_from_ints(inp), O.fr_from_ints(table)
+            case = ("permute", u, bad)
+            try:
+                ga, gs = h.permute_expression_pair(fi, ft)
+                assert not bad, case
+                oa, os_ = O.permute_expression_pair(fi, ft)
+                assert (ga == oa).all() and (gs == os_).all(), case
+            except ValueError:
+                assert bad, case
         elif kind == "quotient":        # evaluate_h row loops, random shapes / strides / pathological values
             k = rnd.randrange(1, 11); j = rnd.choice([3, 4, 4, 4, 5, 6, 9])
             d, od = h.EvaluationDomain(j, k), O.EvaluationDomain(j, k)
