@@ -199,3 +199,41 @@ def test_gpu_quotient_rejects_bad_arguments(h2v):
     with pytest.raises(ValueError):
         dom.quotient_lookup(buf.ptr, y, y, y, buf.ptr, buf.ptr, None, buf.ptr, buf.ptr, buf.ptr, buf.ptr, buf.ptr)
     dom.quotient_gates(buf.ptr, y, 0, None, 0, None, 0)                          # no gates: no-op, like upstream's empty loop
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,gate_cols", [(5, 2), (7, 3)])
+def test_gpu_lookup_and_products_feed_the_quotient(h2v, k, gate_cols):
+    """A', S' from h2v.permute_expression_pair and every grand product from h2v.grand_product replace the model's own
+    (the arrangement of S' differs from the model's, both are valid): the quotient built from them by the device
+    kernels must still satisfy the verifier's identity."""
+    from plonk_model import DELTA
+    circ = ToyCircuit(k, seed=300 + k, n_gate_cols=gate_cols)
+    u, n, w = circ.u, circ.n, circ.dom.omega
+    beta, gamma = circ.beta, circ.gamma
+    ga, gs = h2v.permute_expression_pair(fr_arr(circ.l_input[:u]), fr_arr(circ.l_table[:u]))
+    oa, os_ = O.permute_expression_pair(fr_arr(circ.l_input[:u]), fr_arr(circ.l_table[:u]))
+    assert np.array_equal(ga, oa) and np.array_equal(gs, os_)
+    circ.perm_input[:u], circ.perm_table[:u] = O.fr_to_ints(ga), O.fr_to_ints(gs)
+    num = [(circ.l_input[r] + beta) * (circ.l_table[r] + gamma) % R for r in range(u)] + [1]
+    den = [(circ.perm_input[r] + beta) * (circ.perm_table[r] + gamma) % R for r in range(u)] + [1]
+    zl = O.fr_to_ints(h2v.grand_product(fr_arr(num), fr_arr(den)))
+    assert zl[0] == 1 and zl[u] == 1
+    circ.z_lookup[:u + 1] = zl
+    last, nc = 1, len(circ.cols)
+    for s_ in range(circ.n_sets):
+        cs = range(s_ * circ.chunk_len, min((s_ + 1) * circ.chunk_len, nc))
+        num, den = [], []
+        for r in range(u):
+            a = b = 1
+            for c in cs:
+                a = a * (circ.cols[c][r] + beta * pow(DELTA, c, R) * pow(w, r, R) + gamma) % R
+                b = b * (circ.cols[c][r] + beta * circ.sigma[c][r] + gamma) % R
+            num.append(a)
+            den.append(b)
+        gp = O.fr_to_ints(h2v.grand_product(fr_arr(num + [1]), fr_arr(den + [1])))
+        circ.z[s_][:u + 1] = [last * v % R for v in gp]
+        last = circ.z[s_][u]
+    assert last == 1
+    coeff, hq, _ = _gpu_quotient(h2v, circ)
+    _check_identity(circ, coeff, hq, seed=k + 50)
