@@ -379,7 +379,91 @@ def bench_prove_shaped(h, torch, dev, srs16, d_cols16, cols16):
     res["latency_s"] = res["kmeans_k16"]["latency_s"]
     res["kmeans_k16_host_facing_s"] = prove_shaped_host(h, torch, srs16)
     res["kmeans_k16_host_in_quotient_on_device_s"] = prove_shaped_resident(h, torch, dev, srs16)
+    res["kmeans_k16_all_built_steps"] = prove_shaped_full(h, torch, dev, srs16, d_cols16)
     return res
+
+
+def prove_shaped_full(h, torch, dev, srs, d_cols):
+    """Every create_proof step this library covers, in the order of SURVEY.md 3.1, for the kmeans k = 16 shape
+    (App. C estimates: 617 advice + lookup-advice columns, 71 lookups, 310 permutation products): commits, the lookup
+    permutations, grand products, lagrange_to_coeff, coeff_to_extended + evaluate_h row loops, the divided quotient and
+    its commits, the evaluations at x * omega^rot and the SHPLONK quotient (kate_division + commits).  Columns are
+    synthetic and device-resident except where the entry point is host-facing (kate_division: host arrays, PCIe
+    included).  Still a PROXY: witness generation, the transcript and the assembly of the product
+    numerators / SHPLONK polynomials are not part of it."""
+    import numpy as np
+    n, ne, bc = N, 4 * N, 96
+    n_adv, n_look, n_perm = 617, 71, 310
+    dom = h.EvaluationDomain(4, K)
+    d_out = torch.zeros((bc, 8), dtype=torch.int64, device=dev)
+    d_coef = d_cols.flip(0).contiguous()         # a second set of non-zero columns (denominators), later the coefficient buffer
+    d_gp = torch.empty_like(d_cols)
+    d_ext = torch.empty((bc, ne, 4), dtype=torch.int64, device=dev)
+    d_h = torch.zeros((ne, 4), dtype=torch.int64, device=dev)
+    d_hq = torch.empty((ne, 4), dtype=torch.int64, device=dev)
+    d_pts = d_cols[0, :2].contiguous()
+    d_ev = torch.zeros((bc, 2, 4), dtype=torch.int64, device=dev)
+    u = n - 6
+    vals = torch.zeros((u, 4), dtype=torch.int64)
+    vals[:, 0] = torch.randint(0, 1 << 15, (u,), dtype=torch.int64)
+    tab = torch.zeros((u, 4), dtype=torch.int64)
+    tab[: 1 << 15, 0] = torch.arange(1 << 15, dtype=torch.int64)
+    from oracle import oracle as O      # setup only: Montgomery form of the small lookup values
+    m_in = torch.from_numpy(O.to_mont(vals.numpy().view(np.uint64)).view(np.int64)).to(dev)
+    m_tab = torch.from_numpy(O.to_mont(tab.numpy().view(np.uint64)).view(np.int64)).to(dev)
+    d_pa, d_ps = torch.empty_like(m_in), torch.empty_like(m_in)
+    hnum = d_cols[1].cpu().pin_memory().numpy().view(np.uint64)
+    y = hnum[:3]
+    spans = {}
+
+    def span(name, fn):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        spans[name] = spans.get(name, 0.0) + time.perf_counter() - t
+
+    def batches(total):
+        return [min(bc, total - i) for i in range(0, total, bc)]
+
+    def commits(total):
+        for c in batches(total):
+            srs.commit_batch_dev(d_cols.data_ptr(), n, c, n, d_out.data_ptr())
+
+    def run():
+        spans.clear()
+        span("commit_lagrange advice", lambda: commits(n_adv))
+        span("permute_expression_pair", lambda: [h.permute_expression_pair_dev(m_in.data_ptr(), m_tab.data_ptr(), u, d_pa.data_ptr(), d_ps.data_ptr())
+                                                 for _ in range(n_look)])
+        span("commit_lagrange lookups", lambda: commits(2 * n_look))
+        span("grand_product", lambda: [h.grand_product_dev(d_cols.data_ptr(), d_coef.data_ptr(), n, c, d_gp.data_ptr())
+                                       for c in batches(n_perm + n_look)])
+        span("commit_lagrange products + random + h + shplonk", lambda: commits(n_perm + n_look + 1 + 3 + 2))
+        total = n_adv + 2 * n_look + n_perm + n_look
+
+        def transforms():
+            for c in batches(total):
+                dom.transform_dev(h.OP_LAGRANGE_TO_COEFF, d_cols.data_ptr(), n, d_coef.data_ptr(), n, c)
+                dom.transform_dev(h.OP_COEFF_TO_EXTENDED, d_coef.data_ptr(), n, d_ext.data_ptr(), ne, c)
+                dom.quotient_gates(d_h.data_ptr(), y[0], c // 2, d_ext.data_ptr(), ne, d_ext.data_ptr(), ne)
+                dom.quotient_permutation(d_h.data_ptr(), y[0], y[1], y[2], c // 2, 2, d_ext.data_ptr(), ne, d_ext.data_ptr(), ne,
+                                         d_ext.data_ptr(), ne, d_ext[0].data_ptr(), d_ext[1].data_ptr(), d_ext[2].data_ptr(), 5)
+            e = lambda i: d_ext[i].data_ptr()
+            for _ in range(n_look):
+                dom.quotient_lookup(d_h.data_ptr(), y[0], y[1], y[2], e(3), e(4), e(5), e(6), e(7), e(0), e(1), e(2))
+            dom.transform_dev(h.OP_DIVIDE_BY_VANISHING, d_h.data_ptr(), ne, d_hq.data_ptr(), ne, 1)
+
+        span("lagrange_to_coeff + coeff_to_extended + evaluate_h + divide", transforms)
+        span("eval_polynomial", lambda: [h._check(h.lib().h2v_eval_polynomial_dev(d_coef.data_ptr(), n, c, n, d_pts.data_ptr(), 2, d_ev.data_ptr()))
+                                         for c in batches(total)])
+        span("kate_division (host-facing)", lambda: [h.kate_division(hnum, y[0]) for _ in range(4)])
+        return sum(spans.values())
+
+    run()
+    t = min(run(), run())
+    dom.close()
+    return {"latency_s": t, "spans_s": {k: round(v, 5) for k, v in spans.items()},
+            "note": "kmeans k=16 shape (App. C estimates), every create_proof step the library covers; proxy"}
 
 
 def prove_shaped_resident(h, torch, dev, srs):

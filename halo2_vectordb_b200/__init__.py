@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "h2v_best_fft", "h2v_domain_new", "h2v_domain_free", "h2v_domain_k", "h2v_domain_extended_k", "h2v_domain_constant",
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
     "h2v_divide_by_vanishing_poly", "h2v_domain_transform_batch", "h2v_domain_transform_dev",
-    "h2v_eval_polynomial_batch", "h2v_eval_polynomial_dev", "h2v_batch_invert", "h2v_grand_product", "h2v_kate_division",
+    "h2v_eval_polynomial_batch", "h2v_eval_polynomial_dev", "h2v_batch_invert", "h2v_grand_product", "h2v_grand_product_dev", "h2v_kate_division",
     "h2v_permute_expression_pair", "h2v_permute_expression_pair_dev",
     "h2v_quotient_gates_dev", "h2v_quotient_permutation_dev", "h2v_quotient_lookup_dev",
     "h2v_g1_to_bytes", "h2v_fr_to_repr",
@@ -93,6 +93,7 @@ def lib():
         L.h2v_eval_polynomial_dev.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_batch_invert.argtypes = [C.c_void_p, C.c_size_t]
         L.h2v_grand_product.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.h2v_grand_product_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
         L.h2v_kate_division.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.h2v_permute_expression_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.h2v_permute_expression_pair_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
@@ -284,6 +285,11 @@ def grand_product(num, den):
     out = np.zeros_like(num)
     _check(lib().h2v_grand_product(_ptr(num), _ptr(den), num.shape[0], _ptr(out)))
     return out
+
+
+def grand_product_dev(d_num, d_den, n, n_cols, d_out):
+    """Running products of n_cols contiguous device-resident columns (one batch inversion for all)."""
+    _check(lib().h2v_grand_product_dev(d_num, d_den, n, n_cols, d_out))
 
 
 def kate_division(a, b):

@@ -1463,6 +1463,22 @@ int h2v_batch_invert(uint64_t *a, size_t n) {
     CU(cudaStreamSynchronize(st));
     return H2V_OK;
 }
+// out[c][0] = 1, out[c][i+1] = out[c][i] * num[c][i] / den[c][i] for `cols` contiguous columns of n elements (device)
+static int run_grand_product(cudaStream_t st, const fe *num, const fe *den, uint32_t n, uint32_t cols, fe *out) {
+    int rc;
+    const uint32_t ntiles = (n + H2V_FR_TILE - 1) / H2V_FR_TILE;
+    const size_t tot = (size_t)n * cols;
+    if ((rc = g_poly.c.ensure(tot * sizeof(fe))) || (rc = g_poly.d.ensure(((size_t)ntiles * cols + 1) * sizeof(fe)))) return rc;
+    // denominators must be non-zero (the reference would panic on invert().unwrap()); one inversion for all columns
+    if ((rc = run_batch_invert<FrP>(st, den, g_poly.c.as<fe>(), (uint32_t)tot, g_poly.tree))) return rc;
+    fr_prod_tiles_kernel<<<dim3(ntiles, cols), 256, 0, st>>>(num, g_poly.c.as<fe>(), n, g_poly.d.as<fe>());
+    LAUNCHED();
+    fr_scan_top_kernel<OpMul><<<dim3(1, cols), 256, 0, st>>>(g_poly.d.as<fe>(), ntiles);
+    LAUNCHED();
+    fr_prod_apply_kernel<<<dim3(ntiles, cols), 256, 0, st>>>(num, g_poly.c.as<fe>(), n, g_poly.d.as<fe>(), out);
+    LAUNCHED();
+    return H2V_OK;
+}
 int h2v_grand_product(const uint64_t *num, const uint64_t *den, size_t n, uint64_t *out) {
     if (!n) return H2V_OK;
     if (!num || !den || !out) return fail(H2V_EINVAL, "grand_product: NULL buffer");
@@ -1472,22 +1488,34 @@ int h2v_grand_product(const uint64_t *num, const uint64_t *den, size_t n, uint64
     std::lock_guard<std::mutex> lk(g_poly.mu);
     if ((rc = poly_ctx_ready())) return rc;
     cudaStream_t st = g_poly.st;
-    const uint32_t ntiles = (uint32_t)((n + H2V_FR_TILE - 1) / H2V_FR_TILE);
-    if ((rc = g_poly.a.ensure(n * sizeof(fe))) || (rc = g_poly.b.ensure(n * sizeof(fe))) || (rc = g_poly.c.ensure(n * sizeof(fe))) ||
-        (rc = g_poly.d.ensure(((size_t)ntiles + 1) * sizeof(fe))))
-        return rc;
+    if ((rc = g_poly.a.ensure(n * sizeof(fe))) || (rc = g_poly.b.ensure(n * sizeof(fe)))) return rc;
     CU(cudaMemcpyAsync(g_poly.a.p, num, n * sizeof(fe), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(g_poly.b.p, den, n * sizeof(fe), cudaMemcpyHostToDevice, st));
-    // denominators must be non-zero (the reference would panic on invert().unwrap()); 1/den in c
-    if ((rc = run_batch_invert<FrP>(st, g_poly.b.as<fe>(), g_poly.c.as<fe>(), (uint32_t)n, g_poly.tree))) return rc;
-    fr_prod_tiles_kernel<<<ntiles, 256, 0, st>>>(g_poly.a.as<fe>(), g_poly.c.as<fe>(), (uint32_t)n, g_poly.d.as<fe>());
-    LAUNCHED();
-    fr_scan_top_kernel<OpMul><<<1, 256, 0, st>>>(g_poly.d.as<fe>(), ntiles);
-    LAUNCHED();
-    fr_prod_apply_kernel<<<ntiles, 256, 0, st>>>(g_poly.a.as<fe>(), g_poly.c.as<fe>(), (uint32_t)n, g_poly.d.as<fe>(), g_poly.b.as<fe>());
-    LAUNCHED();
+    // the running product overwrites the staged denominators once their inverses exist
+    if ((rc = run_grand_product(st, g_poly.a.as<fe>(), g_poly.b.as<fe>(), (uint32_t)n, 1, g_poly.b.as<fe>()))) {
+        cudaStreamSynchronize(st);
+        return rc;
+    }
     CU(cudaMemcpyAsync(out, g_poly.b.p, n * sizeof(fe), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return H2V_OK;
+}
+int h2v_grand_product_dev(const void *d_num, const void *d_den, size_t n, size_t n_cols, void *d_out) {
+    if (!n || !n_cols) return H2V_OK;
+    if (!d_num || !d_den || !d_out) return fail(H2V_EINVAL, "grand_product: NULL buffer");
+    if (n_cols > 65535 || n * n_cols >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "grand_product: batch too large");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_poly.mu);
+    if ((rc = poly_ctx_ready())) return rc;
+    Timer tm(g_poly.st);
+    tm.begin(7);
+    rc = run_grand_product(g_poly.st, (const fe *)d_num, (const fe *)d_den, (uint32_t)n, (uint32_t)n_cols, (fe *)d_out);
+    tm.end();
+    cudaError_t e = cudaStreamSynchronize(g_poly.st);
+    tm.collect(true);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(H2V_ECUDA, "grand_product: %s", cudaGetErrorString(e));
     return H2V_OK;
 }
 int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t *out) {

@@ -117,6 +117,10 @@ __global__ void __launch_bounds__(256) fr_select_inverse_kernel(const fe *__rest
 __global__ void __launch_bounds__(256) fr_prod_tiles_kernel(const fe *__restrict__ num, const fe *__restrict__ dinv, uint32_t n,
                                                             fe *__restrict__ tile_prod) {
     __shared__ fe sm8[8];
+    // grid.y = column: columns are n elements apart, their tile products gridDim.x apart
+    num += (size_t)blockIdx.y * n;
+    dinv += (size_t)blockIdx.y * n;
+    tile_prod += (size_t)blockIdx.y * gridDim.x;
     const uint32_t base = blockIdx.x * H2V_FR_TILE + threadIdx.x * 8;
     fe p = fe_one<Fr>();
 #pragma unroll 1
@@ -126,9 +130,10 @@ __global__ void __launch_bounds__(256) fr_prod_tiles_kernel(const fe *__restrict
     block_excl_scan_256<OpMul>(p, &tot, sm8);
     if (threadIdx.x == 0) pl_st(tile_prod + blockIdx.x, tot);
 }
-// in-place exclusive scan of tile[0..ntiles) by one CTA
+// in-place exclusive scan of tile[0..ntiles) by one CTA (grid.y = column, `ntiles` apart)
 template <class Op> __global__ void __launch_bounds__(256) fr_scan_top_kernel(fe *__restrict__ tile, uint32_t ntiles) {
     __shared__ fe sm8[8];
+    tile += (size_t)blockIdx.y * ntiles;
     const uint32_t per = (ntiles + 255) / 256;
     const uint32_t lo = min(threadIdx.x * per, ntiles), hi = min(lo + per, ntiles);
     fe s = Op::id();
@@ -144,6 +149,10 @@ template <class Op> __global__ void __launch_bounds__(256) fr_scan_top_kernel(fe
 __global__ void __launch_bounds__(256) fr_prod_apply_kernel(const fe *__restrict__ num, const fe *__restrict__ dinv, uint32_t n,
                                                             const fe *__restrict__ tile_pre, fe *__restrict__ out) {
     __shared__ fe sm8[8];
+    num += (size_t)blockIdx.y * n;
+    dinv += (size_t)blockIdx.y * n;
+    out += (size_t)blockIdx.y * n;
+    tile_pre += (size_t)blockIdx.y * gridDim.x;
     const uint32_t base = blockIdx.x * H2V_FR_TILE + threadIdx.x * 8;
     fe r[8];
     fe p = fe_one<Fr>();

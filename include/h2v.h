@@ -130,6 +130,8 @@ int h2v_eval_polynomial_dev(const void *d_polys, size_t stride, size_t n_polys, 
 int h2v_batch_invert(uint64_t *a, size_t n);
 /* running product of the permutation / lookup arguments: out[0] = 1, out[i+1] = out[i] * num[i] / den[i] (den != 0) */
 int h2v_grand_product(const uint64_t *num, const uint64_t *den, size_t n, uint64_t *out);
+/* the same for n_cols device-resident columns, contiguous (n elements apart): one batch inversion for all of them */
+int h2v_grand_product_dev(const void *d_num, const void *d_den, size_t n, size_t n_cols, void *d_out);
 /* arithmetic.rs kate_division(a, b): quotient of a(X) (n coefficients) by (X - b), n - 1 coefficients */
 int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t *out);
 

@@ -675,3 +675,17 @@ def test_sliced_multiexp_equals_whole(h2v, k, world):
     assert np.array_equal(got, whole.commit_lagrange(s))
     assert np.array_equal(got, O.msm_closed_form(s))
     whole.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,cols", [(1, 1), (5, 3), (2048, 2), (2049, 5), (1 << 13, 7), (1 << 16, 4)])
+def test_grand_product_dev_batch_vs_oracle(h2v, n, cols):
+    num = O.fr_fill(n * cols, 40 + cols).reshape(cols, n, 4)
+    den = O.fr_fill(n * cols, 50 + cols).reshape(cols, n, 4)
+    d_num, d_den, d_out = (h2v.DeviceBuffer(n * cols * 32) for _ in range(3))
+    d_num.upload(num); d_den.upload(den)
+    h2v.grand_product_dev(d_num.ptr, d_den.ptr, n, cols, d_out.ptr)
+    got = d_out.download((cols, n, 4))
+    for c in range(cols):
+        assert np.array_equal(got[c], O.fr_grand_product(num[c], den[c])), (n, c)
+        assert np.array_equal(got[c], h2v.grand_product(num[c], den[c]))
