@@ -259,7 +259,9 @@ __device__ __forceinline__ void mont_row(uint32_t *lo, uint32_t *hi, const uint3
     hi[7] += c;
 }
 
-template <class F> __device__ __forceinline__ fe fe_mul(const fe &a, const fe &b) {
+// Montgomery product without the final conditional subtraction: a * b / R + (< m).  For a < 4m and b < m the result
+// is < 2m (4m^2 / R + m = 1.76 m for both BN254 fields) and every intermediate stays below 2^288.
+template <class F> __device__ __forceinline__ fe fe_mul_lazy(const fe &a, const fe &b) {
     uint32_t e[8], o[8];
     mont_row<F, true>(e, o, a.v, b.v[0]);
     mont_row<F, false>(o, e, a.v, b.v[1]);
@@ -282,6 +284,10 @@ template <class F> __device__ __forceinline__ fe fe_mul(const fe &a, const fe &b
         : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7])
         : "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]),
           "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
+    return r;
+}
+template <class F> __device__ __forceinline__ fe fe_mul(const fe &a, const fe &b) {
+    fe r = fe_mul_lazy<F>(a, b);
     fe_reduce_once<F>(r);
     return r;
 }
@@ -315,7 +321,33 @@ template <class F> inline fe fe_mul(const fe &a, const fe &b) {
     fe_reduce_once<F>(r);   // t[8] == 0 here because m < 2^254
     return r;
 }
+template <class F> inline fe fe_mul_lazy(const fe &a, const fe &b) { return fe_mul<F>(a, b); }   // host: always reduced
 #endif
+// if t >= 2m: t -= 2m   (lazy-reduction helpers for the NTT butterflies: values live in [0, 4m), 4m < 2^256)
+template <class F> H2V_HD uint32_t fe_2m_limb(int i) { return (F::m(i) << 1) | (i ? (F::m(i - 1) >> 31) : 0u); }
+template <class F> H2V_HD void fe_csub_2m(fe &t) {
+    uint32_t mm[8], d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mm[i] = fe_2m_limb<F>(i);
+    uint32_t bw = raw_sub(d, t.v, mm);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.v[i] = bw ? t.v[i] : d[i];
+}
+// a + b and a + 2m - b without reduction
+H2V_HD fe fe_add_raw(const fe &a, const fe &b) {
+    fe r;
+    raw_add(r.v, a.v, b.v);
+    return r;
+}
+template <class F> H2V_HD fe fe_sub_plus_2m(const fe &a, const fe &b) {
+    uint32_t mm[8];
+    fe d, r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mm[i] = fe_2m_limb<F>(i);
+    raw_sub(d.v, mm, b.v);       // 2m - b > 0 for b < 2m
+    raw_add(r.v, a.v, d.v);
+    return r;
+}
 template <class F> H2V_HD fe fe_sqr(const fe &a) { return fe_mul<F>(a, a); }
 
 template <class F> H2V_HD fe fe_to_mont(const fe &canon) {

@@ -88,16 +88,28 @@ __device__ __forceinline__ void ntt_stage(fe (&x)[8], const fe *__restrict__ tw,
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if ((k >> U) & 1) continue;
+        // lazy reduction (Harvey): values live in [0, 4r); t < 2r, a < 2r, so a + t and a + 2r - t stay below 4r
         fe t;
         if (unit) {
             t = x[k + (1 << U)];
+            fe_csub_2m<Fr>(t);
         } else {
             fe w = fe_load_ro(tw + e_base + ((uint32_t)(k & ((1 << U) - 1)) << (L - 1 - U)));
-            t = fe_mul<Fr>(x[k + (1 << U)], w);
+            t = fe_mul_lazy<Fr>(x[k + (1 << U)], w);
         }
-        x[k + (1 << U)] = fe_sub<Fr>(x[k], t);
-        x[k] = fe_add<Fr>(x[k], t);
+        fe a = x[k];
+        fe_csub_2m<Fr>(a);
+        x[k + (1 << U)] = fe_sub_plus_2m<Fr>(a, t);
+        x[k] = fe_add_raw(a, t);
     }
+}
+
+// last pass: bring a lazily reduced value (< 4r) back to its canonical representative, folding in the post-scale
+__device__ __forceinline__ fe ntt_finish(fe x, const fe *post) {
+    if (post) return fe_mul<Fr>(x, fe_load_ro(post));     // x < 4r, post < r: product < 2r, one conditional subtraction
+    fe_csub_2m<Fr>(x);
+    fe_reduce_once<Fr>(x);
+    return x;
 }
 
 __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
@@ -188,7 +200,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
             uint32_t j = (bitrev(tile * T + q, H) << S) | mid;
             if (p.last && j >= p.n_out) continue;
             fe x = ntt_sm_load(ntt_sm, plane1, (mid << logT) | q);
-            if (p.last && p.post) x = fe_mul<Fr>(x, fe_load_ro(p.post + (j % p.post_mod)));
+            if (p.last) x = ntt_finish(x, p.post ? p.post + (j % p.post_mod) : nullptr);
             fe_store_global(dst + j, x);
         }
     } else {
@@ -198,7 +210,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
             size_t j = jbase + ((size_t)mid << t0) + q;
             if (p.last && j >= p.n_out) continue;
             fe x = ntt_sm_load(ntt_sm, plane1, e);
-            if (p.last && p.post) x = fe_mul<Fr>(x, fe_load_ro(p.post + (uint32_t)(j % p.post_mod)));
+            if (p.last) x = ntt_finish(x, p.post ? p.post + (uint32_t)(j % p.post_mod) : nullptr);
             fe_store_global(dst + j, x);
         }
     }
