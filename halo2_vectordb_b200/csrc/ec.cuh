@@ -102,6 +102,45 @@ H2V_HD void xyzz_add_mixed(xyzz &acc, const affine &q) {
     acc.zz = fe_mul<Fq>(acc.zz, pp);
     acc.zzz = fe_mul<Fq>(acc.zzz, ppp);
 }
+#ifdef __CUDA_ARCH__
+// The same addition for the MSM inner loop, with lazily reduced accumulator coordinates in [0, 2p): a Montgomery
+// product of two values below 2p is below 4p^2/R + p = 1.76 p, so the products skip their final subtraction and the
+// differences add 2p instead of p when they borrow.  q is canonical.  xyzz_canon() brings the result back to [0, p).
+__device__ __forceinline__ void xyzz_add_mixed_lazy(xyzz &acc, const affine &q) {
+    if (affine_is_identity(q)) return;
+    if (xyzz_is_identity(acc)) {
+        acc = xyzz_from_affine(q);
+        return;
+    }
+    fe u2 = fe_mul_lazy<Fq>(q.x, acc.zz);
+    fe s2 = fe_mul_lazy<Fq>(q.y, acc.zzz);
+    fe p = fe_sub_lazy<Fq>(u2, acc.x);
+    fe r = fe_sub_lazy<Fq>(s2, acc.y);
+    if (fe_is_zero_lazy<Fq>(p)) {
+        if (fe_is_zero_lazy<Fq>(r)) acc = xyzz_double_affine(q);
+        else acc = xyzz_identity();
+        return;
+    }
+    fe pp = fe_mul_lazy<Fq>(p, p);
+    fe ppp = fe_mul_lazy<Fq>(p, pp);
+    fe qq = fe_mul_lazy<Fq>(acc.x, pp);
+    fe x3 = fe_sub_lazy<Fq>(fe_sub_lazy<Fq>(fe_sub_lazy<Fq>(fe_mul_lazy<Fq>(r, r), ppp), qq), qq);
+    fe y3 = fe_sub_lazy<Fq>(fe_mul_lazy<Fq>(r, fe_sub_lazy<Fq>(qq, x3)), fe_mul_lazy<Fq>(acc.y, ppp));
+    acc.x = x3;
+    acc.y = y3;
+    acc.zz = fe_mul_lazy<Fq>(acc.zz, pp);
+    acc.zzz = fe_mul_lazy<Fq>(acc.zzz, ppp);
+}
+__device__ __forceinline__ void xyzz_canon(xyzz &a) {
+    fe_reduce_once<Fq>(a.x);
+    fe_reduce_once<Fq>(a.y);
+    fe_reduce_once<Fq>(a.zz);
+    fe_reduce_once<Fq>(a.zzz);
+}
+#else   // host compilation pass: the names must exist, the host never runs the lazy variant
+inline void xyzz_add_mixed_lazy(xyzz &acc, const affine &q) { xyzz_add_mixed(acc, q); }
+inline void xyzz_canon(xyzz &) {}
+#endif
 // acc += q   (add-2008-s)
 H2V_HD void xyzz_add(xyzz &acc, const xyzz &q) {
     if (xyzz_is_identity(q)) return;

@@ -333,6 +333,26 @@ template <class F> H2V_HD void fe_csub_2m(fe &t) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) t.v[i] = bw ? t.v[i] : d[i];
 }
+// a - b for a, b in [0, 2m), result in [0, 2m)
+template <class F> H2V_HD fe fe_sub_lazy(const fe &a, const fe &b) {
+    fe r;
+    uint32_t bw = raw_sub(r.v, a.v, b.v);
+    uint32_t mm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mm[i] = fe_2m_limb<F>(i) & bw;
+    raw_add(r.v, r.v, mm);
+    return r;
+}
+// x == 0 (mod m) for x in [0, 2m): x is 0 or m
+template <class F> H2V_HD bool fe_is_zero_lazy(const fe &x) {
+    uint32_t z = 0, e = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        z |= x.v[i];
+        e |= x.v[i] ^ F::m(i);
+    }
+    return z == 0 || e == 0;
+}
 // a + b and a + 2m - b without reduction
 H2V_HD fe fe_add_raw(const fe &a, const fe &b) {
     fe r;

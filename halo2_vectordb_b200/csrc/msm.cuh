@@ -251,9 +251,10 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const uint2 *__r
         uint2 nxt = (e + 1 < end) ? entries[e + 1] : make_uint2(0u, 0xffffffffu);
         affine pt = affine_load_ro(points + (ent.x & 0x7fffffffu));
         if (ent.x & 0x80000000u) pt.y = fe_neg<Fq>(pt.y);
-        xyzz_add_mixed(acc, pt);
+        xyzz_add_mixed_lazy(acc, pt);
         if (nxt.y != cur_b) {
             // run ends here (bucket change or end of chunk)
+            xyzz_canon(acc);
             const bool last_run = (e + 1 == end);
             const bool starts_before = first_run && (prev_b == cur_b);
             const bool continues_after = last_run && (next_b == cur_b);
