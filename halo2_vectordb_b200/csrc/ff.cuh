@@ -213,6 +213,21 @@ __device__ __forceinline__ uint32_t row_mad(uint32_t *acc, const uint32_t *x, ui
         : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(y));
     return c;
 }
+// acc[0..7] += sum_t (x[2t] * y) << (64 t), the carry out of limb 7 goes straight into `top` (one instruction
+// instead of a carry capture plus an add)
+__device__ __forceinline__ void row_mad_top(uint32_t *acc, const uint32_t *x, uint32_t y, uint32_t &top) {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+        : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(y));
+}
 // Shift-and-accumulate for the offset accumulator when its partner drops one limb:
 //   lo0 += stray (carry c0);  out[0..7] = {in[2..7],0,0} + sum_t (x[2t] * y) << (64 t) + c0
 __device__ __forceinline__ void row_mad_shift(uint32_t *out, const uint32_t *in, uint32_t &lo0, uint32_t stray,
@@ -250,13 +265,11 @@ __device__ __forceinline__ void mont_row(uint32_t *lo, uint32_t *hi, const uint3
         row_mad_shift(nh, hi, lo[0], hi[1], a + 1, bi);
 #pragma unroll
         for (int i = 0; i < 8; ++i) hi[i] = nh[i];
-        uint32_t c = row_mad(lo, a, bi);
-        hi[7] += c;
+        row_mad_top(lo, a, bi, hi[7]);
     }
     uint32_t q = lo[0] * F::inv();
     row_mad(hi, mm + 1, q);              // cannot carry out: T < 2 * 2^32 * m < 2^288
-    uint32_t c = row_mad(lo, mm, q);
-    hi[7] += c;
+    row_mad_top(lo, mm, q, hi[7]);
 }
 
 // Montgomery product without the final conditional subtraction: a * b / R + (< m).  For a < 4m and b < m the result
