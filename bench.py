@@ -35,7 +35,7 @@ N = 1 << K
 COLS = 96                      # 96 x 2 MiB of scalars = 192 MiB per step (> 126 MB L2), tables 64 MiB more
 MSM_MACS_PER_POINT = {16: 27200, 13: 27200, 20: 20400}   # W(n) * 1360 wide-MACs
 FQ_MUL_MACS = 136
-ACC_DRAM_BYTES_PER_LAUNCH = 4.27e9   # msm_accumulate_kernel, 96 columns x 2^16, c = 15: 3.840 GB read + 0.427 GB written (ncu, r01)
+ACC_DRAM_BYTES_PER_LAUNCH = 4.17e9   # msm_accumulate_kernel, 96 columns x 2^16, c = 15: 3.761 GB read + 0.411 GB written (ncu, r01)
 SYN_A, SYN_B = 0x9E3779B97F4A7C15 >> 2, 0x632BE59BD9B4E019 >> 2
 
 
