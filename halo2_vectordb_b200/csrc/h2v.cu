@@ -1563,30 +1563,29 @@ int run_permute_pair(cudaStream_t st, const fe *d_in_a, const fe *d_in_t, uint32
     uint32_t n_pad = 1;
     while (n_pad < u) n_pad <<= 1;
     const uint32_t ntiles = (u + H2V_SCAN_TILE - 1) / H2V_SCAN_TILE;
-    if ((rc = g_poly.a.ensure((size_t)n_pad * sizeof(fe))) || (rc = g_poly.b.ensure((size_t)n_pad * sizeof(fe))) ||
+    if ((rc = g_poly.a.ensure((size_t)2 * n_pad * sizeof(fe))) ||
         (rc = g_poly.tree.ensure(((size_t)6 * u + 2 * ntiles + 8) * sizeof(uint32_t))))
         return rc;
-    fe *As = g_poly.a.as<fe>(), *Ts = g_poly.b.as<fe>();
+    fe *As = g_poly.a.as<fe>(), *Ts = As + n_pad;      // both key arrays in one buffer: grid.y picks the array
     uint32_t *rep = g_poly.tree.as<uint32_t>(), *free_ = rep + u, *rep_offs = free_ + u, *free_offs = rep_offs + u;
     uint32_t *scratch = free_offs + u, *rep_rows = scratch + u, *tiles = rep_rows + u, *totals = tiles + 2 * ntiles;
     int *err = reinterpret_cast<int *>(totals + 2);
     const unsigned gp = (n_pad + 255) / 256, gu = (u + 255) / 256;
     CU(cudaMemsetAsync(err, 0, sizeof(int), st));
-    for (int which = 0; which < 2; ++which) {
-        fe *keys = which ? Ts : As;
-        lookup_canon_pad_kernel<<<gp, 256, 0, st>>>(which ? d_in_t : d_in_a, keys, u, n_pad);
+    {
+        lookup_canon_pad_kernel<<<dim3(gp, 2), 256, 0, st>>>(d_in_a, d_in_t, As, u, n_pad);
         LAUNCHED();
         const uint32_t tile = std::min<uint32_t>(H2V_SORT_TILE, n_pad);
         const unsigned tiles_n = n_pad / tile;
         const size_t smem = (size_t)tile * sizeof(fe);
-        bitonic_tile_kernel<<<tiles_n, H2V_SORT_TILE / 2, smem, st>>>(keys, n_pad, 0, 1);
+        bitonic_tile_kernel<<<dim3(tiles_n, 2), H2V_SORT_TILE / 2, smem, st>>>(As, n_pad, 0, 1);
         LAUNCHED();
         for (uint32_t k = 2 * tile; k <= n_pad && k; k <<= 1) {
             for (uint32_t j = k >> 1; j >= tile; j >>= 1) {
-                bitonic_global_kernel<<<(n_pad / 2 + 255) / 256, 256, 0, st>>>(keys, n_pad, k, j);
+                bitonic_global_kernel<<<dim3((n_pad / 2 + 255) / 256, 2), 256, 0, st>>>(As, n_pad, k, j);
                 LAUNCHED();
             }
-            bitonic_tile_kernel<<<tiles_n, H2V_SORT_TILE / 2, smem, st>>>(keys, n_pad, k, 0);
+            bitonic_tile_kernel<<<dim3(tiles_n, 2), H2V_SORT_TILE / 2, smem, st>>>(As, n_pad, k, 0);
             LAUNCHED();
         }
     }

@@ -32,9 +32,13 @@ __device__ __forceinline__ bool key_eq(const fe &a, const fe &b) {
 }
 
 // out[i] = canonical(in[i]) for i < n, all-ones (greater than any field element) for n <= i < n_pad
-__global__ void lookup_canon_pad_kernel(const fe *__restrict__ in, fe *__restrict__ out, uint32_t n, uint32_t n_pad) {
+// (grid.y = 0: input -> keys[0 .. n_pad), grid.y = 1: table -> keys[n_pad .. 2 n_pad): both sorts share every launch)
+__global__ void lookup_canon_pad_kernel(const fe *__restrict__ in0, const fe *__restrict__ in1, fe *__restrict__ out, uint32_t n,
+                                        uint32_t n_pad) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
+    const fe *in = blockIdx.y ? in1 : in0;
+    out += (size_t)blockIdx.y * n_pad;
     fe r;
     if (i < n) {
         r = fe_from_mont<FrL>(fe_load_global(in + i));
@@ -57,6 +61,7 @@ __device__ __forceinline__ void bitonic_cx(fe &lo, fe &hi, bool ascending) {
 __global__ void __launch_bounds__(256) bitonic_global_kernel(fe *__restrict__ a, uint32_t n_pad, uint32_t k, uint32_t j) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pad / 2) return;
+    a += (size_t)blockIdx.y * n_pad;
     uint32_t i = 2 * j * (p / j) + (p % j);
     fe x = fe_load_global(a + i), y = fe_load_global(a + i + j);
     bitonic_cx(x, y, (i & k) == 0);
@@ -71,6 +76,7 @@ __global__ void __launch_bounds__(H2V_SORT_TILE / 2) bitonic_tile_kernel(fe *__r
     const uint32_t tile = min(H2V_SORT_TILE, n_pad);
     const uint32_t base = blockIdx.x * tile;
     const uint32_t t = threadIdx.x;
+    a += (size_t)blockIdx.y * n_pad;
     if (t < tile / 2) {
         s[t] = fe_load_global(a + base + t);
         s[t + tile / 2] = fe_load_global(a + base + t + tile / 2);
