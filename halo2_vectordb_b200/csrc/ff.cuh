@@ -9,7 +9,10 @@
 // products of the even limbs of `a`, one the odd limbs, the second offset by 32 bits -- so every
 // 64-bit partial product lands on an aligned limb pair and a whole row is one carry chain of
 // mad.lo.cc / madc.hi.cc pairs, which ptxas fuses into IMAD.WIDE.U32(.X) on sm_100a.
-// 8*16 wide multiply-adds + 8 low multiplies (the Montgomery quotients) = 136 per product.
+// 8*16 wide multiply-adds + 8 low multiplies (the Montgomery quotients) = 136 per product, plus three adds per row
+// (the stray limb and the two carries that land directly in the top limb) -- the SASS of a product is a straight
+// stream of IMAD.WIDE.U32.X.  Lazily reduced variants (fe_mul_lazy, fe_sub_lazy, fe_csub_2m ...) serve the NTT
+// butterflies and the MSM accumulation loop, which keep values in [0, 4m) / [0, 2m) between products.
 // Host path (same file, !__CUDA_ARCH__): portable u64 arithmetic, used for domain constants and
 // by the host-side unit checks.
 #pragma once
