@@ -369,6 +369,21 @@ template <class F> H2V_HD bool fe_is_zero_lazy(const fe &x) {
     }
     return z == 0 || e == 0;
 }
+// Cheap conditional -2m decided by the top limb alone: subtracts when x.v[7] > top(2m), so that (with T = top(2m),
+// theta = (T+1) 2^224 > 2m) any x < theta + 2m comes out in [0, theta).  The NTT butterflies then keep every value
+// below theta + 2m (< 2^256, and still small enough for fe_mul_lazy to return < 2m): a predicated 8-instruction
+// subtraction instead of subtract + 8 selects.
+template <class F> H2V_HD void fe_csub_2m_top(fe &t) {
+    if (t.v[7] > fe_2m_limb<F>(7)) {
+        uint32_t mm[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mm[i] = fe_2m_limb<F>(i);
+        uint32_t d[8];
+        raw_sub(d, t.v, mm);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t.v[i] = d[i];
+    }
+}
 // a + b and a + 2m - b without reduction
 H2V_HD fe fe_add_raw(const fe &a, const fe &b) {
     fe r;

@@ -88,17 +88,18 @@ __device__ __forceinline__ void ntt_stage(fe (&x)[8], const fe *__restrict__ tw,
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if ((k >> U) & 1) continue;
-        // lazy reduction (Harvey): values live in [0, 4r); t < 2r, a < 2r, so a + t and a + 2r - t stay below 4r
+        // lazy reduction (Harvey): t < 2r; a is brought below theta (just above 2r, see fe_csub_2m_top), so a + t and
+        // a + 2r - t stay below theta + 2r < 2^256
         fe t;
         if (unit) {
-            t = x[k + (1 << U)];
+            t = x[k + (1 << U)];       // stage 0 of pass 0 only: canonical inputs
             fe_csub_2m<Fr>(t);
         } else {
             fe w = fe_load_ro(tw + e_base + ((uint32_t)(k & ((1 << U) - 1)) << (L - 1 - U)));
             t = fe_mul_lazy<Fr>(x[k + (1 << U)], w);
         }
         fe a = x[k];
-        fe_csub_2m<Fr>(a);
+        fe_csub_2m_top<Fr>(a);
         x[k + (1 << U)] = fe_sub_plus_2m<Fr>(a, t);
         x[k] = fe_add_raw(a, t);
     }
@@ -107,6 +108,7 @@ __device__ __forceinline__ void ntt_stage(fe (&x)[8], const fe *__restrict__ tw,
 // last pass: bring a lazily reduced value (< 4r) back to its canonical representative, folding in the post-scale
 __device__ __forceinline__ fe ntt_finish(fe x, const fe *post) {
     if (post) return fe_mul<Fr>(x, fe_load_ro(post));     // x < 4r, post < r: product < 2r, one conditional subtraction
+    fe_csub_2m<Fr>(x);      // x < theta + 2r, slightly above 4r: two exact steps of 2r, then one of r
     fe_csub_2m<Fr>(x);
     fe_reduce_once<Fr>(x);
     return x;
