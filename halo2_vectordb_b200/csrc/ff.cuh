@@ -168,10 +168,12 @@ template <class F> H2V_HD fe fe_add(const fe &a, const fe &b) {
 template <class F> H2V_HD fe fe_sub(const fe &a, const fe &b) {
     fe r;
     uint32_t bw = raw_sub(r.v, a.v, b.v);
-    uint32_t mm[8];
+    if (bw) {      // predicated add of m (no masks)
+        uint32_t mm[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) mm[i] = F::m(i) & bw;
-    raw_add(r.v, r.v, mm);
+        for (int i = 0; i < 8; ++i) mm[i] = F::m(i);
+        raw_add(r.v, r.v, mm);
+    }
     return r;
 }
 template <class F> H2V_HD fe fe_neg(const fe &a) {
@@ -353,10 +355,12 @@ template <class F> H2V_HD void fe_csub_2m(fe &t) {
 template <class F> H2V_HD fe fe_sub_lazy(const fe &a, const fe &b) {
     fe r;
     uint32_t bw = raw_sub(r.v, a.v, b.v);
-    uint32_t mm[8];
+    if (bw) {      // predicated add of 2m (no masks)
+        uint32_t mm[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) mm[i] = fe_2m_limb<F>(i) & bw;
-    raw_add(r.v, r.v, mm);
+        for (int i = 0; i < 8; ++i) mm[i] = fe_2m_limb<F>(i);
+        raw_add(r.v, r.v, mm);
+    }
     return r;
 }
 // x == 0 (mod m) for x in [0, 2m): x is 0 or m
