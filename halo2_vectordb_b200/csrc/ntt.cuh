@@ -58,6 +58,18 @@ __device__ __forceinline__ void ntt_sm_store(uint4 *sm, uint32_t plane1, uint32_
     sm[p] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
     sm[plane1 + p] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
 }
+// the same with the swizzled slot already computed
+__device__ __forceinline__ fe ntt_sm_load_slot(const uint4 *sm, uint32_t plane1, uint32_t p) {
+    uint4 a = sm[p], b = sm[plane1 + p];
+    fe r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void ntt_sm_store_slot(uint4 *sm, uint32_t plane1, uint32_t p, const fe &x) {
+    sm[p] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    sm[plane1 + p] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
 __device__ __forceinline__ fe fe_load_global(const fe *p) {
     const uint4 *q = reinterpret_cast<const uint4 *>(p);
     uint4 a = q[0], b = q[1];
@@ -161,9 +173,16 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
             uint32_t q = w & (T - 1), rest = w >> logT;
             uint32_t low = rest & ((1u << bp) - 1);
             uint32_t mid_base = low | ((rest >> bp) << (bp + 3));
+            // the swizzle is XOR-linear and k << (bp + logT) touches bits the base index leaves clear, so the eight
+            // shared-memory slots are the base slot XOR a per-round constant: one LOP3 per slot instead of the full swizzle
+            const uint32_t slot0 = ntt_swz((mid_base << logT) | q);
+            const uint32_t d1 = ntt_swz(1u << (bp + logT)), d2 = ntt_swz(2u << (bp + logT)), d4 = ntt_swz(4u << (bp + logT));
+            uint32_t slot[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) slot[k] = slot0 ^ ((k & 1) ? d1 : 0u) ^ ((k & 2) ? d2 : 0u) ^ ((k & 4) ? d4 : 0u);
             fe x[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = ntt_sm_load(ntt_sm, plane1, ((mid_base + ((uint32_t)k << bp)) << logT) | q);
+            for (int k = 0; k < 8; ++k) x[k] = ntt_sm_load_slot(ntt_sm, plane1, slot[k]);
             // j mod 2^t for the stage at absolute bit t = t0 + bp + u:
             //   lo + ((low + (k mod 2^u) << bp) << t0)
             const uint32_t lo = p.first ? 0u : (lo_tile * T + q);
@@ -188,7 +207,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
                 ntt_stage<2>(x, p.tw, jlow << (L - 1 - t), L, false);
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) ntt_sm_store(ntt_sm, plane1, ((mid_base + ((uint32_t)k << bp)) << logT) | q, x[k]);
+            for (int k = 0; k < 8; ++k) ntt_sm_store_slot(ntt_sm, plane1, slot[k], x[k]);
         }
         __syncthreads();
     }
