@@ -408,9 +408,9 @@ def prove_shaped_full(h, torch, dev, srs, d_cols):
     vals[:, 0] = torch.randint(0, 1 << 15, (u,), dtype=torch.int64)
     tab = torch.zeros((u, 4), dtype=torch.int64)
     tab[: 1 << 15, 0] = torch.arange(1 << 15, dtype=torch.int64)
-    from oracle import oracle as O      # setup only: Montgomery form of the small lookup values
-    m_in = torch.from_numpy(O.to_mont(vals.numpy().view(np.uint64)).view(np.int64)).to(dev)
-    m_tab = torch.from_numpy(O.to_mont(tab.numpy().view(np.uint64)).view(np.int64)).to(dev)
+    from halo2_vectordb_b200.synthetic import to_mont      # setup only: Montgomery form of the small lookup values
+    m_in = torch.from_numpy(to_mont(vals.numpy().view(np.uint64)).view(np.int64)).to(dev)
+    m_tab = torch.from_numpy(to_mont(tab.numpy().view(np.uint64)).view(np.int64)).to(dev)
     d_pa, d_ps = torch.empty_like(m_in), torch.empty_like(m_in)
     hnum = d_cols[1].cpu().pin_memory().numpy().view(np.uint64)
     y = hnum[:3]
@@ -602,9 +602,10 @@ def bench_row2(h, torch, dev, d_cols, cols):
     vals[:, 0] = torch.randint(0, 1 << bits, (u,), dtype=torch.int64, generator=g, device=dev)
     tab = torch.zeros((u, 4), dtype=torch.int64, device=dev)
     tab[: 1 << bits, 0] = torch.arange(1 << bits, dtype=torch.int64, device=dev)
-    # inputs must be Montgomery: convert the small canonical values through the oracle once (setup, untimed)
-    m_in = torch.from_numpy(O.to_mont(vals.cpu().numpy().view(np.uint64)).view(np.int64)).to(dev)
-    m_tab = torch.from_numpy(O.to_mont(tab.cpu().numpy().view(np.uint64)).view(np.int64)).to(dev)
+    # inputs must be Montgomery: convert the small canonical values on the device once (setup, untimed)
+    from halo2_vectordb_b200.synthetic import to_mont
+    m_in = torch.from_numpy(to_mont(vals.cpu().numpy().view(np.uint64)).view(np.int64)).to(dev)
+    m_tab = torch.from_numpy(to_mont(tab.cpu().numpy().view(np.uint64)).view(np.int64)).to(dev)
     o_a, o_s = torch.empty_like(m_in), torch.empty_like(m_in)
     pm = []
     for i in range(6):

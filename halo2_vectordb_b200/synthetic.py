@@ -41,3 +41,12 @@ def witness_like(cols, n, lookup_bits, seed):
     canon[neg] = negv
     r2 = np.tile(np.array(_limbs(R2), dtype=np.uint64), (tot, 1))
     return selftest_field(0, 0, canon, r2).reshape(cols, n, 4)
+
+
+def to_mont(canon):
+    """Canonical Fr values ((n, 4) uint64 limbs) -> Montgomery form, on the device (x * R^2 * R^-1)."""
+    from . import selftest_field
+
+    canon = np.ascontiguousarray(canon, dtype=np.uint64).reshape(-1, 4)
+    r2 = np.tile(np.array(_limbs(R2), dtype=np.uint64), (canon.shape[0], 1))
+    return selftest_field(0, 0, canon, r2)
