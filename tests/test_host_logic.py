@@ -53,6 +53,17 @@ def test_no_cpu_fallback(built):
         h.EvaluationDomain(4, 4)
     with pytest.raises(h.H2VError):
         h.ParamsKZG(2, np.zeros((4, 8), dtype=np.uint64), None)
+    one = np.ones((3, 4), dtype=np.uint64)
+    with pytest.raises(h.H2VError):
+        h.permute_expression_pair(one, one)
+    with pytest.raises(h.H2VError):
+        h.grand_product(one, one)
+    with pytest.raises(h.H2VError):
+        h.g1_sum(np.zeros((2, 8), dtype=np.uint64))
+    with pytest.raises(h.H2VError):
+        h.eval_polynomial_batch([one], one[:1])
+    with pytest.raises(h.H2VError):
+        h.DeviceBuffer(64)
 
 
 def test_product_does_not_import_oracle():
