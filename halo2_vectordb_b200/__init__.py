@@ -34,6 +34,12 @@ ABI_SYMBOLS = [
     "h2v_permute_expression_pair", "h2v_permute_expression_pair_dev",
     "h2v_quotient_gates_dev", "h2v_quotient_permutation_dev", "h2v_quotient_lookup_dev",
     "h2v_g1_to_bytes", "h2v_fr_to_repr",
+    "h2v_domain_rotate_omega", "h2v_domain_rotate_extended", "h2v_domain_l_i_range", "h2v_domain_fill", "h2v_kate_division_dev",
+    "h2v_quotient_gates_ptrs_dev", "h2v_quotient_permutation_ptrs_dev",
+    "h2v_pk_load", "h2v_pk_free", "h2v_create_proof", "h2v_proof_size", "h2v_pk_last_phase_ms",
+    "h2v_transcript_new", "h2v_transcript_free", "h2v_transcript_common_point", "h2v_transcript_common_scalar",
+    "h2v_transcript_write_point", "h2v_transcript_write_scalar", "h2v_transcript_squeeze_challenge", "h2v_transcript_bytes",
+    "h2v_poseidon_permutation", "h2v_chacha20_fr_random", "h2v_chacha20_block",
     "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_op_rate", "h2v_set_tuning", "h2v_launch_count", "h2v_last_kernel_ms",
 ]
 
@@ -110,6 +116,31 @@ def lib():
         L.h2v_selftest_op_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.h2v_set_tuning.argtypes = [C.c_int, C.c_int]
         L.h2v_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
+        L.h2v_domain_rotate_omega.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.h2v_domain_rotate_extended.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.h2v_domain_l_i_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.h2v_domain_fill.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.h2v_kate_division_dev.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.h2v_quotient_gates_ptrs_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.h2v_quotient_permutation_ptrs_dev.argtypes = ([C.c_void_p] * 5 + [C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                        C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32])
+        L.h2v_pk_load.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_void_p)]
+        L.h2v_pk_free.argtypes = [C.c_void_p]
+        L.h2v_pk_free.restype = None
+        L.h2v_create_proof.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_size_t, C.POINTER(C.c_size_t)]
+        L.h2v_proof_size.argtypes = [C.c_void_p]
+        L.h2v_proof_size.restype = C.c_size_t
+        L.h2v_pk_last_phase_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.h2v_transcript_new.argtypes = [C.POINTER(C.c_void_p)]
+        L.h2v_transcript_free.argtypes = [C.c_void_p]
+        L.h2v_transcript_free.restype = None
+        for name in ("common_point", "common_scalar", "write_point", "write_scalar", "squeeze_challenge"):
+            getattr(L, "h2v_transcript_" + name).argtypes = [C.c_void_p, C.c_void_p]
+        L.h2v_transcript_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.h2v_poseidon_permutation.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.h2v_chacha20_fr_random.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
+        L.h2v_chacha20_block.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p]
         _lib = L
     return _lib
 
@@ -290,6 +321,10 @@ def grand_product(num, den):
 def grand_product_dev(d_num, d_den, n, n_cols, d_out):
     """Running products of n_cols contiguous device-resident columns (one batch inversion for all)."""
     _check(lib().h2v_grand_product_dev(d_num, d_den, n, n_cols, d_out))
+
+
+def kate_division_dev(d_a, n, b, d_out):
+    _check(lib().h2v_kate_division_dev(d_a, n, _ptr(_fr1(b)), d_out))
 
 
 def kate_division(a, b):
@@ -509,6 +544,207 @@ class EvaluationDomain:
     def quotient_lookup(self, d_h, y, beta, gamma, d_input, d_table, d_perm_input, d_perm_table, d_z, d_l0, d_l_last, d_l_active):
         _check(lib().h2v_quotient_lookup_dev(self._h, d_h, _ptr(_fr1(y)), _ptr(_fr1(beta)), _ptr(_fr1(gamma)),
                                              d_input, d_table, d_perm_input, d_perm_table, d_z, d_l0, d_l_last, d_l_active))
+
+
+    # --- scalar / index helpers of poly/domain.rs (host-side)
+    def rotate_omega(self, value, rotation):
+        """`rotate_omega(value, Rotation(rotation))` = value * omega^rotation"""
+        out = np.zeros(4, dtype=np.uint64)
+        _check(lib().h2v_domain_rotate_omega(self._h, _ptr(_fr1(value)), rotation, _ptr(out)))
+        return out
+
+    def rotate_extended(self, poly, rotation):
+        """`rotate_extended(&poly, Rotation(rotation))` on an extended-domain column (returns a new array)"""
+        a = _fr(poly, self.extended_n)
+        out = np.zeros_like(a)
+        _check(lib().h2v_domain_rotate_extended(self._h, _ptr(a), rotation, _ptr(out)))
+        return out
+
+    def l_i_range(self, x, xn, rotations):
+        """`l_i_range(x, xn, rotations)` for a contiguous `range(lo, hi)` of rotations -> (hi - lo, 4)"""
+        rot = list(rotations)
+        if rot != list(range(rot[0], rot[0] + len(rot))) if rot else False:
+            raise ValueError("l_i_range: rotations must be a contiguous ascending range")
+        out = np.zeros((len(rot), 4), dtype=np.uint64)
+        if rot:
+            _check(lib().h2v_domain_l_i_range(self._h, _ptr(_fr1(x)), _ptr(_fr1(xn)), rot[0], rot[0] + len(rot), _ptr(out)))
+        return out
+
+    def _fill(self, basis, scalar):
+        out = np.zeros((self.extended_n if basis == 2 else self.n, 4), dtype=np.uint64)
+        _check(lib().h2v_domain_fill(self._h, basis, None if scalar is None else _ptr(_fr1(scalar)), _ptr(out)))
+        return out
+
+    def empty_coeff(self):
+        return self._fill(0, None)
+
+    def empty_lagrange(self):
+        return self._fill(1, None)
+
+    def empty_extended(self):
+        return self._fill(2, None)
+
+    def constant_lagrange(self, scalar):
+        return self._fill(1, scalar)
+
+    def constant_extended(self, scalar):
+        return self._fill(2, scalar)
+
+    def extended_len(self):
+        return self.extended_n
+
+    def get_omega(self):
+        return self.omega
+
+    def get_omega_inv(self):
+        return self.omega_inv
+
+    def get_extended_omega(self):
+        return self.extended_omega
+
+
+# ----------------------------------------------------------------------------- transcript / RNG (host-side)
+class PoseidonTranscript:
+    """snark-verifier `PoseidonTranscript<G1Affine, NativeLoader, Vec<u8>, 5, 4, 8, 60>::new::<0>` (writer)."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        _check(lib().h2v_transcript_new(C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h.value and _lib is not None:
+                _lib.h2v_transcript_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def _pt(self, p):
+        return _ptr(np.ascontiguousarray(p, dtype=np.uint64).reshape(8))
+
+    def common_point(self, p):
+        _check(lib().h2v_transcript_common_point(self._h, self._pt(p)))
+
+    def common_scalar(self, s):
+        _check(lib().h2v_transcript_common_scalar(self._h, _ptr(_fr1(s))))
+
+    def write_point(self, p):
+        _check(lib().h2v_transcript_write_point(self._h, self._pt(p)))
+
+    def write_scalar(self, s):
+        _check(lib().h2v_transcript_write_scalar(self._h, _ptr(_fr1(s))))
+
+    def squeeze_challenge(self):
+        out = np.zeros(4, dtype=np.uint64)
+        _check(lib().h2v_transcript_squeeze_challenge(self._h, _ptr(out)))
+        return out
+
+    def finalize(self):
+        ln = C.c_size_t()
+        _check(lib().h2v_transcript_bytes(self._h, None, 0, C.byref(ln)))
+        buf = np.zeros(max(ln.value, 1), dtype=np.uint8)
+        _check(lib().h2v_transcript_bytes(self._h, _ptr(buf), ln.value, C.byref(ln)))
+        return bytes(buf[:ln.value])
+
+
+def poseidon_permutation(state, r_f, r_p):
+    """the Poseidon permutation over BN254 Fr (t = len(state) in {3, 5}) on Montgomery-form words; returns a new array"""
+    st = np.array(_fr(state), copy=True)
+    _check(lib().h2v_poseidon_permutation(st.shape[0], r_f, r_p, _ptr(st)))
+    return st
+
+
+def chacha20_fr_random(seed, n):
+    """the first n `Fr::random(&mut ChaCha20Rng::from_seed(seed))` draws, Montgomery form (n, 4)"""
+    out = np.zeros((n, 4), dtype=np.uint64)
+    _check(lib().h2v_chacha20_fr_random(bytes(seed), n, _ptr(out)))
+    return out
+
+
+def chacha20_block(seed, counter):
+    out = np.zeros(64, dtype=np.uint8)
+    _check(lib().h2v_chacha20_block(bytes(seed), counter, _ptr(out)))
+    return bytes(out)
+
+
+# ----------------------------------------------------------------------------- plonk/prover.rs
+class _CircuitT(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("degree", C.c_uint32), ("blinding_factors", C.c_uint32),
+                ("n_advice", C.c_uint32), ("n_fixed", C.c_uint32), ("n_instance", C.c_uint32),
+                ("n_gates", C.c_uint32), ("gate_advice", C.c_void_p), ("gate_selector", C.c_void_p),
+                ("n_lookups", C.c_uint32), ("lookup_input", C.c_void_p), ("lookup_table", C.c_void_p),
+                ("n_perm", C.c_uint32), ("perm_kind", C.c_void_p), ("perm_index", C.c_void_p),
+                ("n_advice_queries", C.c_uint32), ("advice_query_col", C.c_void_p), ("advice_query_rot", C.c_void_p),
+                ("n_fixed_queries", C.c_uint32), ("fixed_query_col", C.c_void_p), ("fixed_query_rot", C.c_void_p)]
+
+
+class ProvingKey:
+    """halo2 `ProvingKey` for a halo2-base-shaped constraint system, resident on the device.
+
+    cs: dict with k, degree, blinding_factors, n_advice, n_fixed, n_instance, gates [(advice, selector)],
+    lookups [(input advice, table fixed)], permutation [(kind, index)] (kind 0 advice, 1 fixed, 2 instance),
+    advice_queries [(column, rotation)], fixed_queries [(column, rotation)]."""
+
+    def __init__(self, params, cs, fixed, sigma, vk_transcript_repr):
+        self.params, self.cs = params, cs
+        u32 = lambda xs: np.ascontiguousarray(xs, dtype=np.uint32)
+        self._arrs = dict(
+            ga=u32([g[0] for g in cs["gates"]]), gs=u32([g[1] for g in cs["gates"]]),
+            li=u32([l[0] for l in cs["lookups"]]), lt=u32([l[1] for l in cs["lookups"]]),
+            pk=np.ascontiguousarray([p[0] for p in cs["permutation"]], dtype=np.uint8), pi=u32([p[1] for p in cs["permutation"]]),
+            aqc=u32([q[0] for q in cs["advice_queries"]]), aqr=np.ascontiguousarray([q[1] for q in cs["advice_queries"]], dtype=np.int32),
+            fqc=u32([q[0] for q in cs["fixed_queries"]]), fqr=np.ascontiguousarray([q[1] for q in cs["fixed_queries"]], dtype=np.int32))
+        a = self._arrs
+        p = lambda x: x.ctypes.data if x.size else None
+        ct = _CircuitT(cs["k"], cs["degree"], cs["blinding_factors"], cs["n_advice"], cs["n_fixed"], cs["n_instance"],
+                       len(cs["gates"]), p(a["ga"]), p(a["gs"]), len(cs["lookups"]), p(a["li"]), p(a["lt"]),
+                       len(cs["permutation"]), p(a["pk"]), p(a["pi"]), len(cs["advice_queries"]), p(a["aqc"]), p(a["aqr"]),
+                       len(cs["fixed_queries"]), p(a["fqc"]), p(a["fqr"]))
+        n = 1 << cs["k"]
+        fx = [_fr(c, n) for c in fixed]
+        sg = [_fr(c, n) for c in sigma]
+        if len(fx) != cs["n_fixed"] or len(sg) != len(cs["permutation"]):
+            raise ValueError("ProvingKey: fixed / sigma column count does not match the constraint system")
+        fa = (C.c_void_p * max(1, len(fx)))(*[c.ctypes.data for c in fx])
+        sa = (C.c_void_p * max(1, len(sg)))(*[c.ctypes.data for c in sg])
+        self._h = C.c_void_p()
+        _check(lib().h2v_pk_load(params._h, C.byref(ct), fa, sa, _ptr(_fr1(vk_transcript_repr)), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.h2v_pk_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def proof_size(self):
+        return int(lib().h2v_proof_size(self._h))
+
+    def create_proof(self, advice, instances, rng_seed=bytes(32)):
+        """`create_proof(params, pk, &[circuit], &[instances], ChaCha20Rng::from_seed(rng_seed), transcript)` -> proof bytes"""
+        n = 1 << self.cs["k"]
+        adv = [_fr(c, n) for c in advice]
+        if len(adv) != self.cs["n_advice"] or len(instances) != self.cs["n_instance"]:
+            raise ValueError("create_proof: advice / instance column count does not match the constraint system")
+        inst = [_fr(np.asarray(c, dtype=np.uint64).reshape(-1, 4)) for c in instances]
+        aa = (C.c_void_p * max(1, len(adv)))(*[c.ctypes.data for c in adv])
+        ia = (C.c_void_p * max(1, len(inst)))(*[c.ctypes.data for c in inst])
+        il = np.ascontiguousarray([c.shape[0] for c in inst] or [0], dtype=np.uint32)
+        cap = self.proof_size()
+        out = np.zeros(cap, dtype=np.uint8)
+        ln = C.c_size_t()
+        _check(lib().h2v_create_proof(self._h, aa, ia, _ptr(il), bytes(rng_seed), _ptr(out), cap, C.byref(ln)))
+        return bytes(out[:ln.value])
+
+    def last_phase_ms(self):
+        buf = (C.c_double * 8)()
+        _check(lib().h2v_pk_last_phase_ms(self._h, buf))
+        names = ["advice_commit", "lookup_permute", "grand_products", "transforms", "quotient", "evaluations", "multiopen"]
+        return dict(zip(names, [float(x) for x in buf]))
 
 
 # ----------------------------------------------------------------------------- device self-tests

@@ -197,8 +197,8 @@ H2V_HD affine xyzz_to_affine_fast(const xyzz &p) {
 // a Jacobian representative of the same point, no inversion: Z = ZZZ  =>  X' = X*ZZ^2, Y' = Y*ZZZ^2
 H2V_HD jacobian xyzz_to_jacobian(const xyzz &p) {
     jacobian r;
-    if (xyzz_is_identity(p)) {
-        r.x = fe_zero(); r.y = fe_zero(); r.z = fe_zero();
+    if (xyzz_is_identity(p)) {     // halo2curves `G1::identity()` is (0, 1, 0): keep the raw value byte-compatible
+        r.x = fe_zero(); r.y = fe_one<Fq>(); r.z = fe_zero();
         return r;
     }
     r.x = fe_mul<Fq>(p.x, fe_sqr<Fq>(p.zz));

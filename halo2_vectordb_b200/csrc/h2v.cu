@@ -23,6 +23,7 @@
 #include "poly.cuh"
 #include "quotient.cuh"
 #include "lookup.cuh"
+#include "poseidon.hpp"
 
 using namespace h2v;
 
@@ -31,8 +32,8 @@ namespace {
 thread_local std::string g_err;
 int g_device = 0;
 std::atomic<uint64_t> g_launches{0};
-float g_last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-std::mutex g_ms_mu;
+// device-side timing of the calling thread's last `_dev` call (per thread: concurrent callers do not mix their records)
+thread_local float g_last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -43,6 +44,17 @@ int fail(int code, const char *fmt, ...) {
     g_err = buf;
     return code;
 }
+}  // namespace
+// shared with the other translation units of the library (internal.hpp)
+namespace h2v {
+int set_error(int code, const char *msg) {
+    g_err = msg;
+    return code;
+}
+void count_launches(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int current_device() { return g_device; }
+}  // namespace h2v
+namespace {
 #define CU(x)                                                                                      \
     do {                                                                                           \
         cudaError_t e_ = (x);                                                                      \
@@ -106,7 +118,6 @@ struct Timer {   // CUDA-event stopwatch on one stream, accumulating per kernel 
     }
     void end() { cudaEventRecord(spans.back().second.second, st); }
     void collect(bool reset) {   // call after the stream is synchronised
-        std::lock_guard<std::mutex> lk(g_ms_mu);
         if (reset)
             for (float &v : g_last_ms) v = 0;
         for (auto &s : spans) {
@@ -379,8 +390,11 @@ int tuning(std::atomic<int> &slot, const char *env) {
     }
     return v;
 }
+// run_msm snapshots both knobs once per call (h2v_set_tuning from another thread must not change the workspace layout
+// between the sizing pass and the launches)
+thread_local int t_tune_chunk = -1, t_tune_ba = -1;
 uint32_t pick_chunk(uint64_t max_entries) {
-    const int forced = tuning(g_tune_chunk, "H2V_CHUNK");
+    const int forced = t_tune_chunk;
     if (forced > 0) return (uint32_t)forced;
     // small inputs are latency-bound: chunk * t(mixed add) in the accumulate thread against
     // (bucket load / chunk) * t(full add) in the finish thread is flattest around 12..24 (measured)
@@ -415,7 +429,7 @@ struct MsmLayout {
 // 96 columns x 2^16 take 17.0 ms with 5 rounds vs 17.0 ms for the pure XYZZ path (best: 3 rounds, 16.2 ms).
 // h2v_set_tuning / H2V_BA_ROUNDS switch them on (tests run them for the tuning-invariance check).
 uint32_t pick_ba_rounds(const MsmShape &, uint32_t) {
-    const int forced = tuning(g_tune_ba, "H2V_BA_ROUNDS");
+    const int forced = t_tune_ba;
     if (forced >= 0) return std::min<uint32_t>((uint32_t)forced, H2V_BA_MAX_ROUNDS);
     return 0;
 }
@@ -486,11 +500,18 @@ const size_t MSM_WS_BUDGET = (size_t)16 << 30;   // per handle; columns per laun
 int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_stride, size_t n_cols, size_t len,
             const affine *points, MsmCfg cfg, size_t pstride, affine *d_out_aff, jacobian *d_out_jac, Timer *tm) {
     if (n_cols == 0) return H2V_OK;
-    if (len == 0) {   // empty sum = identity (zeros in both encodings)
+    if (len == 0) {   // empty sum = identity: affine (0, 0); Jacobian (0, 1, 0) as halo2curves `G1::identity()`
         if (d_out_aff) CU(cudaMemsetAsync(d_out_aff, 0, n_cols * sizeof(affine), st));
-        if (d_out_jac) CU(cudaMemsetAsync(d_out_jac, 0, n_cols * sizeof(jacobian), st));
+        if (d_out_jac) {
+            std::vector<jacobian> id(n_cols);
+            for (auto &j : id) { j.x = fe_zero(); j.y = fe_one<Fq>(); j.z = fe_zero(); }
+            CU(cudaMemcpyAsync(d_out_jac, id.data(), n_cols * sizeof(jacobian), cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+        }
         return H2V_OK;
     }
+    t_tune_chunk = tuning(g_tune_chunk, "H2V_CHUNK");
+    t_tune_ba = tuning(g_tune_ba, "H2V_BA_ROUNDS");
     MsmShape sh;
     memset(&sh, 0, sizeof sh);
     sh.n = (uint32_t)len;
@@ -740,7 +761,7 @@ int h2v_init(int device) {
     return H2V_OK;
 }
 // Proof wire format of a commitment: halo2curves 0.3.x `G1Affine::to_bytes()` =
-// canonical x, little-endian, with the parity of canonical y in bit 6 of byte 31; identity = 32 zero bytes.
+// canonical x, little-endian, with the parity of canonical y in the top bit of byte 31 (poseidon.hpp); identity = 32 zero bytes.
 // Host-side (a proof holds ~10^3 commitments); uses the host instantiation of the field code.
 int h2v_g1_to_bytes(const uint64_t *affine_pts, size_t n, uint8_t *out) {
     if (n && (!affine_pts || !out)) return fail(H2V_EINVAL, "g1_to_bytes: NULL buffer");
@@ -752,9 +773,7 @@ int h2v_g1_to_bytes(const uint64_t *affine_pts, size_t n, uint8_t *out) {
             memset(o, 0, 32);
             continue;
         }
-        fe x = fe_from_mont<Fq>(p.x), y = fe_from_mont<Fq>(p.y);
-        memcpy(o, x.v, 32);
-        o[31] |= (uint8_t)((y.v[0] & 1u) << 6);
+        g1_affine_to_bytes(p, o);
     }
     return H2V_OK;
 }
@@ -819,7 +838,7 @@ int h2v_set_tuning(int chunk, int ba_rounds) {
     return H2V_OK;
 }
 int h2v_last_kernel_ms(float out[8]) {
-    std::lock_guard<std::mutex> lk(g_ms_mu);
+    if (!out) return fail(H2V_EINVAL, "last_kernel_ms: NULL");
     memcpy(out, g_last_ms, sizeof g_last_ms);
     return H2V_OK;
 }
@@ -1060,7 +1079,9 @@ int h2v_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, u
     if (n == 0) {
         int rc = use_device();
         if (rc) return rc;
-        memset(out_jacobian, 0, 96);
+        jacobian id;      // halo2curves `G1::identity()` = (0, 1, 0)
+        id.x = fe_zero(); id.y = fe_one<Fq>(); id.z = fe_zero();
+        memcpy(out_jacobian, &id, 96);
         return H2V_OK;
     }
     return multiexp_raw(coeffs, bases, n, out_jacobian, nullptr);
@@ -1207,6 +1228,72 @@ int h2v_domain_constant(h2v_domain_t d, int which, uint64_t out[4]) {
     return H2V_OK;
 }
 
+// ---- the scalar / index helpers of poly/domain.rs; host-side, no device work
+// EvaluationDomain::rotate_omega(value, rotation) = value * omega^rotation
+int h2v_domain_rotate_omega(h2v_domain_t d, const uint64_t value[4], int32_t rotation, uint64_t out[4]) {
+    if (!d || !value || !out) return fail(H2V_EINVAL, "rotate_omega: NULL argument");
+    fe w = rotation >= 0 ? fe_pow_u64<Fr>(d->omega, (uint64_t)rotation) : fe_pow_u64<Fr>(d->omega_inv, (uint64_t)(-(int64_t)rotation));
+    fe_to_u64x4(fe_mul<Fr>(fe_from_u64x4(value), w), out);
+    return H2V_OK;
+}
+// EvaluationDomain::rotate_extended(poly, rotation): cyclic shift of an extended-domain column by
+// rotation * 2^(extended_k - k) positions (out[i] = in[i + shift]); in != out
+int h2v_domain_rotate_extended(h2v_domain_t d, const uint64_t *in, int32_t rotation, uint64_t *out) {
+    if (!d || !in || !out || in == out) return fail(H2V_EINVAL, "rotate_extended: NULL or aliased buffers");
+    const size_t en = (size_t)1 << d->ek;
+    const uint64_t per = (uint64_t)1 << (d->ek - d->k);
+    const uint64_t mag = (uint64_t)(rotation < 0 ? -(int64_t)rotation : (int64_t)rotation) * per % en;
+    const size_t sh = (size_t)(rotation >= 0 ? mag : (en - mag) % en);     // rotate_left(mag) / rotate_right(mag)
+    memcpy(out, in + 4 * sh, (en - sh) * 32);
+    memcpy(out + 4 * (en - sh), in, sh * 32);
+    return H2V_OK;
+}
+// EvaluationDomain::l_i_range(x, xn, rotations): out[t] = l_i(x) for i = rot_lo + t, rot_lo <= i < rot_hi, where
+// l_i(x) = omega^i (x^n - 1) / (n (x - omega^i)); xn = x^n is supplied as upstream's callers do.
+int h2v_domain_l_i_range(h2v_domain_t d, const uint64_t x[4], const uint64_t xn[4], int32_t rot_lo, int32_t rot_hi, uint64_t *out) {
+    if (!d || !x || !xn || (rot_hi > rot_lo && !out)) return fail(H2V_EINVAL, "l_i_range: NULL argument");
+    if (rot_hi < rot_lo || (int64_t)rot_hi - rot_lo > (1 << 24)) return fail(H2V_EINVAL, "l_i_range: bad rotation range");
+    const fe X = fe_from_u64x4(x), one = fe_one<Fr>();
+    const fe common = fe_mul<Fr>(fe_sub<Fr>(fe_from_u64x4(xn), one), d->ifft_divisor);    // barycentric_weight = 1 / n
+    const size_t cnt = (size_t)((int64_t)rot_hi - rot_lo);
+    std::vector<fe> w(cnt), den(cnt), pre(cnt);
+    fe cur = rot_lo >= 0 ? fe_pow_u64<Fr>(d->omega, (uint64_t)rot_lo) : fe_pow_u64<Fr>(d->omega_inv, (uint64_t)(-(int64_t)rot_lo));
+    for (size_t t = 0; t < cnt; ++t) {
+        w[t] = cur;
+        den[t] = fe_sub<Fr>(X, cur);
+        cur = fe_mul<Fr>(cur, d->omega);
+    }
+    // batch_invert (zeros skipped, as ff::BatchInvert does: x on the domain gives l_i(x) = 0 there, like upstream)
+    fe acc = one;
+    for (size_t t = 0; t < cnt; ++t) {
+        pre[t] = acc;
+        if (!fe_is_zero(den[t])) acc = fe_mul<Fr>(acc, den[t]);
+    }
+    fe inv = fe_inv<Fr>(acc);
+    for (size_t t = cnt; t-- > 0;) {
+        fe r = fe_zero();
+        if (!fe_is_zero(den[t])) {
+            r = fe_mul<Fr>(inv, pre[t]);
+            inv = fe_mul<Fr>(inv, den[t]);
+        }
+        fe_to_u64x4(fe_mul<Fr>(fe_mul<Fr>(r, common), w[t]), out + 4 * t);
+    }
+    return H2V_OK;
+}
+// EvaluationDomain::{empty_coeff, empty_lagrange, empty_extended, constant_lagrange, constant_extended}: a column of
+// the basis' length filled with `scalar` (NULL = zero).  basis: 0 coeff, 1 lagrange (both 2^k), 2 extended (2^extended_k)
+int h2v_domain_fill(h2v_domain_t d, int basis, const uint64_t scalar[4], uint64_t *out) {
+    if (!d || !out) return fail(H2V_EINVAL, "domain_fill: NULL argument");
+    if (basis < 0 || basis > 2) return fail(H2V_EINVAL, "domain_fill: basis must be 0, 1 or 2");
+    const size_t len = (size_t)1 << (basis == 2 ? d->ek : d->k);
+    if (!scalar) {
+        memset(out, 0, len * 32);
+    } else {
+        for (size_t i = 0; i < len; ++i) memcpy(out + 4 * i, scalar, 32);
+    }
+    return H2V_OK;
+}
+
 int h2v_domain_transform_dev(h2v_domain_t d, int op, const void *d_in, size_t in_stride, void *d_out, size_t out_stride,
                              size_t n_cols) {
     if (!d) return fail(H2V_EINVAL, "transform: NULL domain");
@@ -1341,7 +1428,7 @@ namespace {
 struct PolyCtx {
     std::mutex mu;
     cudaStream_t st = nullptr;
-    DevBuf a, b, c, d, tree;
+    DevBuf a, b, c, d, e, tree;
 };
 PolyCtx g_poly;
 int poly_ctx_ready() {
@@ -1468,14 +1555,23 @@ static int run_grand_product(cudaStream_t st, const fe *num, const fe *den, uint
     int rc;
     const uint32_t ntiles = (n + H2V_FR_TILE - 1) / H2V_FR_TILE;
     const size_t tot = (size_t)n * cols;
-    if ((rc = g_poly.c.ensure(tot * sizeof(fe))) || (rc = g_poly.d.ensure(((size_t)ntiles * cols + 1) * sizeof(fe)))) return rc;
-    // denominators must be non-zero (the reference would panic on invert().unwrap()); one inversion for all columns
-    if ((rc = run_batch_invert<FrP>(st, den, g_poly.c.as<fe>(), (uint32_t)tot, g_poly.tree))) return rc;
-    fr_prod_tiles_kernel<<<dim3(ntiles, cols), 256, 0, st>>>(num, g_poly.c.as<fe>(), n, g_poly.d.as<fe>());
+    if ((rc = g_poly.c.ensure(tot * sizeof(fe))) || (rc = g_poly.e.ensure(tot * sizeof(fe))) ||
+        (rc = g_poly.d.ensure(((size_t)ntiles * cols + 1) * sizeof(fe))))
+        return rc;
+    // One inversion for all columns, with the semantics of ff `BatchInvert::batch_invert` that upstream's permutation and
+    // lookup provers call: a zero denominator is skipped (its "inverse" stays 0, the running product is 0 from there on)
+    // and does not disturb any other element of the batch.
+    const unsigned gt = (unsigned)((tot + 255) / 256);
+    fr_zero_to_one_kernel<<<gt, 256, 0, st>>>(den, g_poly.e.as<fe>(), (uint32_t)tot);
+    LAUNCHED();
+    if ((rc = run_batch_invert<FrP>(st, g_poly.e.as<fe>(), g_poly.c.as<fe>(), (uint32_t)tot, g_poly.tree))) return rc;
+    fr_select_inverse_kernel<<<gt, 256, 0, st>>>(den, g_poly.c.as<fe>(), g_poly.e.as<fe>(), (uint32_t)tot);
+    LAUNCHED();
+    fr_prod_tiles_kernel<<<dim3(ntiles, cols), 256, 0, st>>>(num, g_poly.e.as<fe>(), n, g_poly.d.as<fe>());
     LAUNCHED();
     fr_scan_top_kernel<OpMul><<<dim3(1, cols), 256, 0, st>>>(g_poly.d.as<fe>(), ntiles);
     LAUNCHED();
-    fr_prod_apply_kernel<<<dim3(ntiles, cols), 256, 0, st>>>(num, g_poly.c.as<fe>(), n, g_poly.d.as<fe>(), out);
+    fr_prod_apply_kernel<<<dim3(ntiles, cols), 256, 0, st>>>(num, g_poly.e.as<fe>(), n, g_poly.d.as<fe>(), out);
     LAUNCHED();
     return H2V_OK;
 }
@@ -1518,27 +1614,19 @@ int h2v_grand_product_dev(const void *d_num, const void *d_den, size_t n, size_t
     if (e != cudaSuccess) return fail(H2V_ECUDA, "grand_product: %s", cudaGetErrorString(e));
     return H2V_OK;
 }
-int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t *out) {
-    if (n <= 1) return H2V_OK;
-    if (!a || !b || !out) return fail(H2V_EINVAL, "kate_division: NULL buffer");
-    if (n >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "kate_division: n too large");
-    int rc = use_device();
-    if (rc) return rc;
-    std::lock_guard<std::mutex> lk(g_poly.mu);
-    if ((rc = poly_ctx_ready())) return rc;
-    cudaStream_t st = g_poly.st;
-    const uint32_t ntiles = (uint32_t)((n + H2V_FR_TILE - 1) / H2V_FR_TILE);
-    if ((rc = g_poly.a.ensure(n * sizeof(fe))) || (rc = g_poly.b.ensure(n * sizeof(fe))) || (rc = g_poly.d.ensure(((size_t)ntiles + 1) * sizeof(fe))))
-        return rc;
-    CU(cudaMemcpyAsync(g_poly.a.p, a, n * sizeof(fe), cudaMemcpyHostToDevice, st));
+// a, q device-resident (q: n - 1 coefficients, must not overlap a); g_poly.mu held by the caller
+static int run_kate_division(cudaStream_t st, const fe *a, uint32_t n, const fe &b, fe *q) {
+    int rc;
+    const uint32_t ntiles = (n + H2V_FR_TILE - 1) / H2V_FR_TILE;
+    if ((rc = g_poly.d.ensure(((size_t)ntiles + 1) * sizeof(fe)))) return rc;
     KateParams kp;
-    kp.a = g_poly.a.as<fe>();
-    kp.q = g_poly.b.as<fe>();
-    kp.n = (uint32_t)n;
-    kp.b = fe_from_u64x4(b);
+    kp.a = a;
+    kp.q = q;
+    kp.n = n;
+    kp.b = b;
     kp.tile = g_poly.d.as<fe>();
     if (fe_is_zero(kp.b)) {
-        kate_shift_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kp.a, kp.q, kp.n);
+        kate_shift_kernel<<<(n + 255) / 256, 256, 0, st>>>(kp.a, kp.q, kp.n);
         LAUNCHED();
     } else {
         kp.binv = fe_inv<Fr>(kp.b);      // one host-side inversion of the evaluation point
@@ -1548,6 +1636,37 @@ int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t
         LAUNCHED();
         kate_apply_kernel<<<ntiles, 256, 0, st>>>(kp);
         LAUNCHED();
+    }
+    return H2V_OK;
+}
+int h2v_kate_division_dev(const void *d_a, size_t n, const uint64_t b[4], void *d_out) {
+    if (n <= 1) return H2V_OK;
+    if (!d_a || !b || !d_out) return fail(H2V_EINVAL, "kate_division: NULL buffer");
+    if (n >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "kate_division: n too large");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_poly.mu);
+    if ((rc = poly_ctx_ready())) return rc;
+    rc = run_kate_division(g_poly.st, (const fe *)d_a, (uint32_t)n, fe_from_u64x4(b), (fe *)d_out);
+    cudaError_t e = cudaStreamSynchronize(g_poly.st);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(H2V_ECUDA, "kate_division: %s", cudaGetErrorString(e));
+    return H2V_OK;
+}
+int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t *out) {
+    if (n <= 1) return H2V_OK;
+    if (!a || !b || !out) return fail(H2V_EINVAL, "kate_division: NULL buffer");
+    if (n >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "kate_division: n too large");
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_poly.mu);
+    if ((rc = poly_ctx_ready())) return rc;
+    cudaStream_t st = g_poly.st;
+    if ((rc = g_poly.a.ensure(n * sizeof(fe))) || (rc = g_poly.b.ensure(n * sizeof(fe)))) return rc;
+    CU(cudaMemcpyAsync(g_poly.a.p, a, n * sizeof(fe), cudaMemcpyHostToDevice, st));
+    if ((rc = run_kate_division(st, g_poly.a.as<fe>(), (uint32_t)n, fe_from_u64x4(b), g_poly.b.as<fe>()))) {
+        cudaStreamSynchronize(st);
+        return rc;
     }
     CU(cudaMemcpyAsync(out, g_poly.b.p, (n - 1) * sizeof(fe), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -1693,15 +1812,31 @@ int h2v_quotient_gates_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], size_
     std::lock_guard<std::mutex> lk(d->mu);
     Timer tm(d->stream);
     tm.begin(7);
-    quotient_gates_kernel<<<(c.n_ext + 255) / 256, 256, 0, d->stream>>>((fe *)d_h, c, (uint32_t)n_gates, (const fe *)d_q, q_stride,
-                                                                        (const fe *)d_a, a_stride);
+    quotient_gates_kernel<<<(c.n_ext + 255) / 256, 256, 0, d->stream>>>((fe *)d_h, c, (uint32_t)n_gates, ColsStrided{(const fe *)d_q, q_stride},
+                                                                        ColsStrided{(const fe *)d_a, a_stride});
     LAUNCHED();
     return quotient_finish(d, tm);
 }
-int h2v_quotient_permutation_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
-                                 size_t n_cols, size_t chunk_len, const void *d_cols, size_t cols_stride, const void *d_sigma,
-                                 size_t sigma_stride, const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last,
-                                 const void *d_l_active, uint32_t blinding_factors) {
+int h2v_quotient_gates_ptrs_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], size_t n_gates, const void *const *d_q_ptrs,
+                                const void *const *d_a_ptrs) {
+    QuotientCommon c;
+    int rc = quotient_common(d, d_h, y, &c);
+    if (rc) return rc;
+    if (!n_gates) return H2V_OK;
+    if (!d_q_ptrs || !d_a_ptrs) return fail(H2V_EINVAL, "quotient_gates: NULL pointer table");
+    if (n_gates > (1u << 20)) return fail(H2V_EINVAL, "quotient_gates: too many gates");
+    std::lock_guard<std::mutex> lk(d->mu);
+    Timer tm(d->stream);
+    tm.begin(7);
+    quotient_gates_kernel<<<(c.n_ext + 255) / 256, 256, 0, d->stream>>>((fe *)d_h, c, (uint32_t)n_gates, ColsTable{(const fe *const *)d_q_ptrs},
+                                                                        ColsTable{(const fe *const *)d_a_ptrs});
+    LAUNCHED();
+    return quotient_finish(d, tm);
+}
+static int quotient_permutation_any(h2v_domain_t d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                                    size_t n_cols, size_t chunk_len, const void *d_cols, size_t cols_stride, const void *d_sigma,
+                                    size_t sigma_stride, const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last,
+                                    const void *d_l_active, uint32_t blinding_factors, bool tables) {
     QuotientCommon c;
     int rc = quotient_common(d, d_h, y, &c);
     if (rc) return rc;
@@ -1710,7 +1845,7 @@ int h2v_quotient_permutation_dev(h2v_domain_t d, void *d_h, const uint64_t y[4],
         return fail(H2V_EINVAL, "quotient_permutation: NULL buffer");
     if (!chunk_len || n_cols > (1u << 20) || blinding_factors + 1 >= (1u << d->k))
         return fail(H2V_EINVAL, "quotient_permutation: chunk_len = 0, too many columns, or blinding_factors >= n - 1");
-    if (cols_stride < c.n_ext || sigma_stride < c.n_ext || z_stride < c.n_ext)
+    if ((!tables && (cols_stride < c.n_ext || sigma_stride < c.n_ext)) || z_stride < c.n_ext)
         return fail(H2V_EINVAL, "quotient_permutation: stride shorter than 2^extended_k");
     QuotientPerm p;
     p.beta = fe_from_u64x4(beta);
@@ -1721,16 +1856,35 @@ int h2v_quotient_permutation_dev(h2v_domain_t d, void *d_h, const uint64_t y[4],
     p.chunk_len = (uint32_t)std::min<size_t>(chunk_len, n_cols);
     p.n_sets = (p.n_cols + p.chunk_len - 1) / p.chunk_len;
     p.last_rot = -(int)(blinding_factors + 1);
-    p.cols = (const fe *)d_cols; p.sigma = (const fe *)d_sigma; p.z = (const fe *)d_z;
-    p.cols_stride = cols_stride; p.sigma_stride = sigma_stride; p.z_stride = z_stride;
+    p.z = (const fe *)d_z;
+    p.z_stride = z_stride;
     p.l0 = (const fe *)d_l0; p.l_last = (const fe *)d_l_last; p.l_active = (const fe *)d_l_active;
     if ((rc = domain_twiddles(d, 2, &p.tw))) return rc;
     std::lock_guard<std::mutex> lk(d->mu);
     Timer tm(d->stream);
     tm.begin(7);
-    quotient_permutation_kernel<<<(c.n_ext + 255) / 256, 256, 0, d->stream>>>((fe *)d_h, c, p);
+    if (tables)
+        quotient_permutation_kernel<<<(c.n_ext + 255) / 256, 256, 0, d->stream>>>((fe *)d_h, c, p, ColsTable{(const fe *const *)d_cols},
+                                                                                  ColsTable{(const fe *const *)d_sigma});
+    else
+        quotient_permutation_kernel<<<(c.n_ext + 255) / 256, 256, 0, d->stream>>>((fe *)d_h, c, p, ColsStrided{(const fe *)d_cols, cols_stride},
+                                                                                  ColsStrided{(const fe *)d_sigma, sigma_stride});
     LAUNCHED();
     return quotient_finish(d, tm);
+}
+int h2v_quotient_permutation_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                                 size_t n_cols, size_t chunk_len, const void *d_cols, size_t cols_stride, const void *d_sigma,
+                                 size_t sigma_stride, const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last,
+                                 const void *d_l_active, uint32_t blinding_factors) {
+    return quotient_permutation_any(d, d_h, y, beta, gamma, n_cols, chunk_len, d_cols, cols_stride, d_sigma, sigma_stride, d_z, z_stride,
+                                    d_l0, d_l_last, d_l_active, blinding_factors, false);
+}
+int h2v_quotient_permutation_ptrs_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                                      size_t n_cols, size_t chunk_len, const void *const *d_col_ptrs, const void *const *d_sigma_ptrs,
+                                      const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last, const void *d_l_active,
+                                      uint32_t blinding_factors) {
+    return quotient_permutation_any(d, d_h, y, beta, gamma, n_cols, chunk_len, d_col_ptrs, 0, d_sigma_ptrs, 0, d_z, z_stride, d_l0, d_l_last,
+                                    d_l_active, blinding_factors, true);
 }
 int h2v_quotient_lookup_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
                             const void *d_input, const void *d_table, const void *d_perm_input, const void *d_perm_table,

@@ -31,18 +31,30 @@ __device__ __forceinline__ uint32_t q_rot(uint32_t idx, int r, const QuotientCom
     return (idx + (uint32_t)(r * (int)c.rot)) & (c.n_ext - 1);
 }
 
+// a set of equally long device columns: either `stride` elements apart from a base, or through a device-resident
+// table of column pointers (the prover's columns live in several allocations: advice, fixed, instance)
+struct ColsStrided {
+    const fe *base;
+    size_t stride;
+    __device__ __forceinline__ const fe *col(uint32_t j) const { return base + (size_t)j * stride; }
+};
+struct ColsTable {
+    const fe *const *ptrs;
+    __device__ __forceinline__ const fe *col(uint32_t j) const { return ptrs[j]; }
+};
+
 // h[i] = fold_j ( q_j[i] * (a_j[i] + a_j[i+r] * a_j[i+2r] - a_j[i+3r]) )
-__global__ void __launch_bounds__(256)
-quotient_gates_kernel(fe *h, QuotientCommon c, uint32_t n_gates, const fe *q, size_t q_stride, const fe *a, size_t a_stride) {
+template <class QC, class AC>
+__global__ void __launch_bounds__(256) quotient_gates_kernel(fe *h, QuotientCommon c, uint32_t n_gates, QC q, AC a) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= c.n_ext) return;
     const uint32_t i1 = q_rot(idx, 1, c), i2 = q_rot(idx, 2, c), i3 = q_rot(idx, 3, c);
     fe v = fe_load_global(h + idx);
     for (uint32_t j = 0; j < n_gates; ++j) {
-        const fe *aj = a + (size_t)j * a_stride;
+        const fe *aj = a.col(j);
         fe t = fe_mul<FrQ>(fe_load_global(aj + i1), fe_load_global(aj + i2));
         t = fe_sub<FrQ>(fe_add<FrQ>(fe_load_global(aj + idx), t), fe_load_global(aj + i3));
-        t = fe_mul<FrQ>(t, fe_load_global(q + (size_t)j * q_stride + idx));
+        t = fe_mul<FrQ>(t, fe_load_global(q.col(j) + idx));
         v = fe_add<FrQ>(fe_mul<FrQ>(v, c.y), t);
     }
     fe_store_global(h + idx, v);
@@ -52,13 +64,14 @@ struct QuotientPerm {
     fe beta, gamma, delta, beta_zeta;   // delta = Fr::DELTA, beta_zeta = beta * g_coset
     uint32_t n_cols, chunk_len, n_sets;
     int last_rot;                       // -(blinding_factors + 1)
-    const fe *cols, *sigma, *z;         // n_cols, n_cols, n_sets columns
-    size_t cols_stride, sigma_stride, z_stride;
+    const fe *z;                        // n_sets columns
+    size_t z_stride;
     const fe *l0, *l_last, *l_active;
     const fe *tw;                       // extended_omega^i, i < n_ext / 2
 };
 
-__global__ void __launch_bounds__(256) quotient_permutation_kernel(fe *h, QuotientCommon c, QuotientPerm p) {
+template <class CC, class SC>
+__global__ void __launch_bounds__(256) quotient_permutation_kernel(fe *h, QuotientCommon c, QuotientPerm p, CC cols, SC sigma) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= c.n_ext) return;
     const uint32_t r_next = q_rot(idx, 1, c), r_last = q_rot(idx, p.last_rot, c);
@@ -91,8 +104,8 @@ __global__ void __launch_bounds__(256) quotient_permutation_kernel(fe *h, Quotie
         fe left = fe_load_global(p.z + (size_t)s * p.z_stride + r_next);
         fe right = fe_load_global(p.z + (size_t)s * p.z_stride + idx);
         for (uint32_t j = c0; j < c1; ++j) {
-            fe val = fe_add<FrQ>(fe_load_global(p.cols + (size_t)j * p.cols_stride + idx), p.gamma);
-            fe sg = fe_mul<FrQ>(p.beta, fe_load_global(p.sigma + (size_t)j * p.sigma_stride + idx));
+            fe val = fe_add<FrQ>(fe_load_global(cols.col(j) + idx), p.gamma);
+            fe sg = fe_mul<FrQ>(p.beta, fe_load_global(sigma.col(j) + idx));
             left = fe_mul<FrQ>(left, fe_add<FrQ>(val, sg));
             right = fe_mul<FrQ>(right, fe_add<FrQ>(val, cur));
             cur = fe_mul<FrQ>(cur, p.delta);

@@ -100,6 +100,17 @@ uint32_t h2v_domain_extended_k(h2v_domain_t dom);
 /* scalar getters: 0 omega, 1 omega_inv, 2 extended_omega, 3 extended_omega_inv, 4 g_coset, 5 g_coset_inv,
  * 6 ifft_divisor, 7 extended_ifft_divisor, 8+i t_evaluations[i] */
 int h2v_domain_constant(h2v_domain_t dom, int which, uint64_t out[4]);
+/* EvaluationDomain::rotate_omega(value, Rotation(rotation)) = value * omega^rotation (host-side scalar helper) */
+int h2v_domain_rotate_omega(h2v_domain_t dom, const uint64_t value[4], int32_t rotation, uint64_t out[4]);
+/* EvaluationDomain::rotate_extended(poly, Rotation(rotation)): out[i] = in[(i + rotation * 2^(extended_k - k)) mod 2^extended_k];
+ * host columns of 2^extended_k Fr, in != out */
+int h2v_domain_rotate_extended(h2v_domain_t dom, const uint64_t *in, int32_t rotation, uint64_t *out);
+/* EvaluationDomain::l_i_range(x, xn, rot_lo..rot_hi): out[t] = l_{rot_lo + t}(x), the Lagrange basis polynomials of the
+ * 2^k domain at x (xn = x^n supplied by the caller, as upstream's verifier does) */
+int h2v_domain_l_i_range(h2v_domain_t dom, const uint64_t x[4], const uint64_t xn[4], int32_t rot_lo, int32_t rot_hi, uint64_t *out);
+/* EvaluationDomain::{empty_coeff, empty_lagrange, empty_extended, constant_lagrange, constant_extended}: fill a host column
+ * of the basis' length with `scalar` (NULL = zero); basis 0 coeff, 1 lagrange (2^k each), 2 extended (2^extended_k) */
+int h2v_domain_fill(h2v_domain_t dom, int basis, const uint64_t scalar[4], uint64_t *out);
 /* EvaluationDomain::lagrange_to_coeff / coeff_to_lagrange (private fft/ifft on the 2^k domain); in place */
 int h2v_lagrange_to_coeff(h2v_domain_t dom, uint64_t *a);
 int h2v_coeff_to_lagrange(h2v_domain_t dom, uint64_t *a);
@@ -134,6 +145,7 @@ int h2v_grand_product(const uint64_t *num, const uint64_t *den, size_t n, uint64
 int h2v_grand_product_dev(const void *d_num, const void *d_den, size_t n, size_t n_cols, void *d_out);
 /* arithmetic.rs kate_division(a, b): quotient of a(X) (n coefficients) by (X - b), n - 1 coefficients */
 int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t *out);
+int h2v_kate_division_dev(const void *d_a, size_t n, const uint64_t b[4], void *d_out /* n - 1, no overlap with d_a */);
 
 /* halo2-axiom plonk/lookup/prover.rs permute_expression_pair [UPSTREAM] (create_proof step 5): from the first
  * `usable_rows` values of the compressed input and table expressions, permuted_input = the input sorted ascending
@@ -156,6 +168,10 @@ int h2v_permute_expression_pair_dev(const void *d_input, const void *d_table, si
 /* custom gates: halo2-base's vertical gate on advice column j,  q_j * (a_j + a_j(wX) * a_j(w^2 X) - a_j(w^3 X)) */
 int h2v_quotient_gates_dev(h2v_domain_t dom, void *d_h, const uint64_t y[4], size_t n_gates, const void *d_q, size_t q_stride,
                            const void *d_a, size_t a_stride);
+/* the same with the selector / advice columns given as device-resident tables of n_gates column pointers (the prover's
+ * columns live in different allocations: fixed columns in the proving key, advice columns in the proof workspace) */
+int h2v_quotient_gates_ptrs_dev(h2v_domain_t dom, void *d_h, const uint64_t y[4], size_t n_gates, const void *const *d_q_ptrs,
+                                const void *const *d_a_ptrs);
 /* permutation argument: `n_cols` permuted columns (advice / fixed / instance values, in permutation-column order) with
  * their sigma polynomials, ceil(n_cols / chunk_len) grand products z (chunk_len = cs.degree() - 2), l_0, l_last and
  * l_active_row; X = g_coset * extended_omega^i and Fr::DELTA come from the domain. */
@@ -163,15 +179,83 @@ int h2v_quotient_permutation_dev(h2v_domain_t dom, void *d_h, const uint64_t y[4
                                  size_t n_cols, size_t chunk_len, const void *d_cols, size_t cols_stride, const void *d_sigma,
                                  size_t sigma_stride, const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last,
                                  const void *d_l_active, uint32_t blinding_factors);
+int h2v_quotient_permutation_ptrs_dev(h2v_domain_t dom, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                                      size_t n_cols, size_t chunk_len, const void *const *d_col_ptrs, const void *const *d_sigma_ptrs,
+                                      const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last, const void *d_l_active,
+                                      uint32_t blinding_factors);
 /* one lookup argument: compressed input / table expressions (theta-folded by the caller; for halo2-base's range
  * lookup they are the lookup advice column and the fixed table column), permuted A' / S', grand product z */
 int h2v_quotient_lookup_dev(h2v_domain_t dom, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
                             const void *d_input, const void *d_table, const void *d_perm_input, const void *d_perm_table,
                             const void *d_z, const void *d_l0, const void *d_l_last, const void *d_l_active);
 
+/* ---- create_proof ("next": SURVEY.md 8(f) rows 2-3) ---------------------------------------------------------
+ * One Halo2-KZG (SHPLONK) proof of one circuit, restating halo2-axiom plonk/prover.rs create_proof [UPSTREAM] as reached
+ * from /root/reference/src/scaffold/mod.rs:296 (gen_snark_shplonk) with the transcript of mod.rs:309-310.  The constraint
+ * system must have the shape halo2-base builds (one vertical gate per basic-gate advice column, single-expression range
+ * lookups, a permutation over any columns); witness generation and keygen stay with the caller (the Rust side), which
+ * hands over what halo2's ProvingKey holds. */
+typedef struct {
+    uint32_t k;                 /* 2^k rows */
+    uint32_t degree;            /* cs.degree(): EvaluationDomain::new(degree, k); permutation chunk = degree - 2 */
+    uint32_t blinding_factors;  /* cs.blinding_factors(): the last blinding_factors + 1 rows of every column are unusable */
+    uint32_t n_advice, n_fixed, n_instance;
+    uint32_t n_gates;           /* gate j: fixed[gate_selector[j]] * (a + a(wX) a(w^2 X) - a(w^3 X)), a = advice[gate_advice[j]] */
+    const uint32_t *gate_advice, *gate_selector;
+    uint32_t n_lookups;         /* lookup l: advice[lookup_input[l]] must lie in fixed[lookup_table[l]] */
+    const uint32_t *lookup_input, *lookup_table;
+    uint32_t n_perm;            /* cs.permutation.columns in order: kind 0 advice, 1 fixed, 2 instance */
+    const uint8_t *perm_kind;
+    const uint32_t *perm_index;
+    uint32_t n_advice_queries;  /* cs.advice_queries in order: (column, rotation) */
+    const uint32_t *advice_query_col;
+    const int32_t *advice_query_rot;
+    uint32_t n_fixed_queries;   /* cs.fixed_queries in order */
+    const uint32_t *fixed_query_col;
+    const int32_t *fixed_query_rot;
+} h2v_circuit_t;
+typedef struct h2v_pk *h2v_pk_t; /* ProvingKey: fixed / sigma polynomials in Lagrange, coefficient and extended form, resident */
+/* fixed: pk.fixed_values (n_fixed Lagrange columns of 2^k); sigma: pk.permutation.permutations (n_perm Lagrange columns);
+ * vk_transcript_repr: vk.transcript_repr (upstream hashes the pinned verifying key's Debug text; the caller supplies it).
+ * The srs handle must outlive the pk and hold both bases. */
+int h2v_pk_load(h2v_srs_t srs, const h2v_circuit_t *cs, const uint64_t *const *fixed, const uint64_t *const *sigma,
+                const uint64_t vk_transcript_repr[4], h2v_pk_t *out);
+void h2v_pk_free(h2v_pk_t pk);
+/* advice: n_advice Lagrange columns of 2^k (the unusable rows are overwritten with blinding values); instances[c]: the
+ * instance_len[c] public inputs of instance column c; rng_seed: ChaCha20Rng::from_seed.  Writes the proof (the transcript's
+ * byte stream, exactly h2v_proof_size(pk) bytes) to proof_out. */
+int h2v_create_proof(h2v_pk_t pk, const uint64_t *const *advice, const uint64_t *const *instances, const uint32_t *instance_len,
+                     const uint8_t rng_seed[32], uint8_t *proof_out, size_t proof_cap, size_t *proof_len);
+size_t h2v_proof_size(h2v_pk_t pk);
+/* wall-clock milliseconds per phase of the last create_proof on this key: 0 upload + advice commitments, 1 lookup
+ * permutations, 2 grand products, 3 random polynomial + transforms, 4 evaluate_h + quotient commitments, 5 evaluations,
+ * 6 multi-open argument */
+int h2v_pk_last_phase_ms(h2v_pk_t pk, double out[8]);
+
+/* ---- Fiat-Shamir transcript, RNG ("next": SURVEY.md 8(f) row 3; host-side, no device needed) ---------------------
+ * snark-verifier PoseidonTranscript<G1Affine, NativeLoader, Vec<u8>, T = 5, RATE = 4, R_F = 8, R_P = 60>::new::<0>
+ * (scaffold mod.rs:309-310): points are absorbed as (x mod r, y mod r), scalars as themselves; write_* also append the
+ * 32-byte encodings below to the proof stream. */
+typedef struct h2v_transcript *h2v_transcript_t;
+int h2v_transcript_new(h2v_transcript_t *out);
+void h2v_transcript_free(h2v_transcript_t t);
+int h2v_transcript_common_point(h2v_transcript_t t, const uint64_t affine_pt[8]);
+int h2v_transcript_common_scalar(h2v_transcript_t t, const uint64_t scalar[4]);
+int h2v_transcript_write_point(h2v_transcript_t t, const uint64_t affine_pt[8]);
+int h2v_transcript_write_scalar(h2v_transcript_t t, const uint64_t scalar[4]);
+int h2v_transcript_squeeze_challenge(h2v_transcript_t t, uint64_t out[4]);
+/* the proof bytes written so far (`finalize()`); out may be NULL to query the length */
+int h2v_transcript_bytes(h2v_transcript_t t, uint8_t *out, size_t cap, size_t *len);
+/* the Poseidon permutation itself (Grain-LFSR constants, Cauchy MDS; t = 3 or 5) on a Montgomery-form state, in place */
+int h2v_poseidon_permutation(uint32_t t, uint32_t r_f, uint32_t r_p, uint64_t *state);
+/* rand_chacha ChaCha20Rng::from_seed(seed): out[i] = the i-th `Fr::random(&mut rng)` draw (Montgomery form);
+ * h2v_chacha20_block = 64 bytes of key stream at a block counter (RFC 7539 block function) */
+int h2v_chacha20_fr_random(const uint8_t seed[32], size_t n, uint64_t *out);
+int h2v_chacha20_block(const uint8_t seed[32], uint64_t counter, uint8_t out[64]);
+
 /* ---- wire format of commitments and evaluations ("next": SURVEY.md 8(f) row 3; host-side) --------------- */
-/* halo2curves 0.3.x G1Affine::to_bytes(): 32 bytes = canonical x little-endian, bit 6 of byte 31 = parity of
- * canonical y, identity = zeros (the flag convention is recalled, not verified against the crate) */
+/* halo2curves 0.3.x G1Affine::to_bytes(): 32 bytes = canonical x little-endian, top bit of byte 31 = parity of
+ * canonical y, identity = zeros (recalled, not verified against the crate; halo2curves >= 0.4 uses bit 6) */
 int h2v_g1_to_bytes(const uint64_t *affine_pts, size_t n, uint8_t *out);
 /* Fr::to_repr(): canonical little-endian 32 bytes per scalar */
 int h2v_fr_to_repr(const uint64_t *fr_mont, size_t n, uint8_t *out);
@@ -200,7 +284,7 @@ int h2v_set_tuning(int chunk, int ba_rounds);
 uint64_t h2v_launch_count(void);
 /* device-side timing of the last commit_batch_dev / transform_dev call, in milliseconds per kernel class:
  * MSM 0 digits 1 scan 2 scatter 3 accumulate 4 finish 5 reduce 6 final; NTT 7 */
-int h2v_last_kernel_ms(float out[8]);
+int h2v_last_kernel_ms(float out[8]);   /* the calling thread's last call */
 
 #ifdef __cplusplus
 }
