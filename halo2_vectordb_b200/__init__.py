@@ -40,6 +40,7 @@ ABI_SYMBOLS = [
     "h2v_transcript_new", "h2v_transcript_free", "h2v_transcript_common_point", "h2v_transcript_common_scalar",
     "h2v_transcript_write_point", "h2v_transcript_write_scalar", "h2v_transcript_squeeze_challenge", "h2v_transcript_bytes",
     "h2v_poseidon_permutation", "h2v_chacha20_fr_random", "h2v_chacha20_block",
+    "h2v_srs_gen", "h2v_g2_mul_generator", "h2v_srs_write_file", "h2v_srs_read_file",
     "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_op_rate", "h2v_set_tuning", "h2v_launch_count", "h2v_last_kernel_ms",
 ]
 
@@ -141,6 +142,10 @@ def lib():
         L.h2v_poseidon_permutation.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.h2v_chacha20_fr_random.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
         L.h2v_chacha20_block.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p]
+        L.h2v_srs_gen.argtypes = [C.c_uint32, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.h2v_g2_mul_generator.argtypes = [C.c_void_p, C.c_void_p]
+        L.h2v_srs_write_file.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.h2v_srs_read_file.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -377,6 +382,39 @@ def srs_setup(k, s):
     return g, gl
 
 
+def g2_mul_generator(s):
+    """s * G2 generator as a raw G2Affine (16 limbs: x.c0, x.c1, y.c0, y.c1 Montgomery); host-side"""
+    out = np.zeros(16, dtype=np.uint64)
+    _check(lib().h2v_g2_mul_generator(_ptr(_fr1(s)), _ptr(out)))
+    return out
+
+
+def gen_srs_secret(seed=bytes(32)):
+    """the setup secret of `ParamsKZG::setup(k, ChaCha20Rng::from_seed(seed))` (gen_srs: seed of zeros), Montgomery (4,)"""
+    return chacha20_fr_random(seed, 1)[0]
+
+
+def write_srs(path, k, g, g_lagrange, g2, s_g2):
+    """`ParamsKZG::write` (RawBytes) -- the reference's params/kzg_bn254_{k}.srs"""
+    g = np.ascontiguousarray(g, dtype=np.uint64).reshape(1 << k, 8)
+    gl = np.ascontiguousarray(g_lagrange, dtype=np.uint64).reshape(1 << k, 8)
+    _check(lib().h2v_srs_write_file(os.fsencode(path), k, _ptr(g), _ptr(gl), _ptr(np.ascontiguousarray(g2, dtype=np.uint64).reshape(16)),
+                                    _ptr(np.ascontiguousarray(s_g2, dtype=np.uint64).reshape(16))))
+
+
+def read_srs(path):
+    """`ParamsKZG::read` -> (k, g, g_lagrange, g2, s_g2)"""
+    k = C.c_uint32()
+    lib().h2v_srs_read_file(os.fsencode(path), C.byref(k), None, None, 0, None, None)      # header only
+    if k.value == 0 and not os.path.exists(path):
+        raise ValueError(f"cannot open {path}")
+    n = 1 << k.value
+    g, gl = np.zeros((n, 8), dtype=np.uint64), np.zeros((n, 8), dtype=np.uint64)
+    g2, sg2 = np.zeros(16, dtype=np.uint64), np.zeros(16, dtype=np.uint64)
+    _check(lib().h2v_srs_read_file(os.fsencode(path), C.byref(k), _ptr(g), _ptr(gl), n, _ptr(g2), _ptr(sg2)))
+    return k.value, g, gl, g2, sg2
+
+
 class ParamsKZG:
     """halo2-axiom `ParamsKZG<Bn256>` restricted to the commit path: {k, n, g, g_lagrange}."""
 
@@ -401,6 +439,27 @@ class ParamsKZG:
         g, gl = srs_setup(k, s)
         p = cls(k, g, gl)
         p.g, p.g_lagrange = g, gl
+        return p
+
+    @classmethod
+    def gen_srs(cls, k, seed=bytes(32), params_dir=None):
+        """halo2-base `gen_srs(k)` (scaffold mod.rs:260): read `params_dir/kzg_bn254_{k}.srs` if it exists, else run the
+        seeded setup (seed of zeros upstream) on the device and write the file; the bases are loaded either way."""
+        path = None if params_dir is None else os.path.join(params_dir, f"kzg_bn254_{k}.srs")
+        if path and os.path.exists(path):
+            fk, g, gl, g2, sg2 = read_srs(path)
+            if fk != k:
+                raise ValueError(f"{path} holds k = {fk}")
+        else:
+            n = 1 << k
+            g, gl = np.zeros((n, 8), dtype=np.uint64), np.zeros((n, 8), dtype=np.uint64)
+            g2, sg2 = np.zeros(16, dtype=np.uint64), np.zeros(16, dtype=np.uint64)
+            _check(lib().h2v_srs_gen(k, bytes(seed), _ptr(g), _ptr(gl), _ptr(g2), _ptr(sg2)))
+            if path:
+                os.makedirs(params_dir, exist_ok=True)
+                write_srs(path, k, g, gl, g2, sg2)
+        p = cls(k, g, gl)
+        p.g, p.g_lagrange, p.g2, p.s_g2 = g, gl, g2, sg2
         return p
 
     def close(self):

@@ -17,6 +17,7 @@
 // One advice phase, no challenges inside the witness (halo2-base's default), QUERY_INSTANCE = false (KZG).
 // What is recalled rather than verified against upstream text is listed in DESIGN.md ("recalled conventions").
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -31,6 +32,7 @@
 #include "fr_host.hpp"
 #include "chacha.hpp"
 #include "poseidon.hpp"
+#include "g2_host.hpp"
 
 using namespace h2v;
 
@@ -1014,6 +1016,68 @@ int h2v_chacha20_fr_random(const uint8_t seed[32], size_t n, uint64_t *out) {
     if (!seed || (n && !out)) return failf(H2V_EINVAL, "chacha20_fr_random: NULL argument");
     ChaCha20Rng rng(seed);
     for (size_t i = 0; i < n; ++i) frh::store(out + 4 * i, rng.fr_random());
+    return H2V_OK;
+}
+// ---------------------------------------------------------------- gen_srs: seeded setup and the .srs file
+// [UPSTREAM] halo2-base utils/fs.rs gen_srs(k): read $PARAMS_DIR/kzg_bn254_{k}.srs, else
+// ParamsKZG::setup(k, ChaCha20Rng::from_seed([0; 32])) and write it (scaffold mod.rs:260-261).
+int h2v_g2_mul_generator(const uint64_t s_mont[4], uint64_t out[16]) {
+    if (!s_mont || !out) return failf(H2V_EINVAL, "g2_mul_generator: NULL argument");
+    const Fr64 sc = frh::from_mont(frh::load(s_mont));
+    g2h::affine2 r = g2h::mul(g2h::generator(), frh::to_fe(sc));
+    memcpy(out, &r, 128);
+    return H2V_OK;
+}
+int h2v_srs_gen(uint32_t k, const uint8_t seed[32], uint64_t *g_out, uint64_t *g_lagrange_out, uint64_t g2_out[16], uint64_t s_g2_out[16]) {
+    if (!seed) return failf(H2V_EINVAL, "srs_gen: NULL seed");
+    ChaCha20Rng rng(seed);
+    const Fr64 s = rng.fr_random();                       // `let s = <E::Scalar>::random(rng);`
+    if (g_out || g_lagrange_out) H2V_TRY(h2v_srs_setup(k, s.l, g_out, g_lagrange_out));
+    if (g2_out) {
+        g2h::affine2 g = g2h::generator();
+        memcpy(g2_out, &g, 128);
+    }
+    if (s_g2_out) H2V_TRY(h2v_g2_mul_generator(s.l, s_g2_out));
+    return H2V_OK;
+}
+// `ParamsKZG::write` (SerdeFormat::RawBytes): k as u32 LE, then g, g_lagrange (2^k G1Affine each: x, y Montgomery limbs,
+// 64 bytes), g2, s_g2 (G2Affine: x.c0, x.c1, y.c0, y.c1, 128 bytes)
+int h2v_srs_write_file(const char *path, uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, const uint64_t g2[16],
+                       const uint64_t s_g2[16]) {
+    if (!path || !g || !g_lagrange || !g2 || !s_g2) return failf(H2V_EINVAL, "srs_write_file: NULL argument");
+    if (k > 28) return failf(H2V_EINVAL, "srs_write_file: k = %u", k);
+    FILE *f = fopen(path, "wb");
+    if (!f) return failf(H2V_EINVAL, "srs_write_file: cannot open %s", path);
+    const size_t n = (size_t)1 << k;
+    bool ok = fwrite(&k, 4, 1, f) == 1 && fwrite(g, 64, n, f) == n && fwrite(g_lagrange, 64, n, f) == n && fwrite(g2, 128, 1, f) == 1 &&
+              fwrite(s_g2, 128, 1, f) == 1;
+    ok = (fclose(f) == 0) && ok;
+    return ok ? H2V_OK : failf(H2V_EINVAL, "srs_write_file: short write to %s", path);
+}
+// `ParamsKZG::read`: *k_out always receives the file's k; the bases are read when cap_points >= 2^k (else H2V_EINVAL)
+int h2v_srs_read_file(const char *path, uint32_t *k_out, uint64_t *g, uint64_t *g_lagrange, size_t cap_points, uint64_t g2[16],
+                      uint64_t s_g2[16]) {
+    if (!path || !k_out) return failf(H2V_EINVAL, "srs_read_file: NULL argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) return failf(H2V_EINVAL, "srs_read_file: cannot open %s", path);
+    uint32_t k = 0;
+    if (fread(&k, 4, 1, f) != 1 || k > 28) {
+        fclose(f);
+        return failf(H2V_EINVAL, "srs_read_file: bad header in %s", path);
+    }
+    *k_out = k;
+    const size_t n = (size_t)1 << k;
+    if (!g || !g_lagrange || !g2 || !s_g2 || cap_points < n) {
+        fclose(f);
+        return failf(H2V_EINVAL, "srs_read_file: buffers hold %zu points, the file has 2^%u", cap_points, k);
+    }
+    bool ok = fread(g, 64, n, f) == n && fread(g_lagrange, 64, n, f) == n && fread(g2, 128, 1, f) == 1 && fread(s_g2, 128, 1, f) == 1;
+    fclose(f);
+    if (!ok) return failf(H2V_EINVAL, "srs_read_file: %s is truncated", path);
+    g2h::affine2 a, b;
+    memcpy(&a, g2, 128);
+    memcpy(&b, s_g2, 128);
+    if (!g2h::is_on_curve(a) || !g2h::is_on_curve(b)) return failf(H2V_EINVAL, "srs_read_file: G2 point not on the curve");
     return H2V_OK;
 }
 int h2v_chacha20_block(const uint8_t seed[32], uint64_t counter, uint8_t out[64]) {

@@ -66,6 +66,18 @@ int h2v_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, h2v_
  * seeds ChaCha20 with zeros -- "unsafe" by design): g[i] = s^i G and g_lagrange[i] = L_i(s) G, each 2^k affine
  * points (either output may be NULL).  One-time work; g2 / s_g2 are verifier-side and not produced. */
 int h2v_srs_setup(uint32_t k, const uint64_t s_mont[4], uint64_t *g_out, uint64_t *g_lagrange_out);
+/* halo2-base gen_srs(k)'s setup branch (scaffold mod.rs:260): ParamsKZG::setup(k, ChaCha20Rng::from_seed(seed)) -- the
+ * secret is the generator's first Fr::random draw (seed = 32 zero bytes upstream: "unsafe" by design).  Outputs (each may
+ * be NULL): g, g_lagrange (2^k affine points, computed on the device), g2 = the G2 generator and s_g2 = s * g2 (G2Affine:
+ * x.c0, x.c1, y.c0, y.c1 Montgomery Fq, 128 bytes; host-side). */
+int h2v_srs_gen(uint32_t k, const uint8_t seed[32], uint64_t *g_out, uint64_t *g_lagrange_out, uint64_t g2_out[16], uint64_t s_g2_out[16]);
+int h2v_g2_mul_generator(const uint64_t s_mont[4], uint64_t out[16]);
+/* ParamsKZG::write / read, SerdeFormat::RawBytes (params/kzg_bn254_{k}.srs): k as u32 LE, g, g_lagrange, g2, s_g2 as raw
+ * Montgomery limbs.  read: *k_out always receives the file's k; buffers must hold cap_points >= 2^k points each. */
+int h2v_srs_write_file(const char *path, uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, const uint64_t g2[16],
+                       const uint64_t s_g2[16]);
+int h2v_srs_read_file(const char *path, uint32_t *k_out, uint64_t *g, uint64_t *g_lagrange, size_t cap_points, uint64_t g2[16],
+                      uint64_t s_g2[16]);
 void h2v_srs_free(h2v_srs_t srs);
 /* window size c and number of windows W = ceil(255 / c) the handle's tables were built for (diagnostics) */
 int h2v_srs_info(h2v_srs_t srs, uint32_t *window_bits, uint32_t *windows);
