@@ -243,9 +243,9 @@ def imad_peak():
     return out.value
 
 
-def set_tuning(chunk=-1, ba_rounds=-1):
+def set_tuning(chunk=-1, table=-1):
     """MSM tuning knobs (-1 = automatic): results never depend on them."""
-    _check(lib().h2v_set_tuning(chunk, ba_rounds))
+    _check(lib().h2v_set_tuning(chunk, table))
 
 
 def op_rate(which):

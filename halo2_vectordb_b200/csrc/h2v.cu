@@ -18,7 +18,6 @@
 
 #include "h2v.h"
 #include "msm.cuh"
-#include "msm_affine.cuh"
 #include "ntt.cuh"
 #include "poly.cuh"
 #include "quotient.cuh"
@@ -380,7 +379,7 @@ struct Carver {
 };
 // sorted entries per accumulate thread: long enough that the per-chunk edge merge (one full add) is
 // amortised, short enough that a single small MSM still fills the GPU.  H2V_CHUNK overrides (tuning).
-std::atomic<int> g_tune_chunk{-2}, g_tune_ba{-2};   // -2: read the environment on first use; -1: automatic
+std::atomic<int> g_tune_chunk{-2}, g_tune_table{-2};   // -2: read the environment on first use; -1: automatic
 int tuning(std::atomic<int> &slot, const char *env) {
     int v = slot.load();
     if (v == -2) {
@@ -390,74 +389,42 @@ int tuning(std::atomic<int> &slot, const char *env) {
     }
     return v;
 }
-// run_msm snapshots both knobs once per call (h2v_set_tuning from another thread must not change the workspace layout
+// run_msm snapshots the knob once per call (h2v_set_tuning from another thread must not change the workspace layout
 // between the sizing pass and the launches)
-thread_local int t_tune_chunk = -1, t_tune_ba = -1;
-uint32_t pick_chunk(uint64_t max_entries) {
+thread_local int t_tune_chunk = -1;
+uint32_t pick_chunk(uint64_t entries) {
     const int forced = t_tune_chunk;
     if (forced > 0) return (uint32_t)forced;
     // small inputs are latency-bound: chunk * t(mixed add) in the accumulate thread against
     // (bucket load / chunk) * t(full add) in the finish thread is flattest around 12..24 (measured)
-    uint64_t c = max_entries / (148ull * 2048ull);
+    uint64_t c = entries / (148ull * 2048ull);
     if (c < 12) c = 12;
     if (c > 64) c = 64;
     return (uint32_t)c;
 }
-#define H2V_BA_MAX_ROUNDS 8
-#define H2V_BA_MAX_LEVELS 12
 struct MsmLayout {
     size_t bytes;
-    uint32_t *keys, *counts, *offsets, *cursor, *tile_sums, *long_list, *long_count;
-    uint2 *entries;
-    xyzz *buckets, *edges, *S[2], *A[2], *T;
+    uint32_t *counts, *offsets, *cursor, *tile_sums, *long_list, *long_count, *strad_count, *density;
+    uint2 *entries, *strad_list;
+    xyzz *buckets, *edges, *S[2], *A[2];
     uint32_t nthreads, n_buckets, l1;
-    // batch-affine rounds (ba_rounds > 0)
-    uint32_t ba_rounds, ba_K, ba_G;
-    uint64_t ba_slots[H2V_BA_MAX_ROUNDS];      // upper bound of the output slots of round r
-    uint32_t ba_chunk;                         // chunk of the final XYZZ pass over the surviving list
-    uint32_t *ba_off[2];
-    affine *ba_list[2];
-    fe *ba_P0;
-    uint2 *ba_entries;
-    uint32_t ba_levels;                        // inversion tree: level sizes n[0] = threads of round 0, ...
-    uint32_t ba_n[H2V_BA_MAX_LEVELS];
-    fe *ba_X[H2V_BA_MAX_LEVELS], *ba_P[H2V_BA_MAX_LEVELS], *ba_I[H2V_BA_MAX_LEVELS];
 };
-// Batch-affine pair rounds in front of the XYZZ accumulation (msm_affine.cuh).  OFF by default: measured on
-// B200 (profiles/r01_msm_batch_affine_launches.txt) the 6-product additions are paid for with ~350 B of
-// list / prefix-product traffic per pair and ~0.5 ms of serial inversion-tree latency per round, so
-// 96 columns x 2^16 take 17.0 ms with 5 rounds vs 17.0 ms for the pure XYZZ path (best: 3 rounds, 16.2 ms).
-// h2v_set_tuning / H2V_BA_ROUNDS switch them on (tests run them for the tuning-invariance check).
-uint32_t pick_ba_rounds(const MsmShape &, uint32_t) {
-    const int forced = t_tune_ba;
-    if (forced >= 0) return std::min<uint32_t>((uint32_t)forced, H2V_BA_MAX_ROUNDS);
-    return 0;
-}
 MsmLayout msm_layout(void *base, const MsmShape &sh, uint32_t cols) {
     MsmLayout L;
     memset(&L, 0, sizeof L);
     Carver cv(base);
     uint64_t ent = (uint64_t)cols * sh.W * sh.n;
     L.n_buckets = cols * sh.G * sh.nb;
-    L.ba_rounds = pick_ba_rounds(sh, cols);
-    L.ba_K = 16;
-    L.ba_G = 16;
-    uint64_t final_len = ent;
-    for (uint32_t r = 0; r < L.ba_rounds; ++r) {
-        // a round maps each bucket of length l to ceil(l/2): at most (len + non-empty buckets)/2 slots and never
-        // more than it had (the bound must not grow: every later round reuses the buffers sized for round 0)
-        final_len = std::min<uint64_t>(final_len, (final_len + L.n_buckets + 1) / 2);
-        L.ba_slots[r] = std::max<uint64_t>(final_len, 1);
-    }
-    L.ba_chunk = L.ba_rounds ? pick_chunk(final_len) : sh.chunk;
-    L.nthreads = (uint32_t)std::max<uint64_t>((ent + sh.chunk - 1) / sh.chunk, (final_len + L.ba_chunk - 1) / L.ba_chunk);
-    if (!L.ba_rounds) L.nthreads = (uint32_t)((ent + sh.chunk - 1) / sh.chunk);
+    L.nthreads = (uint32_t)((ent + sh.chunk - 1) / sh.chunk);
     L.l1 = (sh.nb + 7) / 8;            // the reduction tree uses segments of 8..32: size for the worst case
     size_t l2 = (L.l1 + 7) / 8;
-    L.keys = cv.take<uint32_t>(ent);
-    L.counts = cv.take<uint32_t>((size_t)L.n_buckets + 1);   // [n_buckets] doubles as the long-bucket counter
+    // counters cleared by ONE memset per launch: histogram, long-bucket count, straddler count, density sample
+    L.counts = cv.take<uint32_t>((size_t)L.n_buckets + 8);
     L.long_count = L.counts + L.n_buckets;
+    L.strad_count = L.counts + L.n_buckets + 1;
+    L.density = L.counts + L.n_buckets + 2;
     L.long_list = cv.take<uint32_t>((size_t)L.nthreads / H2V_LONG_SPAN + 2);
+    L.strad_list = cv.take<uint2>((size_t)L.nthreads + 1);
     L.offsets = cv.take<uint32_t>((size_t)L.n_buckets + 1);
     L.cursor = cv.take<uint32_t>(L.n_buckets);
     L.tile_sums = cv.take<uint32_t>((size_t)L.n_buckets / H2V_SCAN_TILE + 2);
@@ -468,37 +435,31 @@ MsmLayout msm_layout(void *base, const MsmShape &sh, uint32_t cols) {
     L.A[0] = cv.take<xyzz>((size_t)cols * sh.G * L.l1);
     L.S[1] = cv.take<xyzz>((size_t)cols * sh.G * l2);
     L.A[1] = cv.take<xyzz>((size_t)cols * sh.G * l2);
-    L.T = cv.take<xyzz>((size_t)cols * sh.G * 16);      // bit sums of the reduction tail: <= 13 + 2 per instance
-    if (L.ba_rounds) {
-        L.ba_off[0] = cv.take<uint32_t>((size_t)L.n_buckets + 1);
-        L.ba_off[1] = cv.take<uint32_t>((size_t)L.n_buckets + 1);
-        L.ba_list[0] = cv.take<affine>(L.ba_slots[0]);
-        L.ba_list[1] = cv.take<affine>(L.ba_rounds > 1 ? L.ba_slots[1] : 1);
-        L.ba_P0 = cv.take<fe>(L.ba_slots[0]);
-        L.ba_entries = cv.take<uint2>(L.ba_slots[L.ba_rounds - 1]);
-        // inversion tree sized for round 0 (the largest)
-        uint64_t nlev = (L.ba_slots[0] + L.ba_K - 1) / L.ba_K;
-        L.ba_levels = 0;
-        for (;;) {
-            L.ba_n[L.ba_levels] = (uint32_t)nlev;
-            L.ba_X[L.ba_levels] = cv.take<fe>(nlev);
-            L.ba_P[L.ba_levels] = cv.take<fe>(nlev);
-            L.ba_I[L.ba_levels] = cv.take<fe>(nlev);
-            ++L.ba_levels;
-            if (nlev <= 1 || L.ba_levels >= H2V_BA_MAX_LEVELS) break;
-            nlev = (nlev + L.ba_G - 1) / L.ba_G;
-        }
-    }
     L.bytes = cv.off + 256;
     return L;
 }
 
 const size_t MSM_WS_BUDGET = (size_t)16 << 30;   // per handle; columns per launch are sized to fit
+std::once_flag g_tree_attr_once;
+
+MsmShape make_shape(size_t len, const MsmCfg &cfg, size_t pstride) {
+    MsmShape sh;
+    memset(&sh, 0, sizeof sh);
+    sh.n = (uint32_t)len;
+    sh.c = cfg.c;
+    sh.W = cfg.W;
+    sh.G = cfg.G;
+    sh.nb = 1u << (cfg.c - 1);
+    sh.pstride = (uint32_t)pstride;
+    fill_kadd(sh);
+    return sh;
+}
 
 // d_scalars: n_cols columns of `len` Fr (Montgomery), col_stride apart.  points: bases (raw) or
 // window tables (precomputed, level stride `pstride`).  Results: affine and/or Jacobian per column.
+// `density` in (0, 1]: expected share of non-zero digits (sizes the accumulate chunks; 1 = uniform scalars).
 int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_stride, size_t n_cols, size_t len,
-            const affine *points, MsmCfg cfg, size_t pstride, affine *d_out_aff, jacobian *d_out_jac, Timer *tm) {
+            const affine *points, MsmCfg cfg, size_t pstride, affine *d_out_aff, jacobian *d_out_jac, Timer *tm, double density = 1.0) {
     if (n_cols == 0) return H2V_OK;
     if (len == 0) {   // empty sum = identity: affine (0, 0); Jacobian (0, 1, 0) as halo2curves `G1::identity()`
         if (d_out_aff) CU(cudaMemsetAsync(d_out_aff, 0, n_cols * sizeof(affine), st));
@@ -511,28 +472,20 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
         return H2V_OK;
     }
     t_tune_chunk = tuning(g_tune_chunk, "H2V_CHUNK");
-    t_tune_ba = tuning(g_tune_ba, "H2V_BA_ROUNDS");
-    MsmShape sh;
-    memset(&sh, 0, sizeof sh);
-    sh.n = (uint32_t)len;
-    sh.c = cfg.c;
-    sh.W = cfg.W;
-    sh.G = cfg.G;
-    sh.nb = 1u << (cfg.c - 1);
-    sh.pstride = (uint32_t)pstride;
-    fill_kadd(sh);
+    MsmShape sh = make_shape(len, cfg, pstride);
+    if (!(density > 0.0) || density > 1.0) density = 1.0;
     // columns per launch: workspace budget, 2^31 entries, grid.z
     size_t max_cols = std::min<size_t>(n_cols, 16384);
-    sh.chunk = pick_chunk((uint64_t)max_cols * sh.W * sh.n);
+    auto chunk_for = [&](size_t cols) { return pick_chunk((uint64_t)((double)cols * sh.W * sh.n * density)); };
     while (max_cols > 1) {
-        sh.chunk = pick_chunk((uint64_t)max_cols * sh.W * sh.n);
+        sh.chunk = chunk_for(max_cols);
         MsmLayout probe = msm_layout(nullptr, sh, (uint32_t)max_cols);
         uint64_t ent = (uint64_t)max_cols * sh.W * sh.n;
         uint64_t nbk = (uint64_t)max_cols * sh.G * sh.nb;
         if (probe.bytes <= MSM_WS_BUDGET && ent < (1ull << 31) && nbk < (1ull << 31)) break;
         max_cols = (max_cols + 1) / 2;
     }
-    sh.chunk = pick_chunk((uint64_t)max_cols * sh.W * sh.n);
+    sh.chunk = chunk_for(max_cols);
     {
         MsmLayout probe = msm_layout(nullptr, sh, (uint32_t)max_cols);
         uint64_t ent = (uint64_t)max_cols * sh.W * sh.n;
@@ -540,15 +493,19 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
         int rc = ws.buf.ensure(probe.bytes);
         if (rc) return rc;
     }
+    std::call_once(g_tree_attr_once, [] {
+        cudaFuncSetAttribute(msm_reduce_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(H2V_TREE_MAX * sizeof(xyzz)));
+    });
     for (size_t c0 = 0; c0 < n_cols; c0 += max_cols) {
         uint32_t cols = (uint32_t)std::min(max_cols, n_cols - c0);
         sh.n_cols = cols;
+        sh.chunk = chunk_for(cols);
         MsmLayout L = msm_layout(ws.buf.p, sh, cols);
         const fe *sc = d_scalars + c0 * col_stride;
-        CU(cudaMemsetAsync(L.counts, 0, ((size_t)L.n_buckets + 1) * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(L.counts, 0, ((size_t)L.n_buckets + 8) * sizeof(uint32_t), st));
         unsigned gx = (unsigned)((len + 255) / 256);
         if (tm) tm->begin(0);
-        msm_digits_kernel<<<dim3(gx, cols), 256, 0, st>>>(sc, col_stride, L.keys, L.counts, sh);
+        msm_count_kernel<<<dim3(gx, cols), 256, 0, st>>>(sc, col_stride, L.counts, sh);
         LAUNCHED();
         if (tm) { tm->end(); tm->begin(1); }
         {
@@ -564,130 +521,62 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
         {
             // A single very large MSM (>= 1 GiB of sorted entries) sweeps the bucket space in 4 slices: the
             // randomly written quarter of `entries` thrashes DRAM less (2^24: 7.4 -> 5.1 ms; more slices lose
-            // again to the repeated key reads, smaller MSMs and batches gain nothing).  H2V_SCATTER_SLICES: tuning.
+            // again to the repeated passes, smaller MSMs and batches gain nothing).  H2V_SCATTER_SLICES: tuning.
             static const uint32_t forced = [] {
                 const char *e = getenv("H2V_SCATTER_SLICES");
                 return e ? (uint32_t)atoi(e) : 0u;
             }();
-            const uint64_t ent_bytes = (uint64_t)cols * sh.W * sh.n * sizeof(uint2);
+            const uint64_t ent_bytes = (uint64_t)((double)cols * sh.W * sh.n * density) * sizeof(uint2);
             uint32_t slices = forced ? forced : ((cols == 1 && ent_bytes >= (1ull << 30)) ? 4u : 1u);
             slices = std::max(1u, std::min(slices, sh.nb));
             const uint32_t per = (sh.nb + slices - 1) / slices;
             for (uint32_t sl = 0; sl < slices; ++sl) {
-                msm_scatter_kernel<<<dim3(gx, cols), 256, 0, st>>>(L.keys, L.cursor, L.entries, sh, sl * per,
+                msm_scatter_kernel<<<dim3(gx, cols), 256, 0, st>>>(sc, col_stride, L.cursor, L.entries, sh, sl * per,
                                                                          std::min(sh.nb, (sl + 1) * per));
                 LAUNCHED();
             }
         }
         if (tm) { tm->end(); tm->begin(3); }
-        const uint2 *acc_entries = L.entries;
-        const uint32_t *acc_offsets = L.offsets;
-        const affine *acc_points = points;
-        uint32_t acc_chunk = sh.chunk, acc_threads = (uint32_t)(((uint64_t)cols * sh.W * sh.n + sh.chunk - 1) / sh.chunk);
-        if (L.ba_rounds) {
-            // batch-affine pair rounds: every round halves each bucket with 6 products per addition
-            const uint32_t ntiles = (L.n_buckets + H2V_SCAN_TILE - 1) / H2V_SCAN_TILE;
-            const uint32_t *off_in = L.offsets;
-            const affine *list_in = nullptr;
-            for (uint32_t r = 0; r < L.ba_rounds; ++r) {
-                uint32_t *off_out = L.ba_off[r & 1];
-                affine *list_out = L.ba_list[r & 1];
-                ba_count_kernel<<<(L.n_buckets + 255) / 256, 256, 0, st>>>(off_in, L.counts, L.n_buckets);
-                LAUNCHED();
-                msm_scan_tiles_kernel<<<ntiles, 256, 0, st>>>(L.counts, L.tile_sums, L.n_buckets);
-                LAUNCHED();
-                msm_scan_top_kernel<<<1, 256, 0, st>>>(L.tile_sums, ntiles, off_out + L.n_buckets);
-                LAUNCHED();
-                msm_scan_apply_kernel<<<ntiles, 256, 0, st>>>(L.counts, L.tile_sums, off_out, L.cursor, L.n_buckets);
-                LAUNCHED();
-                BaRound br;
-                memset(&br, 0, sizeof br);
-                br.entries = L.entries;
-                br.table = points;
-                br.list_in = list_in;
-                br.off_in = off_in;
-                br.off_out = off_out;
-                br.n_buckets = L.n_buckets;
-                br.K = L.ba_K;
-                br.P0 = L.ba_P0;
-                br.X1 = L.ba_X[0];
-                br.I1 = L.ba_I[0];
-                br.list_out = list_out;
-                br.entries_out = (r + 1 == L.ba_rounds) ? L.ba_entries : nullptr;
-                br.n_threads = (uint32_t)((L.ba_slots[r] + L.ba_K - 1) / L.ba_K);
-                // inversion tree levels for this round's thread count
-                uint32_t nlev[H2V_BA_MAX_LEVELS], levels = 0;
-                for (uint64_t v = br.n_threads;;) {
-                    nlev[levels++] = (uint32_t)v;
-                    if (v <= 1 || levels >= H2V_BA_MAX_LEVELS) break;
-                    v = (v + L.ba_G - 1) / L.ba_G;
-                }
-                if (nlev[levels - 1] != 1) return fail(H2V_EINVAL, "MSM too large for the inversion tree");
-                const unsigned gb = (br.n_threads + 127) / 128;
-                if (r == 0) ba_forward_kernel<true><<<gb, 128, 0, st>>>(br);
-                else ba_forward_kernel<false><<<gb, 128, 0, st>>>(br);
-                LAUNCHED();
-                for (uint32_t l = 0; l + 1 < levels; ++l) {
-                    binv_up_kernel<Fq><<<(nlev[l + 1] + 127) / 128, 128, 0, st>>>(L.ba_X[l], L.ba_P[l], L.ba_X[l + 1], nlev[l], L.ba_G);
-                    LAUNCHED();
-                }
-                binv_top_kernel<Fq><<<1, 32, 0, st>>>(L.ba_X[levels - 1], L.ba_I[levels - 1]);
-                LAUNCHED();
-                for (uint32_t l = levels - 1; l-- > 0;) {
-                    binv_down_kernel<Fq><<<(nlev[l + 1] + 127) / 128, 128, 0, st>>>(L.ba_X[l], L.ba_P[l], L.ba_I[l + 1], L.ba_I[l], nlev[l], L.ba_G);
-                    LAUNCHED();
-                }
-                if (r == 0) ba_backward_kernel<true><<<gb, 128, 0, st>>>(br);
-                else ba_backward_kernel<false><<<gb, 128, 0, st>>>(br);
-                LAUNCHED();
-                off_in = off_out;
-                list_in = list_out;
-            }
-            acc_entries = L.ba_entries;
-            acc_offsets = off_in;
-            acc_points = list_in;
-            acc_chunk = L.ba_chunk;
-            acc_threads = (uint32_t)((L.ba_slots[L.ba_rounds - 1] + acc_chunk - 1) / acc_chunk);
-        }
-        msm_accumulate_kernel<<<(acc_threads + 127) / 128, 128, 0, st>>>(acc_entries, acc_offsets, L.n_buckets, acc_points, L.buckets,
-                                                                        L.edges, acc_chunk);
+        const uint32_t acc_threads = L.nthreads;
+        msm_accumulate_kernel<<<(acc_threads + 127) / 128, 128, 0, st>>>(L.entries, L.offsets, L.n_buckets, points, L.buckets, L.edges, sh.chunk,
+                                                                        L.strad_list, L.strad_count);
         LAUNCHED();
         if (tm) { tm->end(); tm->begin(4); }
-        // long_count shares the histogram buffer, which the rounds reuse: clear it again
-        CU(cudaMemsetAsync(L.long_count, 0, sizeof(uint32_t), st));
-        msm_finish_kernel<<<(L.n_buckets + 127) / 128, 128, 0, st>>>(acc_offsets, L.n_buckets, L.edges, L.buckets, acc_chunk, L.long_list,
-                                                                     L.long_count);
-        LAUNCHED();
-        msm_finish_long_kernel<<<148 * 2, 256, 0, st>>>(acc_offsets, L.edges, L.buckets, acc_chunk, L.long_list, L.long_count);
-        LAUNCHED();
+        {
+            const unsigned fg = (unsigned)std::min<uint64_t>(((uint64_t)acc_threads + 127) / 128, 148ull * 16);
+            msm_finish_kernel<<<fg, 128, 0, st>>>(L.offsets, L.strad_list, L.strad_count, L.edges, L.buckets, sh.chunk, L.long_list,
+                                                  L.long_count);
+            LAUNCHED();
+            msm_finish_long_kernel<<<148 * 2, 256, 0, st>>>(L.offsets, L.edges, L.buckets, sh.chunk, L.long_list, L.long_count);
+            LAUNCHED();
+        }
         if (tm) { tm->end(); tm->begin(5); }
-        // reduction tree over each (column, group)
+        // reduction over each (column, group): serial radix levels while they fill the GPU, then one log-depth tree
         const uint32_t n_inst = cols * sh.G;
         const xyzz *Sin = L.buckets, *Ain = nullptr;
+        const uint32_t *occ = L.offsets;
         uint32_t cnt = sh.nb, shift = 0;
         int pp = 0;
         while (cnt > 1) {
-            if (cnt <= 8192 && Ain && (uint64_t)n_inst * cnt <= (1u << 16)) {
-                // few partials left: bit-decomposed tree sums instead of latency-bound serial levels
-                uint32_t nbits = 0;
-                while ((1u << nbits) < cnt) ++nbits;
-                unsigned threads = std::min(256u, std::max(32u, ((cnt / 4 + 31) / 32) * 32));
-                msm_reduce_bits_kernel<<<dim3(nbits + 2, n_inst), threads, 0, st>>>(Sin, Ain, cnt, nbits, L.T);
-                LAUNCHED();
-                msm_reduce_combine_kernel<<<n_inst, 32, 0, st>>>(L.T, nbits, shift, n_inst, L.S[pp], L.A[pp]);
+            if (cnt <= H2V_TREE_MAX && !occ) {
+                const unsigned threads = std::max(32u, std::min(256u, cnt / 2));
+                msm_reduce_tree_kernel<<<n_inst, threads, cnt * sizeof(xyzz), st>>>(Sin, Ain, cnt, shift, L.S[pp], L.A[pp]);
                 LAUNCHED();
                 Sin = L.S[pp];
                 Ain = L.A[pp];
                 cnt = 1;
                 break;
             }
-            // shorter segments while the level would otherwise leave SMs idle (each thread is a serial chain)
+            // segments of 32 while that still fills the GPU once (each thread is a serial chain), shorter otherwise;
+            // never below what brings the level to the tree's size in one step
             uint32_t log_seg = 5;
-            while (log_seg > 3 && (uint64_t)n_inst * (cnt >> log_seg) < 148ull * 1024) --log_seg;
+            while (log_seg > 3 && (uint64_t)n_inst * (cnt >> log_seg) < 148ull * 256 && (cnt >> (log_seg - 1)) <= H2V_TREE_MAX) --log_seg;
+            while (log_seg > 1 && (cnt >> log_seg) < 2) --log_seg;
             uint32_t cnt_out = (cnt + (1u << log_seg) - 1) >> log_seg;
             uint32_t total = n_inst * cnt_out;
-            msm_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(Sin, Ain, L.S[pp], L.A[pp], cnt, cnt_out, n_inst, shift, log_seg);
+            msm_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(Sin, Ain, L.S[pp], L.A[pp], cnt, cnt_out, n_inst, shift, log_seg, occ);
             LAUNCHED();
+            occ = nullptr;
             Sin = L.S[pp];
             Ain = L.A[pp];
             pp ^= 1;
@@ -695,7 +584,7 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
             shift += log_seg;
         }
         if (!Ain) {   // nb == 1: a single bucket per group, its weight is 1 and there is no weighted part
-            msm_reduce_kernel<<<(n_inst + 127) / 128, 128, 0, st>>>(Sin, nullptr, L.S[pp], L.A[pp], 1, 1, n_inst, 0, 3);
+            msm_reduce_kernel<<<(n_inst + 127) / 128, 128, 0, st>>>(Sin, nullptr, L.S[pp], L.A[pp], 1, 1, n_inst, 0, 3, occ);
             LAUNCHED();
             Sin = L.S[pp];
             Ain = L.A[pp];
@@ -714,9 +603,14 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
 struct h2v_srs {
     uint32_t k;
     size_t n;
-    DevBuf table[2];     // [basis]: W levels of n affine points (level 0 = the bases)
+    // Window tables, two per basis: [0] the window the cost model picks for uniform scalars, [1] a smaller window
+    // (fewer buckets, more digits per scalar) for columns whose scalars are mostly 0 / 1 / small -- real witness
+    // columns -- and for single small calls, where the bucket reduction would otherwise dominate.  W levels of n
+    // affine points each (level 0 = the bases).
+    DevBuf table[2][2];
     bool have[2] = {false, false};
-    MsmCfg cfg;
+    bool have_small = false;
+    MsmCfg cfg[2];
     MsmWorkspace ws, ws2;
     DevBuf stage, out;
     cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr;
@@ -734,7 +628,49 @@ struct h2v_srs {
     static const int H2V_LANES = 4;
     Lane lanes[H2V_LANES];
     std::atomic<unsigned> next_lane{0};
+    int last_variant = 0;
 };
+
+namespace {
+// Window choice per call: the share of non-zero digits under both window sizes is estimated from a strided sample of
+// the batch (one small kernel + a 16-byte read-back), then the cheaper plan wins under the cost model
+//   10 products per bucket addition (mixed add) + 28 per bucket of the reduction (two full additions).
+// Results never depend on the choice.  h2v_set_tuning(_, table) / H2V_TABLE force a table (tests).
+int msm_srs(h2v_srs *s, cudaStream_t st, MsmWorkspace &ws, int basis, const fe *d_scalars, size_t col_stride, size_t n_cols, size_t len,
+            affine *d_out, Timer *tm) {
+    int variant = 0;
+    double density = 1.0;
+    const int forced = tuning(g_tune_table, "H2V_TABLE");
+    if (n_cols && len && s->have_small) {
+        if (forced == 0 || forced == 1) {
+            variant = forced;
+        } else {
+            const uint32_t samples = (uint32_t)std::min<uint64_t>(4096, (uint64_t)n_cols * len);
+            int rc = ws.buf.ensure(4096);
+            if (rc) return rc;
+            uint32_t *d_cnt = ws.buf.as<uint32_t>();
+            CU(cudaMemsetAsync(d_cnt, 0, 8, st));
+            MsmShape s0 = make_shape(len, s->cfg[0], s->n), s1 = make_shape(len, s->cfg[1], s->n);
+            msm_density_kernel<<<(samples + 255) / 256, 256, 0, st>>>(d_scalars, col_stride, (uint32_t)n_cols, (uint32_t)len, samples, s0, s1, d_cnt);
+            LAUNCHED();
+            uint32_t h_cnt[2] = {0, 0};
+            CU(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            const double e0 = (double)h_cnt[0] / samples * len, e1 = (double)h_cnt[1] / samples * len;      // entries per column
+            // the reduction is latency-bound when few columns share it: weigh it up for small batches
+            const double inst_w = n_cols >= 32 ? 28.0 : 28.0 * (1.0 + 24.0 / (double)n_cols);
+            const double cost0 = 10.0 * e0 + inst_w * (double)(1u << (s->cfg[0].c - 1));
+            const double cost1 = 10.0 * e1 + inst_w * (double)(1u << (s->cfg[1].c - 1));
+            variant = cost1 < cost0 ? 1 : 0;
+            density = (variant ? e1 : e0) / ((double)s->cfg[variant].W * len);
+            density = std::min(1.0, density * 1.1 + 0.01);
+        }
+    }
+    s->last_variant = variant;
+    return run_msm(st, ws, d_scalars, col_stride, n_cols, len, s->table[basis][variant].as<affine>(), s->cfg[variant], s->n, d_out, nullptr, tm,
+                   density);
+}
+}  // namespace
 
 // ================================================================== C ABI
 extern "C" {
@@ -832,9 +768,9 @@ int h2v_host_unregister(void *ptr) {
     CU(cudaHostUnregister(ptr));
     return H2V_OK;
 }
-int h2v_set_tuning(int chunk, int ba_rounds) {
+int h2v_set_tuning(int chunk, int table) {
     g_tune_chunk.store(chunk > 0 ? chunk : -1);
-    g_tune_ba.store(ba_rounds >= 0 ? ba_rounds : -1);
+    g_tune_table.store(table == 0 || table == 1 ? table : -1);
     return H2V_OK;
 }
 int h2v_last_kernel_ms(float out[8]) {
@@ -853,11 +789,22 @@ int h2v_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, h2v_
     h2v_srs *s = new h2v_srs();
     s->k = k;
     s->n = (size_t)1 << k;
-    s->cfg = choose_cfg(s->n, true);
+    s->cfg[0] = choose_cfg(s->n, true);
     // cap the table footprint at 24 GB per basis by shrinking the number of levels (bigger windows)
-    while ((size_t)s->cfg.W * s->n * sizeof(affine) > ((size_t)24 << 30) && s->cfg.c < 24) {
-        s->cfg.c++;
-        s->cfg.W = windows_for(s->cfg.c);
+    while ((size_t)s->cfg[0].W * s->n * sizeof(affine) > ((size_t)24 << 30) && s->cfg[0].c < 24) {
+        s->cfg[0].c++;
+        s->cfg[0].W = windows_for(s->cfg[0].c);
+    }
+    // second table with a window two bits smaller: a quarter of the buckets (H2V_SMALL_WINDOW_DELTA: tuning; 0 = none)
+    static const int small_delta = [] {
+        const char *e = getenv("H2V_SMALL_WINDOW_DELTA");
+        return e ? atoi(e) : 2;
+    }();
+    s->cfg[1] = s->cfg[0];
+    if (small_delta > 0 && (int)s->cfg[0].c - small_delta >= 3) {
+        s->cfg[1].c = s->cfg[0].c - (uint32_t)small_delta;
+        s->cfg[1].W = windows_for(s->cfg[1].c);
+        s->have_small = (size_t)s->cfg[1].W * s->n * sizeof(affine) <= ((size_t)8 << 30);
     }
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -867,14 +814,17 @@ int h2v_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, h2v_
     const uint64_t *src[2] = {g, g_lagrange};
     for (int b = 0; b < 2; ++b) {
         if (!src[b]) continue;
-        rc = s->table[b].ensure((size_t)s->cfg.W * s->n * sizeof(affine));
-        if (rc) { h2v_srs_free(s); return rc; }
-        e = cudaMemcpyAsync(s->table[b].p, src[b], s->n * sizeof(affine), cudaMemcpyHostToDevice, s->stream);
-        if (e != cudaSuccess) { h2v_srs_free(s); return fail(H2V_ECUDA, "SRS upload: %s", cudaGetErrorString(e)); }
-        for (uint32_t lvl = 1; lvl < s->cfg.W; ++lvl) {
-            msm_precompute_kernel<<<(unsigned)((s->n + 127) / 128), 128, 0, s->stream>>>(s->table[b].as<affine>(), (uint32_t)s->n, lvl,
-                                                                                        s->cfg.c);
-            g_launches.fetch_add(1);
+        for (int v = 0; v < (s->have_small ? 2 : 1); ++v) {
+            DevBuf &tb = s->table[b][v];
+            rc = tb.ensure((size_t)s->cfg[v].W * s->n * sizeof(affine));
+            if (rc) { h2v_srs_free(s); return rc; }
+            if (v == 0) e = cudaMemcpyAsync(tb.p, src[b], s->n * sizeof(affine), cudaMemcpyHostToDevice, s->stream);
+            else e = cudaMemcpyAsync(tb.p, s->table[b][0].p, s->n * sizeof(affine), cudaMemcpyDeviceToDevice, s->stream);
+            if (e != cudaSuccess) { h2v_srs_free(s); return fail(H2V_ECUDA, "SRS upload: %s", cudaGetErrorString(e)); }
+            for (uint32_t lvl = 1; lvl < s->cfg[v].W; ++lvl) {
+                msm_precompute_kernel<<<(unsigned)((s->n + 127) / 128), 128, 0, s->stream>>>(tb.as<affine>(), (uint32_t)s->n, lvl, s->cfg[v].c);
+                g_launches.fetch_add(1);
+            }
         }
         s->have[b] = true;
     }
@@ -886,15 +836,16 @@ int h2v_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, h2v_
 }
 int h2v_srs_info(h2v_srs_t s, uint32_t *window_bits, uint32_t *windows) {
     if (!s) return fail(H2V_EINVAL, "srs_info: NULL srs");
-    if (window_bits) *window_bits = s->cfg.c;
-    if (windows) *windows = s->cfg.W;
+    // the table the last commit on this handle used (the main one before any commit)
+    if (window_bits) *window_bits = s->cfg[s->last_variant].c;
+    if (windows) *windows = s->cfg[s->last_variant].W;
     return H2V_OK;
 }
 void h2v_srs_free(h2v_srs_t s) {
     if (!s) return;
     cudaSetDevice(g_device);
-    s->table[0].release();
-    s->table[1].release();
+    for (auto &tb : s->table)
+        for (auto &t : tb) t.release();
     s->ws.buf.release();
     s->ws2.buf.release();
     for (auto &ln : s->lanes) {
@@ -928,8 +879,7 @@ int h2v_commit_batch_dev(h2v_srs_t s, int basis, const void *d_polys, size_t col
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(s->mu);
     Timer tm(s->stream);
-    rc = run_msm(s->stream, s->ws, (const fe *)d_polys, col_stride, n_polys, len, s->table[basis].as<affine>(), s->cfg, s->n,
-                 (affine *)d_out_affine, nullptr, &tm);
+    rc = msm_srs(s, s->stream, s->ws, basis, (const fe *)d_polys, col_stride, n_polys, len, (affine *)d_out_affine, &tm);
     cudaError_t e = cudaStreamSynchronize(s->stream);
     tm.collect(true);
     if (rc) return rc;
@@ -968,8 +918,7 @@ int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_
             }
             if (len) CU(cudaMemcpyAsync(ln->stage.as<fe>() + c * stride_small, polys[c], len * sizeof(fe), cudaMemcpyHostToDevice, ln->st));
         }
-        rc = run_msm(ln->st, ln->ws, ln->stage.as<fe>(), stride_small, n_polys, len, s->table[basis].as<affine>(), s->cfg, s->n,
-                     ln->out.as<affine>(), nullptr, nullptr);
+        rc = msm_srs(s, ln->st, ln->ws, basis, ln->stage.as<fe>(), stride_small, n_polys, len, ln->out.as<affine>(), nullptr);
         if (rc) {
             cudaStreamSynchronize(ln->st);
             return rc;
@@ -1027,8 +976,7 @@ int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_
         CU(cudaEventRecord(s->copied[b], s->copy_stream));
         cudaStream_t cst = b ? s->stream2 : s->stream;
         CU(cudaStreamWaitEvent(cst, s->copied[b], 0));
-        rc = run_msm(cst, b ? s->ws2 : s->ws, stg, stride, cols, len, s->table[basis].as<affine>(), s->cfg, s->n,
-                     s->out.as<affine>() + c0, nullptr, nullptr);
+        rc = msm_srs(s, cst, b ? s->ws2 : s->ws, basis, stg, stride, cols, len, s->out.as<affine>() + c0, nullptr);
         if (rc) {
             cudaStreamSynchronize(s->stream);
             cudaStreamSynchronize(s->stream2);

@@ -75,17 +75,14 @@ __device__ __forceinline__ xyzz xyzz_ld(const xyzz *p) {
     return r;
 }
 
-// ------------------------------------------------------------------ digits + histogram
-// keys[(col*W + j)*n + i] = (|d|-1) | sign<<31, or INVALID for d == 0
-__global__ void __launch_bounds__(256) msm_digits_kernel(const fe *__restrict__ scalars, size_t col_stride,
-                                                         uint32_t *__restrict__ keys, uint32_t *__restrict__ counts,
-                                                         MsmShape sh) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t col = blockIdx.y;
-    if (i >= sh.n) return;
-    fe s = fe_from_mont<Fr>(fe_ld(scalars + (size_t)col * col_stride + i));
+// ------------------------------------------------------------------ digits
+// The W signed c-bit digits of s + K (K = sum_j (2^(c-1) - 1) 2^(jc)): d_j = digit_j(s + K) - (2^(c-1) - 1) lies in
+// [-(2^(c-1) - 1), 2^(c-1)] and sum_j d_j 2^(jc) = s.  Both passes over the scalars (histogram, scatter) recompute them
+// from the scalar -- one Montgomery product and W shifts -- instead of staging 4 W bytes per scalar in HBM.
+struct MsmDigits {
     uint32_t t[9];
-    {   // s + K  (K can reach W*c <= 288 bits: 9 limbs)
+    __device__ __forceinline__ void load(const fe *p, const MsmShape &sh) {
+        fe s = fe_from_mont<Fr>(fe_ld(p));
         uint64_t cy = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -95,20 +92,73 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const fe *__restrict__ 
         }
         t[8] = (uint32_t)cy + sh.kadd[8];
     }
-    const uint32_t c = sh.c, mask = (1u << c) - 1, half = (1u << (c - 1)) - 1;
-    for (uint32_t j = 0; j < sh.W; ++j) {
-        uint32_t bit = j * c, w = bit >> 5, sft = bit & 31;
-        uint32_t lo = w < 9 ? t[w] : 0u, hi = (w + 1) < 9 ? t[w + 1] : 0u;
-        uint32_t d = (uint32_t)((((uint64_t)hi << 32) | lo) >> sft) & mask;
-        int32_t sd = (int32_t)d - (int32_t)half;
-        uint32_t key = H2V_KEY_INVALID;
-        if (sd != 0) {
-            uint32_t mag = (uint32_t)(sd < 0 ? -sd : sd) - 1;
-            key = mag | (sd < 0 ? 0x80000000u : 0u);
-            uint32_t g = sh.G > 1 ? j : 0;
-            atomicAdd(&counts[((size_t)col * sh.G + g) * sh.nb + mag], 1u);
+    // digit j: false for a zero digit, else magnitude - 1 and sign
+    __device__ __forceinline__ bool get(uint32_t j, const MsmShape &sh, uint32_t &mag, uint32_t &neg) const {
+        const uint32_t bit = j * sh.c, w = bit >> 5, sft = bit & 31;
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {       // t stays in registers: no dynamic indexing
+            lo = (w == (uint32_t)k) ? t[k] : lo;
+            hi = (w + 1 == (uint32_t)k) ? t[k] : hi;
         }
-        keys[((size_t)col * sh.W + j) * sh.n + i] = key;
+        const uint32_t d = (uint32_t)((((uint64_t)hi << 32) | lo) >> sft) & ((1u << sh.c) - 1);
+        const int32_t sd = (int32_t)d - (int32_t)((1u << (sh.c - 1)) - 1);
+        if (sd == 0) return false;
+        neg = sd < 0 ? 0x80000000u : 0u;
+        mag = (uint32_t)(sd < 0 ? -sd : sd) - 1;
+        return true;
+    }
+};
+// Lanes of a warp that hit the same counter are served by ONE atomic (skewed witness columns put a third of a column
+// into one bucket: scalar 1, the shared high digits of r - small).  Returns this lane's slot: base + rank in its group.
+__device__ __forceinline__ uint32_t warp_agg_add(uint32_t *counter_base, uint32_t idx, bool valid) {
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? idx : 0xffffffffu);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (valid && (int)lane == leader) base = atomicAdd(counter_base + idx, (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1));
+}
+
+// ------------------------------------------------------------------ pass 1: histogram
+__global__ void __launch_bounds__(256) msm_count_kernel(const fe *__restrict__ scalars, size_t col_stride, uint32_t *__restrict__ counts,
+                                                        MsmShape sh) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    const bool in = i < sh.n;
+    MsmDigits dg;
+    dg.load(scalars + (size_t)col * col_stride + (in ? i : 0), sh);
+    for (uint32_t j = 0; j < sh.W; ++j) {
+        uint32_t mag = 0, neg = 0;
+        const bool ok = in && dg.get(j, sh, mag, neg);
+        const uint32_t g = sh.G > 1 ? j : 0;
+        warp_agg_add(counts, (col * sh.G + g) * sh.nb + mag, ok);
+    }
+}
+// estimate of the number of non-zero digits under two window sizes, from a strided sample of the batch (window choice)
+__global__ void __launch_bounds__(256) msm_density_kernel(const fe *__restrict__ scalars, size_t col_stride, uint32_t n_cols, uint32_t n,
+                                                          uint32_t samples, MsmShape sh0, MsmShape sh1, uint32_t *__restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c0 = 0, c1 = 0;
+    if (t < samples) {
+        const uint64_t tot = (uint64_t)n_cols * n;
+        const uint64_t pos = ((uint64_t)t * 0x9E3779B97F4A7C15ull >> 11) % tot;       // spread over columns and rows
+        const fe *p = scalars + (size_t)(pos / n) * col_stride + (pos % n);
+        MsmDigits dg;
+        uint32_t mag, neg;
+        dg.load(p, sh0);
+        for (uint32_t j = 0; j < sh0.W; ++j) c0 += dg.get(j, sh0, mag, neg) ? 1u : 0u;
+        dg.load(p, sh1);
+        for (uint32_t j = 0; j < sh1.W; ++j) c1 += dg.get(j, sh1, mag, neg) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        c0 += __shfl_down_sync(0xffffffffu, c0, o);
+        c1 += __shfl_down_sync(0xffffffffu, c1, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, c0);
+        atomicAdd(out + 1, c1);
     }
 }
 
@@ -190,39 +240,24 @@ __global__ void __launch_bounds__(256) msm_scan_apply_kernel(const uint32_t *__r
     }
 }
 
-// ------------------------------------------------------------------ scatter
-// entries[pos] = (point_ref | sign<<31, global bucket)
+// ------------------------------------------------------------------ pass 2: scatter
+// entries[pos] = (point_ref | sign<<31, global bucket), counting sort by bucket.
 // Only digits with magnitude in [mag_lo, mag_hi) are placed: for a very large MSM the host sweeps the bucket
-// space in slices so that the randomly written part of `entries` stays L2-resident (the keys are re-read per
-// slice, which is sequential and cheap).
-__global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t *__restrict__ keys, uint32_t *__restrict__ cursor,
+// space in slices so that the randomly written part of `entries` stays L2-resident.
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const fe *__restrict__ scalars, size_t col_stride, uint32_t *__restrict__ cursor,
                                                           uint2 *__restrict__ entries, MsmShape sh, uint32_t mag_lo, uint32_t mag_hi) {
-    // one thread per scalar, looping over its W digits four at a time: four independent atomics in flight
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t col = blockIdx.y;
-    if (i >= sh.n) return;
-    const uint32_t *kp = keys + (size_t)col * sh.W * sh.n + i;
-    for (uint32_t j0 = 0; j0 < sh.W; j0 += 4) {
-        uint32_t key[4], b[4], pos[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) key[u] = (j0 + u < sh.W) ? kp[(size_t)(j0 + u) * sh.n] : H2V_KEY_INVALID;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            uint32_t mag = key[u] & 0x7fffffffu;
-            if (key[u] == H2V_KEY_INVALID || mag < mag_lo || mag >= mag_hi) {
-                key[u] = H2V_KEY_INVALID;
-                continue;
-            }
-            uint32_t g = sh.G > 1 ? j0 + u : 0;
-            b[u] = (col * sh.G + g) * sh.nb + mag;
-            pos[u] = atomicAdd(&cursor[b[u]], 1u);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (key[u] == H2V_KEY_INVALID) continue;
-            uint32_t pref = (sh.G > 1 ? i : (j0 + u) * sh.pstride + i) | (key[u] & 0x80000000u);
-            entries[pos[u]] = make_uint2(pref, b[u]);
-        }
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    const bool in = i < sh.n;
+    MsmDigits dg;
+    dg.load(scalars + (size_t)col * col_stride + (in ? i : 0), sh);
+    for (uint32_t j = 0; j < sh.W; ++j) {
+        uint32_t mag = 0, neg = 0;
+        bool ok = in && dg.get(j, sh, mag, neg);
+        ok = ok && mag >= mag_lo && mag < mag_hi;
+        const uint32_t g = sh.G > 1 ? j : 0;
+        const uint32_t b = (col * sh.G + g) * sh.nb + mag;
+        const uint32_t pos = warp_agg_add(cursor, b, ok);
+        if (ok) entries[pos] = make_uint2((sh.G > 1 ? i : j * sh.pstride + i) | neg, b);
     }
 }
 
@@ -234,68 +269,83 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t *__rest
 __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const uint2 *__restrict__ entries,
                                                              const uint32_t *__restrict__ offsets, uint32_t n_buckets,
                                                              const affine *__restrict__ points, xyzz *__restrict__ buckets,
-                                                             xyzz *__restrict__ edges, uint32_t chunk) {
+                                                             xyzz *__restrict__ edges, uint32_t chunk,
+                                                             uint2 *__restrict__ strad_list, uint32_t *__restrict__ strad_count) {
     const uint32_t M = offsets[n_buckets];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t start64 = (uint64_t)t * chunk;
-    if (start64 >= M) return;
-    const uint32_t start = (uint32_t)start64;
-    const uint32_t end = min(start + chunk, M);
-    const uint32_t prev_b = start > 0 ? entries[start - 1].y : 0xffffffffu;
-    const uint32_t next_b = end < M ? entries[end].y : 0xffffffffu;
-    xyzz acc = xyzz_identity();
-    uint2 ent = entries[start];
-    uint32_t cur_b = ent.y;
-    bool first_run = true;
-    for (uint32_t e = start; e < end; ++e) {
-        uint2 nxt = (e + 1 < end) ? entries[e + 1] : make_uint2(0u, 0xffffffffu);
-        affine pt = affine_load_ro(points + (ent.x & 0x7fffffffu));
-        if (ent.x & 0x80000000u) pt.y = fe_neg<Fq>(pt.y);
-        xyzz_add_mixed_lazy(acc, pt);
-        if (nxt.y != cur_b) {
-            // run ends here (bucket change or end of chunk)
-            xyzz_canon(acc);
-            const bool last_run = (e + 1 == end);
-            const bool starts_before = first_run && (prev_b == cur_b);
-            const bool continues_after = last_run && (next_b == cur_b);
-            if (!starts_before && !continues_after) xyzz_st(buckets + cur_b, acc);
-            else if (starts_before) xyzz_st(edges + 2 * (size_t)t, acc);
-            else xyzz_st(edges + 2 * (size_t)t + 1, acc);
-            acc = xyzz_identity();
-            cur_b = nxt.y;
-            first_run = false;
+    bool opens = false;          // this chunk holds the first part of a bucket that continues into later chunks
+    uint32_t open_b = 0;
+    if (start64 < M) {
+        const uint32_t start = (uint32_t)start64;
+        const uint32_t end = min(start + chunk, M);
+        const uint32_t prev_b = start > 0 ? entries[start - 1].y : 0xffffffffu;
+        const uint32_t next_b = end < M ? entries[end].y : 0xffffffffu;
+        xyzz acc = xyzz_identity();
+        uint2 ent = entries[start];
+        uint32_t cur_b = ent.y;
+        bool first_run = true;
+        for (uint32_t e = start; e < end; ++e) {
+            uint2 nxt = (e + 1 < end) ? entries[e + 1] : make_uint2(0u, 0xffffffffu);
+            affine pt = affine_load_ro(points + (ent.x & 0x7fffffffu));
+            if (ent.x & 0x80000000u) pt.y = fe_neg<Fq>(pt.y);
+            xyzz_add_mixed_lazy(acc, pt);
+            if (nxt.y != cur_b) {
+                // run ends here (bucket change or end of chunk)
+                xyzz_canon(acc);
+                const bool last_run = (e + 1 == end);
+                const bool starts_before = first_run && (prev_b == cur_b);
+                const bool continues_after = last_run && (next_b == cur_b);
+                if (!starts_before && !continues_after) xyzz_st(buckets + cur_b, acc);
+                else if (starts_before) xyzz_st(edges + 2 * (size_t)t, acc);
+                else xyzz_st(edges + 2 * (size_t)t + 1, acc);
+                if (continues_after && !starts_before) {
+                    opens = true;
+                    open_b = cur_b;
+                }
+                acc = xyzz_identity();
+                cur_b = nxt.y;
+                first_run = false;
+            }
+            ent = nxt;
         }
-        ent = nxt;
+    }
+    // the straddling buckets, one list entry each (first chunk, bucket): msm_finish works on this list only
+    const unsigned m = __ballot_sync(0xffffffffu, opens);
+    if (m) {
+        const uint32_t lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(strad_count, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (opens) strad_list[base + __popc(m & ((1u << lane) - 1))] = make_uint2(t, open_b);
     }
 }
 
-// one thread per bucket: empty -> identity; straddling -> tail(t0) + heads(t0+1..t1).  Buckets that span
-// more than `long_span` chunks (skewed witness columns put a large share of a column into a few buckets:
-// scalar 1, the shared high digits of r - small) are queued for msm_finish_long_kernel instead.
+// One thread per straddling bucket (the list msm_accumulate wrote): tail(t0) + heads(t0+1..t1).  Buckets that span
+// more than H2V_LONG_SPAN chunks (skewed witness columns put a large share of a column into a few buckets:
+// scalar 1, the shared high digits of r - small) are queued for msm_finish_long_kernel instead.  Empty buckets are
+// never touched: the reduction skips them by their offsets.
 #define H2V_LONG_SPAN 16
-__global__ void __launch_bounds__(128) msm_finish_kernel(const uint32_t *__restrict__ offsets, uint32_t n_buckets,
-                                                         const xyzz *__restrict__ edges, xyzz *__restrict__ buckets,
-                                                         uint32_t chunk, uint32_t *__restrict__ long_list,
+__global__ void __launch_bounds__(128) msm_finish_kernel(const uint32_t *__restrict__ offsets, const uint2 *__restrict__ strad_list,
+                                                         const uint32_t *__restrict__ strad_count, const xyzz *__restrict__ edges,
+                                                         xyzz *__restrict__ buckets, uint32_t chunk, uint32_t *__restrict__ long_list,
                                                          uint32_t *__restrict__ long_count) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_buckets) return;
-    uint32_t s = offsets[b], e = offsets[b + 1];
-    if (s == e) {
-        xyzz_st(buckets + b, xyzz_identity());
-        return;
+    const uint32_t count = *strad_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint2 it = strad_list[i];
+        const uint32_t t0 = it.x, b = it.y;
+        const uint32_t t1 = (offsets[b + 1] - 1) / chunk;
+        if (t1 - t0 > H2V_LONG_SPAN) {
+            long_list[atomicAdd(long_count, 1u)] = b;
+            continue;
+        }
+        xyzz acc = xyzz_ld(edges + 2 * (size_t)t0 + 1);
+        for (uint32_t t = t0 + 1; t <= t1; ++t) {
+            xyzz h = xyzz_ld(edges + 2 * (size_t)t);
+            xyzz_add(acc, h);
+        }
+        xyzz_st(buckets + b, acc);
     }
-    uint32_t t0 = s / chunk, t1 = (e - 1) / chunk;
-    if (t0 == t1) return;
-    if (t1 - t0 > H2V_LONG_SPAN) {
-        long_list[atomicAdd(long_count, 1u)] = b;
-        return;
-    }
-    xyzz acc = xyzz_ld(edges + 2 * (size_t)t0 + 1);
-    for (uint32_t t = t0 + 1; t <= t1; ++t) {
-        xyzz h = xyzz_ld(edges + 2 * (size_t)t);
-        xyzz_add(acc, h);
-    }
-    xyzz_st(buckets + b, acc);
 }
 __device__ __forceinline__ xyzz xyzz_shfl_down(const xyzz &v, int off) {
     xyzz r;
@@ -385,22 +435,27 @@ __global__ void __launch_bounds__(256) msm_finish_long_kernel(const uint32_t *__
 //   A_out[s] = sum_{r} A_in[seg s + r] + 2^shift * sum_r r * S_in[seg s + r]     (shift = sum of earlier log_seg)
 // Iterating until cnt == 1 gives  A = sum_m m * S0[m],  S = sum_m S0[m];  the group result is A + S
 // (bucket m holds the points of digit magnitude m + 1).
+// `occ` (first level only): the bucket offsets -- element r of instance `inst` is the bucket inst * cnt_in + r, empty
+// (never written) when occ[b] == occ[b + 1].
 __global__ void __launch_bounds__(128, 3) msm_reduce_kernel(const xyzz *__restrict__ S_in, const xyzz *__restrict__ A_in,
                                                             xyzz *__restrict__ S_out, xyzz *__restrict__ A_out,
                                                             uint32_t cnt_in, uint32_t cnt_out, uint32_t n_inst, uint32_t shift,
-                                                            uint32_t log_seg) {
+                                                            uint32_t log_seg, const uint32_t *__restrict__ occ) {
     uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n_inst * cnt_out) return;
     uint32_t inst = gid / cnt_out, s = gid % cnt_out;
     uint32_t lo = s << log_seg, hi = min(lo + (1u << log_seg), cnt_in);
     const xyzz *Sin = S_in + (size_t)inst * cnt_in;
+    const uint32_t *oc = occ ? occ + (size_t)inst * cnt_in : nullptr;
     xyzz run = xyzz_identity(), tz = xyzz_identity();
     for (uint32_t r = hi; r-- > lo + 1;) {
-        xyzz v = xyzz_ld(Sin + r);
-        xyzz_add(run, v);
+        if (!oc || oc[r] != oc[r + 1]) {
+            xyzz v = xyzz_ld(Sin + r);
+            xyzz_add(run, v);
+        }
         xyzz_add(tz, run);
     }
-    {
+    if (!oc || oc[lo] != oc[lo + 1]) {
         xyzz v = xyzz_ld(Sin + lo);
         xyzz_add(run, v);
     }
@@ -416,43 +471,96 @@ __global__ void __launch_bounds__(128, 3) msm_reduce_kernel(const xyzz *__restri
     xyzz_st(A_out + (size_t)inst * cnt_out + s, tz);
 }
 
-// Tail of the reduction once a few thousand partials per instance are left: the serial radix levels would be
-// latency-bound there, so the weighted sum is taken bit by bit with parallel tree sums instead:
-//   sum_i i * S[i] = sum_b 2^b * T_b,   T_b = sum over { i : bit b of i set } of S[i].
-// grid (nbits + 2, n_inst): CTA `which` < nbits computes T_which, nbits the plain sum of A, nbits + 1 that of S.
-__global__ void __launch_bounds__(256) msm_reduce_bits_kernel(const xyzz *__restrict__ S_in, const xyzz *__restrict__ A_in,
-                                                              uint32_t cnt, uint32_t nbits, xyzz *__restrict__ T) {
-    __shared__ xyzz sm8[8];
-    const uint32_t which = blockIdx.x, inst = blockIdx.y;
-    const xyzz *src = (which == nbits ? A_in : S_in) + (size_t)inst * cnt;
-    xyzz acc = xyzz_identity();
-    if (which != nbits || A_in) {
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-            if (which < nbits && !((i >> which) & 1u)) continue;
-            xyzz v = xyzz_ld(src + i);
-            xyzz_add(acc, v);
+// Tail of the reduction, once <= H2V_TREE_MAX partial pairs (S_s, A_s) per instance are left: the serial radix levels
+// are latency-bound there (a lone warp needs ~4 us per full addition), so ONE CTA per instance finishes the job with
+// log-depth sums whose active lanes stay packed:
+//   sum_s s * S_s = sum_b 2^b Z_b,  Z_b = sum over { s : bit b of s set } of S_s.
+// With T the pairwise block sums of S (level l: blocks of 2^l), Z_l is the sum of the ODD blocks of level l.  The tree
+// over T and the accumulation of the Z_l advance together: cnt - 1 additions for T, cnt - 1 for the Z's in total --
+// the same work as the serial running sums -- in ~2 log2(cnt) dependent steps.  A is a plain sum.
+// Shared memory: cnt / 2 + 2 * log2(cnt) + ... XYZZ values (128 B each).
+#define H2V_TREE_MAX 512
+__global__ void __launch_bounds__(256) msm_reduce_tree_kernel(const xyzz *__restrict__ S_in, const xyzz *__restrict__ A_in, uint32_t cnt,
+                                                              uint32_t shift, xyzz *__restrict__ S_out, xyzz *__restrict__ A_out) {
+    extern __shared__ xyzz tsm[];                 // [0, cnt/2): T blocks of the current level; [cnt/2, cnt): odd blocks / A values
+    __shared__ xyzz zb[12];                       // Z_l
+    const uint32_t inst = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+    const xyzz *S = S_in + (size_t)inst * cnt;
+    const uint32_t half0 = cnt >> 1;              // cnt is a power of two >= 2
+    xyzz *T = tsm, *O = tsm + half0;
+    // level 0: T[i] = S[2i] + S[2i+1], O[i] = S[2i+1]
+    for (uint32_t i = tid; i < half0; i += nth) {
+        xyzz a = xyzz_ld(S + 2 * i), b = xyzz_ld(S + 2 * i + 1);
+        O[i] = b;
+        xyzz_add(a, b);
+        T[i] = a;
+    }
+    __syncthreads();
+    uint32_t level = 0;
+    for (uint32_t m = half0; m >= 1; m >>= 1, ++level) {
+        // Z_level = sum of O[0..m): halving sums with packed lanes
+        for (uint32_t w = m; w > 1; w >>= 1) {
+            const uint32_t h = w >> 1;
+            for (uint32_t i = tid; i < h; i += nth) {
+                xyzz a = O[i];
+                xyzz_add(a, O[i + h]);
+                O[i] = a;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) zb[level] = O[0];
+        __syncthreads();
+        if (m == 1) break;
+        // next level: T'[i] = T[2i] + T[2i+1], O[i] = T[2i+1]
+        const uint32_t h = m >> 1;                // h <= cnt / 4 <= blockDim.x (the host launches at least cnt / 4 threads)
+        xyzz a = xyzz_identity(), b = xyzz_identity();
+        if (tid < h) {
+            a = T[2 * tid];
+            b = T[2 * tid + 1];
+        }
+        __syncthreads();                          // the pairwise sums overwrite T in place
+        if (tid < h) {
+            O[tid] = b;
+            xyzz_add(a, b);
+            T[tid] = a;
+        }
+        __syncthreads();
+    }
+    // now T[0] = sum of all S; levels = log2(cnt) values Z_0 .. Z_{levels-1}
+    const uint32_t levels = level + 1;
+    // plain sum of A (if any), through the O area
+    bool haveA = A_in != nullptr;
+    if (haveA) {
+        const xyzz *A = A_in + (size_t)inst * cnt;
+        for (uint32_t i = tid; i < half0; i += nth) {
+            xyzz a = xyzz_ld(A + 2 * i), b = xyzz_ld(A + 2 * i + 1);
+            xyzz_add(a, b);
+            O[i] = a;
+        }
+        __syncthreads();
+        for (uint32_t w = half0; w > 1; w >>= 1) {
+            const uint32_t h = w >> 1;
+            for (uint32_t i = tid; i < h; i += nth) {
+                xyzz a = O[i];
+                xyzz_add(a, O[i + h]);
+                O[i] = a;
+            }
+            __syncthreads();
         }
     }
-    acc = xyzz_block_sum_256(acc, sm8);
-    if (threadIdx.x == 0) xyzz_st(T + (size_t)inst * (nbits + 2) + which, acc);
-}
-// one warp per instance: lane b scales its bit sum by 2^b (b doublings, all lanes in lockstep), a shuffle tree
-// adds them, then the common weight 2^shift and the plain sum of A
-__global__ void msm_reduce_combine_kernel(const xyzz *__restrict__ T, uint32_t nbits, uint32_t shift, uint32_t n_inst,
-                                          xyzz *__restrict__ S_out, xyzz *__restrict__ A_out) {
-    const uint32_t inst = blockIdx.x, lane = threadIdx.x;
-    if (inst >= n_inst) return;
-    const xyzz *t = T + (size_t)inst * (nbits + 2);
-    xyzz acc = lane < nbits ? xyzz_ld(t + lane) : xyzz_identity();
-    for (uint32_t k = 0; k + 1 < nbits; ++k)
-        if (k < lane && lane < nbits) acc = xyzz_double(acc);
-    acc = xyzz_warp_sum(acc);
-    if (lane != 0) return;
-    for (uint32_t k = 0; k < shift; ++k) acc = xyzz_double(acc);
-    xyzz a = xyzz_ld(t + nbits);
-    xyzz_add(acc, a);
-    xyzz_st(S_out + inst, xyzz_ld(t + nbits + 1));
-    xyzz_st(A_out + inst, acc);
+    // weighted part: lane l scales Z_l by 2^l (lockstep doublings), a shuffle tree adds them
+    if (tid < 32) {
+        xyzz acc = tid < levels ? zb[tid] : xyzz_identity();
+        for (uint32_t k = 0; k + 1 < levels; ++k)
+            if (k < tid && tid < levels) acc = xyzz_double(acc);
+        acc = xyzz_warp_sum(acc);
+        if (tid == 0) {
+            for (uint32_t k = 0; k < shift; ++k) acc = xyzz_double(acc);
+            if (haveA) xyzz_add(acc, O[0]);
+            xyzz_st(S_out + inst, T[0]);
+            xyzz_st(A_out + inst, acc);
+        }
+    }
 }
 
 // one warp per column (lane 0 works: the data-dependent inversion would diverge across columns): group results

@@ -97,7 +97,38 @@ __global__ void __launch_bounds__(256) poly_eval_kernel(const fe *__restrict__ p
     }
 }
 
-// ------------------------------------------------------------------ batch inversion helpers (tree in msm_affine.cuh)
+// ------------------------------------------------------------------ batch inversion: radix-G product tree, ONE field inversion at the root (all elements non-zero)
+// P[i] = product of X[j] for j < i inside i's group of G;  Xn[g] = product of group g
+template <class F> __global__ void __launch_bounds__(128) binv_up_kernel(const fe *__restrict__ X, fe *__restrict__ P, fe *__restrict__ Xn, uint32_t n, uint32_t G) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t lo = (uint64_t)g * G;
+    if (lo >= n) return;
+    uint32_t hi = (uint32_t)min((uint64_t)n, lo + G);
+    fe run = fe_one<F>();
+    for (uint32_t i = (uint32_t)lo; i < hi; ++i) {
+        pl_st(P + i, run);
+        run = fe_mul<F>(run, pl_ld(X + i));
+    }
+    pl_st(Xn + g, run);
+}
+template <class F> __global__ void binv_top_kernel(const fe *__restrict__ X, fe *__restrict__ I) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) pl_st(I, fe_inv_fast<F>(pl_ld(X)));
+}
+// I[i] = 1 / X[i] from In[g] = 1 / (product of group g)
+template <class F> __global__ void __launch_bounds__(128) binv_down_kernel(const fe *__restrict__ X, const fe *__restrict__ P, const fe *__restrict__ In,
+                                                        fe *__restrict__ I, uint32_t n, uint32_t G) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t lo = (uint64_t)g * G;
+    if (lo >= n) return;
+    uint32_t hi = (uint32_t)min((uint64_t)n, lo + G);
+    fe inv = pl_ld(In + g);
+    for (uint32_t i = hi; i-- > (uint32_t)lo;) {
+        pl_st(I + i, fe_mul<F>(inv, pl_ld(P + i)));
+        inv = fe_mul<F>(inv, pl_ld(X + i));
+    }
+}
+
+// ------------------------------------------------------------------ batch inversion helpers: zeros are skipped as ff::BatchInvert does
 __global__ void __launch_bounds__(256) fr_zero_to_one_kernel(const fe *__restrict__ a, fe *__restrict__ x, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

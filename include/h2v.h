@@ -79,7 +79,7 @@ int h2v_srs_write_file(const char *path, uint32_t k, const uint64_t *g, const ui
 int h2v_srs_read_file(const char *path, uint32_t *k_out, uint64_t *g, uint64_t *g_lagrange, size_t cap_points, uint64_t g2[16],
                       uint64_t s_g2[16]);
 void h2v_srs_free(h2v_srs_t srs);
-/* window size c and number of windows W = ceil(255 / c) the handle's tables were built for (diagnostics) */
+/* window size c and number of windows W = ceil(255 / c) of the table the handle's last commit used (diagnostics) */
 int h2v_srs_info(h2v_srs_t srs, uint32_t *window_bits, uint32_t *windows);
 /* ParamsKZG::commit(poly, _blind) / commit_lagrange(poly, _blind) = best_multiexp(poly, bases[..len]);
  * the Blind argument is ignored by KZG upstream, so it is not part of the ABI.  len <= 2^k.
@@ -288,10 +288,11 @@ int h2v_selftest_imad_peak(double *out_wmac_per_s);
 /* register-only throughput of the kernels' building blocks, operations per second over the whole GPU:
  * which 0: Fq Montgomery product, one dependent chain per thread; 1: two chains; 2: XYZZ mixed-add chain */
 int h2v_selftest_op_rate(int which, double *out_ops_per_s);
-/* MSM tuning knobs (tests / tuning; -1 = automatic, the default; also H2V_CHUNK / H2V_BA_ROUNDS in the
- * environment): `chunk` = sorted entries per accumulate thread, `ba_rounds` = batch-affine pair rounds in
- * front of the XYZZ accumulation (0 disables them).  Results do not depend on either. */
-int h2v_set_tuning(int chunk, int ba_rounds);
+/* MSM tuning knobs (tests / tuning; -1 = automatic, the default; also H2V_CHUNK / H2V_TABLE in the environment):
+ * `chunk` = sorted entries per accumulate thread; `table` = which of the handle's two window tables a commit uses
+ * (0: the window sized for uniform scalars, 1: the smaller window for sparse columns and small calls; automatic =
+ * chosen per call from a sampled digit density).  Results do not depend on either. */
+int h2v_set_tuning(int chunk, int table);
 /* kernels launched by this process so far (for bench.py's gpu_launches) */
 uint64_t h2v_launch_count(void);
 /* device-side timing of the last commit_batch_dev / transform_dev call, in milliseconds per kernel class:

@@ -415,7 +415,7 @@ int orc_g1_is_on_curve(const u64 aff[8]) {
     f_add(&FQ, &x3, &x3, &three);
     return f_eq(&y2, &x3);
 }
-/* halo2curves to_bytes(): canonical x LE, bit 6 of byte 31 = lsb(canonical y); identity = zeros */
+/* halo2curves 0.3.x to_bytes(): canonical x LE, top bit of byte 31 = lsb(canonical y); identity = zeros (recalled; >= 0.4 uses bit 6) */
 void orc_g1_compress(const u64 aff[8], uint8_t out[32]) {
     const g1a *p = (const g1a *)aff;
     if (a_is_identity(p)) { memset(out, 0, 32); return; }
@@ -423,7 +423,7 @@ void orc_g1_compress(const u64 aff[8], uint8_t out[32]) {
     f_from_mont(&FQ, x, &p->x);
     f_from_mont(&FQ, y, &p->y);
     memcpy(out, x, 32);
-    out[31] |= (uint8_t)((y[0] & 1) << 6);
+    out[31] |= (uint8_t)((y[0] & 1) << 7);
 }
 
 /* ------------------------------------------------------------------ synthetic inputs */

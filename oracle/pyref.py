@@ -98,12 +98,12 @@ def g1_msm(scalars, points):
 
 
 def g1_compress(pt):
-    """halo2curves 0.3.x `to_bytes()`: x LE, bit 6 of byte 31 = lsb(y); identity = zeros
+    """halo2curves 0.3.x `to_bytes()`: x LE, top bit of byte 31 = lsb(y); identity = zeros
     (SURVEY.md App. A.2 -- recalled, unverified)."""
     if pt is None:
         return bytes(32)
     b = bytearray(pt[0].to_bytes(32, "little"))
-    b[31] |= (pt[1] & 1) << 6
+    b[31] |= (pt[1] & 1) << 7
     return bytes(b)
 
 

@@ -41,7 +41,7 @@ while time.time() < t_end:
     it += 1
     kind = rnd.choice(["commit", "commit", "multiexp", "ntt", "domain", "row2", "quotient", "permute"] if not BIG else ["commit_big", "domain_big", "dev_big"])
     stats[kind] = stats.get(kind, 0) + 1
-    tune = (rnd.choice([-1, -1, 1, 3, 5, 17, 64]), rnd.choice([-1, -1, 0, 1, 2, 4, 7]))
+    tune = (rnd.choice([-1, -1, 1, 3, 5, 17, 64]), rnd.choice([-1, -1, 0, 1]))
     h.set_tuning(*tune)
     case = None
     try:

@@ -336,12 +336,13 @@ def test_cpp_mirror(h2v, tmp_path):
     assert out.returncode == 0 and "cpp mirror ok" in out.stdout, out.stdout + out.stderr
 
 
-@pytest.mark.parametrize("ba_rounds,chunk", [(1, 4), (3, 7), (6, 64), (0, 5)])
-def test_msm_tuning_invariance(h2v, ba_rounds, chunk):
-    """Batch-affine pair rounds and the chunk length change the schedule, never the result: force them on
-    small inputs (uniform, witness-like with giant buckets, duplicate / opposite / identity bases)."""
+@pytest.mark.parametrize("table,chunk", [(1, 4), (0, 7), (1, 64), (0, 5), (-1, 1), (1, 1)])
+def test_msm_tuning_invariance(h2v, table, chunk):
+    """The window table (main / small window) and the chunk length change the schedule, never the result: force
+    them on small inputs (uniform, witness-like with giant buckets, duplicate / opposite / identity bases)."""
+    ba_rounds = table + 1
     try:
-        h2v.set_tuning(chunk, ba_rounds)
+        h2v.set_tuning(chunk, table)
         k, n = 11, 1 << 11
         b = O.gen_bases(n)
         srs = h2v.ParamsKZG(k, None, b)
@@ -605,11 +606,16 @@ def test_large_batches_take_the_pipelined_paths(h2v):
     dom.close()
 
 
-def test_forced_pair_rounds_on_sparse_input_regression(h2v):
-    """Found by scripts/fuzz.py: 7 forced batch-affine rounds on 6 columns of 14 scalars against a 2^10 SRS --
-    far fewer entries than buckets.  The per-round slot bound must never grow past the round-0 buffers."""
+def test_sparse_input_short_columns(h2v):
+    """6 columns of 14 scalars against a 2^10 SRS -- far fewer entries than buckets -- with one entry per accumulate
+    thread, on both window tables."""
+    for table in (0, 1):
+        _sparse_short_columns(h2v, table)
+
+
+def _sparse_short_columns(h2v, table):
     try:
-        h2v.set_tuning(1, 7)
+        h2v.set_tuning(1, table)
         k, n, ln = 10, 1 << 10, 14
         b = O.gen_bases(n)
         srs = h2v.ParamsKZG(k, None, b)
