@@ -321,9 +321,9 @@ struct MsmCfg {
 uint32_t windows_for(uint32_t c) { return (255 + c - 1) / c; }
 // cost model in group additions per column: bucket adds + ~3 per bucket for the reduction
 MsmCfg choose_cfg(size_t n, bool precomp) {
-    MsmCfg best = {1, 255, precomp ? 1u : 255u};
+    MsmCfg best = {3, 85, precomp ? 1u : 85u};
     double best_cost = 1e300;
-    for (uint32_t c = 2; c <= 22; ++c) {
+    for (uint32_t c = 3; c <= 22; ++c) {
         uint32_t W = windows_for(c);
         double nb = (double)(1u << (c - 1));
         // cost of one bucket in the reduction, in bucket additions.  Measured: 3 fits large n; at 2^16 the value 5
@@ -416,8 +416,9 @@ MsmLayout msm_layout(void *base, const MsmShape &sh, uint32_t cols) {
     uint64_t ent = (uint64_t)cols * sh.W * sh.n;
     L.n_buckets = cols * sh.G * sh.nb;
     L.nthreads = (uint32_t)((ent + sh.chunk - 1) / sh.chunk);
-    L.l1 = (sh.nb + 7) / 8;            // the reduction tree uses segments of 8..32: size for the worst case
-    size_t l2 = (L.l1 + 7) / 8;
+    // the reduction levels use segments of 8..32 (2 or 4 for a handful of buckets): size for the worst case
+    L.l1 = sh.nb <= 64 ? sh.nb : (sh.nb + 7) / 8;
+    size_t l2 = L.l1 <= 64 ? L.l1 : (L.l1 + 7) / 8;
     // counters cleared by ONE memset per launch: histogram, long-bucket count, straddler count, density sample
     L.counts = cv.take<uint32_t>((size_t)L.n_buckets + 8);
     L.long_count = L.counts + L.n_buckets;
@@ -441,6 +442,36 @@ MsmLayout msm_layout(void *base, const MsmShape &sh, uint32_t cols) {
 
 const size_t MSM_WS_BUDGET = (size_t)16 << 30;   // per handle; columns per launch are sized to fit
 std::once_flag g_tree_attr_once;
+
+// the two passes over the scalars are instantiated per window size (compile-time limb indices and shifts)
+template <int C> struct WindowDispatch {
+    static bool count(uint32_t c, dim3 grid, cudaStream_t st, const fe *sc, size_t stride, uint32_t *counts, const MsmShape &sh) {
+        if (c == (uint32_t)C) {
+            msm_count_kernel<C><<<grid, 256, 0, st>>>(sc, stride, counts, sh);
+            return true;
+        }
+        return WindowDispatch<C - 1>::count(c, grid, st, sc, stride, counts, sh);
+    }
+    static bool scatter(uint32_t c, dim3 grid, cudaStream_t st, const fe *sc, size_t stride, uint32_t *cursor, uint2 *entries, const MsmShape &sh,
+                        uint32_t lo, uint32_t hi) {
+        if (c == (uint32_t)C) {
+            msm_scatter_kernel<C><<<grid, 256, 0, st>>>(sc, stride, cursor, entries, sh, lo, hi);
+            return true;
+        }
+        return WindowDispatch<C - 1>::scatter(c, grid, st, sc, stride, cursor, entries, sh, lo, hi);
+    }
+};
+template <> struct WindowDispatch<2> {
+    static bool count(uint32_t, dim3, cudaStream_t, const fe *, size_t, uint32_t *, const MsmShape &) { return false; }
+    static bool scatter(uint32_t, dim3, cudaStream_t, const fe *, size_t, uint32_t *, uint2 *, const MsmShape &, uint32_t, uint32_t) { return false; }
+};
+bool launch_count(uint32_t c, dim3 grid, cudaStream_t st, const fe *sc, size_t stride, uint32_t *counts, const MsmShape &sh) {
+    return WindowDispatch<24>::count(c, grid, st, sc, stride, counts, sh);
+}
+bool launch_scatter(uint32_t c, dim3 grid, cudaStream_t st, const fe *sc, size_t stride, uint32_t *cursor, uint2 *entries, const MsmShape &sh,
+                    uint32_t lo, uint32_t hi) {
+    return WindowDispatch<24>::scatter(c, grid, st, sc, stride, cursor, entries, sh, lo, hi);
+}
 
 MsmShape make_shape(size_t len, const MsmCfg &cfg, size_t pstride) {
     MsmShape sh;
@@ -494,7 +525,7 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
         if (rc) return rc;
     }
     std::call_once(g_tree_attr_once, [] {
-        cudaFuncSetAttribute(msm_reduce_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(H2V_TREE_MAX * sizeof(xyzz)));
+        cudaFuncSetAttribute(msm_reduce_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * H2V_TREE_MAX * sizeof(xyzz)));
     });
     for (size_t c0 = 0; c0 < n_cols; c0 += max_cols) {
         uint32_t cols = (uint32_t)std::min(max_cols, n_cols - c0);
@@ -505,7 +536,7 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
         CU(cudaMemsetAsync(L.counts, 0, ((size_t)L.n_buckets + 8) * sizeof(uint32_t), st));
         unsigned gx = (unsigned)((len + 255) / 256);
         if (tm) tm->begin(0);
-        msm_count_kernel<<<dim3(gx, cols), 256, 0, st>>>(sc, col_stride, L.counts, sh);
+        if (!launch_count(sh.c, dim3(gx, cols), st, sc, col_stride, L.counts, sh)) return fail(H2V_EINVAL, "MSM window size %u unsupported", sh.c);
         LAUNCHED();
         if (tm) { tm->end(); tm->begin(1); }
         {
@@ -531,8 +562,7 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
             slices = std::max(1u, std::min(slices, sh.nb));
             const uint32_t per = (sh.nb + slices - 1) / slices;
             for (uint32_t sl = 0; sl < slices; ++sl) {
-                msm_scatter_kernel<<<dim3(gx, cols), 256, 0, st>>>(sc, col_stride, L.cursor, L.entries, sh, sl * per,
-                                                                         std::min(sh.nb, (sl + 1) * per));
+                launch_scatter(sh.c, dim3(gx, cols), st, sc, col_stride, L.cursor, L.entries, sh, sl * per, std::min(sh.nb, (sl + 1) * per));
                 LAUNCHED();
             }
         }
@@ -560,7 +590,7 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
         while (cnt > 1) {
             if (cnt <= H2V_TREE_MAX && !occ) {
                 const unsigned threads = std::max(32u, std::min(256u, cnt / 2));
-                msm_reduce_tree_kernel<<<n_inst, threads, cnt * sizeof(xyzz), st>>>(Sin, Ain, cnt, shift, L.S[pp], L.A[pp]);
+                msm_reduce_tree_kernel<<<n_inst, threads, 2 * cnt * sizeof(xyzz), st>>>(Sin, Ain, cnt, shift, L.S[pp], L.A[pp]);
                 LAUNCHED();
                 Sin = L.S[pp];
                 Ain = L.A[pp];

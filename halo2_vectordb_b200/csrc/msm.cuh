@@ -122,18 +122,53 @@ __device__ __forceinline__ uint32_t warp_agg_add(uint32_t *counter_base, uint32_
 }
 
 // ------------------------------------------------------------------ pass 1: histogram
+// The window size is a template parameter (host dispatch over 2..24): after unrolling over the windows every limb
+// index and shift is a constant, so a digit costs a funnel shift and a compare instead of a 9-way select.
+template <int C> struct MsmDigitsC {
+    static constexpr uint32_t W = (255 + C - 1) / C;
+    uint32_t t[9];
+    __device__ __forceinline__ void load(const fe *p, const MsmShape &sh) {
+        fe s = fe_from_mont<Fr>(fe_ld(p));
+        uint64_t cy = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            cy += (uint64_t)s.v[k] + sh.kadd[k];
+            t[k] = (uint32_t)cy;
+            cy >>= 32;
+        }
+        t[8] = (uint32_t)cy + sh.kadd[8];
+    }
+    template <uint32_t J> __device__ __forceinline__ bool get(uint32_t &mag, uint32_t &neg) const {
+        constexpr uint32_t bit = J * C, w = bit >> 5, sft = bit & 31;
+        const uint32_t lo = w < 9 ? t[w < 9 ? w : 0] : 0u, hi = (w + 1) < 9 ? t[(w + 1) < 9 ? w + 1 : 0] : 0u;
+        const uint32_t d = (sft ? __funnelshift_r(lo, hi, sft) : lo) & ((1u << C) - 1);
+        const int32_t sd = (int32_t)d - (int32_t)((1u << (C - 1)) - 1);
+        if (sd == 0) return false;
+        neg = sd < 0 ? 0x80000000u : 0u;
+        mag = (uint32_t)(sd < 0 ? -sd : sd) - 1;
+        return true;
+    }
+};
+template <int C, uint32_t J> struct MsmCountStep {
+    static __device__ __forceinline__ void run(const MsmDigitsC<C> &dg, bool in, uint32_t col, uint32_t *counts, const MsmShape &sh) {
+        uint32_t mag = 0, neg = 0;
+        const bool ok = in && dg.template get<J>(mag, neg);
+        const uint32_t g = sh.G > 1 ? J : 0;
+        warp_agg_add(counts, (col * sh.G + g) * sh.nb + mag, ok);
+        MsmCountStep<C, J + 1>::run(dg, in, col, counts, sh);
+    }
+};
+template <int C> struct MsmCountStep<C, MsmDigitsC<C>::W> {
+    static __device__ __forceinline__ void run(const MsmDigitsC<C> &, bool, uint32_t, uint32_t *, const MsmShape &) {}
+};
+template <int C>
 __global__ void __launch_bounds__(256) msm_count_kernel(const fe *__restrict__ scalars, size_t col_stride, uint32_t *__restrict__ counts,
                                                         MsmShape sh) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
     const bool in = i < sh.n;
-    MsmDigits dg;
+    MsmDigitsC<C> dg;
     dg.load(scalars + (size_t)col * col_stride + (in ? i : 0), sh);
-    for (uint32_t j = 0; j < sh.W; ++j) {
-        uint32_t mag = 0, neg = 0;
-        const bool ok = in && dg.get(j, sh, mag, neg);
-        const uint32_t g = sh.G > 1 ? j : 0;
-        warp_agg_add(counts, (col * sh.G + g) * sh.nb + mag, ok);
-    }
+    MsmCountStep<C, 0>::run(dg, in, col, counts, sh);
 }
 // estimate of the number of non-zero digits under two window sizes, from a strided sample of the batch (window choice)
 __global__ void __launch_bounds__(256) msm_density_kernel(const fe *__restrict__ scalars, size_t col_stride, uint32_t n_cols, uint32_t n,
@@ -244,21 +279,31 @@ __global__ void __launch_bounds__(256) msm_scan_apply_kernel(const uint32_t *__r
 // entries[pos] = (point_ref | sign<<31, global bucket), counting sort by bucket.
 // Only digits with magnitude in [mag_lo, mag_hi) are placed: for a very large MSM the host sweeps the bucket
 // space in slices so that the randomly written part of `entries` stays L2-resident.
+template <int C, uint32_t J> struct MsmScatterStep {
+    static __device__ __forceinline__ void run(const MsmDigitsC<C> &dg, bool in, uint32_t i, uint32_t col, uint32_t *cursor, uint2 *entries,
+                                               const MsmShape &sh, uint32_t mag_lo, uint32_t mag_hi) {
+        uint32_t mag = 0, neg = 0;
+        bool ok = in && dg.template get<J>(mag, neg);
+        ok = ok && mag >= mag_lo && mag < mag_hi;
+        const uint32_t g = sh.G > 1 ? J : 0;
+        const uint32_t b = (col * sh.G + g) * sh.nb + mag;
+        const uint32_t pos = warp_agg_add(cursor, b, ok);
+        if (ok) entries[pos] = make_uint2((sh.G > 1 ? i : J * sh.pstride + i) | neg, b);
+        MsmScatterStep<C, J + 1>::run(dg, in, i, col, cursor, entries, sh, mag_lo, mag_hi);
+    }
+};
+template <int C> struct MsmScatterStep<C, MsmDigitsC<C>::W> {
+    static __device__ __forceinline__ void run(const MsmDigitsC<C> &, bool, uint32_t, uint32_t, uint32_t *, uint2 *, const MsmShape &, uint32_t,
+                                               uint32_t) {}
+};
+template <int C>
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const fe *__restrict__ scalars, size_t col_stride, uint32_t *__restrict__ cursor,
                                                           uint2 *__restrict__ entries, MsmShape sh, uint32_t mag_lo, uint32_t mag_hi) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
     const bool in = i < sh.n;
-    MsmDigits dg;
+    MsmDigitsC<C> dg;
     dg.load(scalars + (size_t)col * col_stride + (in ? i : 0), sh);
-    for (uint32_t j = 0; j < sh.W; ++j) {
-        uint32_t mag = 0, neg = 0;
-        bool ok = in && dg.get(j, sh, mag, neg);
-        ok = ok && mag >= mag_lo && mag < mag_hi;
-        const uint32_t g = sh.G > 1 ? j : 0;
-        const uint32_t b = (col * sh.G + g) * sh.nb + mag;
-        const uint32_t pos = warp_agg_add(cursor, b, ok);
-        if (ok) entries[pos] = make_uint2((sh.G > 1 ? i : j * sh.pstride + i) | neg, b);
-    }
+    MsmScatterStep<C, 0>::run(dg, in, i, col, cursor, entries, sh, mag_lo, mag_hi);
 }
 
 // ------------------------------------------------------------------ chunked accumulation
@@ -475,44 +520,39 @@ __global__ void __launch_bounds__(128, 3) msm_reduce_kernel(const xyzz *__restri
 // are latency-bound there (a lone warp needs ~4 us per full addition), so ONE CTA per instance finishes the job with
 // log-depth sums whose active lanes stay packed:
 //   sum_s s * S_s = sum_b 2^b Z_b,  Z_b = sum over { s : bit b of s set } of S_s.
-// With T the pairwise block sums of S (level l: blocks of 2^l), Z_l is the sum of the ODD blocks of level l.  The tree
-// over T and the accumulation of the Z_l advance together: cnt - 1 additions for T, cnt - 1 for the Z's in total --
-// the same work as the serial running sums -- in ~2 log2(cnt) dependent steps.  A is a plain sum.
-// Shared memory: cnt / 2 + 2 * log2(cnt) + ... XYZZ values (128 B each).
+// With T the pairwise block sums of S (level l: blocks of 2^l), Z_l is the sum of the ODD blocks of level l.
+// Phase A builds the T tree (log2 cnt steps) and keeps every level's odd blocks; phase B sums all levels' odd blocks and
+// the A values at the same time (log2 cnt - 1 halving steps over packed lanes); phase C scales Z_l by 2^l and adds.
+// cnt - 1 additions for T and cnt - 1 for the Z's in total -- the same work as the serial running sums.
+// Shared memory: T (cnt / 2) + odd blocks of all levels (cnt) + A (cnt / 2) XYZZ values, 128 B each.
 #define H2V_TREE_MAX 512
 __global__ void __launch_bounds__(256) msm_reduce_tree_kernel(const xyzz *__restrict__ S_in, const xyzz *__restrict__ A_in, uint32_t cnt,
                                                               uint32_t shift, xyzz *__restrict__ S_out, xyzz *__restrict__ A_out) {
-    extern __shared__ xyzz tsm[];                 // [0, cnt/2): T blocks of the current level; [cnt/2, cnt): odd blocks / A values
-    __shared__ xyzz zb[12];                       // Z_l
+    extern __shared__ xyzz tsm[];
     const uint32_t inst = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     const xyzz *S = S_in + (size_t)inst * cnt;
     const uint32_t half0 = cnt >> 1;              // cnt is a power of two >= 2
-    xyzz *T = tsm, *O = tsm + half0;
-    // level 0: T[i] = S[2i] + S[2i+1], O[i] = S[2i+1]
+    uint32_t lg = 0;
+    while ((1u << lg) < cnt) ++lg;                // levels 0 .. lg - 1; level l has cnt >> (l + 1) odd blocks
+    xyzz *T = tsm, *O = tsm + half0, *AA = tsm + half0 + cnt;
+    // odd blocks of level l start at O + (cnt - (cnt >> l))
+    const bool haveA = A_in != nullptr;
+    // ---- phase A, level 0 (from global memory): T[i] = S[2i] + S[2i+1], O_0[i] = S[2i+1], AA[i] = A[2i] + A[2i+1]
     for (uint32_t i = tid; i < half0; i += nth) {
         xyzz a = xyzz_ld(S + 2 * i), b = xyzz_ld(S + 2 * i + 1);
         O[i] = b;
         xyzz_add(a, b);
         T[i] = a;
+        if (haveA) {
+            const xyzz *A = A_in + (size_t)inst * cnt;
+            xyzz c = xyzz_ld(A + 2 * i), d = xyzz_ld(A + 2 * i + 1);
+            xyzz_add(c, d);
+            AA[i] = c;
+        }
     }
     __syncthreads();
-    uint32_t level = 0;
-    for (uint32_t m = half0; m >= 1; m >>= 1, ++level) {
-        // Z_level = sum of O[0..m): halving sums with packed lanes
-        for (uint32_t w = m; w > 1; w >>= 1) {
-            const uint32_t h = w >> 1;
-            for (uint32_t i = tid; i < h; i += nth) {
-                xyzz a = O[i];
-                xyzz_add(a, O[i + h]);
-                O[i] = a;
-            }
-            __syncthreads();
-        }
-        if (tid == 0) zb[level] = O[0];
-        __syncthreads();
-        if (m == 1) break;
-        // next level: T'[i] = T[2i] + T[2i+1], O[i] = T[2i+1]
-        const uint32_t h = m >> 1;                // h <= cnt / 4 <= blockDim.x (the host launches at least cnt / 4 threads)
+    for (uint32_t l = 1; l < lg; ++l) {
+        const uint32_t h = cnt >> (l + 1);        // h <= cnt / 4 <= blockDim.x (the host launches at least cnt / 4 threads)
         xyzz a = xyzz_identity(), b = xyzz_identity();
         if (tid < h) {
             a = T[2 * tid];
@@ -520,43 +560,52 @@ __global__ void __launch_bounds__(256) msm_reduce_tree_kernel(const xyzz *__rest
         }
         __syncthreads();                          // the pairwise sums overwrite T in place
         if (tid < h) {
-            O[tid] = b;
+            O[cnt - (cnt >> l) + tid] = b;
             xyzz_add(a, b);
             T[tid] = a;
         }
         __syncthreads();
     }
-    // now T[0] = sum of all S; levels = log2(cnt) values Z_0 .. Z_{levels-1}
-    const uint32_t levels = level + 1;
-    // plain sum of A (if any), through the O area
-    bool haveA = A_in != nullptr;
-    if (haveA) {
-        const xyzz *A = A_in + (size_t)inst * cnt;
-        for (uint32_t i = tid; i < half0; i += nth) {
-            xyzz a = xyzz_ld(A + 2 * i), b = xyzz_ld(A + 2 * i + 1);
-            xyzz_add(a, b);
-            O[i] = a;
+    // ---- phase B: every level's odd blocks (and AA) are halved together until one value per level is left
+    for (uint32_t step = 1; (half0 >> step) >= 1; ++step) {
+        // work items of this step: for level l, the first (cnt >> (l + 1 + step)) elements; AA likewise (as level 0)
+        for (uint32_t w = tid;; w += nth) {
+            uint32_t rem = w;
+            xyzz *seg = nullptr;
+            uint32_t hcount = 0;
+            for (uint32_t l = 0; l < lg; ++l) {
+                const uint32_t hc = cnt >> (l + 1 + step);
+                if (hc == 0) break;
+                if (rem < hc) {
+                    seg = O + (cnt - (cnt >> l));
+                    hcount = hc;
+                    break;
+                }
+                rem -= hc;
+            }
+            if (!seg && haveA) {
+                const uint32_t hc = half0 >> step;
+                if (rem < hc) {
+                    seg = AA;
+                    hcount = hc;
+                }
+            }
+            if (!seg) break;
+            xyzz a = seg[rem];
+            xyzz_add(a, seg[rem + hcount]);
+            seg[rem] = a;
         }
         __syncthreads();
-        for (uint32_t w = half0; w > 1; w >>= 1) {
-            const uint32_t h = w >> 1;
-            for (uint32_t i = tid; i < h; i += nth) {
-                xyzz a = O[i];
-                xyzz_add(a, O[i + h]);
-                O[i] = a;
-            }
-            __syncthreads();
-        }
     }
-    // weighted part: lane l scales Z_l by 2^l (lockstep doublings), a shuffle tree adds them
+    // ---- phase C: lane l scales Z_l by 2^l (lockstep doublings), a shuffle tree adds them
     if (tid < 32) {
-        xyzz acc = tid < levels ? zb[tid] : xyzz_identity();
-        for (uint32_t k = 0; k + 1 < levels; ++k)
-            if (k < tid && tid < levels) acc = xyzz_double(acc);
+        xyzz acc = tid < lg ? O[cnt - (cnt >> tid)] : xyzz_identity();
+        for (uint32_t k = 0; k + 1 < lg; ++k)
+            if (k < tid && tid < lg) acc = xyzz_double(acc);
         acc = xyzz_warp_sum(acc);
         if (tid == 0) {
             for (uint32_t k = 0; k < shift; ++k) acc = xyzz_double(acc);
-            if (haveA) xyzz_add(acc, O[0]);
+            if (haveA) xyzz_add(acc, AA[0]);
             xyzz_st(S_out + inst, T[0]);
             xyzz_st(A_out + inst, acc);
         }
