@@ -290,6 +290,10 @@ def _main(args, real_stdout):
         line["ntt"] = bench_ntt(h, torch, dev, peak)
         line["witness_like"] = bench_witness(h, torch, dev, srs)
         line["prove_shaped"] = bench_prove_shaped(h, torch, dev, srs, d_cols, cols)
+        if not os.environ.get("H2V_BENCH_SKIP_REAL"):
+            rf = bench_real_flow(h, torch)
+            line["prove_shaped"]["real_flow"] = rf
+            line["prove_shaped"]["kmeans_k16_real_flow_s"] = rf["kmeans_k16"]["prove_s"]
         line["next_row2"] = bench_row2(h, torch, dev, d_cols, cols)
         line["next_row1"] = bench_row1(h, torch, dev)
         if world == 1:
@@ -309,6 +313,61 @@ def _main(args, real_stdout):
     srs.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+REAL_SHAPES = {    # SURVEY.md App. C column counts: (k, basic-gate advice columns, lookup-advice columns, LOOKUP_BITS)
+    "distances_k13": (13, 10, 2, 12),
+    "query_k13": (13, 152, 18, 12),
+    "kmeans_k16": (16, 546, 71, 15),
+}
+
+
+def bench_real_flow(h, torch, names=("distances_k13", "query_k13", "kmeans_k16")):
+    """ONE real proof per circuit shape through the library's create_proof (h2v_create_proof): a satisfied synthetic
+    circuit with halo2-base's constraint system and the column counts of SURVEY.md App. C, witness-shaped cell values,
+    the seed-zero SRS of gen_srs, ChaCha20 blinding, the Poseidon transcript, real challenge dependencies between the
+    phases, SHPLONK opening -- every step of SURVEY.md 3.1 from the advice columns (pinned host memory) to the proof
+    bytes.  What it leaves out of `prove`: witness generation by the chips and reading the proving key from disk."""
+    import numpy as np
+    from halo2_vectordb_b200.synthetic import synthetic_circuit
+    res = {}
+    for name in names:
+        k, G, Lc, bits = REAL_SHAPES[name]
+        n = 1 << k
+        t0 = time.perf_counter()
+        circ = synthetic_circuit(k, G, Lc, bits, seed=k)
+        t_gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        srs = h.ParamsKZG.gen_srs(k)
+        t_srs = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        pk = h.ProvingKey(srs, circ["cs"], circ["fixed"], circ["sigma"], circ["vk_repr"])
+        t_pk = time.perf_counter() - t0
+        A = len(circ["advice"])
+        pinned = torch.empty((A, n, 4), dtype=torch.int64).pin_memory()
+        adv = pinned.numpy().view(np.uint64)
+        for i, c in enumerate(circ["advice"]):
+            adv[i] = c
+        cols = [adv[i] for i in range(A)]
+        circ["advice"] = None
+        proof = pk.create_proof(cols, circ["instances"], bytes(32))
+        ts, phases = [], None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            p2 = pk.create_proof(cols, circ["instances"], bytes(32))
+            ts.append(time.perf_counter() - t0)
+            phases = pk.last_phase_ms()
+            assert p2 == proof, "create_proof is not deterministic in the seed"
+        res[name] = {"prove_s": min(ts), "k": k, "advice_columns": A, "lookups": Lc, "fixed_columns": len(circ["fixed"]),
+                     "permutation_columns": len(circ["cs"]["permutation"]), "proof_bytes": len(proof),
+                     "phase_ms": {kk: round(v, 2) for kk, v in phases.items()},
+                     "setup_s": {"circuit_generation": round(t_gen, 2), "gen_srs": round(t_srs, 2), "pk_load": round(t_pk, 2)}}
+        pk.close()
+        srs.close()
+        del pinned, adv, cols, circ
+    res["note"] = ("one real create_proof per shape (App. C column counts, satisfied synthetic halo2-base circuit, witness-shaped values, "
+                   "advice columns in pinned host memory, proof bytes out); excludes witness generation and reading the pk")
+    return res
 
 
 PROVE_SHAPES = {   # SURVEY.md App. C: hot-path call counts per proof (estimates; labelled as such)

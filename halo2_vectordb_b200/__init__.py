@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "h2v_pk_load", "h2v_pk_free", "h2v_create_proof", "h2v_proof_size", "h2v_pk_last_phase_ms",
     "h2v_transcript_new", "h2v_transcript_free", "h2v_transcript_common_point", "h2v_transcript_common_scalar",
     "h2v_transcript_write_point", "h2v_transcript_write_scalar", "h2v_transcript_squeeze_challenge", "h2v_transcript_bytes",
-    "h2v_poseidon_permutation", "h2v_chacha20_fr_random", "h2v_chacha20_block",
+    "h2v_poseidon_permutation", "h2v_poseidon_permutation_variant", "h2v_chacha20_fr_random", "h2v_chacha20_block",
     "h2v_srs_gen", "h2v_g2_mul_generator", "h2v_srs_write_file", "h2v_srs_read_file",
     "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_op_rate", "h2v_set_tuning", "h2v_launch_count", "h2v_last_kernel_ms",
 ]
@@ -140,6 +140,7 @@ def lib():
             getattr(L, "h2v_transcript_" + name).argtypes = [C.c_void_p, C.c_void_p]
         L.h2v_transcript_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.h2v_poseidon_permutation.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.h2v_poseidon_permutation_variant.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
         L.h2v_chacha20_fr_random.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
         L.h2v_chacha20_block.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p]
         L.h2v_srs_gen.argtypes = [C.c_uint32, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -706,10 +707,11 @@ class PoseidonTranscript:
         return bytes(buf[:ln.value])
 
 
-def poseidon_permutation(state, r_f, r_p):
-    """the Poseidon permutation over BN254 Fr (t = len(state) in {3, 5}) on Montgomery-form words; returns a new array"""
+def poseidon_permutation(state, r_f, r_p, variant=1):
+    """the Poseidon permutation over BN254 Fr (t = len(state) in {3, 5}) on Montgomery-form words; returns a new array.
+    variant 0 = plain rounds, 1 = the sparse form the transcript uses (identical results)"""
     st = np.array(_fr(state), copy=True)
-    _check(lib().h2v_poseidon_permutation(st.shape[0], r_f, r_p, _ptr(st)))
+    _check(lib().h2v_poseidon_permutation_variant(st.shape[0], r_f, r_p, variant, _ptr(st)))
     return st
 
 

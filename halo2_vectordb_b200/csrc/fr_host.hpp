@@ -44,16 +44,33 @@ inline void sub_mod(uint64_t *a) {
         bw = (d >> 64) & 1;
     }
 }
-inline Fr64 add(const Fr64 &a, const Fr64 &b) {
+// r = t - MOD if t >= MOD (or `top` set) else t; branch-free (the comparison outcome is a coin flip on random data)
+inline Fr64 csub_mod(uint64_t t0, uint64_t t1, uint64_t t2, uint64_t t3, uint64_t top) {
+    unsigned long long r0, r1, r2, r3;
+    unsigned char b = __builtin_sub_overflow(t0, MOD[0], &r0);
+    unsigned char b1 = __builtin_sub_overflow(t1, MOD[1], &r1);
+    b1 |= __builtin_sub_overflow(r1, (uint64_t)b, &r1);
+    unsigned char b2 = __builtin_sub_overflow(t2, MOD[2], &r2);
+    b2 |= __builtin_sub_overflow(r2, (uint64_t)b1, &r2);
+    unsigned char b3 = __builtin_sub_overflow(t3, MOD[3], &r3);
+    b3 |= __builtin_sub_overflow(r3, (uint64_t)b2, &r3);
+    const uint64_t keep = (uint64_t)0 - (uint64_t)((b3 != 0) & (top == 0));      // all ones: t < MOD, keep t
     Fr64 r;
-    u128 c = 0;
-    for (int i = 0; i < 4; ++i) {
-        c += (u128)a.l[i] + b.l[i];
-        r.l[i] = (uint64_t)c;
-        c >>= 64;
-    }
-    if (geq_mod(r.l)) sub_mod(r.l);     // a + b < 2r < 2^255: no carry out
+    r.l[0] = (t0 & keep) | (r0 & ~keep);
+    r.l[1] = (t1 & keep) | (r1 & ~keep);
+    r.l[2] = (t2 & keep) | (r2 & ~keep);
+    r.l[3] = (t3 & keep) | (r3 & ~keep);
     return r;
+}
+inline Fr64 add(const Fr64 &a, const Fr64 &b) {
+    u128 c = (u128)a.l[0] + b.l[0];
+    const uint64_t t0 = (uint64_t)c;
+    c = (c >> 64) + a.l[1] + b.l[1];
+    const uint64_t t1 = (uint64_t)c;
+    c = (c >> 64) + a.l[2] + b.l[2];
+    const uint64_t t2 = (uint64_t)c;
+    c = (c >> 64) + a.l[3] + b.l[3];
+    return csub_mod(t0, t1, t2, (uint64_t)c, 0);      // a + b < 2r < 2^255: no carry out
 }
 inline Fr64 sub(const Fr64 &a, const Fr64 &b) {
     Fr64 r;
@@ -63,13 +80,12 @@ inline Fr64 sub(const Fr64 &a, const Fr64 &b) {
         r.l[i] = (uint64_t)d;
         bw = (d >> 64) & 1;
     }
-    if (bw) {
-        u128 c = 0;
-        for (int i = 0; i < 4; ++i) {
-            c += (u128)r.l[i] + MOD[i];
-            r.l[i] = (uint64_t)c;
-            c >>= 64;
-        }
+    const uint64_t m = (uint64_t)0 - (uint64_t)bw;      // add MOD back when the difference went negative
+    u128 c = 0;
+    for (int i = 0; i < 4; ++i) {
+        c += (u128)r.l[i] + (MOD[i] & m);
+        r.l[i] = (uint64_t)c;
+        c >>= 64;
     }
     return r;
 }
@@ -99,9 +115,70 @@ inline Fr64 mul(const Fr64 &a, const Fr64 &b) {
         t[3] = (uint64_t)c;
         t[4] = t[5] + (uint64_t)(c >> 64);
     }
-    Fr64 r = {{t[0], t[1], t[2], t[3]}};
-    if (geq_mod(r.l)) sub_mod(r.l);
-    return r;
+    return csub_mod(t[0], t[1], t[2], t[3], 0);
+}
+// ---- wide (unreduced) products for dot products with ONE Montgomery reduction (the Poseidon MDS rows)
+// t[0..8) += a * b as a 512-bit integer; the caller keeps the total below 2^512.  Fixed-length carry chains only.
+inline void mul_acc_wide(uint64_t t[8], const Fr64 &a, const Fr64 &b) {
+    uint64_t p[8];
+    {
+        u128 c = (u128)a.l[0] * b.l[0];
+        p[0] = (uint64_t)c;
+        c = (c >> 64) + (u128)a.l[0] * b.l[1];
+        p[1] = (uint64_t)c;
+        c = (c >> 64) + (u128)a.l[0] * b.l[2];
+        p[2] = (uint64_t)c;
+        c = (c >> 64) + (u128)a.l[0] * b.l[3];
+        p[3] = (uint64_t)c;
+        p[4] = (uint64_t)(c >> 64);
+    }
+    for (int i = 1; i < 4; ++i) {
+        u128 c = (u128)a.l[i] * b.l[0] + p[i];
+        p[i] = (uint64_t)c;
+        c = (c >> 64) + (u128)a.l[i] * b.l[1] + p[i + 1];
+        p[i + 1] = (uint64_t)c;
+        c = (c >> 64) + (u128)a.l[i] * b.l[2] + p[i + 2];
+        p[i + 2] = (uint64_t)c;
+        c = (c >> 64) + (u128)a.l[i] * b.l[3] + p[i + 3];
+        p[i + 3] = (uint64_t)c;
+        p[i + 4] = (uint64_t)(c >> 64);
+    }
+    u128 c = 0;
+    for (int k = 0; k < 8; ++k) {
+        c += (u128)t[k] + p[k];
+        t[k] = (uint64_t)c;
+        c >>= 64;
+    }
+}
+// Montgomery reduction of T < 2^511 with T / R < 2r: (T + m r) / R, one conditional subtraction
+inline Fr64 redc_wide(const uint64_t t_in[8]) {
+    uint64_t t[8];
+    for (int i = 0; i < 8; ++i) t[i] = t_in[i];
+    uint64_t top = 0;          // carries out of the running window land here
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t q = t[i] * INV;
+        u128 c = (u128)q * MOD[0] + t[i];
+        c = (c >> 64) + (u128)q * MOD[1] + t[i + 1];
+        t[i + 1] = (uint64_t)c;
+        c = (c >> 64) + (u128)q * MOD[2] + t[i + 2];
+        t[i + 2] = (uint64_t)c;
+        c = (c >> 64) + (u128)q * MOD[3] + t[i + 3];
+        t[i + 3] = (uint64_t)c;
+        c >>= 64;
+        for (int k = i + 4; k < 8; ++k) {
+            c += t[k];
+            t[k] = (uint64_t)c;
+            c >>= 64;
+        }
+        top += (uint64_t)c;
+    }
+    return csub_mod(t[4], t[5], t[6], t[7], top);
+}
+// sum_k a[k] * b[k] (Montgomery), cnt <= 5: the products are summed unreduced (5 r^2 < 2^511), one reduction
+inline Fr64 dot(const Fr64 *a, const Fr64 *b, int cnt) {
+    uint64_t t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < cnt; ++k) mul_acc_wide(t, a[k], b[k]);
+    return redc_wide(t);
 }
 inline Fr64 sqr(const Fr64 &a) { return mul(a, a); }
 inline Fr64 from_u64(uint64_t x) { return mul(Fr64{{x, 0, 0, 0}}, R2); }

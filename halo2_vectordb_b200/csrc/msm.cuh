@@ -121,6 +121,13 @@ __device__ __forceinline__ uint32_t warp_agg_add(uint32_t *counter_base, uint32_
     return base + __popc(peers & ((1u << lane) - 1));
 }
 
+// the same without a result: the leader's atomic is a fire-and-forget reduction (no round trip to wait for)
+__device__ __forceinline__ void warp_agg_inc(uint32_t *counter_base, uint32_t idx, bool valid) {
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? idx : 0xffffffffu);
+    if (valid && (int)lane == __ffs(peers) - 1) atomicAdd(counter_base + idx, (uint32_t)__popc(peers));
+}
+
 // ------------------------------------------------------------------ pass 1: histogram
 // The window size is a template parameter (host dispatch over 2..24): after unrolling over the windows every limb
 // index and shift is a constant, so a digit costs a funnel shift and a compare instead of a 9-way select.
@@ -154,7 +161,7 @@ template <int C, uint32_t J> struct MsmCountStep {
         uint32_t mag = 0, neg = 0;
         const bool ok = in && dg.template get<J>(mag, neg);
         const uint32_t g = sh.G > 1 ? J : 0;
-        warp_agg_add(counts, (col * sh.G + g) * sh.nb + mag, ok);
+        warp_agg_inc(counts, (col * sh.G + g) * sh.nb + mag, ok);
         MsmCountStep<C, J + 1>::run(dg, in, col, counts, sh);
     }
 };

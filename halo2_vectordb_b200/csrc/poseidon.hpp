@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "ec.cuh"
@@ -27,6 +28,16 @@ template <int T> struct PoseidonSpec {
     int r_f, r_p;
     std::vector<Fr64> rc;     // (r_f + r_p) * T round constants
     Fr64 mds[T][T];
+    // Partial rounds in their sparse form (an exact rewriting of the same permutation, checked against the plain
+    // rounds by tests/): with M = [[m00, v^T], [w, M^]] = diag(1, M^) * [[m00, v^T], [M^^-1 w, I]] the dense factor
+    // commutes with the one-word S-box and is applied once after the last partial round (as diag(1, M^^r_p)), and only
+    // the first word needs a round constant (the rest is pushed forward into the next full round's constants):
+    //   round j: s0 <- (s0 + pc[j])^5;  (s0, s_rest) <- (m00 s0 + pv[j] . s_rest,  s_rest + pw[j] s0)
+    std::vector<Fr64> pc;             // r_p scalars
+    std::vector<Fr64> pv, pw;         // r_p x (T - 1) each
+    Fr64 m00;
+    Fr64 dense[T - 1][T - 1];         // M^^r_p
+    Fr64 rc_after[T];                 // the constants of the first full round after the partial rounds, adjusted
 };
 
 namespace poseidon_detail {
@@ -71,6 +82,98 @@ struct Grain {
 };
 }  // namespace poseidon_detail
 
+namespace poseidon_detail {
+// (T-1) x (T-1) inverse by Gauss-Jordan over Fr (the MDS submatrix is invertible)
+template <int N> inline void mat_inverse(const Fr64 (&a)[N][N], Fr64 (&out)[N][N]) {
+    Fr64 m[N][2 * N];
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            m[i][j] = a[i][j];
+            m[i][N + j] = i == j ? frh::ONE : frh::zero();
+        }
+    for (int c = 0; c < N; ++c) {
+        int p = c;
+        while (p < N && frh::is_zero(m[p][c])) ++p;
+        if (p != c)
+            for (int j = 0; j < 2 * N; ++j) std::swap(m[p][j], m[c][j]);
+        const Fr64 iv = frh::inv(m[c][c]);
+        for (int j = 0; j < 2 * N; ++j) m[c][j] = frh::mul(m[c][j], iv);
+        for (int r = 0; r < N; ++r) {
+            if (r == c || frh::is_zero(m[r][c])) continue;
+            const Fr64 f = m[r][c];
+            for (int j = 0; j < 2 * N; ++j) m[r][j] = frh::sub(m[r][j], frh::mul(f, m[c][j]));
+        }
+    }
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) out[i][j] = m[i][N + j];
+}
+template <int T> inline void build_sparse(PoseidonSpec<T> &s) {
+    constexpr int N = T - 1;
+    const int half = s.r_f / 2;
+    Fr64 mh[N][N], mhi[N][N];
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) mh[i][j] = s.mds[i + 1][j + 1];
+    mat_inverse<N>(mh, mhi);
+    s.m00 = s.mds[0][0];
+    Fr64 v[N], w[N];
+    for (int j = 0; j < N; ++j) v[j] = s.mds[0][j + 1];
+    for (int i = 0; i < N; ++i) {       // w^ = M^^-1 w
+        Fr64 acc = frh::zero();
+        for (int j = 0; j < N; ++j) acc = frh::add(acc, frh::mul(mhi[i][j], s.mds[j + 1][0]));
+        w[i] = acc;
+    }
+    // constants: a_0 = c[half]; a_{j+1} = c[half + j + 1] + M (0, a_j[1..])
+    Fr64 a[T];
+    for (int i = 0; i < T; ++i) a[i] = s.rc[(size_t)half * T + i];
+    Fr64 dense[N][N];
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) dense[i][j] = i == j ? frh::ONE : frh::zero();
+    s.pc.resize(s.r_p);
+    s.pv.resize((size_t)s.r_p * N);
+    s.pw.resize((size_t)s.r_p * N);
+    for (int r = 0; r < s.r_p; ++r) {
+        s.pc[r] = a[0];
+        for (int j = 0; j < N; ++j) {
+            s.pv[(size_t)r * N + j] = v[j];
+            s.pw[(size_t)r * N + j] = w[j];
+        }
+        // next round's sparse factors: v^T <- v^T M^,  w^ <- M^^-1 w^
+        Fr64 nv[N], nw[N];
+        for (int j = 0; j < N; ++j) {
+            Fr64 acc = frh::zero(), acc2 = frh::zero();
+            for (int i = 0; i < N; ++i) {
+                acc = frh::add(acc, frh::mul(v[i], mh[i][j]));
+                acc2 = frh::add(acc2, frh::mul(mhi[j][i], w[i]));
+            }
+            nv[j] = acc;
+            nw[j] = acc2;
+        }
+        for (int j = 0; j < N; ++j) { v[j] = nv[j]; w[j] = nw[j]; }
+        // dense <- dense * M^
+        Fr64 nd[N][N];
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) {
+                Fr64 acc = frh::zero();
+                for (int k = 0; k < N; ++k) acc = frh::add(acc, frh::mul(dense[i][k], mh[k][j]));
+                nd[i][j] = acc;
+            }
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) dense[i][j] = nd[i][j];
+        // pending constants pushed through M: a <- c[next] + M (0, a[1..])
+        Fr64 na[T];
+        for (int i = 0; i < T; ++i) {
+            Fr64 acc = s.rc[(size_t)(half + r + 1) * T + i];
+            for (int j = 1; j < T; ++j) acc = frh::add(acc, frh::mul(s.mds[i][j], a[j]));
+            na[i] = acc;
+        }
+        for (int i = 0; i < T; ++i) a[i] = na[i];
+    }
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) s.dense[i][j] = dense[i][j];
+    for (int i = 0; i < T; ++i) s.rc_after[i] = a[i];
+}
+}  // namespace poseidon_detail
+
 template <int T> inline PoseidonSpec<T> poseidon_make_spec(int r_f, int r_p) {
     PoseidonSpec<T> s;
     s.r_f = r_f;
@@ -93,10 +196,12 @@ template <int T> inline PoseidonSpec<T> poseidon_make_spec(int r_f, int r_p) {
         }
     for (int i = 0; i < T; ++i)
         for (int j = 0; j < T; ++j) s.mds[i][j] = frh::inv(frh::add(xs[i], ys[j]));
+    poseidon_detail::build_sparse<T>(s);
     return s;
 }
 
-template <int T> inline void poseidon_permute(const PoseidonSpec<T> &sp, Fr64 (&st)[T]) {
+// the permutation as the Poseidon paper writes it (every round: constants, S-box layer, dense MDS)
+template <int T> inline void poseidon_permute_plain(const PoseidonSpec<T> &sp, Fr64 (&st)[T]) {
     const int half = sp.r_f / 2;
     const Fr64 *rc = sp.rc.data();
     for (int rnd = 0; rnd < sp.r_f + sp.r_p; ++rnd) {
@@ -114,6 +219,35 @@ template <int T> inline void poseidon_permute(const PoseidonSpec<T> &sp, Fr64 (&
         }
         for (int i = 0; i < T; ++i) st[i] = nx[i];
     }
+}
+// the same permutation with the partial rounds in sparse form and one Montgomery reduction per matrix row
+// (the transcript is a single dependent chain of ~10^3 permutations per proof: host latency that nothing can hide)
+template <int T> inline void poseidon_permute(const PoseidonSpec<T> &sp, Fr64 (&st)[T]) {
+    constexpr int N = T - 1;
+    const int half = sp.r_f / 2;
+    auto full_round = [&](const Fr64 *rc) {
+        for (int i = 0; i < T; ++i) st[i] = frh::pow5(frh::add(st[i], rc[i]));
+        Fr64 nx[T];
+        for (int i = 0; i < T; ++i) nx[i] = frh::dot(sp.mds[i], st, T);
+        for (int i = 0; i < T; ++i) st[i] = nx[i];
+    };
+    for (int r = 0; r < half; ++r) full_round(sp.rc.data() + (size_t)r * T);
+    for (int r = 0; r < sp.r_p; ++r) {
+        const Fr64 s0 = frh::pow5(frh::add(st[0], sp.pc[r]));
+        const Fr64 *v = sp.pv.data() + (size_t)r * N, *w = sp.pw.data() + (size_t)r * N;
+        uint64_t t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        frh::mul_acc_wide(t, sp.m00, s0);
+        for (int j = 0; j < N; ++j) frh::mul_acc_wide(t, v[j], st[j + 1]);
+        for (int j = 0; j < N; ++j) st[j + 1] = frh::add(st[j + 1], frh::mul(w[j], s0));
+        st[0] = frh::redc_wide(t);
+    }
+    {   // the dense factor collected over the partial rounds: diag(1, M^^r_p)
+        Fr64 nx[N];
+        for (int i = 0; i < N; ++i) nx[i] = frh::dot(sp.dense[i], st + 1, N);
+        for (int i = 0; i < N; ++i) st[i + 1] = nx[i];
+    }
+    full_round(sp.rc_after);
+    for (int r = half + sp.r_p + 1; r < sp.r_f + sp.r_p; ++r) full_round(sp.rc.data() + (size_t)r * T);
 }
 
 template <int T, int RATE> struct PoseidonSponge {

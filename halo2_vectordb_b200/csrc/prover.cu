@@ -991,14 +991,19 @@ int h2v_transcript_bytes(h2v_transcript_t t, uint8_t *out, size_t cap, size_t *l
     }
     return out ? failf(H2V_EINVAL, "transcript_bytes: buffer too small") : H2V_OK;
 }
+// variant 0: the plain rounds of the Poseidon paper; 1: the sparse form the transcript runs (must agree)
+int h2v_poseidon_permutation_variant(uint32_t t, uint32_t r_f, uint32_t r_p, int variant, uint64_t *state);
 int h2v_poseidon_permutation(uint32_t t, uint32_t r_f, uint32_t r_p, uint64_t *state) {
+    return h2v_poseidon_permutation_variant(t, r_f, r_p, 1, state);
+}
+int h2v_poseidon_permutation_variant(uint32_t t, uint32_t r_f, uint32_t r_p, int variant, uint64_t *state) {
     if (!state) return failf(H2V_EINVAL, "poseidon_permutation: NULL state");
     if (r_f < 2 || (r_f & 1) || r_f > 64 || r_p > 512) return failf(H2V_EINVAL, "poseidon_permutation: bad round numbers");
     if (t == 3) {
         PoseidonSpec<3> sp = poseidon_make_spec<3>((int)r_f, (int)r_p);
         Fr64 st3[3];
         for (int i = 0; i < 3; ++i) st3[i] = frh::load(state + 4 * i);
-        poseidon_permute<3>(sp, st3);
+        if (variant) poseidon_permute<3>(sp, st3); else poseidon_permute_plain<3>(sp, st3);
         for (int i = 0; i < 3; ++i) frh::store(state + 4 * i, st3[i]);
         return H2V_OK;
     }
@@ -1006,7 +1011,7 @@ int h2v_poseidon_permutation(uint32_t t, uint32_t r_f, uint32_t r_p, uint64_t *s
         PoseidonSpec<5> sp = poseidon_make_spec<5>((int)r_f, (int)r_p);
         Fr64 st5[5];
         for (int i = 0; i < 5; ++i) st5[i] = frh::load(state + 4 * i);
-        poseidon_permute<5>(sp, st5);
+        if (variant) poseidon_permute<5>(sp, st5); else poseidon_permute_plain<5>(sp, st5);
         for (int i = 0; i < 5; ++i) frh::store(state + 4 * i, st5[i]);
         return H2V_OK;
     }

@@ -260,6 +260,9 @@ int h2v_transcript_squeeze_challenge(h2v_transcript_t t, uint64_t out[4]);
 int h2v_transcript_bytes(h2v_transcript_t t, uint8_t *out, size_t cap, size_t *len);
 /* the Poseidon permutation itself (Grain-LFSR constants, Cauchy MDS; t = 3 or 5) on a Montgomery-form state, in place */
 int h2v_poseidon_permutation(uint32_t t, uint32_t r_f, uint32_t r_p, uint64_t *state);
+/* variant 0: every round as the Poseidon paper writes it (constants, S-boxes, dense MDS); variant 1: the form the
+ * transcript runs (sparse partial rounds, one reduction per matrix row) -- the same permutation, tests compare them */
+int h2v_poseidon_permutation_variant(uint32_t t, uint32_t r_f, uint32_t r_p, int variant, uint64_t *state);
 /* rand_chacha ChaCha20Rng::from_seed(seed): out[i] = the i-th `Fr::random(&mut rng)` draw (Montgomery form);
  * h2v_chacha20_block = 64 bytes of key stream at a block counter (RFC 7539 block function) */
 int h2v_chacha20_fr_random(const uint8_t seed[32], size_t n, uint64_t *out);

@@ -185,3 +185,25 @@ def test_gpu_prover_errors(h2v):
     assert _gpu_proof(pk, t) == _oracle_proof(params, t)
     pk.close()
     srs.close()
+
+
+@pytest.mark.gpu
+def test_gpu_proof_of_generated_circuit_verifies(h2v):
+    """the vectorised circuit generator bench.py uses for the full-size shapes (halo2_vectordb_b200.synthetic): its
+    circuits are satisfied -- the oracle verifier accepts the device proof -- and the oracle prover produces the same bytes"""
+    from halo2_vectordb_b200.synthetic import synthetic_circuit
+
+    k = 9
+    c = synthetic_circuit(k, n_gate_cols=5, n_lookup_cols=2, lookup_bits=6, seed=3)
+    params = PL.Params.setup(k, SECRET)
+    srs = h2v.ParamsKZG(k, params.g, params.g_lagrange)
+    pk = h2v.ProvingKey(srs, c["cs"], c["fixed"], c["sigma"], c["vk_repr"])
+    proof = pk.create_proof(c["advice"], c["instances"], SEED)
+    ints = lambda cols: [O.fr_to_ints(col) for col in cols]
+    fixed, sigma, advice, inst = ints(c["fixed"]), ints(c["sigma"]), ints(c["advice"]), ints(c["instances"])
+    vk_repr = O.fr_to_ints(c["vk_repr"].reshape(1, 4))[0]
+    vk = PL.keygen_vk(params, c["cs"], fixed, sigma)
+    assert PL.verify_proof(params, c["cs"], vk, vk_repr, inst, proof)
+    assert proof == PL.create_proof(params, c["cs"], fixed, sigma, vk_repr, advice, inst, SEED)
+    pk.close()
+    srs.close()
