@@ -286,6 +286,10 @@ def _main(args, real_stdout):
                      "algorithmic": f"{MSM_MACS_PER_POINT[K]} wide-MAC/pt x {cols * N} pts per launch (SURVEY.md 8d)"},
     }
 
+    # ---- strong scaling: ONE fixed commit phase of the kmeans k = 16 proof (1 150 columns of 2^16) split
+    # over the ranks by column index, host columns in, commitments gathered back in column order inside the timed region
+    line["strong"] = bench_strong_phase(h, torch, dev, srs, host_np, rank, world, barrier, max_over_ranks)
+
     if not args.no_extras and rank == 0:
         line["ntt"] = bench_ntt(h, torch, dev, peak)
         line["witness_like"] = bench_witness(h, torch, dev, srs)
@@ -313,6 +317,52 @@ def _main(args, real_stdout):
     srs.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+STRONG_COLS = 1150     # commit_lagrange calls of one kmeans k = 16 proof
+
+
+def bench_strong_phase(h, torch, dev, srs, host_np, rank, world, barrier, max_over_ranks):
+    """One fixed phase split over the ranks (scaling = strong): column j of STRONG_COLS goes to rank j mod world; every rank
+    commits its share through the host-facing entry point (pinned host columns, H2D inside), then the commitments are
+    all-gathered and put back in column order -- what the host transcript of ONE proof needs before the next challenge.
+    The same columns are reused round-robin from the step's pinned batch (the data does not matter for the timing of
+    uniform scalars).  Timed as max over ranks, gather included."""
+    import ctypes as C
+    import numpy as np
+    mine = [j for j in range(STRONG_COLS) if j % world == rank]
+    per = (STRONG_COLS + world - 1) // world
+    ptrs = (C.c_void_p * len(mine))(*[host_np[j % host_np.shape[0]].ctypes.data for j in mine])
+    out = np.zeros((per, 8), dtype=np.uint64)
+    out_t = torch.from_numpy(out.view(np.int64))
+    gathered = torch.zeros((world, per, 8), dtype=torch.int64, device=dev)
+    ordered = torch.zeros((STRONG_COLS, 8), dtype=torch.int64)
+
+    def phase():
+        h._check(h.lib().h2v_commit_batch(srs._h, h.H2V_BASIS_LAGRANGE, ptrs, len(mine), N, out.ctypes.data_as(C.c_void_p)))
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(gathered, out_t.to(dev))
+            g = gathered.cpu()
+        else:
+            g = out_t.unsqueeze(0)
+        for r in range(world):                       # rank r holds columns r, r + world, ...
+            cnt = len(range(r, STRONG_COLS, world))
+            ordered[r::world] = g[r, :cnt]
+        return ordered
+
+    phase()
+    ts = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        phase()
+        torch.cuda.synchronize()
+        ts.append(max_over_ranks(time.perf_counter() - t0))
+    t = min(ts)
+    return {"scaling": "strong", "phase": f"commit_lagrange of {STRONG_COLS} columns x 2^16 (one kmeans k=16 proof's commits), host columns in, "
+                                          "commitments gathered in column order", "n_gpus": world, "ms": t * 1e3,
+            "mpts_per_s": STRONG_COLS * N / t / 1e6, "cols_per_rank": len(mine)}
 
 
 REAL_SHAPES = {    # SURVEY.md App. C column counts: (k, basic-gate advice columns, lookup-advice columns, LOOKUP_BITS)

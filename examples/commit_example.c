@@ -13,8 +13,8 @@
 int main(void) {
     const uint32_t k = 10;
     const size_t n = (size_t)1 << k;
-    if (h2v_device_count() <= 0) { printf("no CUDA device: %s\n", h2v_init(0) ? h2v_last_error() : "?"); return 0; }
-    CHECK(h2v_init(0));
+    if (h2v_device_count() <= 0) { printf("no CUDA device: %s\n", h2v_init(NULL, 0) ? h2v_last_error() : "?"); return 0; }
+    CHECK(h2v_init(NULL, 0));      /* device 0; a list of devices makes the batch calls use all of them */
     /* any non-zero value below r is a valid Montgomery-form scalar */
     uint64_t s[4] = {0x0123456789abcdefULL, 0xfedcba9876543210ULL, 0x1111111111111111ULL, 0x0222222222222222ULL};
     uint64_t *g = malloc(n * 64), *gl = malloc(n * 64), *col = malloc(n * 32), *coef = malloc(n * 32);

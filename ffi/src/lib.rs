@@ -27,7 +27,7 @@ pub const H2V_OP_EXTENDED_TO_COEFF: c_int = 3;
 pub const H2V_OP_DIVIDE_BY_VANISHING: c_int = 4;
 
 extern "C" {
-    pub fn h2v_init(device: c_int) -> c_int;
+    pub fn h2v_init(devices: *const c_int, n_dev: c_int) -> c_int;
     pub fn h2v_device_count() -> c_int;
     pub fn h2v_last_error() -> *const c_char;
     pub fn h2v_host_register(ptr: *mut c_void, bytes: usize) -> c_int;

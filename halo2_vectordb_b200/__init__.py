@@ -25,7 +25,7 @@ KERNEL_CLASSES = ["msm_digits", "msm_scan", "msm_scatter", "msm_accumulate", "ms
 
 # every symbol include/h2v.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
-    "h2v_init", "h2v_device_count", "h2v_last_error", "h2v_version", "h2v_host_register", "h2v_host_unregister", "h2v_dev_alloc", "h2v_dev_free", "h2v_dev_upload", "h2v_dev_download",
+    "h2v_init", "h2v_device_list", "h2v_dev_alloc_on", "h2v_device_count", "h2v_last_error", "h2v_version", "h2v_host_register", "h2v_host_unregister", "h2v_dev_alloc", "h2v_dev_free", "h2v_dev_upload", "h2v_dev_download",
     "h2v_srs_load", "h2v_srs_setup", "h2v_srs_free", "h2v_srs_info", "h2v_commit", "h2v_commit_batch", "h2v_commit_batch_dev", "h2v_best_multiexp", "h2v_g1_sum",
     "h2v_best_fft", "h2v_domain_new", "h2v_domain_free", "h2v_domain_k", "h2v_domain_extended_k", "h2v_domain_constant",
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
@@ -68,7 +68,9 @@ def lib():
         L.h2v_domain_extended_k.restype = C.c_uint32
         L.h2v_domain_k.argtypes = [C.c_void_p]
         L.h2v_domain_extended_k.argtypes = [C.c_void_p]
-        L.h2v_init.argtypes = [C.c_int]
+        L.h2v_init.argtypes = [C.POINTER(C.c_int), C.c_int]
+        L.h2v_device_list.argtypes = [C.POINTER(C.c_int), C.c_int]
+        L.h2v_dev_alloc_on.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
         L.h2v_dev_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
         L.h2v_dev_free.argtypes = [C.c_void_p]
         L.h2v_dev_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -174,17 +176,31 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def init(device=0):
-    _check(lib().h2v_init(device))
+def init(devices=0):
+    """`h2v_init(devices, n_dev)`: the CUDA device(s) this process drives -- an int or a list; the first one is the primary
+    device.  With several devices every handle holds a replica per device and the host-facing batch entry points split
+    their columns across them (column j -> device j mod G)."""
+    devs = [int(devices)] if isinstance(devices, (int, np.integer)) else [int(d) for d in devices]
+    arr = (C.c_int * len(devs))(*devs)
+    _check(lib().h2v_init(arr, len(devs)))
+
+
+def device_list():
+    buf = (C.c_int * 16)()
+    n = lib().h2v_device_list(buf, 16)
+    return [int(buf[i]) for i in range(n)]
 
 
 class DeviceBuffer:
     """A device allocation for the `_dev` entry points (columns resident in HBM across several steps)."""
 
-    def __init__(self, nbytes):
+    def __init__(self, nbytes, device=None):
         self.nbytes = nbytes
         self._p = C.c_void_p()
-        _check(lib().h2v_dev_alloc(nbytes, C.byref(self._p)))
+        if device is None:
+            _check(lib().h2v_dev_alloc(nbytes, C.byref(self._p)))
+        else:
+            _check(lib().h2v_dev_alloc_on(device, nbytes, C.byref(self._p)))
 
     @property
     def ptr(self):

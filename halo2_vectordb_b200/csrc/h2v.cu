@@ -14,6 +14,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "h2v.h"
@@ -29,7 +30,22 @@ using namespace h2v;
 namespace {
 
 thread_local std::string g_err;
-int g_device = 0;
+// The devices this process drives (h2v_init): handles hold one replica per device, `_dev` entry points run on the device
+// that owns their buffers, host-facing batch entry points split their columns across all of them.  t_dev is the device
+// the calling thread's current entry point runs on (-1: the primary device, g_devs[0]).
+#define H2V_MAX_DEV 16
+std::vector<int> g_devs = {0};
+thread_local int t_dev = -1;
+int cur_dev() { return t_dev >= 0 ? t_dev : g_devs[0]; }
+// the device a device pointer lives on (the primary one for anything the runtime does not know)
+int device_of(const void *p) {
+    cudaPointerAttributes at;
+    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return g_devs[0];
+    }
+    return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? at.device : g_devs[0];
+}
 std::atomic<uint64_t> g_launches{0};
 // device-side timing of the calling thread's last `_dev` call (per thread: concurrent callers do not mix their records)
 thread_local float g_last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -51,7 +67,7 @@ int set_error(int code, const char *msg) {
     return code;
 }
 void count_launches(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
-int current_device() { return g_device; }
+int current_device() { return g_devs[0]; }
 }  // namespace h2v
 namespace {
 #define CU(x)                                                                                      \
@@ -67,8 +83,8 @@ namespace {
     } while (0)
 
 int use_device() {
-    cudaError_t e = cudaSetDevice(g_device);
-    if (e != cudaSuccess) return fail(H2V_ECUDA, "cudaSetDevice(%d): %s (libh2v has no CPU fallback)", g_device, cudaGetErrorString(e));
+    cudaError_t e = cudaSetDevice(cur_dev());
+    if (e != cudaSuccess) return fail(H2V_ECUDA, "cudaSetDevice(%d): %s (libh2v has no CPU fallback)", cur_dev(), cudaGetErrorString(e));
     return H2V_OK;
 }
 
@@ -241,7 +257,8 @@ const int FR_S = 28;
 
 }  // namespace
 
-struct h2v_domain {
+struct DomRep {
+    int dev = 0;
     uint32_t j, k, ek, nt;
     fe omega, omega_inv, ext_omega, ext_omega_inv, g_coset, g_coset_inv, ifft_divisor, ext_ifft_divisor;
     fe t_eval[64];
@@ -253,7 +270,7 @@ struct h2v_domain {
     DevBuf stage_a, stage_b, pipe_a, pipe_b;
     cudaStream_t stream = nullptr, pipe_stream = nullptr;
     std::mutex mu, tw_mu;
-    struct Lane {            // small host-facing transforms from concurrent caller threads (see h2v_srs::Lane)
+    struct Lane {            // small host-facing transforms from concurrent caller threads (see SrsRep::Lane)
         std::mutex mu;
         cudaStream_t st = nullptr;
         DevBuf stage_a, stage_b;
@@ -266,7 +283,7 @@ struct h2v_domain {
 namespace {
 
 // twiddle tables are built once per domain and direction, synchronously, so that any stream may use them
-int domain_twiddles(h2v_domain *d, int which, const fe **out) {
+int domain_twiddles(DomRep *d, int which, const fe **out) {
     std::lock_guard<std::mutex> lk(d->tw_mu);
     if (!d->tw_ready[which]) {
         const fe &w = which == 0 ? d->omega : which == 1 ? d->omega_inv : which == 2 ? d->ext_omega : d->ext_omega_inv;
@@ -280,7 +297,7 @@ int domain_twiddles(h2v_domain *d, int which, const fe **out) {
 }
 
 // enqueue one EvaluationDomain transform on device-resident columns
-int domain_op_dev(h2v_domain *d, cudaStream_t st, int op, const fe *in, size_t in_stride, fe *out, size_t out_stride, size_t n_cols) {
+int domain_op_dev(DomRep *d, cudaStream_t st, int op, const fe *in, size_t in_stride, fe *out, size_t out_stride, size_t n_cols) {
     const fe *tw;
     const fe *dc = d->dconst.as<fe>();
     const uint32_t n = 1u << d->k, en = 1u << d->ek;
@@ -305,10 +322,10 @@ int domain_op_dev(h2v_domain *d, cudaStream_t st, int op, const fe *in, size_t i
         return fail(H2V_EINVAL, "unknown domain op %d", op);
     }
 }
-size_t op_in_len(const h2v_domain *d, int op) {
+size_t op_in_len(const DomRep *d, int op) {
     return (op == H2V_OP_EXTENDED_TO_COEFF || op == H2V_OP_DIVIDE_BY_VANISHING) ? ((size_t)1 << d->ek) : ((size_t)1 << d->k);
 }
-size_t op_out_len(const h2v_domain *d, int op) {
+size_t op_out_len(const DomRep *d, int op) {
     if (op == H2V_OP_COEFF_TO_EXTENDED) return (size_t)1 << d->ek;
     if (op == H2V_OP_EXTENDED_TO_COEFF || op == H2V_OP_DIVIDE_BY_VANISHING) return ((size_t)1 << d->k) * (d->j - 1);
     return (size_t)1 << d->k;
@@ -630,7 +647,8 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
 
 }  // namespace
 
-struct h2v_srs {
+struct SrsRep {
+    int dev = 0;
     uint32_t k;
     size_t n;
     // Window tables, two per basis: [0] the window the cost model picks for uniform scalars, [1] a smaller window
@@ -666,7 +684,7 @@ namespace {
 // the batch (one small kernel + a 16-byte read-back), then the cheaper plan wins under the cost model
 //   10 products per bucket addition (mixed add) + 28 per bucket of the reduction (two full additions).
 // Results never depend on the choice.  h2v_set_tuning(_, table) / H2V_TABLE force a table (tests).
-int msm_srs(h2v_srs *s, cudaStream_t st, MsmWorkspace &ws, int basis, const fe *d_scalars, size_t col_stride, size_t n_cols, size_t len,
+int msm_srs(SrsRep *s, cudaStream_t st, MsmWorkspace &ws, int basis, const fe *d_scalars, size_t col_stride, size_t n_cols, size_t len,
             affine *d_out, Timer *tm) {
     int variant = 0;
     double density = 1.0;
@@ -717,14 +735,46 @@ int h2v_device_count(void) {
     }
     return n;
 }
-int h2v_init(int device) {
+// The CUDA devices this process drives, in order; devices[0] is the primary one (handle-less and host-facing
+// single-column entry points run there).  Call before creating handles.  NULL / 0 = device 0.
+int h2v_init(const int *devices, int n_dev) {
     int n = h2v_device_count();
     if (n <= 0) return fail(H2V_ECUDA, "no CUDA device visible (libh2v has no CPU fallback)");
-    if (device < 0 || device >= n) return fail(H2V_EINVAL, "device %d out of range (have %d)", device, n);
-    g_device = device;
-    CU(cudaSetDevice(device));
-    CU(cudaFree(0));
+    std::vector<int> devs;
+    if (!devices || n_dev <= 0) {
+        devs.push_back(0);
+    } else {
+        if (n_dev > H2V_MAX_DEV) return fail(H2V_EINVAL, "h2v_init: at most %d devices", H2V_MAX_DEV);
+        for (int i = 0; i < n_dev; ++i) {
+            if (devices[i] < 0 || devices[i] >= n) return fail(H2V_EINVAL, "device %d out of range (have %d)", devices[i], n);
+            for (int d : devs)
+                if (d == devices[i]) return fail(H2V_EINVAL, "h2v_init: device %d listed twice", d);
+            devs.push_back(devices[i]);
+        }
+    }
+    for (int d : devs) {
+        CU(cudaSetDevice(d));
+        CU(cudaFree(0));
+    }
+    // peer access between all pairs (SRS replicas are copied device to device); failure just means staged copies
+    for (int a : devs)
+        for (int b : devs) {
+            if (a == b) continue;
+            int ok = 0;
+            if (cudaDeviceCanAccessPeer(&ok, a, b) == cudaSuccess && ok) {
+                cudaSetDevice(a);
+                cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+                if (e != cudaSuccess) cudaGetLastError();
+            }
+        }
+    g_devs = devs;
+    t_dev = -1;
+    CU(cudaSetDevice(g_devs[0]));
     return H2V_OK;
+}
+int h2v_device_list(int *out, int cap) {
+    for (int i = 0; i < (int)g_devs.size() && i < cap; ++i) out[i] = g_devs[i];
+    return (int)g_devs.size();
 }
 // Proof wire format of a commitment: halo2curves 0.3.x `G1Affine::to_bytes()` =
 // canonical x, little-endian, with the parity of canonical y in the top bit of byte 31 (poseidon.hpp); identity = 32 zero bytes.
@@ -755,6 +805,7 @@ int h2v_fr_to_repr(const uint64_t *fr_mont, size_t n, uint8_t *out) {
     return H2V_OK;
 }
 int h2v_dev_alloc(size_t bytes, void **d_out) {
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     if (!d_out || !bytes) return fail(H2V_EINVAL, "dev_alloc: bad argument");
@@ -766,12 +817,14 @@ int h2v_dev_alloc(size_t bytes, void **d_out) {
     return H2V_OK;
 }
 int h2v_dev_free(void *d_ptr) {
+    t_dev = device_of(d_ptr);
     int rc = use_device();
     if (rc) return rc;
     if (d_ptr) CU(cudaFree(d_ptr));
     return H2V_OK;
 }
 int h2v_dev_upload(void *d_dst, const void *src, size_t bytes) {
+    t_dev = device_of(d_dst);
     int rc = use_device();
     if (rc) return rc;
     if (bytes && (!d_dst || !src)) return fail(H2V_EINVAL, "dev_upload: NULL buffer");
@@ -779,6 +832,7 @@ int h2v_dev_upload(void *d_dst, const void *src, size_t bytes) {
     return H2V_OK;
 }
 int h2v_dev_download(void *dst, const void *d_src, size_t bytes) {
+    t_dev = device_of(d_src);
     int rc = use_device();
     if (rc) return rc;
     if (bytes && (!dst || !d_src)) return fail(H2V_EINVAL, "dev_download: NULL buffer");
@@ -786,6 +840,7 @@ int h2v_dev_download(void *dst, const void *d_src, size_t bytes) {
     return H2V_OK;
 }
 int h2v_host_register(void *ptr, size_t bytes) {
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     if (!ptr || !bytes) return fail(H2V_EINVAL, "host_register: bad argument");
@@ -793,6 +848,7 @@ int h2v_host_register(void *ptr, size_t bytes) {
     return H2V_OK;
 }
 int h2v_host_unregister(void *ptr) {
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     CU(cudaHostUnregister(ptr));
@@ -810,13 +866,15 @@ int h2v_last_kernel_ms(float out[8]) {
 }
 
 // ---------------------------------------------------------------- SRS / commit
-int h2v_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, h2v_srs_t *out) {
+static void rep_srs_free(SrsRep *s);
+static int rep_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, SrsRep **out) {
     if (!out) return fail(H2V_EINVAL, "h2v_srs_load: out is NULL");
     *out = nullptr;
     if (k > 26) return fail(H2V_EINVAL, "h2v_srs_load: k = %u unsupported", k);
     int rc = use_device();
     if (rc) return rc;
-    h2v_srs *s = new h2v_srs();
+    SrsRep *s = new SrsRep();
+    s->dev = cur_dev();
     s->k = k;
     s->n = (size_t)1 << k;
     s->cfg[0] = choose_cfg(s->n, true);
@@ -847,10 +905,10 @@ int h2v_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, h2v_
         for (int v = 0; v < (s->have_small ? 2 : 1); ++v) {
             DevBuf &tb = s->table[b][v];
             rc = tb.ensure((size_t)s->cfg[v].W * s->n * sizeof(affine));
-            if (rc) { h2v_srs_free(s); return rc; }
+            if (rc) { rep_srs_free(s); return rc; }
             if (v == 0) e = cudaMemcpyAsync(tb.p, src[b], s->n * sizeof(affine), cudaMemcpyHostToDevice, s->stream);
             else e = cudaMemcpyAsync(tb.p, s->table[b][0].p, s->n * sizeof(affine), cudaMemcpyDeviceToDevice, s->stream);
-            if (e != cudaSuccess) { h2v_srs_free(s); return fail(H2V_ECUDA, "SRS upload: %s", cudaGetErrorString(e)); }
+            if (e != cudaSuccess) { rep_srs_free(s); return fail(H2V_ECUDA, "SRS upload: %s", cudaGetErrorString(e)); }
             for (uint32_t lvl = 1; lvl < s->cfg[v].W; ++lvl) {
                 msm_precompute_kernel<<<(unsigned)((s->n + 127) / 128), 128, 0, s->stream>>>(tb.as<affine>(), (uint32_t)s->n, lvl, s->cfg[v].c);
                 g_launches.fetch_add(1);
@@ -860,20 +918,20 @@ int h2v_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, h2v_
     }
     e = cudaStreamSynchronize(s->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) { h2v_srs_free(s); return fail(H2V_ECUDA, "SRS table build: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { rep_srs_free(s); return fail(H2V_ECUDA, "SRS table build: %s", cudaGetErrorString(e)); }
     *out = s;
     return H2V_OK;
 }
-int h2v_srs_info(h2v_srs_t s, uint32_t *window_bits, uint32_t *windows) {
+static int rep_srs_info(SrsRep *s, uint32_t *window_bits, uint32_t *windows) {
     if (!s) return fail(H2V_EINVAL, "srs_info: NULL srs");
     // the table the last commit on this handle used (the main one before any commit)
     if (window_bits) *window_bits = s->cfg[s->last_variant].c;
     if (windows) *windows = s->cfg[s->last_variant].W;
     return H2V_OK;
 }
-void h2v_srs_free(h2v_srs_t s) {
+static void rep_srs_free(SrsRep *s) {
     if (!s) return;
-    cudaSetDevice(g_device);
+    cudaSetDevice(cur_dev());
     for (auto &tb : s->table)
         for (auto &t : tb) t.release();
     s->ws.buf.release();
@@ -898,7 +956,7 @@ void h2v_srs_free(h2v_srs_t s) {
     delete s;
 }
 
-int h2v_commit_batch_dev(h2v_srs_t s, int basis, const void *d_polys, size_t col_stride, size_t n_polys, size_t len,
+static int rep_commit_batch_dev(SrsRep *s, int basis, const void *d_polys, size_t col_stride, size_t n_polys, size_t len,
                          void *d_out_affine) {
     if (!s) return fail(H2V_EINVAL, "commit: NULL srs");
     if (basis != 0 && basis != 1) return fail(H2V_EINVAL, "commit: basis must be 0 or 1");
@@ -917,7 +975,7 @@ int h2v_commit_batch_dev(h2v_srs_t s, int basis, const void *d_polys, size_t col
     return H2V_OK;
 }
 
-int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_t n_polys, size_t len, uint64_t *out_affine) {
+static int rep_commit_batch(SrsRep *s, int basis, const uint64_t *const *polys, size_t n_polys, size_t len, uint64_t *out_affine) {
     if (!s) return fail(H2V_EINVAL, "commit: NULL srs");
     if (basis != 0 && basis != 1) return fail(H2V_EINVAL, "commit: basis must be 0 or 1");
     if (!s->have[basis]) return fail(H2V_EINVAL, "commit: basis %d was not loaded", basis);
@@ -930,11 +988,11 @@ int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_
     if (n_polys * stride_small * sizeof(fe) <= ((size_t)48 << 20)) {
         // one sub-batch: take a free lane (or wait for the next one in round-robin order)
         // lowest free lane first (a single-threaded caller keeps reusing lane 0 and its buffers)
-        h2v_srs::Lane *ln = nullptr;
-        for (int i = 0; i < h2v_srs::H2V_LANES && !ln; ++i)
+        SrsRep::Lane *ln = nullptr;
+        for (int i = 0; i < SrsRep::H2V_LANES && !ln; ++i)
             if (s->lanes[i].mu.try_lock()) ln = &s->lanes[i];
         if (!ln) {
-            ln = &s->lanes[s->next_lane.fetch_add(1) % h2v_srs::H2V_LANES];
+            ln = &s->lanes[s->next_lane.fetch_add(1) % SrsRep::H2V_LANES];
             ln->mu.lock();
         }
         std::lock_guard<std::mutex> lk(ln->mu, std::adopt_lock);
@@ -1020,19 +1078,28 @@ int h2v_commit_batch(h2v_srs_t s, int basis, const uint64_t *const *polys, size_
     CU(cudaStreamSynchronize(s->stream));
     return H2V_OK;
 }
-int h2v_commit(h2v_srs_t s, int basis, const uint64_t *poly, size_t len, uint64_t out_affine[8]) {
+static int rep_commit(SrsRep *s, int basis, const uint64_t *poly, size_t len, uint64_t out_affine[8]) {
     const uint64_t *cols[1] = {poly};
-    return h2v_commit_batch(s, basis, cols, 1, len, out_affine);
+    return rep_commit_batch(s, basis, cols, 1, len, out_affine);
 }
 
 // one MSM over caller-supplied bases (no handle, no tables): Jacobian and / or affine result
 static int multiexp_raw(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t *out_jacobian, uint64_t *out_affine) {
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
-    static std::mutex mu;
-    static MsmWorkspace ws;
-    static DevBuf sc, pts, outb;
-    static cudaStream_t st = nullptr;
+    struct RawCtx {
+        std::mutex mu;
+        MsmWorkspace ws;
+        DevBuf sc, pts, outb;
+        cudaStream_t st = nullptr;
+    };
+    static RawCtx ctxs[H2V_MAX_DEV];
+    RawCtx &cx = ctxs[cur_dev()];
+    std::mutex &mu = cx.mu;
+    MsmWorkspace &ws = cx.ws;
+    DevBuf &sc = cx.sc, &pts = cx.pts, &outb = cx.outb;
+    cudaStream_t &st = cx.st;
     std::lock_guard<std::mutex> lk(mu);
     if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if ((rc = sc.ensure(n * sizeof(fe)))) return rc;
@@ -1055,6 +1122,7 @@ int h2v_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, u
     if (n && (!coeffs || !bases)) return fail(H2V_EINVAL, "best_multiexp: NULL input");
     if (n >= ((size_t)1 << 27)) return fail(H2V_EINVAL, "best_multiexp: n = %zu unsupported", n);
     if (n == 0) {
+        t_dev = -1;
         int rc = use_device();
         if (rc) return rc;
         jacobian id;      // halo2curves `G1::identity()` = (0, 1, 0)
@@ -1082,13 +1150,23 @@ int h2v_g1_sum(const uint64_t *affine_pts, size_t n, uint64_t out_affine[8]) {
 int h2v_best_fft(uint64_t *a, const uint64_t omega[4], uint32_t log_n) {
     if (!a || !omega) return fail(H2V_EINVAL, "best_fft: NULL argument");
     if (log_n > 27) return fail(H2V_EINVAL, "best_fft: log_n = %u unsupported", log_n);
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
-    static std::mutex mu;
-    static DevBuf A, B, TW;
-    static cudaStream_t st = nullptr;
-    static fe cached_omega;
-    static int cached_L = -1;
+    struct FftCtx {
+        std::mutex mu;
+        DevBuf A, B, TW;
+        cudaStream_t st = nullptr;
+        fe cached_omega;
+        int cached_L = -1;
+    };
+    static FftCtx ctxs[H2V_MAX_DEV];
+    FftCtx &cx = ctxs[cur_dev()];
+    std::mutex &mu = cx.mu;
+    DevBuf &A = cx.A, &B = cx.B, &TW = cx.TW;
+    cudaStream_t &st = cx.st;
+    fe &cached_omega = cx.cached_omega;
+    int &cached_L = cx.cached_L;
     std::lock_guard<std::mutex> lk(mu);
     if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     size_t n = (size_t)1 << log_n;
@@ -1108,7 +1186,8 @@ int h2v_best_fft(uint64_t *a, const uint64_t omega[4], uint32_t log_n) {
     return H2V_OK;
 }
 
-int h2v_domain_new(uint32_t j, uint32_t k, h2v_domain_t *out) {
+static void rep_domain_free(DomRep *d);
+static int rep_domain_new(uint32_t j, uint32_t k, DomRep **out) {
     if (!out) return fail(H2V_EINVAL, "domain_new: out is NULL");
     *out = nullptr;
     if (j < 2) return fail(H2V_EINVAL, "domain_new: j = %u (need j >= 2)", j);
@@ -1117,7 +1196,8 @@ int h2v_domain_new(uint32_t j, uint32_t k, h2v_domain_t *out) {
     if (ek > 27 || ek - k > 6) return fail(H2V_EINVAL, "domain_new: extended_k = %u unsupported", ek);
     int rc = use_device();
     if (rc) return rc;
-    h2v_domain *d = new h2v_domain();
+    DomRep *d = new DomRep();
+    d->dev = cur_dev();
     d->j = j;
     d->k = k;
     d->ek = ek;
@@ -1156,19 +1236,19 @@ int h2v_domain_new(uint32_t j, uint32_t k, h2v_domain_t *out) {
     cudaError_t e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) {
         rc = d->dconst.ensure(sizeof hc);
-        if (rc) { h2v_domain_free(d); return rc; }
+        if (rc) { rep_domain_free(d); return rc; }
         e = cudaMemcpy(d->dconst.p, hc, sizeof hc, cudaMemcpyHostToDevice);
     }
     if (e != cudaSuccess) {
-        h2v_domain_free(d);
+        rep_domain_free(d);
         return fail(H2V_ECUDA, "domain_new: %s", cudaGetErrorString(e));
     }
     *out = d;
     return H2V_OK;
 }
-void h2v_domain_free(h2v_domain_t d) {
+static void rep_domain_free(DomRep *d) {
     if (!d) return;
-    cudaSetDevice(g_device);
+    cudaSetDevice(cur_dev());
     d->dconst.release();
     for (auto &t : d->tw) t.release();
     d->stage_a.release();
@@ -1184,9 +1264,9 @@ void h2v_domain_free(h2v_domain_t d) {
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }
-uint32_t h2v_domain_k(h2v_domain_t d) { return d ? d->k : 0; }
-uint32_t h2v_domain_extended_k(h2v_domain_t d) { return d ? d->ek : 0; }
-int h2v_domain_constant(h2v_domain_t d, int which, uint64_t out[4]) {
+static uint32_t rep_domain_k(DomRep *d) { return d ? d->k : 0; }
+static uint32_t rep_domain_extended_k(DomRep *d) { return d ? d->ek : 0; }
+static int rep_domain_constant(DomRep *d, int which, uint64_t out[4]) {
     if (!d || !out) return fail(H2V_EINVAL, "domain_constant: NULL argument");
     const fe *p = nullptr;
     switch (which) {
@@ -1208,7 +1288,7 @@ int h2v_domain_constant(h2v_domain_t d, int which, uint64_t out[4]) {
 
 // ---- the scalar / index helpers of poly/domain.rs; host-side, no device work
 // EvaluationDomain::rotate_omega(value, rotation) = value * omega^rotation
-int h2v_domain_rotate_omega(h2v_domain_t d, const uint64_t value[4], int32_t rotation, uint64_t out[4]) {
+static int rep_domain_rotate_omega(DomRep *d, const uint64_t value[4], int32_t rotation, uint64_t out[4]) {
     if (!d || !value || !out) return fail(H2V_EINVAL, "rotate_omega: NULL argument");
     fe w = rotation >= 0 ? fe_pow_u64<Fr>(d->omega, (uint64_t)rotation) : fe_pow_u64<Fr>(d->omega_inv, (uint64_t)(-(int64_t)rotation));
     fe_to_u64x4(fe_mul<Fr>(fe_from_u64x4(value), w), out);
@@ -1216,7 +1296,7 @@ int h2v_domain_rotate_omega(h2v_domain_t d, const uint64_t value[4], int32_t rot
 }
 // EvaluationDomain::rotate_extended(poly, rotation): cyclic shift of an extended-domain column by
 // rotation * 2^(extended_k - k) positions (out[i] = in[i + shift]); in != out
-int h2v_domain_rotate_extended(h2v_domain_t d, const uint64_t *in, int32_t rotation, uint64_t *out) {
+static int rep_domain_rotate_extended(DomRep *d, const uint64_t *in, int32_t rotation, uint64_t *out) {
     if (!d || !in || !out || in == out) return fail(H2V_EINVAL, "rotate_extended: NULL or aliased buffers");
     const size_t en = (size_t)1 << d->ek;
     const uint64_t per = (uint64_t)1 << (d->ek - d->k);
@@ -1228,7 +1308,7 @@ int h2v_domain_rotate_extended(h2v_domain_t d, const uint64_t *in, int32_t rotat
 }
 // EvaluationDomain::l_i_range(x, xn, rotations): out[t] = l_i(x) for i = rot_lo + t, rot_lo <= i < rot_hi, where
 // l_i(x) = omega^i (x^n - 1) / (n (x - omega^i)); xn = x^n is supplied as upstream's callers do.
-int h2v_domain_l_i_range(h2v_domain_t d, const uint64_t x[4], const uint64_t xn[4], int32_t rot_lo, int32_t rot_hi, uint64_t *out) {
+static int rep_domain_l_i_range(DomRep *d, const uint64_t x[4], const uint64_t xn[4], int32_t rot_lo, int32_t rot_hi, uint64_t *out) {
     if (!d || !x || !xn || (rot_hi > rot_lo && !out)) return fail(H2V_EINVAL, "l_i_range: NULL argument");
     if (rot_hi < rot_lo || (int64_t)rot_hi - rot_lo > (1 << 24)) return fail(H2V_EINVAL, "l_i_range: bad rotation range");
     const fe X = fe_from_u64x4(x), one = fe_one<Fr>();
@@ -1260,7 +1340,7 @@ int h2v_domain_l_i_range(h2v_domain_t d, const uint64_t x[4], const uint64_t xn[
 }
 // EvaluationDomain::{empty_coeff, empty_lagrange, empty_extended, constant_lagrange, constant_extended}: a column of
 // the basis' length filled with `scalar` (NULL = zero).  basis: 0 coeff, 1 lagrange (both 2^k), 2 extended (2^extended_k)
-int h2v_domain_fill(h2v_domain_t d, int basis, const uint64_t scalar[4], uint64_t *out) {
+static int rep_domain_fill(DomRep *d, int basis, const uint64_t scalar[4], uint64_t *out) {
     if (!d || !out) return fail(H2V_EINVAL, "domain_fill: NULL argument");
     if (basis < 0 || basis > 2) return fail(H2V_EINVAL, "domain_fill: basis must be 0, 1 or 2");
     const size_t len = (size_t)1 << (basis == 2 ? d->ek : d->k);
@@ -1272,7 +1352,7 @@ int h2v_domain_fill(h2v_domain_t d, int basis, const uint64_t scalar[4], uint64_
     return H2V_OK;
 }
 
-int h2v_domain_transform_dev(h2v_domain_t d, int op, const void *d_in, size_t in_stride, void *d_out, size_t out_stride,
+static int rep_domain_transform_dev(DomRep *d, int op, const void *d_in, size_t in_stride, void *d_out, size_t out_stride,
                              size_t n_cols) {
     if (!d) return fail(H2V_EINVAL, "transform: NULL domain");
     if (n_cols && (!d_in || !d_out)) return fail(H2V_EINVAL, "transform: NULL buffer");
@@ -1296,7 +1376,7 @@ int h2v_domain_transform_dev(h2v_domain_t d, int op, const void *d_in, size_t in
     return H2V_OK;
 }
 
-int h2v_domain_transform_batch(h2v_domain_t d, int op, const uint64_t *const *in, uint64_t *const *out, size_t n_cols) {
+static int rep_domain_transform_batch(DomRep *d, int op, const uint64_t *const *in, uint64_t *const *out, size_t n_cols) {
     if (!d) return fail(H2V_EINVAL, "transform: NULL domain");
     if (op < 0 || op > H2V_OP_DIVIDE_BY_VANISHING) return fail(H2V_EINVAL, "unknown domain op %d", op);
     if (n_cols == 0) return H2V_OK;
@@ -1306,11 +1386,11 @@ int h2v_domain_transform_batch(h2v_domain_t d, int op, const uint64_t *const *in
     const size_t nin = op_in_len(d, op), nout = op_out_len(d, op);
     const size_t out_stride = std::max(nout, (size_t)1 << (op >= H2V_OP_COEFF_TO_EXTENDED ? d->ek : d->k));
     if (n_cols * out_stride * sizeof(fe) <= ((size_t)64 << 20)) {
-        h2v_domain::Lane *ln = nullptr;
-        for (int i = 0; i < h2v_domain::H2V_LANES && !ln; ++i)
+        DomRep::Lane *ln = nullptr;
+        for (int i = 0; i < DomRep::H2V_LANES && !ln; ++i)
             if (d->lanes[i].mu.try_lock()) ln = &d->lanes[i];
         if (!ln) {
-            ln = &d->lanes[d->next_lane.fetch_add(1) % h2v_domain::H2V_LANES];
+            ln = &d->lanes[d->next_lane.fetch_add(1) % DomRep::H2V_LANES];
             ln->mu.lock();
         }
         std::lock_guard<std::mutex> lk(ln->mu, std::adopt_lock);
@@ -1374,16 +1454,16 @@ int h2v_domain_transform_batch(h2v_domain_t d, int op, const uint64_t *const *in
     CU(cudaStreamSynchronize(pst[1]));
     return H2V_OK;
 }
-static int one_col(h2v_domain_t d, int op, const uint64_t *in, uint64_t *out) {
+static int one_col(DomRep *d, int op, const uint64_t *in, uint64_t *out) {
     const uint64_t *i1[1] = {in};
     uint64_t *o1[1] = {out};
-    return h2v_domain_transform_batch(d, op, i1, o1, 1);
+    return rep_domain_transform_batch(d, op, i1, o1, 1);
 }
-int h2v_lagrange_to_coeff(h2v_domain_t d, uint64_t *a) { return one_col(d, H2V_OP_LAGRANGE_TO_COEFF, a, a); }
-int h2v_coeff_to_lagrange(h2v_domain_t d, uint64_t *a) { return one_col(d, H2V_OP_COEFF_TO_LAGRANGE, a, a); }
-int h2v_coeff_to_extended(h2v_domain_t d, const uint64_t *in, uint64_t *out) { return one_col(d, H2V_OP_COEFF_TO_EXTENDED, in, out); }
-int h2v_extended_to_coeff(h2v_domain_t d, const uint64_t *in, uint64_t *out) { return one_col(d, H2V_OP_EXTENDED_TO_COEFF, in, out); }
-int h2v_divide_by_vanishing_poly(h2v_domain_t d, uint64_t *a) {
+static int rep_lagrange_to_coeff(DomRep *d, uint64_t *a) { return one_col(d, H2V_OP_LAGRANGE_TO_COEFF, a, a); }
+static int rep_coeff_to_lagrange(DomRep *d, uint64_t *a) { return one_col(d, H2V_OP_COEFF_TO_LAGRANGE, a, a); }
+static int rep_coeff_to_extended(DomRep *d, const uint64_t *in, uint64_t *out) { return one_col(d, H2V_OP_COEFF_TO_EXTENDED, in, out); }
+static int rep_extended_to_coeff(DomRep *d, const uint64_t *in, uint64_t *out) { return one_col(d, H2V_OP_EXTENDED_TO_COEFF, in, out); }
+static int rep_divide_by_vanishing_poly(DomRep *d, uint64_t *a) {
     if (!d || !a) return fail(H2V_EINVAL, "divide_by_vanishing_poly: NULL argument");
     int rc = use_device();
     if (rc) return rc;
@@ -1408,7 +1488,8 @@ struct PolyCtx {
     cudaStream_t st = nullptr;
     DevBuf a, b, c, d, e, tree;
 };
-PolyCtx g_poly;
+PolyCtx g_poly_all[H2V_MAX_DEV];
+#define g_poly (g_poly_all[cur_dev()])
 int poly_ctx_ready() {
     if (!g_poly.st) CU(cudaStreamCreateWithFlags(&g_poly.st, cudaStreamNonBlocking));
     return H2V_OK;
@@ -1462,6 +1543,7 @@ int h2v_eval_polynomial_dev(const void *d_polys, size_t stride, size_t n_polys, 
     if (!n_polys || !n_points) return H2V_OK;
     if (!d_polys || !d_points || !d_out) return fail(H2V_EINVAL, "eval_polynomial: NULL buffer");
     if (n_polys > 65535 || n_points > (1u << 20) || len >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "eval_polynomial: batch too large");
+    t_dev = device_of(d_polys);
     int rc = use_device();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(g_poly.mu);
@@ -1481,6 +1563,7 @@ int h2v_eval_polynomial_batch(const uint64_t *const *polys, size_t n_polys, size
     if (!n_polys || !n_points) return H2V_OK;
     if (!polys || !points || !out) return fail(H2V_EINVAL, "eval_polynomial: NULL buffer");
     if (n_points > (1u << 20) || len >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "eval_polynomial: batch too large");
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(g_poly.mu);
@@ -1511,6 +1594,7 @@ int h2v_batch_invert(uint64_t *a, size_t n) {
     if (!n) return H2V_OK;
     if (!a) return fail(H2V_EINVAL, "batch_invert: NULL buffer");
     if (n >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "batch_invert: n too large");
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(g_poly.mu);
@@ -1557,6 +1641,7 @@ int h2v_grand_product(const uint64_t *num, const uint64_t *den, size_t n, uint64
     if (!n) return H2V_OK;
     if (!num || !den || !out) return fail(H2V_EINVAL, "grand_product: NULL buffer");
     if (n >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "grand_product: n too large");
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(g_poly.mu);
@@ -1578,6 +1663,7 @@ int h2v_grand_product_dev(const void *d_num, const void *d_den, size_t n, size_t
     if (!n || !n_cols) return H2V_OK;
     if (!d_num || !d_den || !d_out) return fail(H2V_EINVAL, "grand_product: NULL buffer");
     if (n_cols > 65535 || n * n_cols >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "grand_product: batch too large");
+    t_dev = device_of(d_num);
     int rc = use_device();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(g_poly.mu);
@@ -1621,6 +1707,7 @@ int h2v_kate_division_dev(const void *d_a, size_t n, const uint64_t b[4], void *
     if (n <= 1) return H2V_OK;
     if (!d_a || !b || !d_out) return fail(H2V_EINVAL, "kate_division: NULL buffer");
     if (n >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "kate_division: n too large");
+    t_dev = device_of(d_a);
     int rc = use_device();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(g_poly.mu);
@@ -1635,6 +1722,7 @@ int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t
     if (n <= 1) return H2V_OK;
     if (!a || !b || !out) return fail(H2V_EINVAL, "kate_division: NULL buffer");
     if (n >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "kate_division: n too large");
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(g_poly.mu);
@@ -1719,6 +1807,7 @@ int h2v_permute_expression_pair_dev(const void *d_input, const void *d_table, si
     if (!usable_rows) return H2V_OK;
     if (!d_input || !d_table || !d_permuted_input || !d_permuted_table) return fail(H2V_EINVAL, "permute_expression_pair: NULL buffer");
     if (usable_rows > ((size_t)1 << 28)) return fail(H2V_EINVAL, "permute_expression_pair: too many rows");
+    t_dev = device_of(d_input);
     int rc = use_device();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(g_poly.mu);
@@ -1737,6 +1826,7 @@ int h2v_permute_expression_pair(const uint64_t *input, const uint64_t *table, si
     if (!usable_rows) return H2V_OK;
     if (!input || !table || !permuted_input || !permuted_table) return fail(H2V_EINVAL, "permute_expression_pair: NULL buffer");
     if (usable_rows > ((size_t)1 << 28)) return fail(H2V_EINVAL, "permute_expression_pair: too many rows");
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(g_poly.mu);
@@ -1760,7 +1850,7 @@ int h2v_permute_expression_pair(const uint64_t *input, const uint64_t *table, si
 
 // ================================================================== quotient evaluation ("next" row 1)
 namespace {
-int quotient_common(h2v_domain_t d, const void *d_h, const uint64_t *y, QuotientCommon *c) {
+int quotient_common(DomRep *d, const void *d_h, const uint64_t *y, QuotientCommon *c) {
     if (!d) return fail(H2V_EINVAL, "quotient: NULL domain");
     if (!d_h || !y) return fail(H2V_EINVAL, "quotient: NULL buffer");
     c->y = fe_from_u64x4(y);
@@ -1768,7 +1858,7 @@ int quotient_common(h2v_domain_t d, const void *d_h, const uint64_t *y, Quotient
     c->rot = 1u << (d->ek - d->k);
     return use_device();
 }
-int quotient_finish(h2v_domain_t d, Timer &tm) {
+int quotient_finish(DomRep *d, Timer &tm) {
     tm.end();
     cudaError_t e = cudaStreamSynchronize(d->stream);
     tm.collect(true);
@@ -1778,7 +1868,7 @@ int quotient_finish(h2v_domain_t d, Timer &tm) {
 }  // namespace
 
 extern "C" {
-int h2v_quotient_gates_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], size_t n_gates, const void *d_q, size_t q_stride,
+static int rep_quotient_gates_dev(DomRep *d, void *d_h, const uint64_t y[4], size_t n_gates, const void *d_q, size_t q_stride,
                            const void *d_a, size_t a_stride) {
     QuotientCommon c;
     int rc = quotient_common(d, d_h, y, &c);
@@ -1795,7 +1885,7 @@ int h2v_quotient_gates_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], size_
     LAUNCHED();
     return quotient_finish(d, tm);
 }
-int h2v_quotient_gates_ptrs_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], size_t n_gates, const void *const *d_q_ptrs,
+static int rep_quotient_gates_ptrs_dev(DomRep *d, void *d_h, const uint64_t y[4], size_t n_gates, const void *const *d_q_ptrs,
                                 const void *const *d_a_ptrs) {
     QuotientCommon c;
     int rc = quotient_common(d, d_h, y, &c);
@@ -1811,7 +1901,7 @@ int h2v_quotient_gates_ptrs_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], 
     LAUNCHED();
     return quotient_finish(d, tm);
 }
-static int quotient_permutation_any(h2v_domain_t d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+static int quotient_permutation_any(DomRep *d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
                                     size_t n_cols, size_t chunk_len, const void *d_cols, size_t cols_stride, const void *d_sigma,
                                     size_t sigma_stride, const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last,
                                     const void *d_l_active, uint32_t blinding_factors, bool tables) {
@@ -1850,21 +1940,21 @@ static int quotient_permutation_any(h2v_domain_t d, void *d_h, const uint64_t y[
     LAUNCHED();
     return quotient_finish(d, tm);
 }
-int h2v_quotient_permutation_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+static int rep_quotient_permutation_dev(DomRep *d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
                                  size_t n_cols, size_t chunk_len, const void *d_cols, size_t cols_stride, const void *d_sigma,
                                  size_t sigma_stride, const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last,
                                  const void *d_l_active, uint32_t blinding_factors) {
     return quotient_permutation_any(d, d_h, y, beta, gamma, n_cols, chunk_len, d_cols, cols_stride, d_sigma, sigma_stride, d_z, z_stride,
                                     d_l0, d_l_last, d_l_active, blinding_factors, false);
 }
-int h2v_quotient_permutation_ptrs_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+static int rep_quotient_permutation_ptrs_dev(DomRep *d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
                                       size_t n_cols, size_t chunk_len, const void *const *d_col_ptrs, const void *const *d_sigma_ptrs,
                                       const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last, const void *d_l_active,
                                       uint32_t blinding_factors) {
     return quotient_permutation_any(d, d_h, y, beta, gamma, n_cols, chunk_len, d_col_ptrs, 0, d_sigma_ptrs, 0, d_z, z_stride, d_l0, d_l_last,
                                     d_l_active, blinding_factors, true);
 }
-int h2v_quotient_lookup_dev(h2v_domain_t d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+static int rep_quotient_lookup_dev(DomRep *d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
                             const void *d_input, const void *d_table, const void *d_perm_input, const void *d_perm_table,
                             const void *d_z, const void *d_l0, const void *d_l_last, const void *d_l_active) {
     QuotientCommon c;
@@ -1996,6 +2086,7 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(uint64_t *out, uint32_t
 
 extern "C" {
 int h2v_selftest_field(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out) {
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     if (!a || !out || n == 0) return fail(H2V_EINVAL, "selftest_field: bad argument");
@@ -2013,6 +2104,7 @@ int h2v_selftest_field(int field, int op, const uint64_t *a, const uint64_t *b, 
     return H2V_OK;
 }
 int h2v_selftest_group(int mode, const uint64_t *p, const uint64_t *q, size_t n, uint64_t *out_affine) {
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     if (!p || !q || !out_affine || n == 0) return fail(H2V_EINVAL, "selftest_group: bad argument");
@@ -2028,6 +2120,7 @@ int h2v_selftest_group(int mode, const uint64_t *p, const uint64_t *q, size_t n,
     return H2V_OK;
 }
 int h2v_srs_setup(uint32_t k, const uint64_t s_mont[4], uint64_t *g_out, uint64_t *g_lagrange_out) {
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     if (!s_mont || (!g_out && !g_lagrange_out)) return fail(H2V_EINVAL, "srs_setup: NULL argument");
@@ -2058,6 +2151,7 @@ int h2v_srs_setup(uint32_t k, const uint64_t s_mont[4], uint64_t *g_out, uint64_
     return H2V_OK;
 }
 int h2v_synthetic_bases(uint64_t a, uint64_t b, size_t n, uint64_t *out_affine) {
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     if (!out_affine || n == 0) return fail(H2V_EINVAL, "synthetic_bases: bad argument");
@@ -2074,13 +2168,14 @@ int h2v_synthetic_bases(uint64_t a, uint64_t b, size_t n, uint64_t *out_affine) 
 // which: 0 Fq mul, one dependent chain per thread; 1 Fq mul, two chains; 2 XYZZ mixed add chain.
 // Returns operations per second over the whole GPU.
 int h2v_selftest_op_rate(int which, double *out) {
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     if (!out || which < 0 || which > 2) return fail(H2V_EINVAL, "selftest_op_rate: bad argument");
     DevBuf O;
     if ((rc = O.ensure(256))) return rc;
     cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, g_device));
+    CU(cudaGetDeviceProperties(&prop, cur_dev()));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
@@ -2115,13 +2210,14 @@ int h2v_selftest_op_rate(int which, double *out) {
     return H2V_OK;
 }
 int h2v_selftest_imad_peak(double *out) {
+    t_dev = -1;
     int rc = use_device();
     if (rc) return rc;
     if (!out) return fail(H2V_EINVAL, "selftest_imad_peak: NULL");
     DevBuf O;
     if ((rc = O.ensure(64))) return rc;
     cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, g_device));
+    CU(cudaGetDeviceProperties(&prop, cur_dev()));
     const unsigned blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
@@ -2145,3 +2241,278 @@ int h2v_selftest_imad_peak(double *out) {
     return H2V_OK;
 }
 }
+
+// ================================================================== public handles: one replica per device
+struct h2v_srs {
+    std::vector<SrsRep *> rep;
+};
+struct h2v_domain {
+    std::vector<DomRep *> rep;
+};
+
+namespace {
+SrsRep *srs_on(h2v_srs *h, int dev) {
+    for (SrsRep *r : h->rep)
+        if (r->dev == dev) return r;
+    return nullptr;
+}
+DomRep *dom_on(h2v_domain *h, int dev) {
+    for (DomRep *r : h->rep)
+        if (r->dev == dev) return r;
+    return nullptr;
+}
+// a replica of `src` on the calling thread's current device: the window tables cross NVLink / PCIe once (peer copy)
+int rep_srs_clone(const SrsRep *src, SrsRep **out) {
+    int rc = use_device();
+    if (rc) return rc;
+    SrsRep *s = new SrsRep();
+    s->dev = cur_dev();
+    s->k = src->k;
+    s->n = src->n;
+    s->cfg[0] = src->cfg[0];
+    s->cfg[1] = src->cfg[1];
+    s->have_small = src->have_small;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(H2V_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    for (int b = 0; b < 2; ++b) {
+        if (!src->have[b]) continue;
+        for (int v = 0; v < (s->have_small ? 2 : 1); ++v) {
+            const size_t bytes = (size_t)s->cfg[v].W * s->n * sizeof(affine);
+            rc = s->table[b][v].ensure(bytes);
+            if (rc) { rep_srs_free(s); return rc; }
+            e = cudaMemcpyPeerAsync(s->table[b][v].p, s->dev, src->table[b][v].p, src->dev, bytes, s->stream);
+            if (e != cudaSuccess) { rep_srs_free(s); return fail(H2V_ECUDA, "SRS replica copy: %s", cudaGetErrorString(e)); }
+        }
+        s->have[b] = true;
+    }
+    e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) { rep_srs_free(s); return fail(H2V_ECUDA, "SRS replica copy: %s", cudaGetErrorString(e)); }
+    *out = s;
+    return H2V_OK;
+}
+// run fn(slot) on one host thread per device (each thread's entry points run on its device); first error wins
+template <class Fn> int fan_out(size_t n_slots, Fn fn) {
+    std::vector<int> rcs(n_slots, H2V_OK);
+    std::vector<std::string> errs(n_slots);
+    std::vector<std::thread> th;
+    for (size_t i = 1; i < n_slots; ++i)
+        th.emplace_back([&, i] {
+            rcs[i] = fn(i);
+            if (rcs[i]) errs[i] = g_err;
+        });
+    rcs[0] = fn(0);
+    if (rcs[0]) errs[0] = g_err;
+    for (auto &t : th) t.join();
+    for (size_t i = 0; i < n_slots; ++i)
+        if (rcs[i]) {
+            g_err = errs[i];
+            return rcs[i];
+        }
+    return H2V_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int h2v_dev_alloc_on(int device, size_t bytes, void **d_out) {
+    bool known = false;
+    for (int d : g_devs) known = known || d == device;
+    if (!known) return fail(H2V_EINVAL, "dev_alloc_on: device %d is not in the h2v_init list", device);
+    if (!d_out || !bytes) return fail(H2V_EINVAL, "dev_alloc: bad argument");
+    t_dev = device;
+    int rc = use_device();
+    if (rc) return rc;
+    cudaError_t e = cudaMalloc(d_out, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(H2V_ENOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+    return H2V_OK;
+}
+
+// ---------------------------------------------------------------- SRS
+int h2v_srs_load(uint32_t k, const uint64_t *g, const uint64_t *g_lagrange, h2v_srs_t *out) {
+    if (!out) return fail(H2V_EINVAL, "h2v_srs_load: out is NULL");
+    *out = nullptr;
+    h2v_srs *h = new h2v_srs();
+    for (size_t i = 0; i < g_devs.size(); ++i) {
+        t_dev = g_devs[i];
+        SrsRep *r = nullptr;
+        int rc = i == 0 ? rep_srs_load(k, g, g_lagrange, &r) : rep_srs_clone(h->rep[0], &r);
+        if (rc) {
+            h2v_srs_free(h);
+            t_dev = -1;
+            return rc;
+        }
+        h->rep.push_back(r);
+    }
+    t_dev = -1;
+    *out = h;
+    return H2V_OK;
+}
+void h2v_srs_free(h2v_srs_t h) {
+    if (!h) return;
+    for (SrsRep *r : h->rep) {
+        t_dev = r->dev;
+        rep_srs_free(r);
+    }
+    t_dev = -1;
+    delete h;
+}
+int h2v_srs_info(h2v_srs_t h, uint32_t *window_bits, uint32_t *windows) {
+    if (!h) return fail(H2V_EINVAL, "srs_info: NULL srs");
+    return rep_srs_info(h->rep[0], window_bits, windows);
+}
+int h2v_commit_batch_dev(h2v_srs_t h, int basis, const void *d_polys, size_t col_stride, size_t n_polys, size_t len, void *d_out_affine) {
+    if (!h) return fail(H2V_EINVAL, "commit: NULL srs");
+    SrsRep *r = srs_on(h, device_of(d_polys));
+    if (!r) return fail(H2V_EINVAL, "commit: the columns live on device %d, which is not in the h2v_init list", device_of(d_polys));
+    t_dev = r->dev;
+    return rep_commit_batch_dev(r, basis, d_polys, col_stride, n_polys, len, d_out_affine);
+}
+// Host columns: with several devices column j goes to device j mod G (each device has its own PCIe link and SRS
+// replica, no collective); the commitments come back in column order.
+int h2v_commit_batch(h2v_srs_t h, int basis, const uint64_t *const *polys, size_t n_polys, size_t len, uint64_t *out_affine) {
+    if (!h) return fail(H2V_EINVAL, "commit: NULL srs");
+    const size_t G = h->rep.size();
+    if (G == 1 || n_polys < 2 * G || !polys || !out_affine) {
+        t_dev = h->rep[0]->dev;
+        return rep_commit_batch(h->rep[0], basis, polys, n_polys, len, out_affine);
+    }
+    std::vector<std::vector<const uint64_t *>> sub(G);
+    std::vector<std::vector<uint64_t>> outs(G);
+    for (size_t j = 0; j < n_polys; ++j) sub[j % G].push_back(polys[j]);
+    for (size_t d = 0; d < G; ++d) outs[d].resize(sub[d].size() * 8);
+    int rc = fan_out(G, [&](size_t d) {
+        t_dev = h->rep[d]->dev;
+        return rep_commit_batch(h->rep[d], basis, sub[d].data(), sub[d].size(), len, outs[d].data());
+    });
+    t_dev = -1;
+    if (rc) return rc;
+    for (size_t j = 0; j < n_polys; ++j) memcpy(out_affine + 8 * j, outs[j % G].data() + 8 * (j / G), 64);
+    return H2V_OK;
+}
+int h2v_commit(h2v_srs_t h, int basis, const uint64_t *poly, size_t len, uint64_t out_affine[8]) {
+    if (!h) return fail(H2V_EINVAL, "commit: NULL srs");
+    t_dev = h->rep[0]->dev;
+    return rep_commit(h->rep[0], basis, poly, len, out_affine);
+}
+
+// ---------------------------------------------------------------- EvaluationDomain
+int h2v_domain_new(uint32_t j, uint32_t k, h2v_domain_t *out) {
+    if (!out) return fail(H2V_EINVAL, "domain_new: out is NULL");
+    *out = nullptr;
+    h2v_domain *h = new h2v_domain();
+    for (size_t i = 0; i < g_devs.size(); ++i) {
+        t_dev = g_devs[i];
+        DomRep *r = nullptr;
+        int rc = rep_domain_new(j, k, &r);
+        if (rc) {
+            h2v_domain_free(h);
+            t_dev = -1;
+            return rc;
+        }
+        h->rep.push_back(r);
+    }
+    t_dev = -1;
+    *out = h;
+    return H2V_OK;
+}
+void h2v_domain_free(h2v_domain_t h) {
+    if (!h) return;
+    for (DomRep *r : h->rep) {
+        t_dev = r->dev;
+        rep_domain_free(r);
+    }
+    t_dev = -1;
+    delete h;
+}
+uint32_t h2v_domain_k(h2v_domain_t h) { return h ? rep_domain_k(h->rep[0]) : 0; }
+uint32_t h2v_domain_extended_k(h2v_domain_t h) { return h ? rep_domain_extended_k(h->rep[0]) : 0; }
+int h2v_domain_constant(h2v_domain_t h, int which, uint64_t out[4]) { return rep_domain_constant(h ? h->rep[0] : nullptr, which, out); }
+int h2v_domain_rotate_omega(h2v_domain_t h, const uint64_t value[4], int32_t rotation, uint64_t out[4]) {
+    return rep_domain_rotate_omega(h ? h->rep[0] : nullptr, value, rotation, out);
+}
+int h2v_domain_rotate_extended(h2v_domain_t h, const uint64_t *in, int32_t rotation, uint64_t *out) {
+    return rep_domain_rotate_extended(h ? h->rep[0] : nullptr, in, rotation, out);
+}
+int h2v_domain_l_i_range(h2v_domain_t h, const uint64_t x[4], const uint64_t xn[4], int32_t rot_lo, int32_t rot_hi, uint64_t *out) {
+    return rep_domain_l_i_range(h ? h->rep[0] : nullptr, x, xn, rot_lo, rot_hi, out);
+}
+int h2v_domain_fill(h2v_domain_t h, int basis, const uint64_t scalar[4], uint64_t *out) {
+    return rep_domain_fill(h ? h->rep[0] : nullptr, basis, scalar, out);
+}
+#define H2V_DOM_ON(ptr)                                                                                                        \
+    if (!h) return fail(H2V_EINVAL, "NULL domain");                                                                            \
+    DomRep *r = dom_on(h, device_of(ptr));                                                                                     \
+    if (!r) return fail(H2V_EINVAL, "the columns live on device %d, which is not in the h2v_init list", device_of(ptr));      \
+    t_dev = r->dev;
+int h2v_domain_transform_dev(h2v_domain_t h, int op, const void *d_in, size_t in_stride, void *d_out, size_t out_stride, size_t n_cols) {
+    H2V_DOM_ON(d_in)
+    return rep_domain_transform_dev(r, op, d_in, in_stride, d_out, out_stride, n_cols);
+}
+int h2v_domain_transform_batch(h2v_domain_t h, int op, const uint64_t *const *in, uint64_t *const *out, size_t n_cols) {
+    if (!h) return fail(H2V_EINVAL, "transform: NULL domain");
+    const size_t G = h->rep.size();
+    if (G == 1 || n_cols < 2 * G || !in || !out) {
+        t_dev = h->rep[0]->dev;
+        return rep_domain_transform_batch(h->rep[0], op, in, out, n_cols);
+    }
+    std::vector<std::vector<const uint64_t *>> si(G);
+    std::vector<std::vector<uint64_t *>> so(G);
+    for (size_t j = 0; j < n_cols; ++j) {
+        si[j % G].push_back(in[j]);
+        so[j % G].push_back(out[j]);
+    }
+    int rc = fan_out(G, [&](size_t d) {
+        t_dev = h->rep[d]->dev;
+        return rep_domain_transform_batch(h->rep[d], op, si[d].data(), so[d].data(), si[d].size());
+    });
+    t_dev = -1;
+    return rc;
+}
+#define H2V_DOM_PRIMARY                                   \
+    if (!h) return fail(H2V_EINVAL, "NULL domain");       \
+    t_dev = h->rep[0]->dev;
+int h2v_lagrange_to_coeff(h2v_domain_t h, uint64_t *a) { H2V_DOM_PRIMARY return rep_lagrange_to_coeff(h->rep[0], a); }
+int h2v_coeff_to_lagrange(h2v_domain_t h, uint64_t *a) { H2V_DOM_PRIMARY return rep_coeff_to_lagrange(h->rep[0], a); }
+int h2v_coeff_to_extended(h2v_domain_t h, const uint64_t *in, uint64_t *out) { H2V_DOM_PRIMARY return rep_coeff_to_extended(h->rep[0], in, out); }
+int h2v_extended_to_coeff(h2v_domain_t h, const uint64_t *in, uint64_t *out) { H2V_DOM_PRIMARY return rep_extended_to_coeff(h->rep[0], in, out); }
+int h2v_divide_by_vanishing_poly(h2v_domain_t h, uint64_t *a) { H2V_DOM_PRIMARY return rep_divide_by_vanishing_poly(h->rep[0], a); }
+int h2v_quotient_gates_dev(h2v_domain_t h, void *d_h, const uint64_t y[4], size_t n_gates, const void *d_q, size_t q_stride, const void *d_a,
+                           size_t a_stride) {
+    H2V_DOM_ON(d_h)
+    return rep_quotient_gates_dev(r, d_h, y, n_gates, d_q, q_stride, d_a, a_stride);
+}
+int h2v_quotient_gates_ptrs_dev(h2v_domain_t h, void *d_h, const uint64_t y[4], size_t n_gates, const void *const *d_q_ptrs,
+                                const void *const *d_a_ptrs) {
+    H2V_DOM_ON(d_h)
+    return rep_quotient_gates_ptrs_dev(r, d_h, y, n_gates, d_q_ptrs, d_a_ptrs);
+}
+int h2v_quotient_permutation_dev(h2v_domain_t h, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                                 size_t n_cols, size_t chunk_len, const void *d_cols, size_t cols_stride, const void *d_sigma,
+                                 size_t sigma_stride, const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last,
+                                 const void *d_l_active, uint32_t blinding_factors) {
+    H2V_DOM_ON(d_h)
+    return rep_quotient_permutation_dev(r, d_h, y, beta, gamma, n_cols, chunk_len, d_cols, cols_stride, d_sigma, sigma_stride, d_z, z_stride,
+                                        d_l0, d_l_last, d_l_active, blinding_factors);
+}
+int h2v_quotient_permutation_ptrs_dev(h2v_domain_t h, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                                      size_t n_cols, size_t chunk_len, const void *const *d_col_ptrs, const void *const *d_sigma_ptrs,
+                                      const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last, const void *d_l_active,
+                                      uint32_t blinding_factors) {
+    H2V_DOM_ON(d_h)
+    return rep_quotient_permutation_ptrs_dev(r, d_h, y, beta, gamma, n_cols, chunk_len, d_col_ptrs, d_sigma_ptrs, d_z, z_stride, d_l0,
+                                             d_l_last, d_l_active, blinding_factors);
+}
+int h2v_quotient_lookup_dev(h2v_domain_t h, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                            const void *d_input, const void *d_table, const void *d_perm_input, const void *d_perm_table, const void *d_z,
+                            const void *d_l0, const void *d_l_last, const void *d_l_active) {
+    H2V_DOM_ON(d_h)
+    return rep_quotient_lookup_dev(r, d_h, y, beta, gamma, d_input, d_table, d_perm_input, d_perm_table, d_z, d_l0, d_l_last, d_l_active);
+}
+
+}  // extern "C"

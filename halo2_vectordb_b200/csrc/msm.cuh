@@ -124,7 +124,15 @@ __device__ __forceinline__ uint32_t warp_agg_add(uint32_t *counter_base, uint32_
 // the same without a result: the leader's atomic is a fire-and-forget reduction (no round trip to wait for)
 __device__ __forceinline__ void warp_agg_inc(uint32_t *counter_base, uint32_t idx, bool valid) {
     const uint32_t lane = threadIdx.x & 31;
-    const unsigned peers = __match_any_sync(0xffffffffu, valid ? idx : 0xffffffffu);
+    const uint32_t key = valid ? idx : 0xffffffffu - lane;
+    // cheap pre-test: uniform scalars practically never put two neighbouring lanes into one bucket; skewed columns do
+    // (a third of a witness column is the scalar 1), and only then is the full match worth its cost
+    const bool dup = __shfl_xor_sync(0xffffffffu, key, 1) == key || __shfl_xor_sync(0xffffffffu, key, 2) == key;
+    if (!__any_sync(0xffffffffu, dup)) {
+        if (valid) atomicAdd(counter_base + idx, 1u);
+        return;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
     if (valid && (int)lane == __ffs(peers) - 1) atomicAdd(counter_base + idx, (uint32_t)__popc(peers));
 }
 

@@ -224,6 +224,7 @@ struct h2v_pk {
     DevBuf adv_L, adv_C, adv_E, inst_L, inst_C, inst_E, pa_L, ps_L, pa_C, ps_C, pa_E, ps_E, z_L, z_C, z_E, zl_L, zl_C, zl_E;
     DevBuf num, den, tails, ptrs, scal, pts, rnd_C, hq, hx_pieces, evals, pairs, sh_S, sh_A, sh_B, sh_h, commits;
     cudaStream_t st = nullptr;
+    int dev = 0;                 // the proof runs on the primary device (columns and key resident there)
     std::mutex mu;
     double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // wall-clock per phase of the last create_proof
 };
@@ -277,6 +278,7 @@ extern "C" {
 
 void h2v_pk_free(h2v_pk_t pk) {
     if (!pk) return;
+    cudaSetDevice(pk->dev);
     DevBuf *all[] = {&pk->fixed_L, &pk->fixed_C, &pk->fixed_E, &pk->sigma_L, &pk->sigma_C, &pk->sigma_E, &pk->lrows_E, &pk->omega_pows,
                      &pk->adv_L, &pk->adv_C, &pk->adv_E, &pk->inst_L, &pk->inst_C, &pk->inst_E, &pk->pa_L, &pk->ps_L, &pk->pa_C, &pk->ps_C,
                      &pk->pa_E, &pk->ps_E, &pk->z_L, &pk->z_C, &pk->z_E, &pk->zl_L, &pk->zl_C, &pk->zl_E, &pk->num, &pk->den, &pk->tails,
@@ -313,7 +315,12 @@ int h2v_pk_load(h2v_srs_t srs, const h2v_circuit_t *cs, const uint64_t *const *f
     uint32_t srs_c = 0;
     H2V_TRY(h2v_srs_info(srs, &srs_c, nullptr));
 
+    if (cudaSetDevice(current_device()) != cudaSuccess) {
+        cudaGetLastError();
+        return failf(H2V_ECUDA, "pk_load: no CUDA device (libh2v has no CPU fallback)");
+    }
     h2v_pk *pk = new h2v_pk();
+    pk->dev = current_device();
     pk->srs = srs;
     pk->k = cs->k; pk->degree = cs->degree; pk->bf = cs->blinding_factors;
     pk->n_advice = cs->n_advice; pk->n_fixed = cs->n_fixed; pk->n_instance = cs->n_instance;
@@ -917,8 +924,7 @@ int h2v_create_proof(h2v_pk_t pk, const uint64_t *const *advice, const uint64_t 
                      const uint8_t rng_seed[32], uint8_t *proof_out, size_t proof_cap, size_t *proof_len) {
     if (!pk || !rng_seed || !proof_len) return failf(H2V_EINVAL, "create_proof: NULL argument");
     if ((pk->n_advice && !advice) || (pk->n_instance && (!instances || !instance_len))) return failf(H2V_EINVAL, "create_proof: NULL column list");
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) {
+    if (cudaSetDevice(pk->dev) != cudaSuccess) {
         cudaGetLastError();
         return failf(H2V_ECUDA, "create_proof: no CUDA device (libh2v has no CPU fallback)");
     }

@@ -15,8 +15,8 @@
  * Return value: 0 on success, a negative H2V_E* code otherwise; h2v_last_error() (thread-local)
  * describes the failure.  There is NO CPU fallback: without a usable CUDA device every compute
  * entry point fails with H2V_ECUDA.  Entry points are thread-safe; calls on one handle serialise.
- * One process drives one GPU (h2v_init), the multi-GPU layout is one process per GPU with
- * polynomial columns partitioned across processes; no collective is needed.
+ * One process drives one or several GPUs (h2v_init): polynomial columns are partitioned across the devices, each
+ * of which holds an SRS replica; no collective is needed.  One process per GPU works as well.
  */
 #ifndef H2V_H
 #define H2V_H
@@ -39,16 +39,24 @@ typedef struct h2v_srs *h2v_srs_t;       /* device-resident ParamsKZG bases (+ w
 typedef struct h2v_domain *h2v_domain_t; /* EvaluationDomain: constants + device twiddles      */
 
 /* ---- runtime ------------------------------------------------------------------------------ */
-/* Select the CUDA device this process drives (call once per process, before anything else;
- * default device 0).  Mirrors nothing upstream: the reference is CPU-only. */
-int h2v_init(int device);
+/* The CUDA devices this process drives, in order; devices[0] is the primary device.  Every handle
+ * created afterwards holds one replica per listed device (the SRS window tables are built on the primary device and
+ * copied device to device once); `_dev` entry points run on the device that owns their buffers; the host-facing batch
+ * entry points (h2v_commit_batch, h2v_domain_transform_batch) send column j to device j mod n_dev -- each device pulls
+ * its columns over its own PCIe link, no collective -- and return results in column order; everything else runs on the
+ * primary device.  Call once, before creating handles; NULL / 0 selects device 0 (the default without a call).
+ * Mirrors nothing upstream: the reference is CPU-only and single-process (scaffold mod.rs:251-323). */
+int h2v_init(const int *devices, int n_dev);
+/* the device list in use; returns its length */
+int h2v_device_list(int *out, int cap);
 int h2v_device_count(void);
 const char *h2v_last_error(void);
 const char *h2v_version(void);
 
 /* Device buffers for the `_dev` entry points (columns that stay in HBM between commit / transform / evaluation
  * steps of one prover phase); plain synchronous copies. */
-int h2v_dev_alloc(size_t bytes, void **d_out);
+int h2v_dev_alloc(size_t bytes, void **d_out);                       /* on the primary device */
+int h2v_dev_alloc_on(int device, size_t bytes, void **d_out);        /* on one of the h2v_init devices */
 int h2v_dev_free(void *d_ptr);
 int h2v_dev_upload(void *d_dst, const void *src, size_t bytes);
 int h2v_dev_download(void *dst, const void *d_src, size_t bytes);

@@ -28,7 +28,8 @@ inline void check(int rc) {
     if (rc == H2V_EINVAL) throw std::invalid_argument(msg);
     throw std::runtime_error(msg);
 }
-inline void init(int device = 0) { check(h2v_init(device)); }
+inline void init(int device = 0) { check(h2v_init(&device, 1)); }
+inline void init(const std::vector<int> &devices) { check(h2v_init(devices.data(), (int)devices.size())); }
 
 inline G1 best_multiexp(const std::vector<Fr> &coeffs, const std::vector<G1Affine> &bases) {
     if (coeffs.size() != bases.size()) throw std::invalid_argument("assertion failed: coeffs.len() == bases.len()");
