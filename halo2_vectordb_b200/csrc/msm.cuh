@@ -127,7 +127,8 @@ __device__ __forceinline__ void warp_agg_inc(uint32_t *counter_base, uint32_t id
     const uint32_t key = valid ? idx : 0xffffffffu - lane;
     // cheap pre-test: uniform scalars practically never put two neighbouring lanes into one bucket; skewed columns do
     // (a third of a witness column is the scalar 1), and only then is the full match worth its cost
-    const bool dup = __shfl_xor_sync(0xffffffffu, key, 1) == key || __shfl_xor_sync(0xffffffffu, key, 2) == key;
+    const uint32_t n1 = __shfl_xor_sync(0xffffffffu, key, 1), n2 = __shfl_xor_sync(0xffffffffu, key, 2);      // all lanes, both
+    const bool dup = n1 == key || n2 == key;
     if (!__any_sync(0xffffffffu, dup)) {
         if (valid) atomicAdd(counter_base + idx, 1u);
         return;
