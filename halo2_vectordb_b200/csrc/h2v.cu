@@ -148,7 +148,7 @@ struct Timer {   // CUDA-event stopwatch on one stream, accumulating per kernel 
 
 // ================================================================== NTT host side
 const size_t NTT_SMEM_BYTES = (2 * 2048 + H2V_NTT_PLANE_PAD) * 16;
-std::once_flag g_ntt_attr_once;
+std::once_flag g_ntt_attr_once[H2V_MAX_DEV];      // function attributes are per device
 
 struct NttPlan {
     int P;
@@ -169,7 +169,7 @@ int run_ntt(cudaStream_t st, const fe *src, size_t src_stride, fe *dst, size_t d
             size_t n_cols) {
     if (n_cols == 0) return H2V_OK;
     if ((const void *)src == (const void *)dst) return fail(H2V_EINVAL, "run_ntt: in-place transform needs distinct buffers");
-    std::call_once(g_ntt_attr_once, [] {
+    std::call_once(g_ntt_attr_once[cur_dev()], [] {
         cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM_BYTES);
     });
     NttPass p;
@@ -458,7 +458,7 @@ MsmLayout msm_layout(void *base, const MsmShape &sh, uint32_t cols) {
 }
 
 const size_t MSM_WS_BUDGET = (size_t)16 << 30;   // per handle; columns per launch are sized to fit
-std::once_flag g_tree_attr_once;
+std::once_flag g_tree_attr_once[H2V_MAX_DEV];
 
 // the two passes over the scalars are instantiated per window size (compile-time limb indices and shifts)
 template <int C> struct WindowDispatch {
@@ -541,7 +541,7 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
         int rc = ws.buf.ensure(probe.bytes);
         if (rc) return rc;
     }
-    std::call_once(g_tree_attr_once, [] {
+    std::call_once(g_tree_attr_once[cur_dev()], [] {
         cudaFuncSetAttribute(msm_reduce_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * H2V_TREE_MAX * sizeof(xyzz)));
     });
     for (size_t c0 = 0; c0 < n_cols; c0 += max_cols) {
