@@ -18,6 +18,18 @@ pub struct H2vSrs(c_void);
 #[repr(C)]
 pub struct H2vDomain(c_void);
 
+#[repr(C)] pub struct H2vPk { _private: [u8; 0] }
+/// `h2v_circuit_t`: the constraint-system description `h2v_pk_load` takes (include/h2v.h)
+#[repr(C)]
+pub struct H2vCircuit {
+    pub k: u32, pub degree: u32, pub blinding_factors: u32,
+    pub n_advice: u32, pub n_fixed: u32, pub n_instance: u32,
+    pub n_gates: u32, pub gate_advice: *const u32, pub gate_selector: *const u32,
+    pub n_lookups: u32, pub lookup_input: *const u32, pub lookup_table: *const u32,
+    pub n_perm: u32, pub perm_kind: *const u8, pub perm_index: *const u32,
+    pub n_advice_queries: u32, pub advice_query_col: *const u32, pub advice_query_rot: *const i32,
+    pub n_fixed_queries: u32, pub fixed_query_col: *const u32, pub fixed_query_rot: *const i32,
+}
 pub const H2V_BASIS_MONOMIAL: c_int = 0;
 pub const H2V_BASIS_LAGRANGE: c_int = 1;
 pub const H2V_OP_LAGRANGE_TO_COEFF: c_int = 0;
@@ -68,6 +80,23 @@ extern "C" {
     pub fn h2v_permute_expression_pair(input: *const u64, table: *const u64, usable_rows: usize, permuted_input: *mut u64,
                                        permuted_table: *mut u64) -> c_int;
     pub fn h2v_g1_sum(affine_pts: *const u64, n: usize, out_affine: *mut u64) -> c_int;
+    // poly/domain.rs helpers
+    pub fn h2v_domain_rotate_omega(dom: *mut H2vDomain, value: *const u64, rotation: i32, out: *mut u64) -> c_int;
+    pub fn h2v_domain_rotate_extended(dom: *mut H2vDomain, inp: *const u64, rotation: i32, out: *mut u64) -> c_int;
+    pub fn h2v_domain_l_i_range(dom: *mut H2vDomain, x: *const u64, xn: *const u64, rot_lo: i32, rot_hi: i32, out: *mut u64) -> c_int;
+    pub fn h2v_domain_fill(dom: *mut H2vDomain, basis: c_int, scalar: *const u64, out: *mut u64) -> c_int;
+    // gen_srs (scaffold mod.rs:260): seeded setup, .srs file
+    pub fn h2v_srs_gen(k: u32, seed: *const u8, g_out: *mut u64, g_lagrange_out: *mut u64, g2_out: *mut u64, s_g2_out: *mut u64) -> c_int;
+    pub fn h2v_srs_write_file(path: *const c_char, k: u32, g: *const u64, g_lagrange: *const u64, g2: *const u64, s_g2: *const u64) -> c_int;
+    pub fn h2v_srs_read_file(path: *const c_char, k_out: *mut u32, g: *mut u64, g_lagrange: *mut u64, cap_points: usize, g2: *mut u64,
+                             s_g2: *mut u64) -> c_int;
+    // create_proof (plonk/prover.rs) on the device, transcript
+    pub fn h2v_pk_load(srs: *mut H2vSrs, cs: *const H2vCircuit, fixed: *const *const u64, sigma: *const *const u64, vk_repr: *const u64,
+                       out: *mut *mut H2vPk) -> c_int;
+    pub fn h2v_pk_free(pk: *mut H2vPk);
+    pub fn h2v_proof_size(pk: *mut H2vPk) -> usize;
+    pub fn h2v_create_proof(pk: *mut H2vPk, advice: *const *const u64, instances: *const *const u64, instance_len: *const u32,
+                            rng_seed: *const u8, proof_out: *mut u8, proof_cap: usize, proof_len: *mut usize) -> c_int;
     pub fn h2v_quotient_gates_dev(dom: *mut H2vDomain, d_h: *mut c_void, y: *const u64, n_gates: usize, d_q: *const c_void,
                                   q_stride: usize, d_a: *const c_void, a_stride: usize) -> c_int;
     pub fn h2v_quotient_permutation_dev(dom: *mut H2vDomain, d_h: *mut c_void, y: *const u64, beta: *const u64, gamma: *const u64,
@@ -167,39 +196,117 @@ impl Drop for DeviceSrs {
 }
 
 /// Device twiddles/constants of an `EvaluationDomain<Fr>`; create inside `EvaluationDomain::new(j, k)`.
-pub struct DeviceDomain(*mut H2vDomain);
+pub struct DeviceDomain { h: *mut H2vDomain, j: u32, k: u32 }
 unsafe impl Send for DeviceDomain {}
 unsafe impl Sync for DeviceDomain {}
 impl DeviceDomain {
     pub fn new(j: u32, k: u32) -> Self {
         let mut h = std::ptr::null_mut();
         ok(unsafe { h2v_domain_new(j, k, &mut h) });
-        DeviceDomain(h)
+        DeviceDomain { h, j, k }
     }
-    pub fn extended_k(&self) -> u32 { unsafe { h2v_domain_extended_k(self.0) } }
-    /// `EvaluationDomain::lagrange_to_coeff` (values in place)
-    pub fn lagrange_to_coeff(&self, a: &mut [Fr]) { ok(unsafe { h2v_lagrange_to_coeff(self.0, a.as_mut_ptr() as *mut u64) }) }
-    pub fn coeff_to_lagrange(&self, a: &mut [Fr]) { ok(unsafe { h2v_coeff_to_lagrange(self.0, a.as_mut_ptr() as *mut u64) }) }
+    pub fn extended_k(&self) -> u32 { unsafe { h2v_domain_extended_k(self.h) } }
+    fn n(&self) -> usize { 1usize << self.k }
+    fn extended_n(&self) -> usize { 1usize << self.extended_k() }
+    /// `EvaluationDomain::lagrange_to_coeff` (values in place); upstream asserts the length, so do we
+    pub fn lagrange_to_coeff(&self, a: &mut [Fr]) {
+        assert_eq!(a.len(), self.n());
+        ok(unsafe { h2v_lagrange_to_coeff(self.h, a.as_mut_ptr() as *mut u64) })
+    }
+    pub fn coeff_to_lagrange(&self, a: &mut [Fr]) {
+        assert_eq!(a.len(), self.n());
+        ok(unsafe { h2v_coeff_to_lagrange(self.h, a.as_mut_ptr() as *mut u64) })
+    }
     /// `EvaluationDomain::coeff_to_extended`: `a.len() == 2^k`, result `2^extended_k`
     pub fn coeff_to_extended(&self, a: &[Fr]) -> Vec<Fr> {
-        let mut out = vec![Fr::zero(); 1 << self.extended_k()];
-        ok(unsafe { h2v_coeff_to_extended(self.0, a.as_ptr() as *const u64, out.as_mut_ptr() as *mut u64) });
+        assert_eq!(a.len(), self.n());
+        let mut out = vec![Fr::zero(); self.extended_n()];
+        ok(unsafe { h2v_coeff_to_extended(self.h, a.as_ptr() as *const u64, out.as_mut_ptr() as *mut u64) });
         out
     }
-    /// `EvaluationDomain::extended_to_coeff`: result `2^k * (j - 1)`
-    pub fn extended_to_coeff(&self, a: &[Fr], out_len: usize) -> Vec<Fr> {
-        let mut out = vec![Fr::zero(); out_len];
-        ok(unsafe { h2v_extended_to_coeff(self.0, a.as_ptr() as *const u64, out.as_mut_ptr() as *mut u64) });
+    /// `EvaluationDomain::extended_to_coeff`: `a.len() == 2^extended_k`, result `2^k * (j - 1)` (computed here, not by the caller)
+    pub fn extended_to_coeff(&self, a: &[Fr]) -> Vec<Fr> {
+        assert_eq!(a.len(), self.extended_n());
+        let mut out = vec![Fr::zero(); self.n() * (self.j as usize - 1)];
+        ok(unsafe { h2v_extended_to_coeff(self.h, a.as_ptr() as *const u64, out.as_mut_ptr() as *mut u64) });
         out
     }
-    pub fn divide_by_vanishing_poly(&self, a: &mut [Fr]) { ok(unsafe { h2v_divide_by_vanishing_poly(self.0, a.as_mut_ptr() as *mut u64) }) }
+    pub fn divide_by_vanishing_poly(&self, a: &mut [Fr]) {
+        assert_eq!(a.len(), self.extended_n());
+        ok(unsafe { h2v_divide_by_vanishing_poly(self.h, a.as_mut_ptr() as *mut u64) })
+    }
+    /// `EvaluationDomain::rotate_omega(value, Rotation(rotation))`
+    pub fn rotate_omega(&self, value: &Fr, rotation: i32) -> Fr {
+        let mut out = Fr::zero();
+        ok(unsafe { h2v_domain_rotate_omega(self.h, value as *const Fr as *const u64, rotation, &mut out as *mut Fr as *mut u64) });
+        out
+    }
+    /// `EvaluationDomain::rotate_extended(&poly, Rotation(rotation))`
+    pub fn rotate_extended(&self, poly: &[Fr], rotation: i32) -> Vec<Fr> {
+        assert_eq!(poly.len(), self.extended_n());
+        let mut out = vec![Fr::zero(); poly.len()];
+        ok(unsafe { h2v_domain_rotate_extended(self.h, poly.as_ptr() as *const u64, rotation, out.as_mut_ptr() as *mut u64) });
+        out
+    }
+    /// `EvaluationDomain::l_i_range(x, xn, lo..hi)`
+    pub fn l_i_range(&self, x: &Fr, xn: &Fr, rotations: std::ops::Range<i32>) -> Vec<Fr> {
+        let mut out = vec![Fr::zero(); rotations.len()];
+        ok(unsafe { h2v_domain_l_i_range(self.h, x as *const Fr as *const u64, xn as *const Fr as *const u64, rotations.start, rotations.end,
+                                         out.as_mut_ptr() as *mut u64) });
+        out
+    }
+    fn fill(&self, basis: c_int, scalar: Option<&Fr>) -> Vec<Fr> {
+        let mut out = vec![Fr::zero(); if basis == 2 { self.extended_n() } else { self.n() }];
+        let p = scalar.map_or(std::ptr::null(), |s| s as *const Fr as *const u64);
+        ok(unsafe { h2v_domain_fill(self.h, basis, p, out.as_mut_ptr() as *mut u64) });
+        out
+    }
+    pub fn empty_coeff(&self) -> Vec<Fr> { self.fill(0, None) }
+    pub fn empty_lagrange(&self) -> Vec<Fr> { self.fill(1, None) }
+    pub fn empty_extended(&self) -> Vec<Fr> { self.fill(2, None) }
+    pub fn constant_lagrange(&self, scalar: &Fr) -> Vec<Fr> { self.fill(1, Some(scalar)) }
+    pub fn constant_extended(&self, scalar: &Fr) -> Vec<Fr> { self.fill(2, Some(scalar)) }
     /// `Evaluator::evaluate_h`, custom-gate loop for halo2-base's vertical gates, on device-resident extended columns
     /// (`d_q`, `d_a`: `n_gates` columns `stride` elements apart, from `h2v_domain_transform_dev(COEFF_TO_EXTENDED)`)
     pub fn quotient_gates(&self, d_h: *mut c_void, y: &Fr, n_gates: usize, d_q: *const c_void, d_a: *const c_void, stride: usize) {
-        ok(unsafe { h2v_quotient_gates_dev(self.0, d_h, y as *const Fr as *const u64, n_gates, d_q, stride, d_a, stride) })
+        ok(unsafe { h2v_quotient_gates_dev(self.h, d_h, y as *const Fr as *const u64, n_gates, d_q, stride, d_a, stride) })
     }
-    pub fn raw(&self) -> *mut H2vDomain { self.0 }
+    pub fn raw(&self) -> *mut H2vDomain { self.h }
 }
 impl Drop for DeviceDomain {
-    fn drop(&mut self) { unsafe { h2v_domain_free(self.0) } }
+    fn drop(&mut self) { unsafe { h2v_domain_free(self.h) } }
+}
+
+/// A halo2 `ProvingKey` (fixed columns, permutation polynomials, constraint-system shape) resident on the device;
+/// `create_proof` = halo2-axiom `plonk::create_proof::<KZGCommitmentScheme<Bn256>, ProverSHPLONK<_>, _, _, PoseidonTranscript<..>, _>`
+/// for one circuit, as `gen_snark_shplonk` runs it (scaffold mod.rs:296).
+pub struct DeviceProvingKey(*mut H2vPk);
+unsafe impl Send for DeviceProvingKey {}
+impl DeviceProvingKey {
+    pub fn new(srs: &DeviceSrs, cs: &H2vCircuit, fixed: &[&[Fr]], sigma: &[&[Fr]], vk_transcript_repr: &Fr) -> Self {
+        let n = 1usize << cs.k;
+        assert!(fixed.len() == cs.n_fixed as usize && sigma.len() == cs.n_perm as usize);
+        assert!(fixed.iter().chain(sigma.iter()).all(|c| c.len() == n));
+        let f: Vec<*const u64> = fixed.iter().map(|c| c.as_ptr() as *const u64).collect();
+        let s: Vec<*const u64> = sigma.iter().map(|c| c.as_ptr() as *const u64).collect();
+        let mut h = std::ptr::null_mut();
+        ok(unsafe { h2v_pk_load(srs.0, cs, f.as_ptr(), s.as_ptr(), vk_transcript_repr as *const Fr as *const u64, &mut h) });
+        DeviceProvingKey(h)
+    }
+    /// advice: every advice column in Lagrange form (2^k values; the unusable rows are overwritten with blinding values);
+    /// instances: the public inputs per instance column; returns the proof bytes (`transcript.finalize()`)
+    pub fn create_proof(&self, n: usize, advice: &[&[Fr]], instances: &[&[Fr]], rng_seed: &[u8; 32]) -> Vec<u8> {
+        assert!(advice.iter().all(|c| c.len() == n));
+        let a: Vec<*const u64> = advice.iter().map(|c| c.as_ptr() as *const u64).collect();
+        let i: Vec<*const u64> = instances.iter().map(|c| c.as_ptr() as *const u64).collect();
+        let il: Vec<u32> = instances.iter().map(|c| c.len() as u32).collect();
+        let mut out = vec![0u8; unsafe { h2v_proof_size(self.0) }];
+        let mut len = 0usize;
+        ok(unsafe { h2v_create_proof(self.0, a.as_ptr(), i.as_ptr(), il.as_ptr(), rng_seed.as_ptr(), out.as_mut_ptr(), out.len(), &mut len) });
+        out.truncate(len);
+        out
+    }
+}
+impl Drop for DeviceProvingKey {
+    fn drop(&mut self) { unsafe { h2v_pk_free(self.0) } }
 }

@@ -132,6 +132,29 @@ class EvaluationDomain {
         return out;
     }
     void divide_by_vanishing_poly(std::vector<Fr> &a) const { need(a.size(), extended_len()); check(h2v_divide_by_vanishing_poly(h_, u(a))); }
+    // poly/domain.rs scalar / index helpers (host-side)
+    Fr rotate_omega(const Fr &value, int32_t rotation) const {
+        Fr f{};
+        check(h2v_domain_rotate_omega(h_, value.l, rotation, f.l));
+        return f;
+    }
+    std::vector<Fr> rotate_extended(const std::vector<Fr> &poly, int32_t rotation) const {
+        need(poly.size(), extended_len());
+        std::vector<Fr> out(poly.size());
+        check(h2v_domain_rotate_extended(h_, reinterpret_cast<const uint64_t *>(poly.data()), rotation, u(out)));
+        return out;
+    }
+    // l_i_range(x, xn, lo..hi): l_i(x) for lo <= i < hi
+    std::vector<Fr> l_i_range(const Fr &x, const Fr &xn, int32_t lo, int32_t hi) const {
+        std::vector<Fr> out(hi > lo ? size_t(hi - lo) : 0);
+        check(h2v_domain_l_i_range(h_, x.l, xn.l, lo, hi, u(out)));
+        return out;
+    }
+    std::vector<Fr> empty_coeff() const { return fill(0, nullptr); }
+    std::vector<Fr> empty_lagrange() const { return fill(1, nullptr); }
+    std::vector<Fr> empty_extended() const { return fill(2, nullptr); }
+    std::vector<Fr> constant_lagrange(const Fr &scalar) const { return fill(1, &scalar); }
+    std::vector<Fr> constant_extended(const Fr &scalar) const { return fill(2, &scalar); }
     h2v_domain_t handle() const { return h_; }
 
     // evaluate_h's row loops on device-resident extended columns (plonk/evaluation.rs [UPSTREAM]); pointers are
@@ -153,6 +176,11 @@ class EvaluationDomain {
     }
 
   private:
+    std::vector<Fr> fill(int basis, const Fr *scalar) const {
+        std::vector<Fr> out(basis == 2 ? extended_len() : size_t(1) << k_);
+        check(h2v_domain_fill(h_, basis, scalar ? scalar->l : nullptr, u(out)));
+        return out;
+    }
     static uint64_t *u(std::vector<Fr> &v) { return reinterpret_cast<uint64_t *>(v.data()); }
     static void need(size_t got, size_t want) {
         if (got != want) throw std::invalid_argument("assertion failed: polynomial length does not match the domain");
@@ -170,5 +198,65 @@ inline std::pair<std::vector<Fr>, std::vector<Fr>> permute_expression_pair(const
                                       input.size(), reinterpret_cast<uint64_t *>(a.data()), reinterpret_cast<uint64_t *>(s.data())));
     return {std::move(a), std::move(s)};
 }
+
+// snark-verifier PoseidonTranscript<G1Affine, NativeLoader, Vec<u8>, 5, 4, 8, 60>::new::<0> (scaffold mod.rs:309-310), host-side
+class PoseidonTranscript {
+  public:
+    PoseidonTranscript() { check(h2v_transcript_new(&h_)); }
+    ~PoseidonTranscript() { h2v_transcript_free(h_); }
+    PoseidonTranscript(const PoseidonTranscript &) = delete;
+    PoseidonTranscript &operator=(const PoseidonTranscript &) = delete;
+    void common_point(const G1Affine &p) { check(h2v_transcript_common_point(h_, reinterpret_cast<const uint64_t *>(&p))); }
+    void common_scalar(const Fr &s) { check(h2v_transcript_common_scalar(h_, s.l)); }
+    void write_point(const G1Affine &p) { check(h2v_transcript_write_point(h_, reinterpret_cast<const uint64_t *>(&p))); }
+    void write_scalar(const Fr &s) { check(h2v_transcript_write_scalar(h_, s.l)); }
+    Fr squeeze_challenge() {
+        Fr f{};
+        check(h2v_transcript_squeeze_challenge(h_, f.l));
+        return f;
+    }
+    std::vector<uint8_t> finalize() const {
+        size_t len = 0;
+        check(h2v_transcript_bytes(h_, nullptr, 0, &len));
+        std::vector<uint8_t> out(len);
+        if (len) check(h2v_transcript_bytes(h_, out.data(), len, &len));
+        return out;
+    }
+
+  private:
+    h2v_transcript_t h_ = nullptr;
+};
+
+// halo2 ProvingKey for a halo2-base-shaped constraint system + create_proof (plonk/prover.rs), resident on the device
+class ProvingKey {
+  public:
+    ProvingKey(const ParamsKZG &params, const h2v_circuit_t &cs, const std::vector<const Fr *> &fixed, const std::vector<const Fr *> &sigma,
+               const Fr &vk_transcript_repr) {
+        check(h2v_pk_load(params.handle(), &cs, reinterpret_cast<const uint64_t *const *>(fixed.data()),
+                          reinterpret_cast<const uint64_t *const *>(sigma.data()), vk_transcript_repr.l, &h_));
+    }
+    ~ProvingKey() { h2v_pk_free(h_); }
+    ProvingKey(const ProvingKey &) = delete;
+    ProvingKey &operator=(const ProvingKey &) = delete;
+    // create_proof(params, pk, &[circuit], &[instances], ChaCha20Rng::from_seed(seed), transcript) -> transcript.finalize()
+    std::vector<uint8_t> create_proof(const std::vector<const Fr *> &advice, const std::vector<std::vector<Fr>> &instances,
+                                      const std::array<uint8_t, 32> &rng_seed) const {
+        std::vector<const uint64_t *> ip;
+        std::vector<uint32_t> il;
+        for (const auto &c : instances) {
+            ip.push_back(reinterpret_cast<const uint64_t *>(c.data()));
+            il.push_back((uint32_t)c.size());
+        }
+        std::vector<uint8_t> out(h2v_proof_size(h_));
+        size_t len = 0;
+        check(h2v_create_proof(h_, reinterpret_cast<const uint64_t *const *>(advice.data()), ip.data(), il.data(), rng_seed.data(), out.data(),
+                               out.size(), &len));
+        out.resize(len);
+        return out;
+    }
+
+  private:
+    h2v_pk_t h_ = nullptr;
+};
 
 }  // namespace h2v_host
