@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "h2v_transcript_write_point", "h2v_transcript_write_scalar", "h2v_transcript_squeeze_challenge", "h2v_transcript_bytes",
     "h2v_poseidon_permutation", "h2v_poseidon_permutation_variant", "h2v_chacha20_fr_random", "h2v_chacha20_block",
     "h2v_srs_gen", "h2v_g2_mul_generator", "h2v_srs_write_file", "h2v_srs_read_file",
-    "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_op_rate", "h2v_set_tuning", "h2v_launch_count", "h2v_last_kernel_ms",
+    "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_imad_probe", "h2v_selftest_op_rate", "h2v_set_tuning", "h2v_launch_count", "h2v_last_kernel_ms",
 ]
 
 
@@ -116,6 +116,7 @@ def lib():
         L.h2v_selftest_group.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_synthetic_bases.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p]
         L.h2v_selftest_imad_peak.argtypes = [C.POINTER(C.c_double)]
+        L.h2v_selftest_imad_probe.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.h2v_selftest_op_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.h2v_set_tuning.argtypes = [C.c_int, C.c_int]
         L.h2v_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
@@ -257,6 +258,13 @@ def last_kernel_ms():
 def imad_peak():
     out = C.c_double()
     _check(lib().h2v_selftest_imad_peak(C.byref(out)))
+    return out.value
+
+
+def imad_probe(which=1):
+    """IMAD.WIDE.U32 issue rate (wide multiply-adds per second): 0 = round-1 probe, 1 = pure chain probe"""
+    out = C.c_double()
+    _check(lib().h2v_selftest_imad_probe(which, C.byref(out)))
     return out.value
 
 

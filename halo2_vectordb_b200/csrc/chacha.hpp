@@ -56,6 +56,11 @@ struct ChaCha20Rng {
         for (int i = 0; i < 8; ++i) w[i] = next_u64();
         return frh::from_u512(w);
     }
+    // `Fr::random` consumes exactly one 64-byte block, so as long as nothing else is drawn the i-th draw is block i of the
+    // key stream: a run of draws can be produced out of line (chacha_fr_kernel) and skipped here
+    bool block_aligned() const { return pos == 16; }
+    uint64_t next_block() const { return counter; }
+    void skip_fr(uint64_t n) { counter += n; }
 };
 
 }  // namespace h2v

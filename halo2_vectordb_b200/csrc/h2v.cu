@@ -2082,6 +2082,29 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(uint64_t *out, uint32_t
     for (int k = 0; k < 8; ++k) s ^= acc[k];
     if (s == 0x1234567812345678ull) out[0] = s;   // keep the chains alive
 }
+// A second, cleaner IMAD.WIDE.U32 issue-rate probe: nothing but the multiply-adds in the loop.  Eight 64-bit
+// accumulator chains per thread; chain k multiplies the LOW WORD of chain k+1 (a register name, no instruction) by a
+// per-chain constant and accumulates, so no product is loop-invariant, no chain depends on itself within 7
+// instructions, and no ALU instruction shares the loop.
+__global__ void __launch_bounds__(256) imad_chain_probe_kernel(uint64_t *out, uint32_t iters, uint32_t seed) {
+    uint64_t acc[8];
+    uint32_t b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        acc[k] = ((uint64_t)(seed + k * 0x9e3779b9u) << 32) | (threadIdx.x * 2654435761u + blockIdx.x + k);
+        b[k] = (seed * (2 * k + 3) + threadIdx.x) | 1u;
+    }
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"((uint32_t)acc[(k + 1) & 7]), "r"(b[k]));
+        }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s ^= acc[k];
+    if (s == 0x1234567812345678ull) out[0] = s;
+}
 }  // namespace
 
 extern "C" {
@@ -2202,6 +2225,42 @@ int h2v_selftest_op_rate(int which, double *out) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, e0, e1));
         if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    O.release();
+    *out = best;
+    return H2V_OK;
+}
+int h2v_selftest_imad_peak(double *out);
+// which 0: the loop-variant stream of round 1 (one xorshift update per 8 multiply-adds); 1: the pure chain probe
+int h2v_selftest_imad_probe(int which, double *out) {
+    t_dev = -1;
+    int rc = use_device();
+    if (rc) return rc;
+    if (!out || which < 0 || which > 1) return fail(H2V_EINVAL, "selftest_imad_probe: bad argument");
+    if (which == 0) return h2v_selftest_imad_peak(out);
+    DevBuf O;
+    if ((rc = O.ensure(64))) return rc;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cur_dev()));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double best = 0;
+    for (int occ = 2; occ <= 8; occ *= 2) {          // resident CTAs per SM: the rate must not depend on it once the pipe is full
+        const unsigned blocks = prop.multiProcessorCount * occ, threads = 256, iters = 1 << 14;
+        for (int rep = 0; rep < 3; ++rep) {
+            CU(cudaEventRecord(e0));
+            imad_chain_probe_kernel<<<blocks, threads>>>(O.as<uint64_t>(), iters, 777u + rep);
+            LAUNCHED();
+            CU(cudaEventRecord(e1));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            const double rate = (double)blocks * threads * iters * 8.0 / (ms * 1e-3);
+            if (rep > 0 && rate > best) best = rate;
+        }
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

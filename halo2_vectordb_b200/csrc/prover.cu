@@ -170,6 +170,57 @@ __global__ void __launch_bounds__(256) eval_pairs_kernel(const EvalPair *pairs, 
     }
 }
 
+// out[i] = the `Fr::random` draw that consumes key-stream block counter0 + i (chacha.hpp): the ChaCha20 block function and
+// the reduction of its 512-bit little-endian value mod r, one thread per draw (the vanishing argument's random
+// polynomial is n consecutive draws)
+__device__ __forceinline__ uint32_t rotl32(uint32_t v, int n) { return (v << n) | (v >> (32 - n)); }
+#define H2V_QR(a, b, c, d)                 \
+    a += b; d = rotl32(d ^ a, 16);         \
+    c += d; b = rotl32(b ^ c, 12);         \
+    a += b; d = rotl32(d ^ a, 8);          \
+    c += d; b = rotl32(b ^ c, 7);
+struct ChaChaKey {
+    uint32_t k[8];
+};
+__device__ __forceinline__ fe canon_below_2_256(fe v) {      // v < 2^256 < 6r  ->  v mod r
+    // subtract 4r, 2r, r when possible
+#pragma unroll
+    for (int sh = 2; sh >= 0; --sh) {
+        uint32_t m[8], d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint64_t w = ((uint64_t)Fr::m(i) << sh) | (i ? ((uint64_t)Fr::m(i - 1) >> (32 - sh)) : 0);
+            m[i] = (uint32_t)w;
+        }
+        const uint32_t bw = raw_sub(d, v.v, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v.v[i] = bw ? v.v[i] : d[i];
+    }
+    return v;
+}
+__global__ void __launch_bounds__(256) chacha_fr_kernel(ChaChaKey key, uint64_t counter0, uint32_t n, fe *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t ctr = counter0 + i;
+    uint32_t x0 = 0x61707865u, x1 = 0x3320646eu, x2 = 0x79622d32u, x3 = 0x6b206574u;
+    uint32_t x4 = key.k[0], x5 = key.k[1], x6 = key.k[2], x7 = key.k[3], x8 = key.k[4], x9 = key.k[5], x10 = key.k[6], x11 = key.k[7];
+    uint32_t x12 = (uint32_t)ctr, x13 = (uint32_t)(ctr >> 32), x14 = 0, x15 = 0;
+    const uint32_t i12 = x12, i13 = x13;
+#pragma unroll 1
+    for (int r = 0; r < 10; ++r) {
+        H2V_QR(x0, x4, x8, x12) H2V_QR(x1, x5, x9, x13) H2V_QR(x2, x6, x10, x14) H2V_QR(x3, x7, x11, x15)
+        H2V_QR(x0, x5, x10, x15) H2V_QR(x1, x6, x11, x12) H2V_QR(x2, x7, x8, x13) H2V_QR(x3, x4, x9, x14)
+    }
+    fe lo, hi;
+    lo.v[0] = x0 + 0x61707865u; lo.v[1] = x1 + 0x3320646eu; lo.v[2] = x2 + 0x79622d32u; lo.v[3] = x3 + 0x6b206574u;
+    lo.v[4] = x4 + key.k[0]; lo.v[5] = x5 + key.k[1]; lo.v[6] = x6 + key.k[2]; lo.v[7] = x7 + key.k[3];
+    hi.v[0] = x8 + key.k[4]; hi.v[1] = x9 + key.k[5]; hi.v[2] = x10 + key.k[6]; hi.v[3] = x11 + key.k[7];
+    hi.v[4] = x12 + i12; hi.v[5] = x13 + i13; hi.v[6] = x14; hi.v[7] = x15;
+    // (lo + hi 2^256) mod r in Montgomery form: to_mont(lo) + to_mont(to_mont(hi))
+    const fe a = fe_to_mont<Fr>(canon_below_2_256(lo)), b = fe_to_mont<Fr>(fe_to_mont<Fr>(canon_below_2_256(hi)));
+    st(out + i, fe_add<Fr>(a, b));
+}
+
 // ------------------------------------------------------------------ small host helpers
 inline const uint64_t *u64(const Fr64 &a) { return a.l; }
 
@@ -459,18 +510,42 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
     // ---- 2-4. advice columns: upload, blind the last blinding_factors + 1 rows, commit
     H2V_TRY(pk->adv_L.ensure((size_t)A * n * sizeof(fe)));
     H2V_TRY(pk->adv_C.ensure((size_t)A * n * sizeof(fe)));
-    for (uint32_t c = 0; c < A; ++c) {
+    for (uint32_t c = 0; c < A; ++c)
         if (!advice[c]) return failf(H2V_EINVAL, "create_proof: advice[%u] is NULL", c);
-        H2V_CU(cudaMemcpyAsync(pk->adv_L.f() + (size_t)c * n, advice[c], n * sizeof(fe), cudaMemcpyHostToDevice, st));
-    }
+    std::vector<affine> pts;
     {
+        // the columns cross PCIe in sub-batches on the proof's stream while the previous sub-batch is being committed
+        // (the commit entry point blocks the host, the copies were queued before it)
         std::vector<Fr64> tails((size_t)A * (bf + 1));
         for (auto &t : tails) t = rng.fr_random();                       // column by column, rows u .. n-1
         for (uint32_t c = 0; c < A; ++c) (void)rng.fr_random();          // one Blind per column (unused by KZG, but drawn)
-        H2V_TRY(write_rows(pk, pk->adv_L.f(), n, u, bf + 1, A, tails));
+        const uint32_t sub = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / (n * sizeof(fe)));
+        const uint32_t nsub = (A + sub - 1) / sub;
+        std::vector<cudaEvent_t> ev(nsub, nullptr);
+        int rc = H2V_OK;
+        for (uint32_t b = 0; b < nsub && !rc; ++b) {
+            const uint32_t c0 = b * sub, c1 = std::min(A, c0 + sub);
+            for (uint32_t c = c0; c < c1; ++c)
+                if (cudaMemcpyAsync(pk->adv_L.f() + (size_t)c * n, advice[c], n * sizeof(fe), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = H2V_ECUDA;
+            if (cudaMemcpy2DAsync(pk->adv_L.f() + (size_t)c0 * n + u, n * sizeof(fe), tails.data() + (size_t)c0 * (bf + 1), (bf + 1) * sizeof(fe),
+                                  (bf + 1) * sizeof(fe), c1 - c0, cudaMemcpyHostToDevice, st) != cudaSuccess)
+                rc = H2V_ECUDA;
+            if (cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ev[b], st) != cudaSuccess) rc = H2V_ECUDA;
+        }
+        pts.resize(A);
+        if (!rc) rc = pk->commits.ensure((size_t)A * sizeof(affine));
+        for (uint32_t b = 0; b < nsub && !rc; ++b) {
+            const uint32_t c0 = b * sub, c1 = std::min(A, c0 + sub);
+            if (cudaEventSynchronize(ev[b]) != cudaSuccess) { rc = H2V_ECUDA; break; }
+            rc = h2v_commit_batch_dev(pk->srs, H2V_BASIS_LAGRANGE, pk->adv_L.f() + (size_t)c0 * n, n, c1 - c0, n, (affine *)pk->commits.p + c0);
+        }
+        cudaStreamSynchronize(st);
+        for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+        if (rc == H2V_ECUDA) return failf(H2V_ECUDA, "create_proof: advice upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc) return rc;
+        H2V_CU(cudaMemcpy(pts.data(), pk->commits.p, (size_t)A * sizeof(affine), cudaMemcpyDeviceToHost));
     }
-    std::vector<affine> pts;
-    H2V_TRY(commit_dev(pk, H2V_BASIS_LAGRANGE, pk->adv_L.f(), A, pts));
     H2V_TRY(write_points(T, pts));
     lap();   // phase 0: upload + advice commitments
     // column pointer helpers
@@ -586,10 +661,14 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
     // ---- 8. vanishing argument: random polynomial                             (vanishing/prover.rs commit)
     H2V_TRY(pk->rnd_C.ensure(n * sizeof(fe)));
     {
-        std::vector<Fr64> rp(n);
-        for (auto &c : rp) c = rng.fr_random();
+        // n consecutive Fr::random draws = n consecutive key-stream blocks: produced on the device
+        ChaChaKey key;
+        memcpy(key.k, rng.key, 32);
+        chacha_fr_kernel<<<gn, 256, 0, st>>>(key, rng.next_block(), (uint32_t)n, pk->rnd_C.f());
+        H2V_LAUNCHED();
+        rng.skip_fr(n);
         (void)rng.fr_random();      // random_blind
-        H2V_TRY(upload(pk, pk->rnd_C, 0, rp.data(), n * sizeof(fe)));
+        H2V_TRY(sync(pk));
         H2V_TRY(commit_dev(pk, H2V_BASIS_MONOMIAL, pk->rnd_C.f(), 1, pts));
         H2V_TRY(write_points(T, pts));
     }

@@ -296,6 +296,9 @@ int h2v_synthetic_bases(uint64_t a, uint64_t b, size_t n, uint64_t *out_affine);
 /* IMAD.WIDE.U32 (32x32+64 -> 64) issue-rate probe with loop-variant operands: wide multiply-adds per second.
  * This is the integer-pipe roofline denominator (MEASURED_PEAKS.json carries no integer peak). */
 int h2v_selftest_imad_peak(double *out_wmac_per_s);
+/* which 0: the probe above; 1: a pure chain probe -- eight accumulator chains per thread feeding each other's
+ * multiplicand, nothing but mad.wide.u32 in the loop (the kernel-independent roofline denominator) */
+int h2v_selftest_imad_probe(int which, double *out_wmac_per_s);
 /* register-only throughput of the kernels' building blocks, operations per second over the whole GPU:
  * which 0: Fq Montgomery product, one dependent chain per thread; 1: two chains; 2: XYZZ mixed-add chain */
 int h2v_selftest_op_rate(int which, double *out_ops_per_s);
