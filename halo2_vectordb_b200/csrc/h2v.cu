@@ -267,8 +267,8 @@ struct DomRep {
     DevBuf dconst;
     DevBuf tw[4];   // 0: omega, 1: omega_inv, 2: ext_omega, 3: ext_omega_inv
     bool tw_ready[4] = {false, false, false, false};
-    DevBuf stage_a, stage_b, pipe_a, pipe_b;
-    cudaStream_t stream = nullptr, pipe_stream = nullptr;
+    DevBuf stage_a, stage_b, pipe_a, pipe_b, pipe_a2, pipe_b2;
+    cudaStream_t stream = nullptr, pipe_stream = nullptr, pipe_stream2 = nullptr;
     std::mutex mu, tw_mu;
     struct Lane {            // small host-facing transforms from concurrent caller threads (see SrsRep::Lane)
         std::mutex mu;
@@ -1255,7 +1255,10 @@ static void rep_domain_free(DomRep *d) {
     d->stage_b.release();
     d->pipe_a.release();
     d->pipe_b.release();
+    d->pipe_a2.release();
+    d->pipe_b2.release();
     if (d->pipe_stream) cudaStreamDestroy(d->pipe_stream);
+    if (d->pipe_stream2) cudaStreamDestroy(d->pipe_stream2);
     for (auto &ln : d->lanes) {
         ln.stage_a.release();
         ln.stage_b.release();
@@ -1385,7 +1388,7 @@ static int rep_domain_transform_batch(DomRep *d, int op, const uint64_t *const *
     if (rc) return rc;
     const size_t nin = op_in_len(d, op), nout = op_out_len(d, op);
     const size_t out_stride = std::max(nout, (size_t)1 << (op >= H2V_OP_COEFF_TO_EXTENDED ? d->ek : d->k));
-    if (n_cols * out_stride * sizeof(fe) <= ((size_t)64 << 20)) {
+    if (n_cols * out_stride * sizeof(fe) <= ((size_t)8 << 20)) {
         DomRep::Lane *ln = nullptr;
         for (int i = 0; i < DomRep::H2V_LANES && !ln; ++i)
             if (d->lanes[i].mu.try_lock()) ln = &d->lanes[i];
@@ -1414,44 +1417,59 @@ static int rep_domain_transform_batch(DomRep *d, int op, const uint64_t *const *
         CU(cudaStreamSynchronize(ln->st));
         return H2V_OK;
     }
-    // Large batch: sub-batches of ~64 MB alternate between two pipelines (stream + staging each) with no sync
-    // in between, so the upload of sub-batch i+1, the kernels of sub-batch i and the download of sub-batch i-1
-    // overlap (PCIe is full duplex; the transforms themselves are ~4x faster than the link).
+    // Pipelined batch: sub-batches rotate over three pipelines (stream + staging each) with no sync in between, so the
+    // upload of sub-batch i+1, the kernels of sub-batch i and the download of sub-batch i-1 overlap -- PCIe is full
+    // duplex and the transforms are several times faster than the link, so the call runs at the slower direction's rate.
+    // Sub-batch size: at least ~6 per call (to fill the pipeline), 4..64 MB of output each.
     std::lock_guard<std::mutex> lk(d->mu);
-    size_t per = std::max<size_t>(1, ((size_t)64 << 20) / (out_stride * sizeof(fe)));
+    const size_t col_bytes = out_stride * sizeof(fe);
+    size_t per = (n_cols + 5) / 6;
+    per = std::max(per, std::max<size_t>(1, ((size_t)4 << 20) / col_bytes));
+    per = std::min(per, std::max<size_t>(1, ((size_t)64 << 20) / col_bytes));
     per = std::min(per, n_cols);
-    cudaStream_t pst[2];
-    DevBuf *pa[2] = {&d->stage_a, &d->pipe_a}, *pb[2] = {&d->stage_b, &d->pipe_b};
-    if (!d->pipe_stream) CU(cudaStreamCreateWithFlags(&d->pipe_stream, cudaStreamNonBlocking));
-    pst[0] = d->stream;
-    pst[1] = d->pipe_stream;
-    for (int b = 0; b < 2; ++b) {
+    const int NP = 3;
+    if (!d->pipe_stream) {
+        CU(cudaStreamCreateWithFlags(&d->pipe_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&d->pipe_stream2, cudaStreamNonBlocking));
+    }
+    cudaStream_t pst[NP] = {d->stream, d->pipe_stream, d->pipe_stream2};
+    DevBuf *pa[NP] = {&d->stage_a, &d->pipe_a, &d->pipe_a2}, *pb[NP] = {&d->stage_b, &d->pipe_b, &d->pipe_b2};
+    auto sync_all = [&] {
+        for (int b = 0; b < NP; ++b) cudaStreamSynchronize(pst[b]);
+    };
+    for (int b = 0; b < NP; ++b) {
         if ((rc = pa[b]->ensure(per * nin * sizeof(fe)))) return rc;
         if ((rc = pb[b]->ensure(per * out_stride * sizeof(fe)))) return rc;
     }
     size_t it = 0;
     for (size_t c0 = 0; c0 < n_cols; c0 += per, ++it) {
         const size_t cols = std::min(per, n_cols - c0);
-        const int b = (int)(it & 1);
+        const int b = (int)(it % NP);
         for (size_t c = 0; c < cols; ++c) {
             if (!in[c0 + c] || !out[c0 + c]) {
-                cudaStreamSynchronize(pst[0]);
-                cudaStreamSynchronize(pst[1]);
+                sync_all();
                 return fail(H2V_EINVAL, "transform: column %zu is NULL", c0 + c);
             }
-            CU(cudaMemcpyAsync(pa[b]->as<fe>() + c * nin, in[c0 + c], nin * sizeof(fe), cudaMemcpyHostToDevice, pst[b]));
+            cudaError_t e = cudaMemcpyAsync(pa[b]->as<fe>() + c * nin, in[c0 + c], nin * sizeof(fe), cudaMemcpyHostToDevice, pst[b]);
+            if (e != cudaSuccess) {
+                sync_all();
+                return fail(H2V_ECUDA, "transform: upload failed: %s", cudaGetErrorString(e));
+            }
         }
         rc = domain_op_dev(d, pst[b], op, pa[b]->as<fe>(), nin, pb[b]->as<fe>(), out_stride, cols);
         if (rc) {
-            cudaStreamSynchronize(pst[0]);
-            cudaStreamSynchronize(pst[1]);
+            sync_all();
             return rc;
         }
-        for (size_t c = 0; c < cols; ++c)
-            CU(cudaMemcpyAsync(out[c0 + c], pb[b]->as<fe>() + c * out_stride, nout * sizeof(fe), cudaMemcpyDeviceToHost, pst[b]));
+        for (size_t c = 0; c < cols; ++c) {
+            cudaError_t e = cudaMemcpyAsync(out[c0 + c], pb[b]->as<fe>() + c * out_stride, nout * sizeof(fe), cudaMemcpyDeviceToHost, pst[b]);
+            if (e != cudaSuccess) {
+                sync_all();
+                return fail(H2V_ECUDA, "transform: download failed: %s", cudaGetErrorString(e));
+            }
+        }
     }
-    CU(cudaStreamSynchronize(pst[0]));
-    CU(cudaStreamSynchronize(pst[1]));
+    for (int b = 0; b < NP; ++b) CU(cudaStreamSynchronize(pst[b]));
     return H2V_OK;
 }
 static int one_col(DomRep *d, int op, const uint64_t *in, uint64_t *out) {
@@ -2082,28 +2100,34 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(uint64_t *out, uint32_t
     for (int k = 0; k < 8; ++k) s ^= acc[k];
     if (s == 0x1234567812345678ull) out[0] = s;   // keep the chains alive
 }
-// A second, cleaner IMAD.WIDE.U32 issue-rate probe: nothing but the multiply-adds in the loop.  Eight 64-bit
-// accumulator chains per thread; chain k multiplies the LOW WORD of chain k+1 (a register name, no instruction) by a
-// per-chain constant and accumulates, so no product is loop-invariant, no chain depends on itself within 7
-// instructions, and no ALU instruction shares the loop.
-__global__ void __launch_bounds__(256) imad_chain_probe_kernel(uint64_t *out, uint32_t iters, uint32_t seed) {
-    uint64_t acc[8];
-    uint32_t b[8];
+// A second IMAD.WIDE.U32 issue-rate probe with nothing but multiplier instructions in the loop.  (A plain
+// `mad.wide.u32 d, a, b, d` does not qualify: ptxas splits its 64-bit accumulate into IMAD.WIDE + IADD3 + IADD3.X.)
+// The loop is made of the carry-chained rows the field code is built from -- mad.lo.cc / madc.hi.cc pairs that ptxas
+// fuses into IMAD.WIDE.U32.X -- on four independent 8-limb accumulators; the multiplier of each row is a limb of
+// another accumulator, so no product is loop-invariant.  4 wide multiply-adds per row, one ADDC per row besides.
+__global__ void __launch_bounds__(256) imad_chain_probe_kernel(uint32_t *out, uint32_t iters, uint32_t seed) {
+#ifdef __CUDA_ARCH__      // the row primitives exist in the device pass only
+    uint32_t a[4][8], x[8], top = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        acc[k] = ((uint64_t)(seed + k * 0x9e3779b9u) << 32) | (threadIdx.x * 2654435761u + blockIdx.x + k);
-        b[k] = (seed * (2 * k + 3) + threadIdx.x) | 1u;
+        x[k] = (seed * (2 * k + 3) + threadIdx.x * 2654435761u) | 1u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a[c][k] = seed + 977u * c + k * 0x9e3779b9u + blockIdx.x;
     }
     for (uint32_t it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"((uint32_t)acc[(k + 1) & 7]), "r"(b[k]));
+        for (int r = 0; r < 4; ++r) {
+            row_mad_top(a[0], x, a[1][2 * r], top);
+            row_mad_top(a[1], x, a[2][2 * r], top);
+            row_mad_top(a[2], x, a[3][2 * r], top);
+            row_mad_top(a[3], x, a[0][2 * r + 1], top);
         }
     }
-    uint64_t s = 0;
+    uint32_t s = top;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s ^= acc[k];
-    if (s == 0x1234567812345678ull) out[0] = s;
+    for (int k = 0; k < 8; ++k) s ^= a[0][k] ^ a[1][k] ^ a[2][k] ^ a[3][k];
+    if (s == 0x12345678u) out[0] = s;
+#endif
 }
 }  // namespace
 
@@ -2249,16 +2273,16 @@ int h2v_selftest_imad_probe(int which, double *out) {
     CU(cudaEventCreate(&e1));
     double best = 0;
     for (int occ = 2; occ <= 8; occ *= 2) {          // resident CTAs per SM: the rate must not depend on it once the pipe is full
-        const unsigned blocks = prop.multiProcessorCount * occ, threads = 256, iters = 1 << 14;
+        const unsigned blocks = prop.multiProcessorCount * occ, threads = 256, iters = 1 << 12;
         for (int rep = 0; rep < 3; ++rep) {
             CU(cudaEventRecord(e0));
-            imad_chain_probe_kernel<<<blocks, threads>>>(O.as<uint64_t>(), iters, 777u + rep);
+            imad_chain_probe_kernel<<<blocks, threads>>>(O.as<uint32_t>(), iters, 777u + rep);
             LAUNCHED();
             CU(cudaEventRecord(e1));
             CU(cudaEventSynchronize(e1));
             float ms = 0;
             CU(cudaEventElapsedTime(&ms, e0, e1));
-            const double rate = (double)blocks * threads * iters * 8.0 / (ms * 1e-3);
+            const double rate = (double)blocks * threads * iters * 64.0 / (ms * 1e-3);      // 16 rows x 4 per iteration
             if (rep > 0 && rate > best) best = rate;
         }
     }

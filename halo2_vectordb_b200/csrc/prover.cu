@@ -519,7 +519,8 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
         std::vector<Fr64> tails((size_t)A * (bf + 1));
         for (auto &t : tails) t = rng.fr_random();                       // column by column, rows u .. n-1
         for (uint32_t c = 0; c < A; ++c) (void)rng.fr_random();          // one Blind per column (unused by KZG, but drawn)
-        const uint32_t sub = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / (n * sizeof(fe)));
+        // few sub-batches: every commit call ends in a latency-bound reduction tail (~1 ms) that only size amortises
+        const uint32_t sub = std::max<uint32_t>((A + 3) / 4, (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / (n * sizeof(fe))));
         const uint32_t nsub = (A + sub - 1) / sub;
         std::vector<cudaEvent_t> ev(nsub, nullptr);
         int rc = H2V_OK;

@@ -296,8 +296,9 @@ int h2v_synthetic_bases(uint64_t a, uint64_t b, size_t n, uint64_t *out_affine);
 /* IMAD.WIDE.U32 (32x32+64 -> 64) issue-rate probe with loop-variant operands: wide multiply-adds per second.
  * This is the integer-pipe roofline denominator (MEASURED_PEAKS.json carries no integer peak). */
 int h2v_selftest_imad_peak(double *out_wmac_per_s);
-/* which 0: the probe above; 1: a pure chain probe -- eight accumulator chains per thread feeding each other's
- * multiplicand, nothing but mad.wide.u32 in the loop (the kernel-independent roofline denominator) */
+/* which 0: the probe above; 1: a loop of nothing but carry-chained IMAD.WIDE.U32.X rows (the mad.lo.cc / madc.hi.cc
+ * pairs the field code is built from) on independent accumulators whose multipliers come from each other -- the
+ * roofline denominator that does not depend on any kernel under test */
 int h2v_selftest_imad_probe(int which, double *out_wmac_per_s);
 /* register-only throughput of the kernels' building blocks, operations per second over the whole GPU:
  * which 0: Fq Montgomery product, one dependent chain per thread; 1: two chains; 2: XYZZ mixed-add chain */
