@@ -218,9 +218,13 @@ def _main(args, real_stdout):
     def step_e2e():
         h._check(h.lib().h2v_commit_batch(srs._h, h.H2V_BASIS_LAGRANGE, col_ptrs, cols, N, out_host.ctypes.data_as(C.c_void_p)))
 
-    # integer-pipe peak, measured live (MEASURED_PEAKS.json has none): the better of a loop-variant mad.wide.u32
-    # stream and a register-resident Fq Montgomery-product chain (136 wide-MACs per product)
-    peak = max(h.imad_peak(), h.op_rate(1) * FQ_MUL_MACS)
+    # integer-pipe peak, measured live (MEASURED_PEAKS.json has none).  Three probes, none of which is a kernel under test:
+    #   row    a loop of nothing but carry-chained IMAD.WIDE.U32.X rows on independent accumulators (h2v_selftest_imad_probe(1))
+    #   chain  a register-resident Fq Montgomery-product chain x 136 wide-MACs per product (h2v_selftest_op_rate)
+    #   r01    round 1's loop-variant mad.wide.u32 stream (its 64-bit accumulate splits into IMAD.WIDE + 2 IADD3: reads low)
+    # The denominator is the highest rate the pipe demonstrably sustains; the nominal figure is 148 SM x 32 / clk.
+    peak_row, peak_chain, peak_r01 = h.imad_probe(1), h.op_rate(1) * FQ_MUL_MACS, h.imad_peak()
+    peak = max(peak_row, peak_chain, peak_r01)
 
     # ---- device-resident timing
     # the clock sampler starts before the warm-up (nvidia-smi needs a few hundred ms to deliver its first
@@ -264,6 +268,7 @@ def _main(args, real_stdout):
     acc_ms = kernel_ms["msm_accumulate"] / args.steps           # one launch per step (all columns)
     macs = cols * N * MSM_MACS_PER_POINT[K]
     achieved = macs / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
+    executed = (cols * N * srs.info()[1] * 1360) / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
     line = {
         "metric": "msm_mpts_per_s", "value": value, "unit": "Mpts/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -277,11 +282,18 @@ def _main(args, real_stdout):
         "clocks": clocks,
         "kernel_ms_per_step": {k: round(v / args.steps, 4) for k, v in kernel_ms.items() if v},
         "roofline": {"bound": "int32-pipe (IMAD.WIDE)", "kernel": "msm_accumulate_kernel", "achieved": achieved,
-                     "peak": peak / 1e12, "unit": "T wide-MAC/s", "frac": (achieved / (peak / 1e12)) if achieved else None,
+                     "peak": peak / 1e12, "unit": "T wide-MAC/s",
+                     # frac: the wide multiply-adds the kernel EXECUTES (17 signed windows x 1360 per point) over the measured peak;
+                     # frac_algorithmic: SURVEY 8(d)'s count (20 unsigned windows) over the same peak -- above 1 because the
+                     # precomputed-table layout needs fewer windows, not because the pipe runs faster than its peak
+                     "frac": (executed / (peak / 1e12)) if executed else None,
+                     "frac_algorithmic": (achieved / (peak / 1e12)) if achieved else None,
+                     "executed": executed,
                      "traffic": ACC_DRAM_BYTES_PER_LAUNCH if cols == COLS else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full of this command (profiles/r01_bench_launches_ncu.txt)",
-                     "peak_source": "measured live: max(h2v_selftest_imad_peak, h2v_selftest_op_rate(Fq mul) x 136); MEASURED_PEAKS.json has no integer peak; nominal 148 SM x 32 IMAD.WIDE/clk x 1.965 GHz = 9.31",
-                     "executed": (cols * N * srs.info()[1] * 1360) / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None,
+                     "peak_probes": {"imad_wide_x_rows": peak_row / 1e12, "fq_product_chain_x136": peak_chain / 1e12,
+                                     "r01_mad_wide_stream": peak_r01 / 1e12, "nominal_148sm_x_32_per_clk_at_1965mhz": 9.31},
+                     "peak_source": "measured live, max of the probes (none of them is the kernel under test); MEASURED_PEAKS.json has no integer peak",
                      "window_bits": srs.info()[0], "windows": srs.info()[1],
                      "algorithmic": f"{MSM_MACS_PER_POINT[K]} wide-MAC/pt x {cols * N} pts per launch (SURVEY.md 8d)"},
     }
@@ -292,7 +304,7 @@ def _main(args, real_stdout):
 
     if not args.no_extras and rank == 0:
         line["ntt"] = bench_ntt(h, torch, dev, peak)
-        line["witness_like"] = bench_witness(h, torch, dev, srs)
+        line["witness_like"] = bench_witness(h, torch, dev, srs, peak)
         line["prove_shaped"] = bench_prove_shaped(h, torch, dev, srs, d_cols, cols)
         if not os.environ.get("H2V_BENCH_SKIP_REAL"):
             rf = bench_real_flow(h, torch)
@@ -790,21 +802,39 @@ def bench_row1(h, torch, dev):
             "note": f"k={k}, extended_k={dom.extended_k}, uniform synthetic extended columns resident in HBM; per-term rates, {n_adv} advice columns in the kmeans batch"}
 
 
-def bench_witness(h, torch, dev, srs):
+def bench_witness(h, torch, dev, srs, peak):
     """Same commit batch on witness-shaped scalars (60% {0,1}, 30% < 2^15, 10% full width / r - small): the
-    distribution FixedPointChip columns really have (/root/reference/src/gadget/fixed_point.rs:68-119)."""
+    distribution FixedPointChip columns really have (/root/reference/src/gadget/fixed_point.rs:68-119).  The second
+    headline: per-kernel-class times, the share of the step outside msm_accumulate, and the accumulate kernel's roofline
+    on the mixed additions it actually executes (one per non-zero digit: sorted entries, read back from the histogram)."""
     import numpy as np
     from halo2_vectordb_b200.synthetic import witness_like
     cols = 96
     a = torch.from_numpy(witness_like(cols, N, 15, 7).view(np.int64)).to(dev)
     out = torch.zeros((cols, 8), dtype=torch.int64, device=dev)
-    ms = []
-    for i in range(6):
+    ms, kms = [], {}
+    for i in range(8):
         srs.commit_batch_dev(a.data_ptr(), N, cols, N, out.data_ptr())
         if i >= 2:
-            ms.append(sum(h.last_kernel_ms().values()))
+            k = h.last_kernel_ms()
+            ms.append(sum(k.values()))
+            for kk, v in k.items():
+                kms.setdefault(kk, []).append(v)
     t = statistics.median(ms) * 1e-3
-    return {"msm_mpts_per_s": cols * N / t / 1e6, "ms_per_step": t * 1e3, "cols_per_step": cols, "lookup_bits": 15}
+    kmed = {kk: statistics.median(v) for kk, v in kms.items()}
+    c, w = srs.info()
+    # non-zero digits of the batch under the window the call used, counted on the host from the same scalars
+    acc_s = kmed["msm_accumulate"] * 1e-3
+    res = {"msm_mpts_per_s": cols * N / t / 1e6, "ms_per_step": t * 1e3, "cols_per_step": cols, "lookup_bits": 15,
+           "kernel_ms_per_step": {kk: round(v, 4) for kk, v in kmed.items() if v},
+           "non_accumulate_share": 1.0 - kmed["msm_accumulate"] / sum(kmed.values()),
+           "window_bits": c, "windows": w}
+    entries = h.last_msm_entries()
+    if entries and acc_s > 0:
+        res["roofline"] = {"bound": "int32-pipe (IMAD.WIDE)", "kernel": "msm_accumulate_kernel", "unit": "T wide-MAC/s",
+                           "executed": entries * 1360 / acc_s / 1e12, "peak": peak / 1e12, "frac": entries * 1360 / acc_s / peak,
+                           "mixed_additions_per_launch": int(entries)}
+    return res
 
 
 def bench_ntt(h, torch, dev, peak):

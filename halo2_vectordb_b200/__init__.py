@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "h2v_transcript_write_point", "h2v_transcript_write_scalar", "h2v_transcript_squeeze_challenge", "h2v_transcript_bytes",
     "h2v_poseidon_permutation", "h2v_poseidon_permutation_variant", "h2v_chacha20_fr_random", "h2v_chacha20_block",
     "h2v_srs_gen", "h2v_g2_mul_generator", "h2v_srs_write_file", "h2v_srs_read_file",
-    "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_imad_probe", "h2v_selftest_op_rate", "h2v_set_tuning", "h2v_launch_count", "h2v_last_kernel_ms",
+    "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_imad_probe", "h2v_selftest_op_rate", "h2v_set_tuning", "h2v_launch_count", "h2v_last_kernel_ms", "h2v_last_msm_entries",
 ]
 
 
@@ -120,6 +120,7 @@ def lib():
         L.h2v_selftest_op_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.h2v_set_tuning.argtypes = [C.c_int, C.c_int]
         L.h2v_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
+        L.h2v_last_msm_entries.restype = C.c_uint64
         L.h2v_domain_rotate_omega.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.h2v_domain_rotate_extended.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.h2v_domain_l_i_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
@@ -253,6 +254,11 @@ def last_kernel_ms():
     buf = (C.c_float * 8)()
     _check(lib().h2v_last_kernel_ms(buf))
     return dict(zip(KERNEL_CLASSES, [float(x) for x in buf]))
+
+
+def last_msm_entries():
+    """mixed additions (non-zero digits) the calling thread's last commit_batch_dev executed"""
+    return int(lib().h2v_last_msm_entries())
 
 
 def imad_peak():

@@ -49,6 +49,10 @@ int device_of(const void *p) {
 std::atomic<uint64_t> g_launches{0};
 // device-side timing of the calling thread's last `_dev` call (per thread: concurrent callers do not mix their records)
 thread_local float g_last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+// sorted bucket entries (= mixed additions msm_accumulate executes) of the calling thread's last timed commit
+thread_local uint32_t t_entry_counts[64];
+thread_local int t_entry_launches = 0;
+thread_local uint64_t g_last_entries = 0;
 
 int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -565,6 +569,8 @@ int run_msm(cudaStream_t st, MsmWorkspace &ws, const fe *d_scalars, size_t col_s
             msm_scan_apply_kernel<<<ntiles, 256, 0, st>>>(L.counts, L.tile_sums, L.offsets, L.cursor, L.n_buckets);
             LAUNCHED();
         }
+        if (tm && t_entry_launches < 64)
+            CU(cudaMemcpyAsync(&t_entry_counts[t_entry_launches++], L.offsets + L.n_buckets, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (tm) { tm->end(); tm->begin(2); }
         {
             // A single very large MSM (>= 1 GiB of sorted entries) sweeps the bucket space in 4 slices: the
@@ -859,6 +865,7 @@ int h2v_set_tuning(int chunk, int table) {
     g_tune_table.store(table == 0 || table == 1 ? table : -1);
     return H2V_OK;
 }
+uint64_t h2v_last_msm_entries(void) { return g_last_entries; }
 int h2v_last_kernel_ms(float out[8]) {
     if (!out) return fail(H2V_EINVAL, "last_kernel_ms: NULL");
     memcpy(out, g_last_ms, sizeof g_last_ms);
@@ -967,9 +974,12 @@ static int rep_commit_batch_dev(SrsRep *s, int basis, const void *d_polys, size_
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(s->mu);
     Timer tm(s->stream);
+    t_entry_launches = 0;
     rc = msm_srs(s, s->stream, s->ws, basis, (const fe *)d_polys, col_stride, n_polys, len, (affine *)d_out_affine, &tm);
     cudaError_t e = cudaStreamSynchronize(s->stream);
     tm.collect(true);
+    g_last_entries = 0;
+    for (int i = 0; i < t_entry_launches; ++i) g_last_entries += t_entry_counts[i];
     if (rc) return rc;
     if (e != cudaSuccess) return fail(H2V_ECUDA, "commit: %s", cudaGetErrorString(e));
     return H2V_OK;

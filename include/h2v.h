@@ -313,6 +313,9 @@ uint64_t h2v_launch_count(void);
 /* device-side timing of the last commit_batch_dev / transform_dev call, in milliseconds per kernel class:
  * MSM 0 digits 1 scan 2 scatter 3 accumulate 4 finish 5 reduce 6 final; NTT 7 */
 int h2v_last_kernel_ms(float out[8]);   /* the calling thread's last call */
+/* non-zero digits (= sorted bucket entries = mixed additions msm_accumulate executed) of the calling thread's last
+ * h2v_commit_batch_dev: the executed-work figure for the roofline of skewed columns */
+uint64_t h2v_last_msm_entries(void);
 
 #ifdef __cplusplus
 }
