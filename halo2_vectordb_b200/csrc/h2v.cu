@@ -116,6 +116,25 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Column staging between caller-owned host columns and a device staging area: columns that are adjacent in host memory
+// (one Vec / tensor holding a whole batch) and land contiguously on the device move as ONE copy -- fewer, larger DMA
+// transfers keep a PCIe link busier, most visibly when several GPUs pull from the same host at once.
+// to_device: dev[c * dev_stride ..] <- host[c];  else host[c] <- dev[c * dev_stride ..];  `len` elements per column
+cudaError_t stage_columns(bool to_device, fe *dev, size_t dev_stride, const uint64_t *const *host, size_t cols, size_t len, cudaStream_t st) {
+    if (!len) return cudaSuccess;
+    size_t c = 0;
+    while (c < cols) {
+        size_t run = 1;
+        if (dev_stride == len)
+            while (c + run < cols && host[c + run] == host[c + run - 1] + 4 * len) ++run;
+        cudaError_t e = to_device ? cudaMemcpyAsync(dev + c * dev_stride, host[c], run * len * sizeof(fe), cudaMemcpyHostToDevice, st)
+                                  : cudaMemcpyAsync(const_cast<uint64_t *>(host[c]), dev + c * dev_stride, run * len * sizeof(fe), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return e;
+        c += run;
+    }
+    return cudaSuccess;
+}
+
 struct Timer {   // CUDA-event stopwatch on one stream, accumulating per kernel class
     cudaStream_t st;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
@@ -1009,13 +1028,9 @@ static int rep_commit_batch(SrsRep *s, int basis, const uint64_t *const *polys, 
         if (!ln->st) CU(cudaStreamCreateWithFlags(&ln->st, cudaStreamNonBlocking));
         if ((rc = ln->stage.ensure(n_polys * stride_small * sizeof(fe)))) return rc;
         if ((rc = ln->out.ensure(n_polys * sizeof(affine)))) return rc;
-        for (size_t c = 0; c < n_polys; ++c) {
-            if (!polys[c] && len) {
-                cudaStreamSynchronize(ln->st);
-                return fail(H2V_EINVAL, "commit: polys[%zu] is NULL", c);
-            }
-            if (len) CU(cudaMemcpyAsync(ln->stage.as<fe>() + c * stride_small, polys[c], len * sizeof(fe), cudaMemcpyHostToDevice, ln->st));
-        }
+        for (size_t c = 0; c < n_polys; ++c)
+            if (!polys[c] && len) return fail(H2V_EINVAL, "commit: polys[%zu] is NULL", c);
+        CU(stage_columns(true, ln->stage.as<fe>(), stride_small, polys, n_polys, len, ln->st));
         rc = msm_srs(s, ln->st, ln->ws, basis, ln->stage.as<fe>(), stride_small, n_polys, len, ln->out.as<affine>(), nullptr);
         if (rc) {
             cudaStreamSynchronize(ln->st);
@@ -1069,8 +1084,8 @@ static int rep_commit_batch(SrsRep *s, int basis, const uint64_t *const *polys, 
                 cudaStreamSynchronize(s->copy_stream);
                 return fail(H2V_EINVAL, "commit: polys[%zu] is NULL", c0 + c);
             }
-            if (len) CU(cudaMemcpyAsync(stg + c * stride, polys[c0 + c], len * sizeof(fe), cudaMemcpyHostToDevice, s->copy_stream));
         }
+        CU(stage_columns(true, stg, stride, polys + c0, cols, len, s->copy_stream));
         CU(cudaEventRecord(s->copied[b], s->copy_stream));
         cudaStream_t cst = b ? s->stream2 : s->stream;
         CU(cudaStreamWaitEvent(cst, s->copied[b], 0));
@@ -1415,15 +1430,14 @@ static int rep_domain_transform_batch(DomRep *d, int op, const uint64_t *const *
                 cudaStreamSynchronize(ln->st);
                 return fail(H2V_EINVAL, "transform: column %zu is NULL", c);
             }
-            CU(cudaMemcpyAsync(ln->stage_a.as<fe>() + c * nin, in[c], nin * sizeof(fe), cudaMemcpyHostToDevice, ln->st));
         }
+        CU(stage_columns(true, ln->stage_a.as<fe>(), nin, in, n_cols, nin, ln->st));
         rc = domain_op_dev(d, ln->st, op, ln->stage_a.as<fe>(), nin, ln->stage_b.as<fe>(), out_stride, n_cols);
         if (rc) {
             cudaStreamSynchronize(ln->st);
             return rc;
         }
-        for (size_t c = 0; c < n_cols; ++c)
-            CU(cudaMemcpyAsync(out[c], ln->stage_b.as<fe>() + c * out_stride, nout * sizeof(fe), cudaMemcpyDeviceToHost, ln->st));
+        CU(stage_columns(false, ln->stage_b.as<fe>(), out_stride, out, n_cols, nout, ln->st));
         CU(cudaStreamSynchronize(ln->st));
         return H2V_OK;
     }
@@ -1460,7 +1474,9 @@ static int rep_domain_transform_batch(DomRep *d, int op, const uint64_t *const *
                 sync_all();
                 return fail(H2V_EINVAL, "transform: column %zu is NULL", c0 + c);
             }
-            cudaError_t e = cudaMemcpyAsync(pa[b]->as<fe>() + c * nin, in[c0 + c], nin * sizeof(fe), cudaMemcpyHostToDevice, pst[b]);
+        }
+        {
+            cudaError_t e = stage_columns(true, pa[b]->as<fe>(), nin, in + c0, cols, nin, pst[b]);
             if (e != cudaSuccess) {
                 sync_all();
                 return fail(H2V_ECUDA, "transform: upload failed: %s", cudaGetErrorString(e));
@@ -1471,8 +1487,8 @@ static int rep_domain_transform_batch(DomRep *d, int op, const uint64_t *const *
             sync_all();
             return rc;
         }
-        for (size_t c = 0; c < cols; ++c) {
-            cudaError_t e = cudaMemcpyAsync(out[c0 + c], pb[b]->as<fe>() + c * out_stride, nout * sizeof(fe), cudaMemcpyDeviceToHost, pst[b]);
+        {
+            cudaError_t e = stage_columns(false, pb[b]->as<fe>(), out_stride, out + c0, cols, nout, pst[b]);
             if (e != cudaSuccess) {
                 sync_all();
                 return fail(H2V_ECUDA, "transform: download failed: %s", cudaGetErrorString(e));
