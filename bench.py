@@ -377,66 +377,85 @@ def bench_strong_phase(h, torch, dev, srs, host_np, rank, world, barrier, max_ov
             "mpts_per_s": STRONG_COLS * N / t / 1e6, "cols_per_rank": len(mine)}
 
 
-REAL_SHAPES = {    # SURVEY.md App. C column counts: (k, basic-gate advice columns, lookup-advice columns, LOOKUP_BITS)
-    "distances_k13": (13, 10, 2, 12),
-    "query_k13": (13, 152, 18, 12),
-    "kmeans_k16": (16, 546, 71, 15),
-}
-
-
-def bench_real_flow(h, torch, names=("distances_k13", "query_k13", "kmeans_k16")):
-    """ONE real proof per circuit shape through the library's create_proof (h2v_create_proof): a satisfied synthetic
-    circuit with halo2-base's constraint system and the column counts of SURVEY.md App. C, witness-shaped cell values,
-    the seed-zero SRS of gen_srs, ChaCha20 blinding, the Poseidon transcript, real challenge dependencies between the
-    phases, SHPLONK opening -- every step of SURVEY.md 3.1 from the advice columns (pinned host memory) to the proof
-    bytes.  What it leaves out of `prove`: witness generation by the chips and reading the proving key from disk."""
+def bench_real_flow(h, torch, names=("distances", "query", "kmeans")):
+    """ONE real proof per reference example (BASELINE configs[0..2]): the witness comes from the restated chips on the
+    example's own input (halo2_vectordb_b200.circuit: /root/reference/examples/{distances,query,kmeans}.rs on
+    data/*.in), the columns from the restated halo2-base layouter, and the proof from h2v_create_proof -- the seed-zero
+    SRS of gen_srs, ChaCha20 blinding, the Poseidon transcript, real challenge dependencies between the phases, SHPLONK
+    opening: every step of SURVEY.md 3.1 from the advice columns (pinned host memory) to the proof bytes.  `prove_s` is
+    create_proof alone; the host-side witness generation and layout (serial upstream as well) are timed beside it."""
     import numpy as np
-    from halo2_vectordb_b200.synthetic import synthetic_circuit
+    from halo2_vectordb_b200 import circuit as Z
     res = {}
     for name in names:
-        k, G, Lc, bits = REAL_SHAPES[name]
+        k, bits = Z.EXAMPLE_PARAMS[name]
         n = 1 << k
+        inp = Z.example_input(name)
+        if name == "query":      # break the five-way ties of data/query.in (tests/test_circuit.py::test_query_layout)
+            inp["database"] = [[x + 1e-3 * (i // 4) for x in v] for i, v in enumerate(inp["database"])]
         t0 = time.perf_counter()
-        circ = synthetic_circuit(k, G, Lc, bits, seed=k)
-        t_gen = time.perf_counter() - t0
+        builder = Z.GateThreadBuilder(bits)
+        public = []
+        Z.EXAMPLES[name](builder.main(0), inp, public)
+        builder.make_public(public)
+        t_wit = time.perf_counter() - t0
+        st = builder.stats()
+        t0 = time.perf_counter()
+        rc = Z.RangeCircuit(builder, k)
+        t_lay = time.perf_counter() - t0
         t0 = time.perf_counter()
         srs = h.ParamsKZG.gen_srs(k)
         t_srs = time.perf_counter() - t0
         t0 = time.perf_counter()
-        pk = h.ProvingKey(srs, circ["cs"], circ["fixed"], circ["sigma"], circ["vk_repr"])
+        vk_repr = np.array([k, 0, 0, 0], dtype=np.uint64)
+        pk = h.ProvingKey(srs, rc.cs, rc.fixed, rc.sigma, vk_repr)
         t_pk = time.perf_counter() - t0
-        A = len(circ["advice"])
+        A = len(rc.advice)
         pinned = torch.empty((A, n, 4), dtype=torch.int64).pin_memory()
         adv = pinned.numpy().view(np.uint64)
-        for i, c in enumerate(circ["advice"]):
+        for i, c in enumerate(rc.advice):
             adv[i] = c
         cols = [adv[i] for i in range(A)]
-        circ["advice"] = None
-        proof = pk.create_proof(cols, circ["instances"], bytes(32))
+        proof = pk.create_proof(cols, rc.instances, bytes(32))
         ts, phases = [], None
         for _ in range(3):
             t0 = time.perf_counter()
-            p2 = pk.create_proof(cols, circ["instances"], bytes(32))
+            p2 = pk.create_proof(cols, rc.instances, bytes(32))
             ts.append(time.perf_counter() - t0)
             phases = pk.last_phase_ms()
             assert p2 == proof, "create_proof is not deterministic in the seed"
-        res[name] = {"prove_s": min(ts), "k": k, "advice_columns": A, "lookups": Lc, "fixed_columns": len(circ["fixed"]),
-                     "permutation_columns": len(circ["cs"]["permutation"]), "proof_bytes": len(proof),
-                     "phase_ms": {kk: round(v, 2) for kk, v in phases.items()},
-                     "setup_s": {"circuit_generation": round(t_gen, 2), "gen_srs": round(t_srs, 2), "pk_load": round(t_pk, 2)}}
+        res[f"{name}_k{k}"] = {
+            "prove_s": min(ts), "k": k, "lookup_bits": bits, "advice_cells": st["advice_cells"], "lookup_cells": st["lookup_cells"],
+            "advice_columns": rc.num_advice, "lookup_advice_columns": rc.num_lookup_advice, "fixed_columns": len(rc.fixed),
+            "permutation_columns": len(rc.cs["permutation"]), "public_inputs": rc.num_instances, "proof_bytes": len(proof),
+            "phase_ms": {kk: round(v, 2) for kk, v in phases.items()},
+            "host_s": {"witness_generation": round(t_wit, 3), "layout_and_sigma": round(t_lay, 3)},
+            "setup_s": {"gen_srs": round(t_srs, 2), "pk_load": round(t_pk, 2)}}
         pk.close()
         srs.close()
-        del pinned, adv, cols, circ
-    res["note"] = ("one real create_proof per shape (App. C column counts, satisfied synthetic halo2-base circuit, witness-shaped values, "
-                   "advice columns in pinned host memory, proof bytes out); excludes witness generation and reading the pk")
+        del pinned, adv, cols
+        rc.close()
+        builder.close()
+    res["note"] = ("one real create_proof per reference example: witness by the restated chips on the example's input, columns by the "
+                   "restated layouter, advice in pinned host memory, proof bytes out; prove_s excludes the (host, serial) witness "
+                   "generation and reading the pk, which are listed under host_s / setup_s")
     return res
 
 
-PROVE_SHAPES = {   # SURVEY.md App. C: hot-path call counts per proof (estimates; labelled as such)
-    "distances_k13": (13, 32, 26, 27, 32),
-    "query_k13": (13, 320, 310, 310, 160),
-    "kmeans_k16": (16, 1150, 1140, 1140, 96),
-    "sift_k20": (20, 360, 360, 360, 8),
+def _calls(adv, lk, fixed_consts=1):
+    """hot-path calls of one proof (SURVEY.md App. C's formulas) from the column counts: commit_lagrange / commit,
+    lagrange_to_coeff, coeff_to_extended"""
+    a, sets = adv + lk, -(-(adv + lk + fixed_consts + 1) // 2)
+    return a + 3 * lk + sets + 6, a + 3 * lk + sets, a + 1 + 3 * lk + sets
+
+
+PROVE_SHAPES = {   # hot-path call counts per proof from the EXACT column counts of the restated chips + layouter
+    # (tests/test_circuit.py; sift_k20: oracle/mock.py's cell count of nearest_vector + merkle_commitment over 1024 x 128
+    # vectors at LOOKUP_BITS = 19: 202 518 253 advice cells, 8 921 058 lookup cells); last entry: columns per batch
+    "distances_k13": (13, *_calls(9, 2), 32),
+    "query_k13": (13, *_calls(147, 19), 160),
+    "kmeans_k16": (16, *_calls(535, 72), 96),
+    "sift_k20": (20, *_calls(194, 9), 8),
 }
 
 

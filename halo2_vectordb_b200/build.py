@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
             common.insert(1, "-Xptxas=-v")
         os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
         procs, objs = [], []
-        for unit in ("h2v", "prover"):
+        for unit in ("h2v", "prover", "circuit"):
             src, obj = os.path.join(CSRC, unit + ".cu"), os.path.join(PKG, "build", unit + ".o")
             objs.append(obj)
             deps = [s_ for s_ in srcs if not s_.endswith(".cu")] + [src]

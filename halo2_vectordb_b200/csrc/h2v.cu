@@ -189,7 +189,7 @@ NttPlan ntt_plan(int L) {
 // dst != src.  Columns are independent; pass 0 goes src -> dst, later passes run in place on dst.
 int run_ntt(cudaStream_t st, const fe *src, size_t src_stride, fe *dst, size_t dst_stride, int L, const fe *tw,
             const fe *pre, uint32_t pre_mod, uint32_t n_in, const fe *post, uint32_t post_mod, uint32_t n_out,
-            size_t n_cols) {
+            size_t n_cols, uint32_t post_shift = 0) {
     if (n_cols == 0) return H2V_OK;
     if ((const void *)src == (const void *)dst) return fail(H2V_EINVAL, "run_ntt: in-place transform needs distinct buffers");
     std::call_once(g_ntt_attr_once[cur_dev()], [] {
@@ -202,6 +202,8 @@ int run_ntt(cudaStream_t st, const fe *src, size_t src_stride, fe *dst, size_t d
     p.pre_mod = pre_mod ? pre_mod : 1;
     p.post = post;
     p.post_mod = post_mod ? post_mod : 1;
+    p.post_shift = (L > 2 && post_shift >= 3 && post_shift <= 31) ? post_shift : 0;      // else the table entry `post`
+    if (p.post_shift) p.post = nullptr;
     p.n_in = n_in;
     p.n_out = n_out;
     p.L = L;
@@ -328,7 +330,7 @@ int domain_op_dev(DomRep *d, cudaStream_t st, int op, const fe *in, size_t in_st
     switch (op) {
     case H2V_OP_LAGRANGE_TO_COEFF:
         if ((rc = domain_twiddles(d, 1, &tw))) return rc;
-        return run_ntt(st, in, in_stride, out, out_stride, d->k, tw, nullptr, 1, n, dc + 3, 1, n, n_cols);
+        return run_ntt(st, in, in_stride, out, out_stride, d->k, tw, nullptr, 1, n, dc + 3, 1, n, n_cols, (uint32_t)d->k);      // 1/n = 2^-k
     case H2V_OP_COEFF_TO_LAGRANGE:
         if ((rc = domain_twiddles(d, 0, &tw))) return rc;
         return run_ntt(st, in, in_stride, out, out_stride, d->k, tw, nullptr, 1, n, nullptr, 1, n, n_cols);

@@ -33,6 +33,7 @@ struct NttPass {
     const fe *pre;          // pass 0: input i is multiplied by pre[i % pre_mod]   (nullptr: none)
     const fe *post;         // last pass: output j is multiplied by post[j % post_mod] (nullptr: none)
     uint32_t pre_mod, post_mod;
+    uint32_t post_shift;    // last pass, instead of `post`: output j is multiplied by 2^-post_shift (the 1/n of an inverse transform)
     uint32_t n_in;          // pass 0: inputs with index >= n_in read as zero
     uint32_t n_out;         // last pass: only outputs j < n_out are stored
     int L, t0, S, logT;
@@ -95,16 +96,18 @@ __device__ __forceinline__ void fe_store_global(fe *p, const fe &x) {
 __device__ __forceinline__ uint32_t bitrev(uint32_t x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
 
 // one radix-2 stage on the 8 register-resident elements: pairs (k, k + 2^U)
+// unit: 0 = every butterfly has a table twiddle; 1 = all twiddles are 1 (stage 0); 2 = e_base is 0, so the butterflies
+// whose in-thread exponent (k mod 2^U) is 0 have twiddle 1 (first round of pass 0: three of its eight products)
 template <int U>
-__device__ __forceinline__ void ntt_stage(fe (&x)[8], const fe *__restrict__ tw, uint32_t e_base, int L, bool unit) {
+__device__ __forceinline__ void ntt_stage(fe (&x)[8], const fe *__restrict__ tw, uint32_t e_base, int L, int unit) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if ((k >> U) & 1) continue;
         // lazy reduction (Harvey): t < 2r; a is brought below theta (just above 2r, see fe_csub_2m_top), so a + t and
         // a + 2r - t stay below theta + 2r < 2^256
         fe t;
-        if (unit) {
-            t = x[k + (1 << U)];       // stage 0 of pass 0 only: canonical inputs
+        if (unit == 1 || (unit == 2 && (k & ((1 << U) - 1)) == 0)) {
+            t = x[k + (1 << U)];       // twiddle 1: no product, only the range step (values < 4r -> t < 2r)
             fe_csub_2m<Fr>(t);
         } else {
             fe w = fe_load_ro(tw + e_base + ((uint32_t)(k & ((1 << U) - 1)) << (L - 1 - U)));
@@ -117,8 +120,33 @@ __device__ __forceinline__ void ntt_stage(fe (&x)[8], const fe *__restrict__ tw,
     }
 }
 
+// x * 2^-s mod r for 3 <= s <= 31 by ONE word of Montgomery reduction: q = -x r^-1 mod 2^s makes x + q r divisible by 2^s.
+// 8 wide multiply-adds instead of the 136 of a product with the field element 2^-s; x < 2^256 gives a result below
+// x / 2^s + r < 2r.  Montgomery form is preserved (the factor R rides along).
+__device__ __forceinline__ fe fe_div_pow2_lazy(const fe &x, uint32_t s) {
+    const uint32_t q = (x.v[0] * Fr::inv()) & ((1u << s) - 1u);
+    uint32_t t[9];
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        c += (uint64_t)q * Fr::m(i) + x.v[i];
+        t[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    t[8] = (uint32_t)c;
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = __funnelshift_r(t[i], t[i + 1], s);
+    return r;
+}
+
 // last pass: bring a lazily reduced value (< 4r) back to its canonical representative, folding in the post-scale
-__device__ __forceinline__ fe ntt_finish(fe x, const fe *post) {
+__device__ __forceinline__ fe ntt_finish(fe x, const fe *post, uint32_t shift) {
+    if (shift) {
+        x = fe_div_pow2_lazy(x, shift);
+        fe_reduce_once<Fr>(x);
+        return x;
+    }
     if (post) return fe_mul<Fr>(x, fe_load_ro(post));     // x < 4r, post < r: product < 2r, one conditional subtraction
     fe_csub_2m<Fr>(x);      // x < theta + 2r, slightly above 4r: two exact steps of 2r, then one of r
     fe_csub_2m<Fr>(x);
@@ -195,16 +223,16 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
             } else {
                 if (u0 <= 0) {
                     int t = t0 + bp;
-                    ntt_stage<0>(x, p.tw, jlow << (L - 1 - t), L, t == 0);
+                    ntt_stage<0>(x, p.tw, jlow << (L - 1 - t), L, t == 0 ? 1 : 0);
                 }
                 if (u0 <= 1) {
                     int t = t0 + bp + 1;
-                    ntt_stage<1>(x, p.tw, jlow << (L - 1 - t), L, false);
+                    ntt_stage<1>(x, p.tw, jlow << (L - 1 - t), L, t == 1 ? 2 : 0);
                 }
             }
             {
                 int t = t0 + bp + 2;
-                ntt_stage<2>(x, p.tw, jlow << (L - 1 - t), L, false);
+                ntt_stage<2>(x, p.tw, jlow << (L - 1 - t), L, t == 2 ? 2 : 0);
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) ntt_sm_store_slot(ntt_sm, plane1, slot[k], x[k]);
@@ -221,7 +249,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
             uint32_t j = (bitrev(tile * T + q, H) << S) | mid;
             if (p.last && j >= p.n_out) continue;
             fe x = ntt_sm_load(ntt_sm, plane1, (mid << logT) | q);
-            if (p.last) x = ntt_finish(x, p.post ? p.post + (j % p.post_mod) : nullptr);
+            if (p.last) x = ntt_finish(x, p.post ? p.post + (j % p.post_mod) : nullptr, p.post_shift);
             fe_store_global(dst + j, x);
         }
     } else {
@@ -231,7 +259,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
             size_t j = jbase + ((size_t)mid << t0) + q;
             if (p.last && j >= p.n_out) continue;
             fe x = ntt_sm_load(ntt_sm, plane1, e);
-            if (p.last) x = ntt_finish(x, p.post ? p.post + (uint32_t)(j % p.post_mod) : nullptr);
+            if (p.last) x = ntt_finish(x, p.post ? p.post + (uint32_t)(j % p.post_mod) : nullptr, p.post_shift);
             fe_store_global(dst + j, x);
         }
     }

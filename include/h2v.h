@@ -252,6 +252,69 @@ size_t h2v_proof_size(h2v_pk_t pk);
  * 6 multi-open argument */
 int h2v_pk_last_phase_ms(h2v_pk_t pk, double out[8]);
 
+/* ---- circuit builder ("next": SURVEY.md 8(f) row 4; host-side, no device needed) -----------------------------------
+ * The step before the hot path: the reference's chips produce the execution trace whose columns create_proof commits.
+ * One builder = halo2-base's GateThreadBuilder with the single Context the scaffold uses (`builder.main(0)`,
+ * /root/reference/src/scaffold/mod.rs:61) plus FixedPointChip<Fr, PRECISION_BITS>::default(lookup_bits)
+ * (/root/reference/src/gadget/fixed_point.rs:100), DistanceChip::default and VectorDBChip::default over it.
+ * Cells are named by their offset in the trace (AssignedValue); values cross the ABI in Montgomery form.
+ * Upstream panics (asserts, division by zero, index out of range) return H2V_EINVAL with the panic text. */
+typedef struct h2v_builder *h2v_builder_t;
+typedef struct h2v_layout *h2v_layout_t;
+enum {
+    /* FixedPointInstructions (fixed_point.rs:217-467), two cells in -> one cell out */
+    H2V_FP_QADD = 1, H2V_FP_QSUB, H2V_FP_QMUL, H2V_FP_QDIV, H2V_FP_QMOD, H2V_FP_QPOW, H2V_FP_QMAX, H2V_FP_QMIN, H2V_FP_BIT_XOR,
+    H2V_FP_COND_NEG, /* (a, is_neg) */
+    /* one cell in -> one cell out */
+    H2V_FP_NEG = 20, H2V_FP_QABS, H2V_FP_IS_NEG, H2V_FP_SIGN, H2V_FP_CLIP, H2V_FP_QEXP2, H2V_FP_QLOG2, H2V_FP_QEXP, H2V_FP_QLOG,
+    H2V_FP_QSQRT, H2V_FP_QSIN, H2V_FP_QCOS, H2V_FP_QTAN, H2V_FP_QSINH, H2V_FP_QCOSH, H2V_FP_QTANH,
+    /* lists: qsum(a...), inner_product(a..., b...) (two halves), polynomial(x, coefficients highest degree first) */
+    H2V_FP_QSUM = 40, H2V_FP_INNER_PRODUCT, H2V_FP_POLYNOMIAL,
+    /* DistanceInstructions (distance.rs:34-82): (a..., b...) -> distance; also the `distance` argument of
+     * nearest_vector / kmeans */
+    H2V_DISTANCE_EUCLIDEAN = 60, H2V_DISTANCE_COSINE, H2V_DISTANCE_HAMMING, H2V_DISTANCE_MANHATTAN
+};
+int h2v_builder_new(uint32_t precision_bits, uint32_t lookup_bits, h2v_builder_t *out);
+void h2v_builder_free(h2v_builder_t b);
+/* FixedPointChip::quantization / dequantization (fixed_point.rs:104-136) */
+int h2v_builder_quantize(h2v_builder_t b, const double *x, size_t n, uint64_t *out_fr);
+int h2v_builder_dequantize(h2v_builder_t b, const uint64_t *x_fr, size_t n, double *out);
+/* Context::assign_witnesses / load_constant; cell values; the scaffold's `make_public` (mod.rs:376, 400) */
+int h2v_builder_assign_witnesses(h2v_builder_t b, const uint64_t *values_fr, size_t n, int64_t *cells_out);
+int h2v_builder_load_constant(h2v_builder_t b, const uint64_t value_fr[4], int64_t *cell_out);
+int h2v_builder_cell_values(h2v_builder_t b, const int64_t *cells, size_t n, uint64_t *out_fr);
+int h2v_builder_make_public(h2v_builder_t b, const int64_t *cells, size_t n);
+/* one chip call (H2V_FP_* / H2V_DISTANCE_*) on existing cells */
+int h2v_builder_call(h2v_builder_t b, int op, const int64_t *in, size_t n_in, int64_t *out_cell);
+/* VectorDBInstructions (/root/reference/src/gadget/vectordb.rs:35-106); vectors: n_vec x dim cells, row-major */
+int h2v_builder_nearest_vector(h2v_builder_t b, int distance, const int64_t *query, const int64_t *vectors, size_t n_vec, size_t dim,
+                               int64_t *indicator_out /* n_vec */, int64_t *result_out /* dim */);
+int h2v_builder_kmeans(h2v_builder_t b, int distance, const int64_t *vectors, size_t n_vec, size_t dim, uint32_t K, uint32_t I,
+                       int64_t *centroids_out /* K x dim */, int64_t *indicators_out /* n_vec x K */);
+/* PoseidonChip::<F, T, RATE>::new(ctx, r_f, r_p) (examples/query.rs:68; T = 3, RATE = 2 only), one hash
+ * (clear / update / squeeze), and merkle_commitment over it */
+int h2v_builder_poseidon_new(h2v_builder_t b, uint32_t t, uint32_t rate, uint32_t r_f, uint32_t r_p);
+int h2v_builder_poseidon_hash(h2v_builder_t b, const int64_t *in, size_t n, int64_t *out_cell);
+int h2v_builder_merkle_commitment(h2v_builder_t b, const int64_t *vectors, size_t n_vec, size_t dim, int64_t *root_out);
+/* out: advice cells, lookup cells, distinct constants, public inputs of the trace so far */
+int h2v_builder_stats(h2v_builder_t b, uint64_t out[4]);
+/* GateThreadBuilder::config(k, Some(minimum_rows)) (mod.rs:383-388): out = num_advice, num_lookup_advice, num_fixed */
+int h2v_builder_config(h2v_builder_t b, uint32_t k, uint32_t minimum_rows, uint32_t out[3]);
+/* the raw trace (any pointer may be NULL): CANONICAL cell values (4 limbs each), gate selectors, lookup cell offsets */
+int h2v_builder_trace(h2v_builder_t b, uint64_t *advice_out, uint8_t *selector_out, int64_t *lookup_out);
+/* RangeCircuitBuilder::{mock, keygen, prover} + RangeWithInstanceCircuitBuilder (mod.rs:391-400): the columns of the
+ * circuit.  Advice: num_advice gate columns then num_lookup_advice lookup columns; fixed: the lookup table, the
+ * constants columns, one selector per gate column; sigma: the permutation over (constants, advice, instance) columns in
+ * that order.  Column pointers stay valid until h2v_layout_free. */
+int h2v_builder_layout(h2v_builder_t b, uint32_t k, uint32_t minimum_rows, h2v_layout_t *out);
+void h2v_layout_free(h2v_layout_t l);
+/* out: k, num_advice, num_lookup_advice, num_fixed (constants), public inputs, break points, lookup_bits, minimum_rows */
+int h2v_layout_info(h2v_layout_t l, uint32_t out[8]);
+int h2v_layout_columns(h2v_layout_t l, int kind /* 0 advice, 1 fixed, 2 sigma */, const uint64_t *const **cols_out, size_t *n_cols);
+int h2v_layout_instance(h2v_layout_t l, const uint64_t **out, size_t *n);
+/* the pinned break points (configs/<name>.json, mod.rs:272, 285-287) */
+int h2v_layout_break_points(h2v_layout_t l, uint32_t *out, size_t cap, size_t *n);
+
 /* ---- Fiat-Shamir transcript, RNG ("next": SURVEY.md 8(f) row 3; host-side, no device needed) ---------------------
  * snark-verifier PoseidonTranscript<G1Affine, NativeLoader, Vec<u8>, T = 5, RATE = 4, R_F = 8, R_P = 60>::new::<0>
  * (scaffold mod.rs:309-310): points are absorbed as (x mod r, y mod r), scalars as themselves; write_* also append the
