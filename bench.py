@@ -885,12 +885,24 @@ def bench_ntt(h, torch, dev, peak):
         size = 1 << L
         passes = (L + 8) // 9
         alg_bytes = 64 * size * passes * cols
-        alg_macs = (size // 2) * L * FQ_MUL_MACS * cols
+        # work(n) = (n/2) log2 n x 136 wide-MACs, + n x 136 for the iNTT / coset scaling (n = the elements
+        # that are scaled: every output of lagrange_to_coeff, the N input coefficients of coeff_to_extended)
+        bfly_macs = (size // 2) * L * FQ_MUL_MACS * cols
+        alg_macs = bfly_macs + N * FQ_MUL_MACS * cols
+        # what the kernel executes: stage 0 has unit twiddles, 3 of the 8 products of the first radix-8 round are by 1, the
+        # 1/n of lagrange_to_coeff is one word of Montgomery reduction (8 wide-MACs) instead of a product; zero-padded
+        # input (coeff_to_extended) turns the first two stages into broadcasts and leaves 3 products in the first round
+        if name == "lagrange_to_coeff":
+            exec_macs = ((size // 2) * (L - 1) - 3 * (size // 8)) * FQ_MUL_MACS * cols + 8 * size * cols
+        else:
+            exec_macs = ((size // 2) * (L - 2) - (size // 8)) * FQ_MUL_MACS * cols + N * FQ_MUL_MACS * cols
         res[name] = {"gelem_per_s": cols * size / t / 1e9, "ms": t * 1e3, "cols": cols, "log_n": L,
                      "roofline": {"bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": hbm, "unit": "GB/s",
                                   "frac": alg_bytes / t / 1e9 / hbm, "peak_source": hbm_src, "traffic": None},
                      "roofline_int": {"achieved": alg_macs / t / 1e12, "peak": peak / 1e12, "unit": "T wide-MAC/s",
-                                      "frac": alg_macs / t / peak}}
+                                      "frac": alg_macs / t / peak, "frac_butterflies_only": bfly_macs / t / peak,
+                                      "frac_executed": exec_macs / t / peak,
+                                      "algorithmic": "SURVEY.md 8(d): ((n/2) log2 n + scaled elements) x 136 wide-MACs"}}
     # end to end through the host-facing batch entry point: pinned host columns in, pinned host columns out
     import ctypes as C
     import numpy as np
