@@ -35,6 +35,8 @@ N = 1 << K
 COLS = 96                      # 96 x 2 MiB of scalars = 192 MiB per step (> 126 MB L2), tables 64 MiB more
 MSM_MACS_PER_POINT = {16: 27200, 13: 27200, 20: 20400}   # W(n) * 1360 wide-MACs
 FQ_MUL_MACS = 136
+FQ_SQR_MACS = 108                 # the dedicated squaring: 28 + 8 products, 64 + 8 reduction
+MIXED_ADD_MACS = 8 * FQ_MUL_MACS + 2 * FQ_SQR_MACS      # what msm_accumulate executes per sorted entry (SURVEY counts 10 x 136 = 1360)
 ACC_DRAM_BYTES_PER_LAUNCH = 4.17e9   # msm_accumulate_kernel, 96 columns x 2^16, c = 15: 3.761 GB read + 0.411 GB written (ncu, r01)
 SYN_A, SYN_B = 0x9E3779B97F4A7C15 >> 2, 0x632BE59BD9B4E019 >> 2
 
@@ -268,7 +270,7 @@ def _main(args, real_stdout):
     acc_ms = kernel_ms["msm_accumulate"] / args.steps           # one launch per step (all columns)
     macs = cols * N * MSM_MACS_PER_POINT[K]
     achieved = macs / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
-    executed = (cols * N * srs.info()[1] * 1360) / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
+    executed = (cols * N * srs.info()[1] * MIXED_ADD_MACS) / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None
     line = {
         "metric": "msm_mpts_per_s", "value": value, "unit": "Mpts/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -283,7 +285,7 @@ def _main(args, real_stdout):
         "kernel_ms_per_step": {k: round(v / args.steps, 4) for k, v in kernel_ms.items() if v},
         "roofline": {"bound": "int32-pipe (IMAD.WIDE)", "kernel": "msm_accumulate_kernel", "achieved": achieved,
                      "peak": peak / 1e12, "unit": "T wide-MAC/s",
-                     # frac: the wide multiply-adds the kernel EXECUTES (17 signed windows x 1360 per point) over the measured peak;
+                     # frac: the wide multiply-adds the kernel EXECUTES (17 signed windows x 1304 per point: 8 products + 2 dedicated squarings per mixed addition) over the measured peak;
                      # frac_algorithmic: SURVEY 8(d)'s count (20 unsigned windows) over the same peak -- above 1 because the
                      # precomputed-table layout needs fewer windows, not because the pipe runs faster than its peak
                      "frac": (executed / (peak / 1e12)) if executed else None,
@@ -851,7 +853,7 @@ def bench_witness(h, torch, dev, srs, peak):
     entries = h.last_msm_entries()
     if entries and acc_s > 0:
         res["roofline"] = {"bound": "int32-pipe (IMAD.WIDE)", "kernel": "msm_accumulate_kernel", "unit": "T wide-MAC/s",
-                           "executed": entries * 1360 / acc_s / 1e12, "peak": peak / 1e12, "frac": entries * 1360 / acc_s / peak,
+                           "executed": entries * MIXED_ADD_MACS / acc_s / 1e12, "peak": peak / 1e12, "frac": entries * MIXED_ADD_MACS / acc_s / peak,
                            "mixed_additions_per_launch": int(entries)}
     return res
 

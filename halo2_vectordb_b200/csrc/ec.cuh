@@ -121,10 +121,10 @@ __device__ __forceinline__ void xyzz_add_mixed_lazy(xyzz &acc, const affine &q) 
         else acc = xyzz_identity();
         return;
     }
-    fe pp = fe_mul_lazy<Fq>(p, p);
+    fe pp = fe_sqr_lazy<Fq>(p);
     fe ppp = fe_mul_lazy<Fq>(p, pp);
     fe qq = fe_mul_lazy<Fq>(acc.x, pp);
-    fe x3 = fe_sub_lazy<Fq>(fe_sub_lazy<Fq>(fe_sub_lazy<Fq>(fe_mul_lazy<Fq>(r, r), ppp), qq), qq);
+    fe x3 = fe_sub_lazy<Fq>(fe_sub_lazy<Fq>(fe_sub_lazy<Fq>(fe_sqr_lazy<Fq>(r), ppp), qq), qq);
     fe y3 = fe_sub_lazy<Fq>(fe_mul_lazy<Fq>(r, fe_sub_lazy<Fq>(qq, x3)), fe_mul_lazy<Fq>(acc.y, ppp));
     acc.x = x3;
     acc.y = y3;

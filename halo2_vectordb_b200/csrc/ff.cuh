@@ -191,16 +191,13 @@ template <class F> H2V_HD fe fe_dbl(const fe &a) { return fe_add<F>(a, a); }
 #ifdef __CUDA_ARCH__
 // acc[0..7] = sum_t (x[2t] * y) << (64 t)            (four independent 64-bit products)
 __device__ __forceinline__ void row_mul(uint32_t *acc, const uint32_t *x, uint32_t y) {
-    asm("mul.lo.u32 %0, %8, %12;\n\t"
-        "mul.hi.u32 %1, %8, %12;\n\t"
-        "mul.lo.u32 %2, %9, %12;\n\t"
-        "mul.hi.u32 %3, %9, %12;\n\t"
-        "mul.lo.u32 %4, %10, %12;\n\t"
-        "mul.hi.u32 %5, %10, %12;\n\t"
-        "mul.lo.u32 %6, %11, %12;\n\t"
-        "mul.hi.u32 %7, %11, %12;"
-        : "=&r"(acc[0]), "=&r"(acc[1]), "=&r"(acc[2]), "=&r"(acc[3]), "=&r"(acc[4]), "=&r"(acc[5]), "=&r"(acc[6]), "=&r"(acc[7])
-        : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(y));
+    // one IMAD.WIDE.U32 per product (a mul.lo / mul.hi pair is NOT fused by ptxas: two multiplier-pipe instructions)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const uint64_t p = (uint64_t)x[2 * t] * y;
+        acc[2 * t] = (uint32_t)p;
+        acc[2 * t + 1] = (uint32_t)(p >> 32);
+    }
 }
 // acc[0..7] += sum_t (x[2t] * y) << (64 t); returns the carry out of limb 7 (0 or 1)
 __device__ __forceinline__ uint32_t row_mad(uint32_t *acc, const uint32_t *x, uint32_t y) {
@@ -309,6 +306,210 @@ template <class F> __device__ __forceinline__ fe fe_mul(const fe &a, const fe &b
     fe_reduce_once<F>(r);
     return r;
 }
+
+// ---- dedicated Montgomery squaring: 108 wide multiply-adds instead of 136.
+// a^2 = 2 S + D with S the 28 products a_i a_j (i < j) and D the 8 squares a_i^2; the 512-bit T = 2 S + D is then
+// reduced by eight CIOS rows that carry no partial product (the quotient digits only depend on the low half, so the
+// rows run on a window seeded with T[0..8) whose top limbs are fresh, exactly like fe_mul_lazy's, and T[8..16) is
+// added at the end).  S is accumulated on an even / odd accumulator pair like the product rows: E holds the products
+// that land on an even limb, O (one limb up) those on an odd limb, so every row is one mad.lo.cc / madc.hi.cc chain.
+// For a < 2m the result is below 4 m^2 / R + m + 1 <= 2m, as for fe_mul_lazy.
+template <class F> __device__ __forceinline__ void red_row(uint32_t *lo, uint32_t *hi) {
+    // fe_mul_lazy's mont_row<F, false> without its partial product: `hi` is the old low accumulator (limb 0 zero, limb 1
+    // the stray), `lo` the old high one
+    uint32_t mm[8], nh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mm[i] = F::m(i);
+    asm("add.cc.u32 %8, %8, %9;\n\t"
+        "addc.cc.u32 %0, %10, 0;\n\t"
+        "addc.cc.u32 %1, %11, 0;\n\t"
+        "addc.cc.u32 %2, %12, 0;\n\t"
+        "addc.cc.u32 %3, %13, 0;\n\t"
+        "addc.cc.u32 %4, %14, 0;\n\t"
+        "addc.cc.u32 %5, %15, 0;\n\t"
+        "addc.cc.u32 %6, 0, 0;\n\t"
+        "addc.u32 %7, 0, 0;"
+        : "=&r"(nh[0]), "=&r"(nh[1]), "=&r"(nh[2]), "=&r"(nh[3]), "=&r"(nh[4]), "=&r"(nh[5]), "=&r"(nh[6]), "=&r"(nh[7]), "+r"(lo[0])
+        : "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hi[i] = nh[i];
+    uint32_t q = lo[0] * F::inv();
+    row_mad(hi, mm + 1, q);
+    row_mad_top(lo, mm, q, hi[7]);
+}
+template <class F> __device__ __forceinline__ fe fe_sqr_lazy(const fe &x) {
+    const uint32_t *a = x.v;
+    uint32_t E2, E3, E4, E5, E6, E7, E8, E9, E10, E11, E12, E13;
+    uint32_t O[14];
+    // row a0: E <- a0 * (a2, a4, a6) on limbs 2..7, O <- a0 * (a1, a3, a5, a7) on limbs 0..7 (fresh limbs: plain products)
+    {
+        const uint64_t p2 = (uint64_t)a[0] * a[2], p4 = (uint64_t)a[0] * a[4], p6 = (uint64_t)a[0] * a[6];
+        E2 = (uint32_t)p2; E3 = (uint32_t)(p2 >> 32);
+        E4 = (uint32_t)p4; E5 = (uint32_t)(p4 >> 32);
+        E6 = (uint32_t)p6; E7 = (uint32_t)(p6 >> 32);
+    }
+    row_mul(O, a + 1, a[0]);
+    // row a1: E += a1 * (a3, a5, a7) on limbs 4..9 (8, 9 fresh); O += a1 * (a2, a4, a6) on limbs 2..7, carry into 8
+    asm("mad.lo.cc.u32 %0, %6, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %8, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %8, %3;\n\t"
+        "madc.lo.cc.u32 %4, %6, %9, 0;\n\t"
+        "madc.hi.u32 %5, %6, %9, 0;"
+        : "+r"(E4), "+r"(E5), "+r"(E6), "+r"(E7), "=&r"(E8), "=&r"(E9)
+        : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]));
+    asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %8, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+        "madc.lo.cc.u32 %4, %7, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %7, %10, %5;\n\t"
+        "addc.u32 %6, 0, 0;"
+        : "+r"(O[2]), "+r"(O[3]), "+r"(O[4]), "+r"(O[5]), "+r"(O[6]), "+r"(O[7]), "=&r"(O[8])
+        : "r"(a[1]), "r"(a[2]), "r"(a[4]), "r"(a[6]));
+    // row a2: E += a2 * (a4, a6) on limbs 6..9, carry into 10; O += a2 * (a3, a5, a7) on limbs 4..9 (9 fresh)
+    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.lo.cc.u32 %2, %5, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %5, %7, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+r"(E6), "+r"(E7), "+r"(E8), "+r"(E9), "=&r"(E10)
+        : "r"(a[2]), "r"(a[4]), "r"(a[6]));
+    asm("mad.lo.cc.u32 %0, %6, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %8, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %8, %3;\n\t"
+        "madc.lo.cc.u32 %4, %6, %9, %4;\n\t"
+        "madc.hi.u32 %5, %6, %9, 0;"
+        : "+r"(O[4]), "+r"(O[5]), "+r"(O[6]), "+r"(O[7]), "+r"(O[8]), "=&r"(O[9])
+        : "r"(a[2]), "r"(a[3]), "r"(a[5]), "r"(a[7]));
+    // row a3: E += a3 * (a5, a7) on limbs 8..11 (11 fresh); O += a3 * (a4, a6) on limbs 6..9, carry into 10
+    asm("mad.lo.cc.u32 %0, %4, %5, %0;\n\t"
+        "madc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+        "madc.lo.cc.u32 %2, %4, %6, %2;\n\t"
+        "madc.hi.u32 %3, %4, %6, 0;"
+        : "+r"(E8), "+r"(E9), "+r"(E10), "=&r"(E11)
+        : "r"(a[3]), "r"(a[5]), "r"(a[7]));
+    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.lo.cc.u32 %2, %5, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %5, %7, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+r"(O[6]), "+r"(O[7]), "+r"(O[8]), "+r"(O[9]), "=&r"(O[10])
+        : "r"(a[3]), "r"(a[4]), "r"(a[6]));
+    // row a4: E += a4 * a6 on limbs 10..11, carry into 12; O += a4 * (a5, a7) on limbs 8..11 (11 fresh)
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, 0, 0;"
+        : "+r"(E10), "+r"(E11), "=&r"(E12)
+        : "r"(a[4]), "r"(a[6]));
+    asm("mad.lo.cc.u32 %0, %4, %5, %0;\n\t"
+        "madc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+        "madc.lo.cc.u32 %2, %4, %6, %2;\n\t"
+        "madc.hi.u32 %3, %4, %6, 0;"
+        : "+r"(O[8]), "+r"(O[9]), "+r"(O[10]), "=&r"(O[11])
+        : "r"(a[4]), "r"(a[5]), "r"(a[7]));
+    // row a5: E += a5 * a7 on limbs 12..13 (13 fresh); O += a5 * a6 on limbs 10..11, carry into 12
+    asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
+        "madc.hi.u32 %1, %2, %3, 0;"
+        : "+r"(E12), "=&r"(E13)
+        : "r"(a[5]), "r"(a[7]));
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, 0, 0;"
+        : "+r"(O[10]), "+r"(O[11]), "=&r"(O[12])
+        : "r"(a[5]), "r"(a[6]));
+    // row a6: O += a6 * a7 on limbs 12..13 (13 fresh)
+    asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
+        "madc.hi.u32 %1, %2, %3, 0;"
+        : "+r"(O[12]), "=&r"(O[13])
+        : "r"(a[6]), "r"(a[7]));
+    // S = E + (O << 32): limbs 1..15 (limb 0 is zero)
+    uint32_t S[16];
+    S[0] = 0;
+    S[1] = O[0];
+    asm("add.cc.u32 %0, %14, %28;\n\t"
+        "addc.cc.u32 %1, %15, %29;\n\t"
+        "addc.cc.u32 %2, %16, %30;\n\t"
+        "addc.cc.u32 %3, %17, %31;\n\t"
+        "addc.cc.u32 %4, %18, %32;\n\t"
+        "addc.cc.u32 %5, %19, %33;\n\t"
+        "addc.cc.u32 %6, %20, %34;\n\t"
+        "addc.cc.u32 %7, %21, %35;\n\t"
+        "addc.cc.u32 %8, %22, %36;\n\t"
+        "addc.cc.u32 %9, %23, %37;\n\t"
+        "addc.cc.u32 %10, %24, %38;\n\t"
+        "addc.cc.u32 %11, %25, %39;\n\t"
+        "addc.cc.u32 %12, %26, 0;\n\t"
+        "addc.u32 %13, 0, 0;"
+        : "=&r"(S[2]), "=&r"(S[3]), "=&r"(S[4]), "=&r"(S[5]), "=&r"(S[6]), "=&r"(S[7]), "=&r"(S[8]), "=&r"(S[9]), "=&r"(S[10]),
+          "=&r"(S[11]), "=&r"(S[12]), "=&r"(S[13]), "=&r"(S[14]), "=&r"(S[15])
+        : "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]),
+          "r"(O[12]), "r"(O[13]), "r"(0u),
+          "r"(E2), "r"(E3), "r"(E4), "r"(E5), "r"(E6), "r"(E7), "r"(E8), "r"(E9), "r"(E10), "r"(E11), "r"(E12), "r"(E13));
+    // T = 2 S + D
+    uint32_t T[16];
+    T[0] = 0;
+#pragma unroll
+    for (int k = 1; k < 16; ++k) T[k] = __funnelshift_l(S[k - 1], S[k], 1);
+    asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+        "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+        "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+        "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+        "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+        "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+        "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+        "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+        "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+        "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+        "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+        "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+        "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+        "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+        "madc.hi.u32 %15, %23, %23, %15;"
+        : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "+r"(T[8]), "+r"(T[9]),
+          "+r"(T[10]), "+r"(T[11]), "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+    // Montgomery reduction of the low half
+    uint32_t e[8], o[8], mm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        e[i] = T[i];
+        mm[i] = F::m(i);
+    }
+    {
+        uint32_t q = e[0] * F::inv();
+        row_mul(o, mm + 1, q);
+        row_mad_top(e, mm, q, o[7]);
+    }
+    red_row<F>(o, e);
+    red_row<F>(e, o);
+    red_row<F>(o, e);
+    red_row<F>(e, o);
+    red_row<F>(o, e);
+    red_row<F>(e, o);
+    red_row<F>(o, e);
+    // low accumulator = o (o[0] == 0), high = e: result = e + (o >> 32) + T[8..16)
+    fe r;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, 0;"
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7])
+        : "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]),
+          "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
+    fe hi_half;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hi_half.v[i] = T[8 + i];
+    fe out;
+    raw_add(out.v, r.v, hi_half.v);
+    return out;
+}
 #else
 template <class F> inline fe fe_mul(const fe &a, const fe &b) {
     uint32_t t[10] = {0};
@@ -340,6 +541,7 @@ template <class F> inline fe fe_mul(const fe &a, const fe &b) {
     return r;
 }
 template <class F> inline fe fe_mul_lazy(const fe &a, const fe &b) { return fe_mul<F>(a, b); }   // host: always reduced
+template <class F> inline fe fe_sqr_lazy(const fe &a) { return fe_mul<F>(a, a); }
 #endif
 // if t >= 2m: t -= 2m   (lazy-reduction helpers for the NTT butterflies: values live in [0, 4m), 4m < 2^256)
 template <class F> H2V_HD uint32_t fe_2m_limb(int i) { return (F::m(i) << 1) | (i ? (F::m(i - 1) >> 31) : 0u); }
@@ -403,7 +605,15 @@ template <class F> H2V_HD fe fe_sub_plus_2m(const fe &a, const fe &b) {
     raw_add(r.v, a.v, d.v);
     return r;
 }
-template <class F> H2V_HD fe fe_sqr(const fe &a) { return fe_mul<F>(a, a); }
+template <class F> H2V_HD fe fe_sqr(const fe &a) {
+#ifdef __CUDA_ARCH__
+    fe r = fe_sqr_lazy<F>(a);      // a canonical: the dedicated squaring (108 instead of 136 wide multiply-adds)
+    fe_reduce_once<F>(r);
+    return r;
+#else
+    return fe_mul<F>(a, a);
+#endif
+}
 
 template <class F> H2V_HD fe fe_to_mont(const fe &canon) {
     fe r2;

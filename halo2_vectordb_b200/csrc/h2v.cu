@@ -2034,7 +2034,15 @@ template <class F> __global__ void selftest_field_kernel(int op, const fe *a, co
     else if (op == 1) r = fe_add<F>(x, y);
     else if (op == 2) r = fe_sub<F>(x, y);
     else if (op == 3) r = fe_inv<F>(x);
-    else r = fe_inv_fast<F>(x);
+    else if (op == 4) r = fe_inv_fast<F>(x);
+    else if (op == 5) r = fe_sqr<F>(x);                       // dedicated squaring, canonical input
+    else {                                                      // op 6: the squaring on a lazily reduced input x + m
+        fe m_;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m_.v[k] = F::m(k);
+        r = fe_sqr_lazy<F>(fe_add_raw(x, m_));
+        fe_reduce_once<F>(r);
+    }
     o[i] = r;
 }
 __global__ void selftest_group_kernel(int mode, const affine *p, const affine *q, affine *o, size_t n) {

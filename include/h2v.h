@@ -348,7 +348,8 @@ int h2v_fr_to_repr(const uint64_t *fr_mont, size_t n, uint8_t *out);
 
 /* ---- device self-tests (used by tests/ to localise failures; not part of the drop-in surface) */
 /* out[i] = a[i] (op) b[i] computed by the device field routines; field 0 = Fr, 1 = Fq;
- * op 0 mul, 1 add, 2 sub, 3 inverse by Fermat (b ignored), 4 inverse by binary Euclid (b ignored) */
+ * op 0 mul, 1 add, 2 sub, 3 inverse by Fermat (b ignored), 4 inverse by binary Euclid (b ignored),
+ * 5 the dedicated squaring of a (b ignored), 6 the same on the lazily reduced representative a + m */
 int h2v_selftest_field(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);
 /* out_affine[i] = affine(p[i] + q[i]) through the XYZZ mixed add (mode 0), full add (mode 1) or
  * doubling of p (mode 2); p, q affine */

@@ -31,6 +31,9 @@ def test_device_field_ops(h2v, field, nm):
         got = h2v.selftest_field(field, op, a, b)
         exp = np.stack([O.field_op(f"{nm}_{opn}", a[i], b[i]) for i in range(len(a))])
         assert (got == exp).all(), opn
+    sq = np.stack([O.field_op(f"{nm}_mul", a[i], a[i]) for i in range(len(a))])
+    for op in (5, 6):           # the dedicated Montgomery squaring on canonical inputs and on lazily reduced ones (x + m)
+        assert (h2v.selftest_field(field, op, a) == sq).all(), op
     exp = np.stack([O.field_op(f"{nm}_inv", a[i]) for i in range(1, 65)])
     for op in (3, 4):           # Fermat and binary-Euclid inversions
         assert (h2v.selftest_field(field, op, a[1:65]) == exp).all(), op
