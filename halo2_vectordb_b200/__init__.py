@@ -43,6 +43,14 @@ ABI_SYMBOLS = [
     "h2v_srs_gen", "h2v_g2_mul_generator", "h2v_srs_write_file", "h2v_srs_read_file",
     "h2v_selftest_field", "h2v_selftest_group", "h2v_synthetic_bases", "h2v_selftest_imad_peak", "h2v_selftest_imad_probe", "h2v_selftest_op_rate", "h2v_set_tuning", "h2v_launch_count", "h2v_last_kernel_ms", "h2v_last_msm_entries",
 ]
+BUILDER_SYMBOLS = [      # the circuit builder (halo2_vectordb_b200.circuit)
+    "h2v_builder_new", "h2v_builder_free", "h2v_builder_quantize", "h2v_builder_dequantize", "h2v_builder_assign_witnesses",
+    "h2v_builder_load_constant", "h2v_builder_cell_values", "h2v_builder_make_public", "h2v_builder_call",
+    "h2v_builder_nearest_vector", "h2v_builder_kmeans", "h2v_builder_poseidon_new", "h2v_builder_poseidon_hash",
+    "h2v_builder_merkle_commitment", "h2v_builder_stats", "h2v_builder_config", "h2v_builder_trace", "h2v_builder_layout",
+    "h2v_layout_free", "h2v_layout_info", "h2v_layout_columns", "h2v_layout_instance", "h2v_layout_break_points",
+]
+ABI_SYMBOLS += BUILDER_SYMBOLS
 
 
 class H2VError(RuntimeError):

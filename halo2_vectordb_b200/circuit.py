@@ -18,7 +18,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import H2VError, _check, _fr, _fr1, _ptr, lib
+from . import BUILDER_SYMBOLS, H2VError, _check, _fr, _fr1, _ptr, lib
 
 (FP_QADD, FP_QSUB, FP_QMUL, FP_QDIV, FP_QMOD, FP_QPOW, FP_QMAX, FP_QMIN, FP_BIT_XOR, FP_COND_NEG) = range(1, 11)
 (FP_NEG, FP_QABS, FP_IS_NEG, FP_SIGN, FP_CLIP, FP_QEXP2, FP_QLOG2, FP_QEXP, FP_QLOG, FP_QSQRT, FP_QSIN, FP_QCOS, FP_QTAN,
@@ -26,13 +26,6 @@ from . import H2VError, _check, _fr, _fr1, _ptr, lib
 FP_QSUM, FP_INNER_PRODUCT, FP_POLYNOMIAL = 40, 41, 42
 DISTANCE_EUCLIDEAN, DISTANCE_COSINE, DISTANCE_HAMMING, DISTANCE_MANHATTAN = 60, 61, 62, 63
 
-BUILDER_SYMBOLS = [
-    "h2v_builder_new", "h2v_builder_free", "h2v_builder_quantize", "h2v_builder_dequantize", "h2v_builder_assign_witnesses",
-    "h2v_builder_load_constant", "h2v_builder_cell_values", "h2v_builder_make_public", "h2v_builder_call",
-    "h2v_builder_nearest_vector", "h2v_builder_kmeans", "h2v_builder_poseidon_new", "h2v_builder_poseidon_hash",
-    "h2v_builder_merkle_commitment", "h2v_builder_stats", "h2v_builder_config", "h2v_builder_trace", "h2v_builder_layout",
-    "h2v_layout_free", "h2v_layout_info", "h2v_layout_columns", "h2v_layout_instance", "h2v_layout_break_points",
-]
 
 _i64p = C.POINTER(C.c_int64)
 _u64pp = C.POINTER(C.POINTER(C.c_uint64))
