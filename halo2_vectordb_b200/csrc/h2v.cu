@@ -293,8 +293,9 @@ struct DomRep {
     DevBuf tw[4];   // 0: omega, 1: omega_inv, 2: ext_omega, 3: ext_omega_inv
     bool tw_ready[4] = {false, false, false, false};
     DevBuf stage_a, stage_b, pipe_a, pipe_b, pipe_a2, pipe_b2;
+    DevBuf peer_in, peer_out;      // columns of another device's batch (h2v_domain_transform_dev with several devices)
     cudaStream_t stream = nullptr, pipe_stream = nullptr, pipe_stream2 = nullptr;
-    std::mutex mu, tw_mu;
+    std::mutex mu, tw_mu, peer_mu;
     struct Lane {            // small host-facing transforms from concurrent caller threads (see SrsRep::Lane)
         std::mutex mu;
         cudaStream_t st = nullptr;
@@ -688,6 +689,8 @@ struct SrsRep {
     MsmCfg cfg[2];
     MsmWorkspace ws, ws2;
     DevBuf stage, out;
+    DevBuf peer_stage, peer_out;      // columns of another device's batch pulled over NVLink (h2v_commit_batch_dev with several devices)
+    std::mutex peer_mu;               // held from the pull to the write-back
     cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, computed[2] = {nullptr, nullptr};
     std::mutex mu;
@@ -972,6 +975,8 @@ static void rep_srs_free(SrsRep *s) {
     }
     s->stage.release();
     s->out.release();
+    s->peer_stage.release();
+    s->peer_out.release();
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) {
         cudaStreamDestroy(s->copy_stream);
@@ -1284,6 +1289,8 @@ static void rep_domain_free(DomRep *d) {
     d->pipe_b.release();
     d->pipe_a2.release();
     d->pipe_b2.release();
+    d->peer_in.release();
+    d->peer_out.release();
     if (d->pipe_stream) cudaStreamDestroy(d->pipe_stream);
     if (d->pipe_stream2) cudaStreamDestroy(d->pipe_stream2);
     for (auto &ln : d->lanes) {
@@ -2489,8 +2496,53 @@ int h2v_commit_batch_dev(h2v_srs_t h, int basis, const void *d_polys, size_t col
     if (!h) return fail(H2V_EINVAL, "commit: NULL srs");
     SrsRep *r = srs_on(h, device_of(d_polys));
     if (!r) return fail(H2V_EINVAL, "commit: the columns live on device %d, which is not in the h2v_init list", device_of(d_polys));
+    const size_t G = h->rep.size();
+    static const bool no_split = getenv("H2V_NO_PEER_SPLIT") != nullptr;
+    if (G == 1 || no_split || n_polys < 8 * G || len == 0 || device_of(d_out_affine) != r->dev) {
+        t_dev = r->dev;
+        return rep_commit_batch_dev(r, basis, d_polys, col_stride, n_polys, len, d_out_affine);
+    }
+    // Several devices, one resident batch (a phase of create_proof): the columns are independent, so the batch is cut
+    // into G contiguous blocks; the owner commits its block in place, every other device pulls its block over NVLink
+    // (peer copy, 32 B x len per column against ~10^3 x that in multiplier work), commits it against its own SRS replica
+    // and writes the 64-byte results back into the owner's output array.  No collective; results in column order.
+    const size_t per = (n_polys + G - 1) / G;
+    const fe *src = (const fe *)d_polys;
+    affine *dst = (affine *)d_out_affine;
+    int rc = fan_out(G, [&](size_t d) -> int {
+        SrsRep *rep = h->rep[d];
+        const size_t c0 = std::min(n_polys, d * per), cnt = std::min(n_polys, c0 + per) - c0;
+        if (!cnt) return H2V_OK;
+        t_dev = rep->dev;
+        if (rep == r) return rep_commit_batch_dev(rep, basis, src + c0 * col_stride, col_stride, cnt, len, dst + c0);
+        int rc2 = use_device();
+        if (rc2) return rc2;
+        std::lock_guard<std::mutex> plk(rep->peer_mu);
+        {
+            std::lock_guard<std::mutex> lk(rep->mu);
+            if ((rc2 = rep->peer_stage.ensure(cnt * len * sizeof(fe)))) return rc2;
+            if ((rc2 = rep->peer_out.ensure(cnt * sizeof(affine)))) return rc2;
+            cudaError_t e = cudaSuccess;
+            if (col_stride == len) {
+                e = cudaMemcpyPeerAsync(rep->peer_stage.p, rep->dev, src + c0 * col_stride, r->dev, cnt * len * sizeof(fe), rep->stream);
+            } else {
+                for (size_t c = 0; c < cnt && e == cudaSuccess; ++c)
+                    e = cudaMemcpyPeerAsync(rep->peer_stage.as<fe>() + c * len, rep->dev, src + (c0 + c) * col_stride, r->dev,
+                                            len * sizeof(fe), rep->stream);
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(rep->stream);
+            if (e != cudaSuccess) return fail(H2V_ECUDA, "commit: peer copy %d -> %d: %s", r->dev, rep->dev, cudaGetErrorString(e));
+        }
+        if ((rc2 = rep_commit_batch_dev(rep, basis, rep->peer_stage.p, len, cnt, len, rep->peer_out.p))) return rc2;
+        // (cudaMemcpyPeer returns before the copy has landed and does not order against non-blocking streams: copy on the
+        // replica's stream and wait for it)
+        cudaError_t e = cudaMemcpyPeerAsync(dst + c0, r->dev, rep->peer_out.p, rep->dev, cnt * sizeof(affine), rep->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(rep->stream);
+        if (e != cudaSuccess) return fail(H2V_ECUDA, "commit: peer copy of the results: %s", cudaGetErrorString(e));
+        return H2V_OK;
+    });
     t_dev = r->dev;
-    return rep_commit_batch_dev(r, basis, d_polys, col_stride, n_polys, len, d_out_affine);
+    return rc;
 }
 // Host columns: with several devices column j goes to device j mod G (each device has its own PCIe link and SRS
 // replica, no collective); the commitments come back in column order.
@@ -2571,7 +2623,58 @@ int h2v_domain_fill(h2v_domain_t h, int basis, const uint64_t scalar[4], uint64_
     t_dev = r->dev;
 int h2v_domain_transform_dev(h2v_domain_t h, int op, const void *d_in, size_t in_stride, void *d_out, size_t out_stride, size_t n_cols) {
     H2V_DOM_ON(d_in)
-    return rep_domain_transform_dev(r, op, d_in, in_stride, d_out, out_stride, n_cols);
+    const size_t G = h->rep.size();
+    static const bool no_split = getenv("H2V_NO_PEER_SPLIT") != nullptr;
+    if (G == 1 || no_split || n_cols < 8 * G || op < 0 || op > H2V_OP_DIVIDE_BY_VANISHING || !d_out || device_of(d_out) != r->dev)
+        return rep_domain_transform_dev(r, op, d_in, in_stride, d_out, out_stride, n_cols);
+    // Several devices, one resident batch: contiguous blocks of columns, as h2v_commit_batch_dev splits them.  A device
+    // other than the owner pulls its input columns over NVLink, transforms them with its own twiddle tables and pushes
+    // the output columns back (32 B per input element in, 32 B per output element out: worth it for the extended
+    // transforms, whose 4n-point butterflies dominate).
+    const size_t nin = op_in_len(r, op), nout = op_out_len(r, op);
+    const size_t work_len = (size_t)1 << (op >= H2V_OP_COEFF_TO_EXTENDED ? r->ek : r->k);
+    if (in_stride < nin || out_stride < work_len) return rep_domain_transform_dev(r, op, d_in, in_stride, d_out, out_stride, n_cols);
+    const size_t per = (n_cols + G - 1) / G;
+    const fe *src = (const fe *)d_in;
+    fe *dst = (fe *)d_out;
+    int rc = fan_out(G, [&](size_t d) -> int {
+        DomRep *rep = h->rep[d];
+        const size_t c0 = std::min(n_cols, d * per), cnt = std::min(n_cols, c0 + per) - c0;
+        if (!cnt) return H2V_OK;
+        t_dev = rep->dev;
+        if (rep == r) return rep_domain_transform_dev(rep, op, src + c0 * in_stride, in_stride, dst + c0 * out_stride, out_stride, cnt);
+        int rc2 = use_device();
+        if (rc2) return rc2;
+        std::lock_guard<std::mutex> plk(rep->peer_mu);
+        cudaError_t e = cudaSuccess;
+        {
+            std::lock_guard<std::mutex> lk(rep->mu);
+            if ((rc2 = rep->peer_in.ensure(cnt * nin * sizeof(fe)))) return rc2;
+            if ((rc2 = rep->peer_out.ensure(cnt * work_len * sizeof(fe)))) return rc2;
+            if (in_stride == nin) {
+                e = cudaMemcpyPeerAsync(rep->peer_in.p, rep->dev, src + c0 * in_stride, r->dev, cnt * nin * sizeof(fe), rep->stream);
+            } else {
+                for (size_t c = 0; c < cnt && e == cudaSuccess; ++c)
+                    e = cudaMemcpyPeerAsync(rep->peer_in.as<fe>() + c * nin, rep->dev, src + (c0 + c) * in_stride, r->dev, nin * sizeof(fe),
+                                            rep->stream);
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(rep->stream);
+            if (e != cudaSuccess) return fail(H2V_ECUDA, "transform: peer copy %d -> %d: %s", r->dev, rep->dev, cudaGetErrorString(e));
+        }
+        if ((rc2 = rep_domain_transform_dev(rep, op, rep->peer_in.p, nin, rep->peer_out.p, work_len, cnt))) return rc2;
+        if (out_stride == work_len && nout == work_len) {
+            e = cudaMemcpyPeerAsync(dst + c0 * out_stride, r->dev, rep->peer_out.p, rep->dev, cnt * nout * sizeof(fe), rep->stream);
+        } else {
+            for (size_t c = 0; c < cnt && e == cudaSuccess; ++c)
+                e = cudaMemcpyPeerAsync(dst + (c0 + c) * out_stride, r->dev, rep->peer_out.as<fe>() + c * work_len, rep->dev,
+                                        nout * sizeof(fe), rep->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(rep->stream);
+        if (e != cudaSuccess) return fail(H2V_ECUDA, "transform: peer copy of the results: %s", cudaGetErrorString(e));
+        return H2V_OK;
+    });
+    t_dev = r->dev;
+    return rc;
 }
 int h2v_domain_transform_batch(h2v_domain_t h, int op, const uint64_t *const *in, uint64_t *const *out, size_t n_cols) {
     if (!h) return fail(H2V_EINVAL, "transform: NULL domain");

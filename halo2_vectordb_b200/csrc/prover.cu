@@ -224,16 +224,13 @@ __global__ void __launch_bounds__(256) chacha_fr_kernel(ChaChaKey key, uint64_t 
 // ------------------------------------------------------------------ small host helpers
 inline const uint64_t *u64(const Fr64 &a) { return a.l; }
 
-// coefficients of the polynomial of degree < m through (xs[i], ys[i])   (arithmetic.rs lagrange_interpolate)
-std::vector<Fr64> lagrange_interpolate(const std::vector<Fr64> &xs, const std::vector<Fr64> &ys) {
+// Lagrange basis over the points xs: basis[j] = coefficients of prod_{k != j} (X - x_k) / prod_{k != j} (x_j - x_k).
+// One rotation set shares its points between hundreds of polynomials, so the basis (and its m inversions) is built once
+// per set; the polynomial through (xs[i], ys[i]) (arithmetic.rs lagrange_interpolate) is then sum_j ys[j] basis[j].
+std::vector<std::vector<Fr64>> lagrange_basis(const std::vector<Fr64> &xs) {
     const size_t m = xs.size();
-    std::vector<Fr64> out(m, frh::zero());
-    if (m == 1) {
-        out[0] = ys[0];
-        return out;
-    }
+    std::vector<std::vector<Fr64>> basis(m);
     for (size_t j = 0; j < m; ++j) {
-        // numerator prod_{k != j} (X - x_k), denominator prod_{k != j} (x_j - x_k)
         std::vector<Fr64> num(1, frh::ONE);
         Fr64 den = frh::ONE;
         for (size_t k = 0; k < m; ++k) {
@@ -246,9 +243,17 @@ std::vector<Fr64> lagrange_interpolate(const std::vector<Fr64> &xs, const std::v
             num.swap(nx);
             den = frh::mul(den, frh::sub(xs[j], xs[k]));
         }
-        const Fr64 sc = frh::mul(ys[j], frh::inv(den));
-        for (size_t t = 0; t < m; ++t) out[t] = frh::add(out[t], frh::mul(num[t], sc));
+        const Fr64 di = m == 1 ? frh::ONE : frh::inv(den);
+        for (Fr64 &c : num) c = frh::mul(c, di);
+        basis[j].swap(num);
     }
+    return basis;
+}
+std::vector<Fr64> lagrange_interpolate(const std::vector<std::vector<Fr64>> &basis, const std::vector<Fr64> &ys) {
+    const size_t m = basis.size();
+    std::vector<Fr64> out(m, frh::zero());
+    for (size_t j = 0; j < m; ++j)
+        for (size_t t = 0; t < m; ++t) out[t] = frh::add(out[t], frh::mul(basis[j][t], ys[j]));
     return out;
 }
 Fr64 eval_small(const std::vector<Fr64> &poly, const Fr64 &x) {
@@ -305,6 +310,7 @@ int commit_dev(h2v_pk *pk, int basis, const fe *cols, size_t n_cols, std::vector
     if (!n_cols) return H2V_OK;
     H2V_TRY(pk->commits.ensure(n_cols * sizeof(affine)));
     H2V_TRY(h2v_commit_batch_dev(pk->srs, basis, cols, pk->n, n_cols, pk->n, pk->commits.p));
+    H2V_CU(cudaSetDevice(pk->dev));
     H2V_CU(cudaMemcpy(out.data(), pk->commits.p, n_cols * sizeof(affine), cudaMemcpyDeviceToHost));
     return H2V_OK;
 }
@@ -397,6 +403,7 @@ int h2v_pk_load(h2v_srs_t srs, const h2v_circuit_t *cs, const uint64_t *const *f
     h2v_domain_constant(pk->dom, 0, tmp); pk->omega = frh::load(tmp);
     h2v_domain_constant(pk->dom, 1, tmp); pk->omega_inv = frh::load(tmp);
     pk->delta = frh::pow_u64(frh::from_u64(7), (uint64_t)1 << 28);      // Fr::DELTA = MULTIPLICATIVE_GENERATOR^(2^S)
+    cudaSetDevice(pk->dev);      // h2v_domain_new built one replica per device and left this thread on the last one
     cudaError_t e = cudaStreamCreateWithFlags(&pk->st, cudaStreamNonBlocking);
     if (e != cudaSuccess) { h2v_pk_free(pk); return failf(H2V_ECUDA, "pk_load: %s", cudaGetErrorString(e)); }
 
@@ -539,6 +546,7 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
             const uint32_t c0 = b * sub, c1 = std::min(A, c0 + sub);
             if (cudaEventSynchronize(ev[b]) != cudaSuccess) { rc = H2V_ECUDA; break; }
             rc = h2v_commit_batch_dev(pk->srs, H2V_BASIS_LAGRANGE, pk->adv_L.f() + (size_t)c0 * n, n, c1 - c0, n, (affine *)pk->commits.p + c0);
+            cudaSetDevice(pk->dev);
         }
         cudaStreamSynchronize(st);
         for (cudaEvent_t e : ev)
@@ -891,6 +899,7 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
     for (size_t i = 0; i < NR; ++i) {
         const std::vector<Fr64> ps = pts_of(rsets[i].mask);
         const size_t m = ps.size(), nc = rsets[i].polys.size();
+        const std::vector<std::vector<Fr64>> basis = lagrange_basis(ps);
         std::vector<Fr64> ypow(nc);
         Fr64 cur = frh::ONE;
         r_comb[i].assign(m, frh::zero());
@@ -900,7 +909,7 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
             std::vector<Fr64> ev;
             for (size_t r = 0; r < NPT; ++r)
                 if ((rsets[i].mask >> r) & 1) ev.push_back(eval_of[{rsets[i].polys[j], (uint32_t)r}]);
-            r_ij[i][j] = lagrange_interpolate(ps, ev);
+            r_ij[i][j] = lagrange_interpolate(basis, ev);
             for (size_t t = 0; t < m; ++t) r_comb[i][t] = frh::add(r_comb[i][t], frh::mul(r_ij[i][j][t], cur));
             cur = frh::mul(cur, ys);
         }

@@ -75,3 +75,78 @@ def test_init_rejects_bad_lists(h2v):
     with pytest.raises(ValueError):
         h2v.init([h2v.device_count()])
     h2v.init(0)
+
+
+def test_commit_batch_dev_split_over_devices(two_devices):
+    """a resident batch of a proof phase: the columns are cut into one block per device, the other device pulls its block
+    over NVLink and the results land in the owner's array in column order"""
+    h = two_devices
+    k, n = 9, 1 << 9
+    bases = O.gen_bases(n)
+    srs = h.ParamsKZG(k, None, bases)
+    ncols = 37
+    cols = np.stack([O.fr_fill(n, 500 + i, mode=i % 2) for i in range(ncols)])
+    want = [O.best_multiexp_affine(cols[i], bases) for i in range(ncols)]
+    for device in (0, 1):
+        # contiguous columns (one peer copy) and columns with a gap between them (one copy per column)
+        for stride in (n, n + 16):
+            padded = np.zeros((ncols, stride, 4), dtype=np.uint64)
+            padded[:, :n] = cols
+            d_in = h.DeviceBuffer(padded.nbytes, device=device)
+            d_in.upload(padded)
+            d_out = h.DeviceBuffer(ncols * 64, device=device)
+            srs.commit_batch_dev(d_in.ptr, stride, ncols, n, d_out.ptr)
+            got = d_out.download((ncols, 8))
+            for i in range(ncols):
+                assert (got[i] == want[i]).all(), (device, stride, i)
+    srs.close()
+
+
+def test_transform_dev_split_over_devices(two_devices):
+    h = two_devices
+    k, n = 9, 1 << 9
+    dom, od = h.EvaluationDomain(4, k), O.EvaluationDomain(4, k)
+    ncols = 21
+    cols = np.stack([O.fr_fill(n, 900 + i) for i in range(ncols)])
+    for device in (0, 1):
+        d_in = h.DeviceBuffer(cols.nbytes, device=device)
+        d_in.upload(cols)
+        d_c = h.DeviceBuffer(cols.nbytes, device=device)
+        dom.transform_dev(h.OP_LAGRANGE_TO_COEFF, d_in.ptr, n, d_c.ptr, n, ncols)
+        coef = d_c.download((ncols, n, 4))
+        d_e = h.DeviceBuffer(4 * cols.nbytes, device=device)
+        dom.transform_dev(h.OP_COEFF_TO_EXTENDED, d_c.ptr, n, d_e.ptr, 4 * n, ncols)
+        ext = d_e.download((ncols, 4 * n, 4))
+        d_b = h.DeviceBuffer(4 * cols.nbytes, device=device)
+        dom.transform_dev(h.OP_EXTENDED_TO_COEFF, d_e.ptr, 4 * n, d_b.ptr, 4 * n, ncols)
+        back = d_b.download((ncols, 4 * n, 4))
+        for i in range(ncols):
+            c = od.lagrange_to_coeff(cols[i])
+            assert (coef[i] == c).all(), (device, i)
+            assert (ext[i] == od.coeff_to_extended(c)).all(), (device, i)
+            assert (back[i][:n] == c).all() and not back[i][n:3 * n].any(), (device, i)
+    dom.close()
+
+
+def test_proof_bytes_do_not_depend_on_the_device_count(h2v):
+    """create_proof with the commit phases spread over two devices: the same bytes as on one device and as the oracle's"""
+    if h2v.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from common import fr_arr
+    from oracle import plonk as PL
+    from toy_circuit import Toy
+
+    k, seed, secret = 8, bytes(range(32)), 0x1CE1CEBABE5EED0123456789ABCDEF0FEDCBA9876543210
+    t = Toy(k, seed=5, n_gate_cols=22, n_lookup_cols=3)
+    params = PL.Params.setup(k, secret)
+    proofs = []
+    for devs in ([0], [0, 1]):
+        h2v.init(devs)
+        srs = h2v.ParamsKZG(k, params.g, params.g_lagrange)
+        pk = h2v.ProvingKey(srs, t.cs, [fr_arr(c) for c in t.fixed], [fr_arr(c) for c in t.sigma], fr_arr([t.vk_repr])[0])
+        proofs.append(pk.create_proof([fr_arr(c) for c in t.advice], [fr_arr(c) for c in t.instances], seed))
+        pk.close()
+        srs.close()
+    h2v.init(0)
+    assert proofs[0] == proofs[1]
+    assert proofs[0] == PL.create_proof(params, t.cs, t.fixed, t.sigma, t.vk_repr, t.advice, t.instances, seed)
