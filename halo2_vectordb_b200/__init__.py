@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "h2v_lagrange_to_coeff", "h2v_coeff_to_lagrange", "h2v_coeff_to_extended", "h2v_extended_to_coeff",
     "h2v_divide_by_vanishing_poly", "h2v_domain_transform_batch", "h2v_domain_transform_dev",
     "h2v_eval_polynomial_batch", "h2v_eval_polynomial_dev", "h2v_batch_invert", "h2v_grand_product", "h2v_grand_product_dev", "h2v_kate_division",
-    "h2v_permute_expression_pair", "h2v_permute_expression_pair_dev",
+    "h2v_permute_expression_pair", "h2v_permute_expression_pair_dev", "h2v_permute_expression_pair_batch_dev",
     "h2v_quotient_gates_dev", "h2v_quotient_permutation_dev", "h2v_quotient_lookup_dev",
     "h2v_g1_to_bytes", "h2v_fr_to_repr",
     "h2v_domain_rotate_omega", "h2v_domain_rotate_extended", "h2v_domain_l_i_range", "h2v_domain_fill", "h2v_kate_division_dev",
@@ -114,6 +114,7 @@ def lib():
         L.h2v_kate_division.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.h2v_permute_expression_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.h2v_permute_expression_pair_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.h2v_permute_expression_pair_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.h2v_quotient_gates_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.h2v_quotient_permutation_dev.argtypes = ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
                                                    + [C.c_void_p, C.c_size_t] * 3 + [C.c_void_p] * 3 + [C.c_uint32])
@@ -388,6 +389,14 @@ def permute_expression_pair(inp, table):
     a, s = np.zeros_like(inp), np.zeros_like(inp)
     _check(lib().h2v_permute_expression_pair(_ptr(inp), _ptr(table), inp.shape[0], _ptr(a), _ptr(s)))
     return a, s
+
+
+def permute_expression_pair_batch_dev(d_inputs, d_tables, usable_rows, d_permuted_inputs, input_stride, d_permuted_tables, table_stride):
+    """all lookups of a phase at once: lists of device column pointers in, strided device output matrices"""
+    L = len(d_inputs)
+    ia = (C.c_void_p * max(1, L))(*d_inputs)
+    ta = (C.c_void_p * max(1, L))(*d_tables)
+    _check(lib().h2v_permute_expression_pair_batch_dev(ia, ta, L, usable_rows, d_permuted_inputs, input_stride, d_permuted_tables, table_stride))
 
 
 def permute_expression_pair_dev(d_input, d_table, usable_rows, d_permuted_input, d_permuted_table):

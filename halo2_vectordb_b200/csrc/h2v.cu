@@ -1796,54 +1796,77 @@ int h2v_kate_division(const uint64_t *a, size_t n, const uint64_t b[4], uint64_t
 // ================================================================== lookup argument: permuted columns
 namespace {
 // A', S' of `u` usable rows from device-resident input / table expressions (Montgomery); g_poly.mu held by the caller
-int run_permute_pair(cudaStream_t st, const fe *d_in_a, const fe *d_in_t, uint32_t u, fe *d_out_a, fe *d_out_s) {
+// All lookup arguments of one proof phase in one set of launches (lookup.cuh): inputs[l] / tables[l] are device columns,
+// the permuted columns land at out_a + l * a_stride / out_s + l * s_stride.  Identical table pointers are sorted once.
+int run_permute_batch(cudaStream_t st, const fe *const *inputs, const fe *const *tables, uint32_t L, uint32_t u, fe *d_out_a, size_t a_stride,
+                      fe *d_out_s, size_t s_stride) {
     int rc;
     uint32_t n_pad = 1;
     while (n_pad < u) n_pad <<= 1;
-    const uint32_t ntiles = (u + H2V_SCAN_TILE - 1) / H2V_SCAN_TILE;
-    if ((rc = g_poly.a.ensure((size_t)2 * n_pad * sizeof(fe))) ||
-        (rc = g_poly.tree.ensure(((size_t)6 * u + 2 * ntiles + 8) * sizeof(uint32_t))))
+    std::vector<const fe *> srcs(inputs, inputs + L);
+    std::vector<uint32_t> tmap(L);
+    for (uint32_t l = 0; l < L; ++l) {
+        uint32_t t = L;
+        for (; t < srcs.size(); ++t)
+            if (srcs[t] == tables[l]) break;
+        if (t == srcs.size()) srcs.push_back(tables[l]);
+        tmap[l] = t;
+    }
+    const uint32_t slices = (uint32_t)srcs.size();
+    const size_t rows = (size_t)L * u;
+    if (rows >= ((size_t)1 << 31)) return fail(H2V_EINVAL, "permute_expression_pair: batch too large");
+    const uint32_t ntiles = (uint32_t)((rows + H2V_SCAN_TILE - 1) / H2V_SCAN_TILE);
+    const size_t ptr_words = ((size_t)slices * sizeof(void *) + 3) / 4;
+    if ((rc = g_poly.a.ensure((size_t)slices * n_pad * sizeof(fe))) ||
+        (rc = g_poly.tree.ensure((6 * rows + 2 * ntiles + 16 + L + ptr_words + 8) * sizeof(uint32_t))))
         return rc;
-    fe *As = g_poly.a.as<fe>(), *Ts = As + n_pad;      // both key arrays in one buffer: grid.y picks the array
-    uint32_t *rep = g_poly.tree.as<uint32_t>(), *free_ = rep + u, *rep_offs = free_ + u, *free_offs = rep_offs + u;
-    uint32_t *scratch = free_offs + u, *rep_rows = scratch + u, *tiles = rep_rows + u, *totals = tiles + 2 * ntiles;
+    fe *keys = g_poly.a.as<fe>();
+    uint32_t *rep = g_poly.tree.as<uint32_t>(), *free_ = rep + rows, *rep_offs = free_ + rows, *free_offs = rep_offs + rows;
+    uint32_t *scratch = free_offs + rows, *rep_rows = scratch + rows, *tiles = rep_rows + rows, *totals = tiles + 2 * ntiles;
     int *err = reinterpret_cast<int *>(totals + 2);
-    const unsigned gp = (n_pad + 255) / 256, gu = (u + 255) / 256;
+    uint32_t *d_tmap = totals + 4;
+    uintptr_t pa = reinterpret_cast<uintptr_t>(d_tmap + L);
+    pa = (pa + 7) & ~(uintptr_t)7;
+    const fe **d_srcs = reinterpret_cast<const fe **>(pa);
     CU(cudaMemsetAsync(err, 0, sizeof(int), st));
+    CU(cudaMemcpyAsync(d_tmap, tmap.data(), L * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_srcs, srcs.data(), slices * sizeof(void *), cudaMemcpyHostToDevice, st));
+    const unsigned gp = (n_pad + 255) / 256, gu = (u + 255) / 256;
     {
-        lookup_canon_pad_kernel<<<dim3(gp, 2), 256, 0, st>>>(d_in_a, d_in_t, As, u, n_pad);
+        lookup_canon_pad_batch_kernel<<<dim3(gp, slices), 256, 0, st>>>(d_srcs, keys, u, n_pad);
         LAUNCHED();
         const uint32_t tile = std::min<uint32_t>(H2V_SORT_TILE, n_pad);
         const unsigned tiles_n = n_pad / tile;
         const size_t smem = (size_t)tile * sizeof(fe);
-        bitonic_tile_kernel<<<dim3(tiles_n, 2), H2V_SORT_TILE / 2, smem, st>>>(As, n_pad, 0, 1);
+        bitonic_tile_kernel<<<dim3(tiles_n, slices), H2V_SORT_TILE / 2, smem, st>>>(keys, n_pad, 0, 1);
         LAUNCHED();
         for (uint32_t k = 2 * tile; k <= n_pad && k; k <<= 1) {
             for (uint32_t j = k >> 1; j >= tile; j >>= 1) {
-                bitonic_global_kernel<<<dim3((n_pad / 2 + 255) / 256, 2), 256, 0, st>>>(As, n_pad, k, j);
+                bitonic_global_kernel<<<dim3((n_pad / 2 + 255) / 256, slices), 256, 0, st>>>(keys, n_pad, k, j);
                 LAUNCHED();
             }
-            bitonic_tile_kernel<<<dim3(tiles_n, 2), H2V_SORT_TILE / 2, smem, st>>>(As, n_pad, k, 0);
+            bitonic_tile_kernel<<<dim3(tiles_n, slices), H2V_SORT_TILE / 2, smem, st>>>(keys, n_pad, k, 0);
             LAUNCHED();
         }
     }
-    lookup_fill_kernel<<<gu, 256, 0, st>>>(free_, 1u, u);
+    lookup_fill_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(free_, 1u, (uint32_t)rows);
     LAUNCHED();
-    lookup_flags_kernel<<<gu, 256, 0, st>>>(As, Ts, u, rep, free_, err);
+    lookup_flags_batch_kernel<<<dim3(gu, L), 256, 0, st>>>(keys, d_tmap, u, n_pad, rep, free_, err);
     LAUNCHED();
     for (int which = 0; which < 2; ++which) {
         const uint32_t *cnt = which ? free_ : rep;
         uint32_t *offs = which ? free_offs : rep_offs, *tl = tiles + which * ntiles;
-        msm_scan_tiles_kernel<<<ntiles, 256, 0, st>>>(cnt, tl, u);
+        msm_scan_tiles_kernel<<<ntiles, 256, 0, st>>>(cnt, tl, (uint32_t)rows);
         LAUNCHED();
         msm_scan_top_kernel<<<1, 256, 0, st>>>(tl, ntiles, totals + which);
         LAUNCHED();
-        msm_scan_apply_kernel<<<ntiles, 256, 0, st>>>(cnt, tl, offs, scratch, u);
+        msm_scan_apply_kernel<<<ntiles, 256, 0, st>>>(cnt, tl, offs, scratch, (uint32_t)rows);
         LAUNCHED();
     }
-    lookup_emit_input_kernel<<<gu, 256, 0, st>>>(As, u, rep, rep_offs, rep_rows, d_out_a, d_out_s);
+    lookup_emit_input_batch_kernel<<<dim3(gu, L), 256, 0, st>>>(keys, u, n_pad, rep, rep_offs, rep_rows, d_out_a, a_stride, d_out_s, s_stride);
     LAUNCHED();
-    lookup_emit_table_kernel<<<gu, 256, 0, st>>>(Ts, u, free_, free_offs, totals, rep_rows, d_out_s, err);
+    lookup_emit_table_batch_kernel<<<dim3(gu, L), 256, 0, st>>>(keys, d_tmap, L, u, n_pad, free_, free_offs, rep_offs, totals, rep_rows, d_out_s,
+                                                                 s_stride, err);
     LAUNCHED();
     int herr = 0;
     CU(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1851,6 +1874,9 @@ int run_permute_pair(cudaStream_t st, const fe *d_in_a, const fe *d_in_t, uint32
     if (herr == 1) return fail(H2V_EINVAL, "permute_expression_pair: an input value is not in the table (ConstraintSystemFailure)");
     if (herr) return fail(H2V_ECUDA, "permute_expression_pair: leftover count mismatch");
     return H2V_OK;
+}
+int run_permute_pair(cudaStream_t st, const fe *d_in_a, const fe *d_in_t, uint32_t u, fe *d_out_a, fe *d_out_s) {
+    return run_permute_batch(st, &d_in_a, &d_in_t, 1, u, d_out_a, 0, d_out_s, 0);
 }
 }  // namespace
 
@@ -1869,6 +1895,29 @@ int h2v_permute_expression_pair_dev(const void *d_input, const void *d_table, si
     tm.begin(7);
     rc = run_permute_pair(g_poly.st, (const fe *)d_input, (const fe *)d_table, (uint32_t)usable_rows, (fe *)d_permuted_input,
                           (fe *)d_permuted_table);
+    tm.end();
+    cudaStreamSynchronize(g_poly.st);
+    tm.collect(true);
+    return rc;
+}
+int h2v_permute_expression_pair_batch_dev(const void *const *d_inputs, const void *const *d_tables, size_t n_lookups, size_t usable_rows,
+                                          void *d_permuted_inputs, size_t input_stride, void *d_permuted_tables, size_t table_stride) {
+    if (!usable_rows || !n_lookups) return H2V_OK;
+    if (!d_inputs || !d_tables || !d_permuted_inputs || !d_permuted_tables) return fail(H2V_EINVAL, "permute_expression_pair: NULL buffer");
+    if (usable_rows > ((size_t)1 << 28) || n_lookups > 65535) return fail(H2V_EINVAL, "permute_expression_pair: too many rows / lookups");
+    if (n_lookups > 1 && (input_stride < usable_rows || table_stride < usable_rows))
+        return fail(H2V_EINVAL, "permute_expression_pair: output stride shorter than the usable rows");
+    for (size_t l = 0; l < n_lookups; ++l)
+        if (!d_inputs[l] || !d_tables[l]) return fail(H2V_EINVAL, "permute_expression_pair: lookup %zu has a NULL column", l);
+    t_dev = device_of(d_inputs[0]);
+    int rc = use_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_poly.mu);
+    if ((rc = poly_ctx_ready())) return rc;
+    Timer tm(g_poly.st);
+    tm.begin(7);
+    rc = run_permute_batch(g_poly.st, (const fe *const *)d_inputs, (const fe *const *)d_tables, (uint32_t)n_lookups, (uint32_t)usable_rows,
+                           (fe *)d_permuted_inputs, input_stride, (fe *)d_permuted_tables, table_stride);
     tm.end();
     cudaStreamSynchronize(g_poly.st);
     tm.collect(true);

@@ -149,4 +149,76 @@ __global__ void lookup_emit_table_kernel(const fe *__restrict__ Ts, uint32_t u, 
     fe_store_global(out_s + row, fe_to_mont<FrL>(fe_load_global(Ts + p)));
 }
 
+// ---- the same plan for ALL lookup arguments of a proof in one set of launches (a kmeans-sized proof has 72 of them over
+// one shared table: one at a time they are 72 x ~35 launches of 32-block grids).  keys[y][0 .. n_pad): slice y < L holds the
+// sorted input of lookup y, slice L + t the sorted t-th DISTINCT table; tmap[l] = the table slice of lookup l.  The
+// per-lookup index arrays are rows of [L][u] matrices scanned as one long array; a row's own offsets are the scanned
+// values minus the value at the row's start.
+__global__ void lookup_canon_pad_batch_kernel(const fe *const *__restrict__ srcs, fe *__restrict__ out, uint32_t n, uint32_t n_pad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    const fe *in = srcs[blockIdx.y];
+    out += (size_t)blockIdx.y * n_pad;
+    fe r;
+    if (i < n) {
+        r = fe_from_mont<FrL>(fe_load_global(in + i));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r.v[k] = 0xffffffffu;
+    }
+    fe_store_global(out + i, r);
+}
+__global__ void lookup_flags_batch_kernel(const fe *__restrict__ keys, const uint32_t *__restrict__ tmap, uint32_t u, uint32_t n_pad,
+                                          uint32_t *__restrict__ rep, uint32_t *__restrict__ free_, int *__restrict__ err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= u) return;
+    const uint32_t l = blockIdx.y;
+    const fe *As = keys + (size_t)l * n_pad, *Ts = keys + (size_t)tmap[l] * n_pad;
+    rep += (size_t)l * u;
+    free_ += (size_t)l * u;
+    fe v = fe_load_global(As + i);
+    bool first = i == 0 || !key_eq(v, fe_load_global(As + i - 1));
+    rep[i] = first ? 0u : 1u;
+    if (!first) return;
+    uint32_t lo = 0, hi = u;      // lower bound of v in Ts[0 .. u)
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (key_less(fe_load_global(Ts + mid), v)) lo = mid + 1;
+        else hi = mid;
+    }
+    if (lo < u && key_eq(fe_load_global(Ts + lo), v)) free_[lo] = 0u;
+    else atomicExch(err, 1);
+}
+__global__ void lookup_emit_input_batch_kernel(const fe *__restrict__ keys, uint32_t u, uint32_t n_pad, const uint32_t *__restrict__ rep,
+                                               const uint32_t *__restrict__ rep_offs, uint32_t *__restrict__ rep_rows,
+                                               fe *__restrict__ out_a, size_t a_stride, fe *__restrict__ out_s, size_t s_stride) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= u) return;
+    const uint32_t l = blockIdx.y;
+    const size_t row0 = (size_t)l * u;
+    fe m = fe_to_mont<FrL>(fe_load_global(keys + (size_t)l * n_pad + i));
+    fe_store_global(out_a + l * a_stride + i, m);
+    if (rep[row0 + i]) rep_rows[row0 + (rep_offs[row0 + i] - rep_offs[row0])] = i;
+    else fe_store_global(out_s + l * s_stride + i, m);
+}
+__global__ void lookup_emit_table_batch_kernel(const fe *__restrict__ keys, const uint32_t *__restrict__ tmap, uint32_t n_lookups, uint32_t u,
+                                               uint32_t n_pad, const uint32_t *__restrict__ free_, const uint32_t *__restrict__ free_offs,
+                                               const uint32_t *__restrict__ rep_offs, const uint32_t *__restrict__ totals,
+                                               const uint32_t *__restrict__ rep_rows, fe *__restrict__ out_s, size_t s_stride,
+                                               int *__restrict__ err) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t l = blockIdx.y;
+    const size_t row0 = (size_t)l * u;
+    if (p >= u || !free_[row0 + p]) return;
+    const bool last = l + 1 == n_lookups;
+    const uint32_t m = (last ? totals[0] : rep_offs[row0 + u]) - rep_offs[row0];            // repeated rows of this lookup
+    const uint32_t mf = (last ? totals[1] : free_offs[row0 + u]) - free_offs[row0];          // leftover table values
+    if (mf != m) {                    // cannot happen when every input value was found; defensive
+        atomicCAS(err, 0, 2);         // keep an earlier "missing value" report
+        return;
+    }
+    uint32_t row = rep_rows[row0 + (m - 1 - (free_offs[row0 + p] - free_offs[row0]))];
+    fe_store_global(out_s + l * s_stride + row, fe_to_mont<FrL>(fe_load_global(keys + (size_t)tmap[l] * n_pad + p)));
+}
+
 }  // namespace h2v

@@ -571,9 +571,16 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
     H2V_TRY(pk->ps_L.ensure(std::max<size_t>(1, L) * n * sizeof(fe)));
     if (L) {
         std::vector<Fr64> ta((size_t)L * (bf + 1)), ts((size_t)L * (bf + 1));
+        {
+            std::vector<const void *> li(L), lt(L);
+            for (uint32_t l = 0; l < L; ++l) {
+                li[l] = col_L(0, pk->lookup_input[l]);
+                lt[l] = col_L(1, pk->lookup_table[l]);
+            }
+            H2V_TRY(h2v_permute_expression_pair_batch_dev(li.data(), lt.data(), L, u, pk->pa_L.f(), n, pk->ps_L.f(), n));
+            H2V_CU(cudaSetDevice(pk->dev));
+        }
         for (uint32_t l = 0; l < L; ++l) {
-            H2V_TRY(h2v_permute_expression_pair_dev(col_L(0, pk->lookup_input[l]), col_L(1, pk->lookup_table[l]), u,
-                                                    pk->pa_L.f() + (size_t)l * n, pk->ps_L.f() + (size_t)l * n));
             for (uint32_t i = 0; i <= bf; ++i) ta[(size_t)l * (bf + 1) + i] = rng.fr_random();
             for (uint32_t i = 0; i <= bf; ++i) ts[(size_t)l * (bf + 1) + i] = rng.fr_random();
             (void)rng.fr_random();     // permuted input blind

@@ -177,6 +177,11 @@ int h2v_permute_expression_pair(const uint64_t *input, const uint64_t *table, si
                                 uint64_t *permuted_table);
 int h2v_permute_expression_pair_dev(const void *d_input, const void *d_table, size_t usable_rows, void *d_permuted_input,
                                     void *d_permuted_table);
+/* every lookup argument of one proof phase in one set of launches: d_inputs[l] / d_tables[l] are device columns (a table
+ * shared by several lookups is sorted once), the permuted columns land at d_permuted_inputs + l * input_stride and
+ * d_permuted_tables + l * table_stride (strides in elements) */
+int h2v_permute_expression_pair_batch_dev(const void *const *d_inputs, const void *const *d_tables, size_t n_lookups, size_t usable_rows,
+                                          void *d_permuted_inputs, size_t input_stride, void *d_permuted_tables, size_t table_stride);
 
 /* ---- quotient evaluation on the extended coset ("next": SURVEY.md 8(f) row 1) ------------------------------
  * The per-row loops of halo2-axiom plonk/evaluation.rs Evaluator::evaluate_h [UPSTREAM; reached from

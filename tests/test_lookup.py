@@ -127,3 +127,43 @@ def test_gpu_permute_errors(h2v):
     # the library is still usable after the error
     a, s = h2v.permute_expression_pair(fr_arr([2, 2, 1]), fr_arr([3, 1, 2]))
     assert O.fr_to_ints(a) == [1, 2, 2] and O.fr_to_ints(s) == [1, 2, 3]
+
+
+@pytest.mark.gpu
+def test_gpu_permute_batch_matches_per_lookup_oracle(h2v):
+    """all lookups of a proof phase in one set of launches: five inputs over two distinct tables (one shared by three of
+    them, as halo2-base's single range table is), ragged sizes, against the oracle one lookup at a time"""
+    for u in (37, 1000, 5000):
+        rng = np.random.default_rng(u)
+        bits = 5 if u < 100 else 9
+        stride = u + 11
+        canon = lambda v: np.stack([v, np.zeros_like(v), np.zeros_like(v), np.zeros_like(v)], axis=1)
+        t0 = np.concatenate([np.arange(1 << bits, dtype=np.uint64), np.zeros(u - (1 << bits), dtype=np.uint64)])
+        t1 = rng.permutation(np.concatenate([np.arange(3, 3 + (1 << bits), dtype=np.uint64), np.full(u - (1 << bits), 7, dtype=np.uint64)]))
+        tables = [O.to_mont(canon(t0)), O.to_mont(canon(t1))]
+        which = [0, 1, 0, 0, 1]
+        inputs = []
+        for l, w in enumerate(which):
+            lo = 0 if w == 0 else 3
+            v = rng.integers(lo, lo + (1 << bits), u, dtype=np.uint64)
+            if l == 2:
+                v[:] = v[0]                      # one value repeated on every row
+            inputs.append(O.to_mont(canon(v)))
+        d_t = [h2v.DeviceBuffer(u * 32) for _ in tables]
+        for b, t in zip(d_t, tables):
+            b.upload(t)
+        d_i = [h2v.DeviceBuffer(u * 32) for _ in inputs]
+        for b, v in zip(d_i, inputs):
+            b.upload(v)
+        L = len(inputs)
+        d_a, d_s = h2v.DeviceBuffer(L * stride * 32), h2v.DeviceBuffer(L * stride * 32)
+        h2v.permute_expression_pair_batch_dev([b.ptr for b in d_i], [d_t[w].ptr for w in which], u, d_a.ptr, stride, d_s.ptr, stride)
+        ga, gs = d_a.download((L, stride, 4)), d_s.download((L, stride, 4))
+        for l, w in enumerate(which):
+            oa, os_ = O.permute_expression_pair(inputs[l], tables[w])
+            assert np.array_equal(ga[l, :u], oa) and np.array_equal(gs[l, :u], os_), (u, l)
+    # a value missing from ONE of the tables fails the whole batch, as the single call does
+    bad = O.to_mont(canon(np.full(u, 9999, dtype=np.uint64)))
+    d_i[3].upload(bad)
+    with pytest.raises(ValueError):
+        h2v.permute_expression_pair_batch_dev([b.ptr for b in d_i], [d_t[w].ptr for w in which], u, d_a.ptr, stride, d_s.ptr, stride)
