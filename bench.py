@@ -128,7 +128,7 @@ def run_reference(args, rank, world, out):
         return
     threads = os.cpu_count() or 1
     from oracle import oracle as O
-    sample_cols = 8
+    sample_cols = min(24, args.cols)      # a bounded sample of the step's 96 columns: the metric is a rate
     bases = O.gen_bases(N, threads=threads)
     cols = [O.fr_fill(N, 7000 + i) for i in range(sample_cols)]
     for _ in range(min(args.warmup, 1)):
@@ -144,7 +144,8 @@ def run_reference(args, rank, world, out):
         "impl": "reference", "metric": "msm_mpts_per_s", "value": v, "unit": "Mpts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "dtype_note": "4 x 64-bit limbs, Montgomery form (CPU restatement)", "data": "synthetic",
-        "config": {"workload": "kmeans k=16 commit_lagrange batch (BASELINE configs[2])", "k": K, "cols_per_step": sample_cols},
+        "config": {"workload": "kmeans k=16 commit_lagrange batch (BASELINE configs[2])", "k": K, "cols_per_step": args.cols,
+                   "scalars": "uniform", "sampled_cols_per_step": sample_cols, "parallelism": f"{threads} host threads"},
         "cpu_baseline": {"value": v, "unit": "Mpts/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated halo2-axiom CPU path (oracle/bn254_oracle.c); the Rust reference cannot be built here (no cargo, un-vendored deps)",
@@ -312,6 +313,14 @@ def _main(args, real_stdout):
             rf = bench_real_flow(h, torch)
             line["prove_shaped"]["real_flow"] = rf
             line["prove_shaped"]["kmeans_k16_real_flow_s"] = rf["kmeans_k16"]["prove_s"]
+            if world > 1 and not os.environ.get("H2V_BENCH_SKIP_MULTI"):
+                # the same kmeans proof with the commit / transform batches of every phase spread over the job's N GPUs in
+                # process (rank 0 drives all of them; the other ranks are idle at the final barrier)
+                try:
+                    line["prove_shaped"]["real_flow_n_gpus"] = bench_real_flow_multi(h, torch, world)
+                except Exception as e:      # never lose the headline line to the extra
+                    line["prove_shaped"]["real_flow_n_gpus"] = {"error": str(e)[:200]}
+                h.init(local_rank)
         line["next_row2"] = bench_row2(h, torch, dev, d_cols, cols)
         line["next_row1"] = bench_row1(h, torch, dev)
         if world == 1:
@@ -444,6 +453,49 @@ def bench_real_flow(h, torch, names=("distances", "query", "kmeans")):
     return res
 
 
+def bench_real_flow_multi(h, torch, n_dev, name="kmeans"):
+    """one real proof of the kmeans example with h2v_init(devices 0 .. n_dev - 1): create_proof's commit and transform
+    batches are cut into one block of columns per device (peer copies over NVLink); the bytes equal the 1-GPU proof's"""
+    import numpy as np
+    from halo2_vectordb_b200 import circuit as Z
+    k, bits = Z.EXAMPLE_PARAMS[name]
+    n = 1 << k
+    builder = Z.GateThreadBuilder(bits)
+    public = []
+    Z.EXAMPLES[name](builder.main(0), Z.example_input(name), public)
+    builder.make_public(public)
+    rc = Z.RangeCircuit(builder, k)
+    A = len(rc.advice)
+    pinned = torch.empty((A, n, 4), dtype=torch.int64).pin_memory()
+    adv = pinned.numpy().view(np.uint64)
+    for i, c in enumerate(rc.advice):
+        adv[i] = c
+    cols = [adv[i] for i in range(A)]
+    out = {}
+    ref = None
+    for devs in ([0], list(range(n_dev))):
+        h.init(devs)
+        srs = h.ParamsKZG.gen_srs(k)
+        pk = h.ProvingKey(srs, rc.cs, rc.fixed, rc.sigma, np.array([k, 0, 0, 0], dtype=np.uint64))
+        proof = pk.create_proof(cols, rc.instances, bytes(32))
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            pk.create_proof(cols, rc.instances, bytes(32))
+            ts.append(time.perf_counter() - t0)
+        if ref is None:
+            ref = proof
+        out[f"{len(devs)}_gpu"] = {"prove_s": min(ts), "phase_ms": {kk: round(v, 1) for kk, v in pk.last_phase_ms().items()},
+                                   "same_bytes_as_1_gpu": proof == ref}
+        pk.close()
+        srs.close()
+    out["example"] = f"{name} k={k}"
+    out["speed_up"] = out["1_gpu"]["prove_s"] / out[f"{n_dev}_gpu"]["prove_s"] if n_dev > 1 else 1.0
+    rc.close()
+    builder.close()
+    return out
+
+
 def _calls(adv, lk, fixed_consts=1):
     """hot-path calls of one proof (SURVEY.md App. C's formulas) from the column counts: commit_lagrange / commit,
     lagrange_to_coeff, coeff_to_extended"""
@@ -517,7 +569,7 @@ def bench_prove_shaped(h, torch, dev, srs16, d_cols16, cols16):
             srs.close()
             del d_cols
         del d_ext, d_h, d_coef
-    res["note"] = "hot-path proxy for one create_proof per circuit (call counts: SURVEY.md App. C estimates), uniform scalars, device-resident"
+    res["note"] = "hot-path proxy for one create_proof per circuit (call counts from the exact column counts of the restated chips, App. C's formulas), uniform scalars, device-resident"
     res["latency_s"] = res["kmeans_k16"]["latency_s"]
     res["kmeans_k16_host_facing_s"] = prove_shaped_host(h, torch, srs16)
     res["kmeans_k16_host_in_quotient_on_device_s"] = prove_shaped_resident(h, torch, dev, srs16)

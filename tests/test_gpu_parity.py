@@ -698,3 +698,28 @@ def test_grand_product_dev_batch_vs_oracle(h2v, n, cols):
     for c in range(cols):
         assert np.array_equal(got[c], O.fr_grand_product(num[c], den[c])), (n, c)
         assert np.array_equal(got[c], h2v.grand_product(num[c], den[c]))
+
+
+@pytest.mark.gpu
+def test_grand_product_zero_denominator_is_skipped_like_batch_invert(h2v):
+    """ff's BatchInvert (which the permutation / lookup provers call) leaves a zero element as zero instead of poisoning
+    the whole batch: one zero denominator in ONE of several columns only zeroes that column's running product from
+    there on; the other columns are untouched"""
+    n, cols = 300, 3
+    num = O.fr_fill(n * cols, 61).reshape(cols, n, 4)
+    den = O.fr_fill(n * cols, 62).reshape(cols, n, 4)
+    den[1, 7] = 0
+    d_num, d_den, d_out = (h2v.DeviceBuffer(n * cols * 32) for _ in range(3))
+    d_num.upload(num); d_den.upload(den)
+    h2v.grand_product_dev(d_num.ptr, d_den.ptr, n, cols, d_out.ptr)
+    got = d_out.download((cols, n, 4))
+    for c in range(cols):
+        ni, di = O.fr_to_ints(num[c]), O.fr_to_ints(den[c])
+        z, want = 1, []
+        for i in range(n):
+            want.append(z)
+            z = z * ni[i] % P.R * (pow(di[i], P.R - 2, P.R) if di[i] else 0) % P.R
+        assert O.fr_to_ints(got[c]) == want, c
+        assert np.array_equal(got[c], h2v.grand_product(num[c], den[c]))
+    assert any(got[1, 8]) is False or not got[1, 8].any()
+    assert got[0, 8].any() and got[2, 8].any()
