@@ -170,14 +170,24 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
         // element (mid, q): source index rev_S(mid) * 2^H + tile*T + q, H = L - S
         const fe *src = p.src + (size_t)blockIdx.y * p.src_stride;
         const int H = L - S;
-        for (uint32_t e = tid; e < nelem; e += nthr) {
-            uint32_t q = e & (T - 1), midr = e >> logT;
-            uint32_t si = (midr << H) + tile * T + q;
-            fe x = fe_zero();
-            if (si < p.n_in) {
-                x = fe_load_global(src + si);
-                if (p.pre) x = fe_mul<Fr>(x, fe_load_ro(p.pre + (si % p.pre_mod)));
-            }
+        // the launch has nelem / 8 threads (run_ntt), so every thread moves exactly 8 elements: all 8 global loads are issued
+        // before the first shared-memory store (one DRAM latency per tile instead of eight dependent load -> store pairs)
+        fe xs[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const uint32_t e = tid + it * nthr;
+            const uint32_t si = ((e >> logT) << H) + tile * T + (e & (T - 1));
+            xs[it] = fe_zero();
+            if (e < nelem && si < p.n_in) xs[it] = fe_load_global(src + si);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const uint32_t e = tid + it * nthr;
+            if (e >= nelem) break;
+            const uint32_t q = e & (T - 1), midr = e >> logT;
+            const uint32_t si = (midr << H) + tile * T + q;
+            fe x = xs[it];
+            if (p.pre && si < p.n_in) x = fe_mul<Fr>(x, fe_load_ro(p.pre + (si % p.pre_mod)));
             ntt_sm_store(ntt_sm, plane1, (bitrev(midr, S) << logT) | q, x);
         }
     } else {
@@ -185,9 +195,16 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
         hi = tile >> (t0 - logT);
         lo_tile = tile & ((1u << (t0 - logT)) - 1);
         const fe *base = dst + ((size_t)hi << (t0 + S)) + (size_t)lo_tile * T;
-        for (uint32_t e = tid; e < nelem; e += nthr) {
-            uint32_t q = e & (T - 1), mid = e >> logT;
-            ntt_sm_store(ntt_sm, plane1, e, fe_load_global(base + ((size_t)mid << t0) + q));
+        fe xs[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const uint32_t e = tid + it * nthr;
+            if (e < nelem) xs[it] = fe_load_global(base + ((size_t)(e >> logT) << t0) + (e & (T - 1)));
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const uint32_t e = tid + it * nthr;
+            if (e < nelem) ntt_sm_store(ntt_sm, plane1, e, xs[it]);
         }
     }
     __syncthreads();

@@ -35,4 +35,8 @@ COLS=64 ncu --set full --clock-control none --import-source on -k regex:ntt_pass
     python scripts/prof_ntt.py > /dev/null 2>&1
 ncu -i $out/${tag}_ntt.ncu-rep --page details > $out/${tag}_ntt_details.txt 2>&1
 ncu -i $out/${tag}_ntt.ncu-rep --page raw --csv > $out/${tag}_ntt_raw.csv 2>&1
+# the .ncu-rep files (≈ 40 MB each) would push gpurun_out/ over its 64 MiB return limit: the text / csv pages are what is kept
+ncu -i $out/${tag}_acc.ncu-rep --page source --csv > $out/${tag}_acc_source.csv 2>&1
+ncu -i $out/${tag}_ntt.ncu-rep --page source --csv > $out/${tag}_ntt_source.csv 2>&1
+rm -f $out/${tag}_acc.ncu-rep $out/${tag}_ntt.ncu-rep
 ls -la $out/${tag}_*
