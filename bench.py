@@ -35,6 +35,7 @@ N = 1 << K
 COLS = 96                      # 96 x 2 MiB of scalars = 192 MiB per step (> 126 MB L2), tables 64 MiB more
 MSM_MACS_PER_POINT = {16: 27200, 13: 27200, 20: 20400}   # W(n) * 1360 wide-MACs
 FQ_MUL_MACS = 136
+SHOUP_MUL_MACS = 107         # twiddle product of the NTT (csrc/shoup.cuh): 99 IMAD.WIDE + 16 low-only IMAD at half the pipe time
 FQ_SQR_MACS = 108                 # the dedicated squaring: 28 + 8 products, 64 + 8 reduction
 MIXED_ADD_MACS = 8 * FQ_MUL_MACS + 2 * FQ_SQR_MACS      # what msm_accumulate executes per sorted entry (SURVEY counts 10 x 136 = 1360)
 ACC_DRAM_BYTES_PER_LAUNCH = 4.17e9   # msm_accumulate_kernel, 96 columns x 2^16, c = 15: 3.761 GB read + 0.411 GB written (ncu, r01)
@@ -946,17 +947,20 @@ def bench_ntt(h, torch, dev, peak):
         # what the kernel executes: stage 0 has unit twiddles, 3 of the 8 products of the first radix-8 round are by 1, the
         # 1/n of lagrange_to_coeff is one word of Montgomery reduction (8 wide-MACs) instead of a product; zero-padded
         # input (coeff_to_extended) turns the first two stages into broadcasts and leaves 3 products in the first round
+        # A twiddle product is Shoup's (csrc/shoup.cuh): 99 IMAD.WIDE + 16 low-only IMAD (half the pipe time) = 107
+        # wide-MAC equivalents instead of the 136 of a Montgomery product.
         if name == "lagrange_to_coeff":
-            exec_macs = ((size // 2) * (L - 1) - 3 * (size // 8)) * FQ_MUL_MACS * cols + 8 * size * cols
+            exec_macs = ((size // 2) * (L - 1) - 3 * (size // 8)) * SHOUP_MUL_MACS * cols + 8 * size * cols
         else:
-            exec_macs = ((size // 2) * (L - 2) - (size // 8)) * FQ_MUL_MACS * cols + N * FQ_MUL_MACS * cols
+            exec_macs = ((size // 2) * (L - 2) - (size // 8)) * SHOUP_MUL_MACS * cols + N * FQ_MUL_MACS * cols
         res[name] = {"gelem_per_s": cols * size / t / 1e9, "ms": t * 1e3, "cols": cols, "log_n": L,
                      "roofline": {"bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": hbm, "unit": "GB/s",
                                   "frac": alg_bytes / t / 1e9 / hbm, "peak_source": hbm_src, "traffic": None},
                      "roofline_int": {"achieved": alg_macs / t / 1e12, "peak": peak / 1e12, "unit": "T wide-MAC/s",
                                       "frac": alg_macs / t / peak, "frac_butterflies_only": bfly_macs / t / peak,
                                       "frac_executed": exec_macs / t / peak,
-                                      "algorithmic": "SURVEY.md 8(d): ((n/2) log2 n + scaled elements) x 136 wide-MACs"}}
+                                      "algorithmic": "SURVEY.md 8(d): ((n/2) log2 n + scaled elements) x 136 wide-MACs",
+                                      "executed": "twiddle products by Shoup's method: 107 wide-MAC equivalents each (99 IMAD.WIDE + 16 IMAD), unit twiddles skipped"}}
     # end to end through the host-facing batch entry point: pinned host columns in, pinned host columns out
     import ctypes as C
     import numpy as np

@@ -198,6 +198,7 @@ int run_ntt(cudaStream_t st, const fe *src, size_t src_stride, fe *dst, size_t d
     NttPass p;
     memset(&p, 0, sizeof p);
     p.tw = tw;
+    p.tws = tw + (L >= 1 ? ((size_t)1 << (L - 1)) : 1);      // build_twiddles: the Shoup pairs follow the Montgomery table
     p.pre = pre;
     p.pre_mod = pre_mod ? pre_mod : 1;
     p.post = post;
@@ -247,7 +248,7 @@ int run_ntt(cudaStream_t st, const fe *src, size_t src_stride, fe *dst, size_t d
 
 int build_twiddles(cudaStream_t st, DevBuf &buf, const fe &omega, int L) {
     size_t half = L >= 1 ? ((size_t)1 << (L - 1)) : 1;
-    int rc = buf.ensure(std::max<size_t>(half, 1) * sizeof(fe));
+    int rc = buf.ensure(3 * std::max<size_t>(half, 1) * sizeof(fe));      // Montgomery table, then (w, w') pairs
     if (rc) return rc;
     TwiddleParams tp;
     memset(&tp, 0, sizeof tp);
@@ -2006,7 +2007,8 @@ static int rep_quotient_gates_ptrs_dev(DomRep *d, void *d_h, const uint64_t y[4]
 static int quotient_permutation_any(DomRep *d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
                                     size_t n_cols, size_t chunk_len, const void *d_cols, size_t cols_stride, const void *d_sigma,
                                     size_t sigma_stride, const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last,
-                                    const void *d_l_active, uint32_t blinding_factors, bool tables) {
+                                    const void *d_l_active, uint32_t blinding_factors, bool tables, size_t set_begin = 0,
+                                    size_t set_end = (size_t)-1, int with_head = 1) {
     QuotientCommon c;
     int rc = quotient_common(d, d_h, y, &c);
     if (rc) return rc;
@@ -2029,6 +2031,12 @@ static int quotient_permutation_any(DomRep *d, void *d_h, const uint64_t y[4], c
     p.z = (const fe *)d_z;
     p.z_stride = z_stride;
     p.l0 = (const fe *)d_l0; p.l_last = (const fe *)d_l_last; p.l_active = (const fe *)d_l_active;
+    if (set_end == (size_t)-1) set_end = p.n_sets;
+    if (set_begin > set_end || set_end > p.n_sets) return fail(H2V_EINVAL, "quotient_permutation: set range [%zu, %zu) of %u sets", set_begin, set_end, p.n_sets);
+    p.set_begin = (uint32_t)set_begin;
+    p.set_end = (uint32_t)set_end;
+    p.head = with_head ? 1u : 0u;
+    p.delta_begin = fe_pow_u64<Fr>(p.delta, (uint64_t)set_begin * p.chunk_len);
     if ((rc = domain_twiddles(d, 2, &p.tw))) return rc;
     std::lock_guard<std::mutex> lk(d->mu);
     Timer tm(d->stream);
@@ -2055,6 +2063,13 @@ static int rep_quotient_permutation_ptrs_dev(DomRep *d, void *d_h, const uint64_
                                       uint32_t blinding_factors) {
     return quotient_permutation_any(d, d_h, y, beta, gamma, n_cols, chunk_len, d_col_ptrs, 0, d_sigma_ptrs, 0, d_z, z_stride, d_l0, d_l_last,
                                     d_l_active, blinding_factors, true);
+}
+static int rep_quotient_permutation_range_ptrs_dev(DomRep *d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                                            size_t n_cols, size_t chunk_len, size_t set_begin, size_t set_end, int with_head,
+                                            const void *const *d_col_ptrs, const void *const *d_sigma_ptrs, const void *d_z, size_t z_stride,
+                                            const void *d_l0, const void *d_l_last, const void *d_l_active, uint32_t blinding_factors) {
+    return quotient_permutation_any(d, d_h, y, beta, gamma, n_cols, chunk_len, d_col_ptrs, 0, d_sigma_ptrs, 0, d_z, z_stride, d_l0, d_l_last,
+                                    d_l_active, blinding_factors, true, set_begin, set_end, with_head);
 }
 static int rep_quotient_lookup_dev(DomRep *d, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
                             const void *d_input, const void *d_table, const void *d_perm_input, const void *d_perm_table,
@@ -2092,7 +2107,10 @@ template <class F> __global__ void selftest_field_kernel(int op, const fe *a, co
     else if (op == 3) r = fe_inv<F>(x);
     else if (op == 4) r = fe_inv_fast<F>(x);
     else if (op == 5) r = fe_sqr<F>(x);                       // dedicated squaring, canonical input
-    else {                                                      // op 6: the squaring on a lazily reduced input x + m
+    else if (op == 7) {                                         // Shoup product (Fr only): ANY 256-bit a times the twiddle b (Montgomery)
+        r = fe_mul_shoup_lazy<F>(x, fe_from_mont<F>(y), fr_shoup_companion(y));
+        fe_reduce_once<F>(r);
+    } else {                                                      // op 6: the squaring on a lazily reduced input x + m
         fe m_;
 #pragma unroll
         for (int k = 0; k < 8; ++k) m_.v[k] = F::m(k);
@@ -2778,6 +2796,14 @@ int h2v_quotient_permutation_ptrs_dev(h2v_domain_t h, void *d_h, const uint64_t 
     H2V_DOM_ON(d_h)
     return rep_quotient_permutation_ptrs_dev(r, d_h, y, beta, gamma, n_cols, chunk_len, d_col_ptrs, d_sigma_ptrs, d_z, z_stride, d_l0,
                                              d_l_last, d_l_active, blinding_factors);
+}
+int h2v_quotient_permutation_range_ptrs_dev(h2v_domain_t h, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                                            size_t n_cols, size_t chunk_len, size_t set_begin, size_t set_end, int with_head,
+                                            const void *const *d_col_ptrs, const void *const *d_sigma_ptrs, const void *d_z, size_t z_stride,
+                                            const void *d_l0, const void *d_l_last, const void *d_l_active, uint32_t blinding_factors) {
+    H2V_DOM_ON(d_h)
+    return rep_quotient_permutation_range_ptrs_dev(r, d_h, y, beta, gamma, n_cols, chunk_len, set_begin, set_end, with_head, d_col_ptrs,
+                                                   d_sigma_ptrs, d_z, z_stride, d_l0, d_l_last, d_l_active, blinding_factors);
 }
 int h2v_quotient_lookup_dev(h2v_domain_t h, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
                             const void *d_input, const void *d_table, const void *d_perm_input, const void *d_perm_table, const void *d_z,

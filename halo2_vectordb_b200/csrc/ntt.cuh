@@ -19,6 +19,7 @@
 // uses w^((j mod 2^t) << (L-1-t)), exactly the table entry best_fft would use.
 #pragma once
 #include "ff.cuh"
+#include "shoup.cuh"
 
 namespace h2v {
 
@@ -30,6 +31,7 @@ struct NttPass {
     size_t src_stride;      // elements between columns
     size_t dst_stride;
     const fe *tw;           // w^i, i < 2^(L-1), Montgomery
+    const fe *tws;          // the same twiddles for fe_mul_shoup_lazy: (canonical w^i, floor(w^i 2^256 / r)) pairs
     const fe *pre;          // pass 0: input i is multiplied by pre[i % pre_mod]   (nullptr: none)
     const fe *post;         // last pass: output j is multiplied by post[j % post_mod] (nullptr: none)
     uint32_t pre_mod, post_mod;
@@ -110,8 +112,10 @@ __device__ __forceinline__ void ntt_stage(fe (&x)[8], const fe *__restrict__ tw,
             t = x[k + (1 << U)];       // twiddle 1: no product, only the range step (values < 4r -> t < 2r)
             fe_csub_2m<Fr>(t);
         } else {
-            fe w = fe_load_ro(tw + e_base + ((uint32_t)(k & ((1 << U) - 1)) << (L - 1 - U)));
-            t = fe_mul_lazy<Fr>(x[k + (1 << U)], w);
+            // twiddle product by Shoup's method (shoup.cuh): 99 + 16 instead of 128 + 8 multiplier instructions, t < 2r
+            const fe *wp = tw + 2 * (size_t)(e_base + ((uint32_t)(k & ((1 << U) - 1)) << (L - 1 - U)));
+            fe w = fe_load_ro(wp), ws = fe_load_ro(wp + 1);
+            t = fe_mul_shoup_lazy<Fr>(x[k + (1 << U)], w, ws);
         }
         fe a = x[k];
         fe_csub_2m_top<Fr>(a);
@@ -240,16 +244,16 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
             } else {
                 if (u0 <= 0) {
                     int t = t0 + bp;
-                    ntt_stage<0>(x, p.tw, jlow << (L - 1 - t), L, t == 0 ? 1 : 0);
+                    ntt_stage<0>(x, p.tws, jlow << (L - 1 - t), L, t == 0 ? 1 : 0);
                 }
                 if (u0 <= 1) {
                     int t = t0 + bp + 1;
-                    ntt_stage<1>(x, p.tw, jlow << (L - 1 - t), L, t == 1 ? 2 : 0);
+                    ntt_stage<1>(x, p.tws, jlow << (L - 1 - t), L, t == 1 ? 2 : 0);
                 }
             }
             {
                 int t = t0 + bp + 2;
-                ntt_stage<2>(x, p.tw, jlow << (L - 1 - t), L, t == 2 ? 2 : 0);
+                ntt_stage<2>(x, p.tws, jlow << (L - 1 - t), L, t == 2 ? 2 : 0);
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) ntt_sm_store_slot(ntt_sm, plane1, slot[k], x[k]);
@@ -323,7 +327,8 @@ struct TwiddleParams {
     fe pows[28];     // w^(2^b), Montgomery
     uint32_t half_n; // table length
 };
-// tw[i] = w^i by binary exponentiation over the precomputed squarings
+// tw[i] = w^i by binary exponentiation over the precomputed squarings (Montgomery); behind the table, at
+// tw + half_n, the Shoup form of the same entries: pairs (canonical w^i, floor(w^i 2^256 / r)) for the NTT butterflies
 __global__ void twiddle_kernel(fe *tw, TwiddleParams p) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.half_n) return;
@@ -333,6 +338,9 @@ __global__ void twiddle_kernel(fe *tw, TwiddleParams p) {
         if ((i >> b) & 1) acc = fe_mul<Fr>(acc, p.pows[b]);
     }
     fe_store_global(tw + i, acc);
+    fe *pair = tw + p.half_n + 2 * (size_t)i;
+    fe_store_global(pair, fe_from_mont<Fr>(acc));
+    fe_store_global(pair + 1, fr_shoup_companion(acc));
 }
 
 // elementwise a[i] *= c[i % mod]   (standalone divide_by_vanishing_poly on a device-resident column)

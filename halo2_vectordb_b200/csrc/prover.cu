@@ -279,6 +279,11 @@ struct h2v_pk {
     // per-proof workspace, kept between proofs
     DevBuf adv_L, adv_C, adv_E, inst_L, inst_C, inst_E, pa_L, ps_L, pa_C, ps_C, pa_E, ps_E, z_L, z_C, z_E, zl_L, zl_C, zl_E;
     DevBuf num, den, tails, ptrs, scal, pts, rnd_C, hq, hx_pieces, evals, pairs, sh_S, sh_A, sh_B, sh_h, commits;
+    // k = 20-sized keys: the extended-coset forms of the fixed / sigma / advice columns (4n each) are not kept -- the
+    // quotient step rebuilds them from the coefficient forms in slices of `scr_cols` columns of `scr_E`
+    bool stream_ext = false;
+    size_t scr_cols = 0;
+    DevBuf scr_E;
     cudaStream_t st = nullptr;
     int dev = 0;                 // the proof runs on the primary device (columns and key resident there)
     std::mutex mu;
@@ -340,7 +345,7 @@ void h2v_pk_free(h2v_pk_t pk) {
                      &pk->adv_L, &pk->adv_C, &pk->adv_E, &pk->inst_L, &pk->inst_C, &pk->inst_E, &pk->pa_L, &pk->ps_L, &pk->pa_C, &pk->ps_C,
                      &pk->pa_E, &pk->ps_E, &pk->z_L, &pk->z_C, &pk->z_E, &pk->zl_L, &pk->zl_C, &pk->zl_E, &pk->num, &pk->den, &pk->tails,
                      &pk->ptrs, &pk->scal, &pk->pts, &pk->rnd_C, &pk->hq, &pk->hx_pieces, &pk->evals, &pk->pairs, &pk->sh_S, &pk->sh_A,
-                     &pk->sh_B, &pk->sh_h, &pk->commits};
+                     &pk->sh_B, &pk->sh_h, &pk->commits, &pk->scr_E};
     for (DevBuf *b : all) b->release();
     if (pk->dom) h2v_domain_free(pk->dom);
     if (pk->st) cudaStreamDestroy(pk->st);
@@ -407,6 +412,19 @@ int h2v_pk_load(h2v_srs_t srs, const h2v_circuit_t *cs, const uint64_t *const *f
     cudaError_t e = cudaStreamCreateWithFlags(&pk->st, cudaStreamNonBlocking);
     if (e != cudaSuccess) { h2v_pk_free(pk); return failf(H2V_ECUDA, "pk_load: %s", cudaGetErrorString(e)); }
 
+    {
+        // everything resident (the default): Lagrange, coefficient and extended forms of every column of the key and of the
+        // proof.  When that exceeds about half of the device's memory (SIFT-shaped k = 20: 204 GB), stream the extended forms.
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const double cols = (double)cs->n_fixed + cs->n_perm + cs->n_advice + cs->n_instance + 3.0 * cs->n_lookups + pk->n_sets;
+        const double resident = cols * (2.0 * n + (double)pk->ne) * sizeof(fe);
+        const char *e = getenv("H2V_STREAM_EXT");
+        pk->stream_ext = e ? atoi(e) != 0 : resident > 0.55 * (double)total_b;
+        const char *ec = getenv("H2V_STREAM_COLS");
+        const size_t want = ec ? (size_t)atoi(ec) : ((size_t)12 << 30) / (pk->ne * sizeof(fe));
+        pk->scr_cols = std::min<size_t>(std::max<size_t>(want, 2 * (size_t)pk->chunk + 2), 512);
+    }
     auto body = [&]() -> int {
         const size_t ne = pk->ne;
         // fixed columns and sigma polynomials: Lagrange (as given) -> coefficients -> extended coset, all resident
@@ -416,14 +434,14 @@ int h2v_pk_load(h2v_srs_t srs, const h2v_circuit_t *cs, const uint64_t *const *f
             if (!g.cnt) continue;
             H2V_TRY(g.L->ensure(g.cnt * n * sizeof(fe)));
             H2V_TRY(g.C->ensure(g.cnt * n * sizeof(fe)));
-            H2V_TRY(g.E->ensure(g.cnt * ne * sizeof(fe)));
+            if (!pk->stream_ext) H2V_TRY(g.E->ensure(g.cnt * ne * sizeof(fe)));
             for (size_t c = 0; c < g.cnt; ++c) {
                 if (!g.src[c]) return failf(H2V_EINVAL, "pk_load: column %zu is NULL", c);
                 H2V_CU(cudaMemcpyAsync(g.L->f() + c * n, g.src[c], n * sizeof(fe), cudaMemcpyHostToDevice, pk->st));
             }
             H2V_TRY(sync(pk));
             H2V_TRY(h2v_domain_transform_dev(pk->dom, H2V_OP_LAGRANGE_TO_COEFF, g.L->p, n, g.C->p, n, g.cnt));
-            H2V_TRY(h2v_domain_transform_dev(pk->dom, H2V_OP_COEFF_TO_EXTENDED, g.C->p, n, g.E->p, ne, g.cnt));
+            if (!pk->stream_ext) H2V_TRY(h2v_domain_transform_dev(pk->dom, H2V_OP_COEFF_TO_EXTENDED, g.C->p, n, g.E->p, ne, g.cnt));
         }
         // l_0, l_last, l_active_row = 1 - (l_last + l_blind) on the extended coset (keygen.rs)
         {
@@ -691,9 +709,15 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
     // ---- 9-11. y; coefficient and extended forms; evaluate_h; quotient pieces
     const Fr64 y = T.squeeze_challenge();
     const int L2C = H2V_OP_LAGRANGE_TO_COEFF, C2E = H2V_OP_COEFF_TO_EXTENDED;
-    H2V_TRY(pk->adv_E.ensure((size_t)A * ne * sizeof(fe)));
+    const bool stream = pk->stream_ext;
+    if (stream) {       // the products' numerators / denominators are dead by now: their memory goes to the extended forms
+        pk->num.release();
+        pk->den.release();
+    } else {
+        H2V_TRY(pk->adv_E.ensure((size_t)A * ne * sizeof(fe)));
+    }
     H2V_TRY(h2v_domain_transform_dev(pk->dom, L2C, pk->adv_L.p, n, pk->adv_C.p, n, A));
-    H2V_TRY(h2v_domain_transform_dev(pk->dom, C2E, pk->adv_C.p, n, pk->adv_E.p, ne, A));
+    if (!stream) H2V_TRY(h2v_domain_transform_dev(pk->dom, C2E, pk->adv_C.p, n, pk->adv_E.p, ne, A));
     if (I) H2V_TRY(h2v_domain_transform_dev(pk->dom, C2E, pk->inst_C.p, n, pk->inst_E.p, ne, I));
     struct Tr { DevBuf *Lb, *Cb, *Eb; size_t cnt; } trs[4] = {{&pk->pa_L, &pk->pa_C, &pk->pa_E, L}, {&pk->ps_L, &pk->ps_C, &pk->ps_E, L},
                                                             {&pk->z_L, &pk->z_C, &pk->z_E, NS}, {&pk->zl_L, &pk->zl_C, &pk->zl_E, L}};
@@ -709,7 +733,8 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
     fe *h_ext = pk->hq.f(), *h_out = pk->hq.f() + ne;
     H2V_CU(cudaMemsetAsync(h_ext, 0, ne * sizeof(fe), st));
     H2V_TRY(sync(pk));
-    {
+    const fe *l0 = pk->lrows_E.f(), *ll = l0 + ne, *la = l0 + 2 * ne;
+    if (!stream) {
         std::vector<const fe *> hp(2 * G + 2 * NP);
         for (uint32_t j = 0; j < G; ++j) {
             hp[j] = col_E(1, pk->gate_selector[j]);
@@ -721,7 +746,6 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
         }
         if (!hp.empty()) H2V_TRY(upload(pk, pk->ptrs, 0, hp.data(), hp.size() * sizeof(void *)));
         const void *const *tab = (const void *const *)pk->ptrs.p;
-        const fe *l0 = pk->lrows_E.f(), *ll = l0 + ne, *la = l0 + 2 * ne;
         H2V_TRY(h2v_quotient_gates_ptrs_dev(pk->dom, h_ext, u64(y), G, tab, tab + G));
         if (NP)
             H2V_TRY(h2v_quotient_permutation_ptrs_dev(pk->dom, h_ext, u64(y), u64(beta), u64(gamma), NP, pk->chunk, tab + 2 * G,
@@ -730,8 +754,64 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
             H2V_TRY(h2v_quotient_lookup_dev(pk->dom, h_ext, u64(y), u64(beta), u64(gamma), col_E(0, pk->lookup_input[l]),
                                             col_E(1, pk->lookup_table[l]), pk->pa_E.f() + (size_t)l * ne, pk->ps_E.f() + (size_t)l * ne,
                                             pk->zl_E.f() + (size_t)l * ne, l0, ll, la));
-        H2V_TRY(h2v_domain_transform_dev(pk->dom, H2V_OP_DIVIDE_BY_VANISHING, h_ext, ne, h_out, ne, 1));
+    } else {
+        // the same folds, in upstream's order, over slices of columns whose extended forms are rebuilt into `scr_E` from
+        // the resident coefficient forms (every term reads columns of its own gate / set / lookup only)
+        const size_t SC = pk->scr_cols;
+        H2V_TRY(pk->scr_E.ensure(SC * ne * sizeof(fe)));
+        fe *scr = pk->scr_E.f();
+        auto col_C = [&](uint8_t kind, uint32_t idx) -> const fe * {
+            return kind == 0 ? pk->adv_C.f() + (size_t)idx * n : kind == 1 ? pk->fixed_C.f() + (size_t)idx * n : pk->inst_C.f() + (size_t)idx * n;
+        };
+        // coeff_to_extended of a list of coefficient columns into consecutive scratch slots; neighbours share one launch
+        auto extend = [&](const std::vector<const fe *> &src, fe *dst) -> int {
+            for (size_t i = 0; i < src.size();) {
+                size_t j = i + 1;
+                while (j < src.size() && src[j] == src[j - 1] + n) ++j;
+                H2V_TRY(h2v_domain_transform_dev(pk->dom, C2E, src[i], n, dst + i * ne, ne, j - i));
+                i = j;
+            }
+            return H2V_OK;
+        };
+        const void *const *tab = (const void *const *)pk->ptrs.p;
+        std::vector<const fe *> src, hp;
+        const size_t BG = SC / 2;
+        for (size_t g0 = 0; g0 < G; g0 += BG) {
+            const size_t b = std::min<size_t>(BG, G - g0);
+            src.clear();
+            hp.assign(2 * b, nullptr);
+            for (size_t j = 0; j < b; ++j) src.push_back(col_C(1, pk->gate_selector[g0 + j]));
+            for (size_t j = 0; j < b; ++j) src.push_back(col_C(0, pk->gate_advice[g0 + j]));
+            H2V_TRY(extend(src, scr));
+            for (size_t j = 0; j < 2 * b; ++j) hp[j] = scr + j * ne;
+            H2V_TRY(upload(pk, pk->ptrs, 0, hp.data(), hp.size() * sizeof(void *)));
+            H2V_TRY(h2v_quotient_gates_ptrs_dev(pk->dom, h_ext, u64(y), b, tab, tab + b));
+        }
+        const size_t BS = std::max<size_t>(1, SC / (2 * (size_t)pk->chunk));
+        for (size_t s0 = 0; s0 < NS; s0 += BS) {
+            const size_t s1 = std::min<size_t>(NS, s0 + BS), c0 = s0 * pk->chunk, c1 = std::min<size_t>(NP, s1 * pk->chunk), cnt = c1 - c0;
+            src.clear();
+            hp.assign(2 * cnt, nullptr);
+            for (size_t c = c0; c < c1; ++c) src.push_back(col_C(pk->perm_kind[c], pk->perm_index[c]));
+            for (size_t c = c0; c < c1; ++c) src.push_back(pk->sigma_C.f() + c * n);
+            H2V_TRY(extend(src, scr));
+            for (size_t j = 0; j < 2 * cnt; ++j) hp[j] = scr + j * ne;
+            H2V_TRY(upload(pk, pk->ptrs, 0, hp.data(), hp.size() * sizeof(void *)));
+            H2V_TRY(h2v_quotient_permutation_range_ptrs_dev(pk->dom, h_ext, u64(y), u64(beta), u64(gamma), NP, pk->chunk, s0, s1, s0 == 0,
+                                                            tab, tab + cnt, pk->z_E.p, ne, l0, ll, la, bf));
+        }
+        uint32_t table_in_slot = UINT32_MAX;
+        for (uint32_t l = 0; l < L; ++l) {
+            if (pk->lookup_table[l] != table_in_slot) {
+                H2V_TRY(h2v_domain_transform_dev(pk->dom, C2E, col_C(1, pk->lookup_table[l]), n, scr, ne, 1));
+                table_in_slot = pk->lookup_table[l];
+            }
+            H2V_TRY(h2v_domain_transform_dev(pk->dom, C2E, col_C(0, pk->lookup_input[l]), n, scr + ne, ne, 1));
+            H2V_TRY(h2v_quotient_lookup_dev(pk->dom, h_ext, u64(y), u64(beta), u64(gamma), scr + ne, scr, pk->pa_E.f() + (size_t)l * ne,
+                                            pk->ps_E.f() + (size_t)l * ne, pk->zl_E.f() + (size_t)l * ne, l0, ll, la));
+        }
     }
+    H2V_TRY(h2v_domain_transform_dev(pk->dom, H2V_OP_DIVIDE_BY_VANISHING, h_ext, ne, h_out, ne, 1));
     const uint32_t NH = pk->degree - 1;          // quotient pieces of n coefficients each
     for (uint32_t i = 0; i < NH; ++i) (void)rng.fr_random();     // h_blinds
     H2V_TRY(commit_dev(pk, H2V_BASIS_MONOMIAL, h_out, NH, pts));

@@ -68,6 +68,11 @@ struct QuotientPerm {
     size_t z_stride;
     const fe *l0, *l_last, *l_active;
     const fe *tw;                       // extended_omega^i, i < n_ext / 2
+    // a call may cover only the sets [set_begin, set_end) (the caller streams the extended columns through HBM in
+    // slices, k = 20 proofs); `head` = fold the terms that precede the per-set products; the column tables then
+    // start at column set_begin * chunk_len and delta_begin = delta^(set_begin * chunk_len)
+    uint32_t set_begin, set_end, head;
+    fe delta_begin;
 };
 
 template <class CC, class SC>
@@ -78,34 +83,38 @@ __global__ void __launch_bounds__(256) quotient_permutation_kernel(fe *h, Quotie
     const fe one = fe_one<FrQ>();
     const fe l0 = fe_load_global(p.l0 + idx), l_last = fe_load_global(p.l_last + idx), l_active = fe_load_global(p.l_active + idx);
     fe v = fe_load_global(h + idx);
-    // l_0 * (1 - z_0)
-    {
-        fe z0 = fe_load_global(p.z + idx);
-        v = fe_add<FrQ>(fe_mul<FrQ>(v, c.y), fe_mul<FrQ>(fe_sub<FrQ>(one, z0), l0));
-    }
-    // l_last * (z_l^2 - z_l)
-    {
-        fe zl = fe_load_global(p.z + (size_t)(p.n_sets - 1) * p.z_stride + idx);
-        v = fe_add<FrQ>(fe_mul<FrQ>(v, c.y), fe_mul<FrQ>(fe_sub<FrQ>(fe_sqr<FrQ>(zl), zl), l_last));
-    }
-    // l_0 * (z_i - z_{i-1}(w^last X)),  i >= 1
-    for (uint32_t s = 1; s < p.n_sets; ++s) {
-        fe zi = fe_load_global(p.z + (size_t)s * p.z_stride + idx);
-        fe zp = fe_load_global(p.z + (size_t)(s - 1) * p.z_stride + r_last);
-        v = fe_add<FrQ>(fe_mul<FrQ>(v, c.y), fe_mul<FrQ>(fe_sub<FrQ>(zi, zp), l0));
+    if (p.head) {
+        // l_0 * (1 - z_0)
+        {
+            fe z0 = fe_load_global(p.z + idx);
+            v = fe_add<FrQ>(fe_mul<FrQ>(v, c.y), fe_mul<FrQ>(fe_sub<FrQ>(one, z0), l0));
+        }
+        // l_last * (z_l^2 - z_l)
+        {
+            fe zl = fe_load_global(p.z + (size_t)(p.n_sets - 1) * p.z_stride + idx);
+            v = fe_add<FrQ>(fe_mul<FrQ>(v, c.y), fe_mul<FrQ>(fe_sub<FrQ>(fe_sqr<FrQ>(zl), zl), l_last));
+        }
+        // l_0 * (z_i - z_{i-1}(w^last X)),  i >= 1
+        for (uint32_t s = 1; s < p.n_sets; ++s) {
+            fe zi = fe_load_global(p.z + (size_t)s * p.z_stride + idx);
+            fe zp = fe_load_global(p.z + (size_t)(s - 1) * p.z_stride + r_last);
+            v = fe_add<FrQ>(fe_mul<FrQ>(v, c.y), fe_mul<FrQ>(fe_sub<FrQ>(zi, zp), l0));
+        }
     }
     // l_active * ( z_i(wX) prod (v + beta sigma + gamma) - z_i(X) prod (v + delta^j beta X + gamma) )
     const uint32_t half = c.n_ext >> 1;
     fe w = fe_load_ro(p.tw + (idx & (half - 1)));
     if (idx >= half) w = fe_neg<FrQ>(w);
     fe cur = fe_mul<FrQ>(p.beta_zeta, w);
-    for (uint32_t s = 0; s < p.n_sets; ++s) {
+    if (p.set_begin) cur = fe_mul<FrQ>(cur, p.delta_begin);
+    const uint32_t col_base = p.set_begin * p.chunk_len;
+    for (uint32_t s = p.set_begin; s < p.set_end; ++s) {
         const uint32_t c0 = s * p.chunk_len, c1 = min(c0 + p.chunk_len, p.n_cols);
         fe left = fe_load_global(p.z + (size_t)s * p.z_stride + r_next);
         fe right = fe_load_global(p.z + (size_t)s * p.z_stride + idx);
         for (uint32_t j = c0; j < c1; ++j) {
-            fe val = fe_add<FrQ>(fe_load_global(cols.col(j) + idx), p.gamma);
-            fe sg = fe_mul<FrQ>(p.beta, fe_load_global(sigma.col(j) + idx));
+            fe val = fe_add<FrQ>(fe_load_global(cols.col(j - col_base) + idx), p.gamma);
+            fe sg = fe_mul<FrQ>(p.beta, fe_load_global(sigma.col(j - col_base) + idx));
             left = fe_mul<FrQ>(left, fe_add<FrQ>(val, sg));
             right = fe_mul<FrQ>(right, fe_add<FrQ>(val, cur));
             cur = fe_mul<FrQ>(cur, p.delta);

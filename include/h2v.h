@@ -208,6 +208,15 @@ int h2v_quotient_permutation_ptrs_dev(h2v_domain_t dom, void *d_h, const uint64_
                                       size_t n_cols, size_t chunk_len, const void *const *d_col_ptrs, const void *const *d_sigma_ptrs,
                                       const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last, const void *d_l_active,
                                       uint32_t blinding_factors);
+/* the same argument folded in slices, for proofs whose extended columns do not all fit in HBM at once (k = 20): this call
+ * folds the terms that precede the per-set products when `with_head` is set (they read every z), then the products of the
+ * sets [set_begin, set_end); the two pointer tables hold only the columns of those sets (entry 0 = column
+ * set_begin * chunk_len).  Calls with with_head = 1 on the first slice and consecutive set ranges give exactly the
+ * result of one h2v_quotient_permutation_ptrs_dev call. */
+int h2v_quotient_permutation_range_ptrs_dev(h2v_domain_t dom, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
+                                            size_t n_cols, size_t chunk_len, size_t set_begin, size_t set_end, int with_head,
+                                            const void *const *d_col_ptrs, const void *const *d_sigma_ptrs, const void *d_z, size_t z_stride,
+                                            const void *d_l0, const void *d_l_last, const void *d_l_active, uint32_t blinding_factors);
 /* one lookup argument: compressed input / table expressions (theta-folded by the caller; for halo2-base's range
  * lookup they are the lookup advice column and the fixed table column), permuted A' / S', grand product z */
 int h2v_quotient_lookup_dev(h2v_domain_t dom, void *d_h, const uint64_t y[4], const uint64_t beta[4], const uint64_t gamma[4],
@@ -354,7 +363,8 @@ int h2v_fr_to_repr(const uint64_t *fr_mont, size_t n, uint8_t *out);
 /* ---- device self-tests (used by tests/ to localise failures; not part of the drop-in surface) */
 /* out[i] = a[i] (op) b[i] computed by the device field routines; field 0 = Fr, 1 = Fq;
  * op 0 mul, 1 add, 2 sub, 3 inverse by Fermat (b ignored), 4 inverse by binary Euclid (b ignored),
- * 5 the dedicated squaring of a (b ignored), 6 the same on the lazily reduced representative a + m */
+ * 5 the dedicated squaring of a (b ignored), 6 the same on the lazily reduced representative a + m,
+ * 7 (Fr only) the NTT's Shoup product: a is ANY 256-bit integer, b a Montgomery twiddle; out = a * from_mont(b) mod r */
 int h2v_selftest_field(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);
 /* out_affine[i] = affine(p[i] + q[i]) through the XYZZ mixed add (mode 0), full add (mode 1) or
  * doubling of p (mode 2); p, q affine */

@@ -40,6 +40,23 @@ def test_device_field_ops(h2v, field, nm):
     assert not h2v.selftest_field(field, 4, a[0:1]).any()      # 0 -> 0
 
 
+def test_device_shoup_product(h2v):
+    """The NTT's twiddle product (shoup.cuh): ANY 256-bit a (the butterflies hold lazily reduced values) times a twiddle,
+    with the truncated high product and the top-limb correction; compared with big-integer arithmetic."""
+    rnd = random.Random(7)
+    edge = [0, 1, P.R - 1, P.R, 2 * P.R, 4 * P.R - 1, (1 << 256) - 1, (1 << 256) - 2, 1 << 255, (1 << 254) - 1, 1 << 254]
+    a_int = edge + [rnd.randrange(1 << 256) for _ in range(4096 - len(edge))]
+    w_int = [0, 1, P.R - 1, P.R - 2, 2, P.R >> 1] + [rnd.randrange(P.R) for _ in range(4090)]
+    a = O.ints_to_limbs(a_int)                               # taken as they are: not reduced, not converted
+    b = O.to_mont(O.ints_to_limbs(w_int), 0)                 # the twiddle arrives in Montgomery form
+    got = h2v.selftest_field(0, 7, a, b)
+    exp = O.ints_to_limbs([(x * w) % P.R for x, w in zip(a_int, w_int)])
+    assert (got == exp).all()
+    # rows that force the worst case of the quotient estimate: a = 2^256 - 1 against every twiddle
+    a2 = O.ints_to_limbs([(1 << 256) - 1] * len(w_int))
+    assert (h2v.selftest_field(0, 7, a2, b) == O.ints_to_limbs([(((1 << 256) - 1) * w) % P.R for w in w_int])).all()
+
+
 def test_device_group_law(h2v):
     pts = O.gen_bases(64)
     p, q = pts[:32].copy(), pts[32:].copy()

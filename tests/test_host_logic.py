@@ -229,3 +229,37 @@ def test_wire_format_helpers(built):
     assert got[-1] == bytes(32)
     vals = [0, 1, P.R - 1, 0x1234567890ABCDEF << 100]
     assert h.fr_to_repr(O.fr_from_ints(vals)) == [v.to_bytes(32, "little") for v in vals]
+
+
+def test_shoup_product_model():
+    """Line-by-line integer model of csrc/shoup.cuh: the companion w' = low256(w_mont * (-r^-1 mod 2^256)) equals
+    floor(w 2^256 / r); the quotient estimate built from the partial products a_i w'_j with i + j >= 6 is q or q - 1;
+    t = low256(a w + q_hat (2^256 - r)) is a w - q_hat r < 3r, and the top-limb correction leaves t < 2r, t = a w (mod r)."""
+    import random
+
+    from oracle import pyref as P
+    r, B, M = P.R, 1 << 256, (1 << 32) - 1
+    ninv = (-pow(r, -1, B)) % B
+    lit = [0xefffffff, 0xc2e1f593, 0x4c6911b3, 0x6586864b, 0x99062391, 0xe39a9828, 0x0d8341b2, 0x73f82f1d]   # fr_ninv256
+    assert ninv == sum(v << (32 * i) for i, v in enumerate(lit))
+    assert r < (1 << 254) <= 2 * r                   # the correction threshold lies in (r, 2r]
+    rnd = random.Random(11)
+    ws = [0, 1, r - 1, r - 2, r >> 1] + [rnd.randrange(r) for _ in range(300)]
+    As = [0, 1, B - 1, B - 2, 4 * r - 1, 1 << 255, r, 2 * r] + [rnd.randrange(B) for _ in range(300)]
+    worst = 0
+    for w in ws:
+        wp = ((w * B % r) * ninv) % B
+        assert wp == (w * B) // r
+        for a in As[:40] if w > 5 else As:
+            al = [(a >> (32 * i)) & M for i in range(8)]
+            wl = [(wp >> (32 * i)) & M for i in range(8)]
+            s_trunc = sum(al[i] * wl[j] << (32 * (i + j)) for i in range(8) for j in range(8) if i + j >= 6)
+            q_hat, q = s_trunc >> 256, (a * wp) >> 256
+            assert q - 1 <= q_hat <= q
+            t = (a * w + q_hat * (B - r)) % B
+            assert t == a * w - q_hat * r and t < 3 * r
+            worst = max(worst, t / r)
+            if (t >> 224) >= 0x40000000:
+                t -= r
+            assert 0 <= t < 2 * r and t % r == (a * w) % r
+    assert worst < 2.76

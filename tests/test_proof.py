@@ -135,6 +135,26 @@ def test_gpu_proof_bytes_equal_oracle(h2v, k, gate_cols, lookup_cols, degree):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("k,gate_cols,lookup_cols,degree,scr", [(8, 5, 3, 4, 6), (7, 3, 2, 5, 8), (10, 6, 2, 4, 7), (6, 4, 0, 4, 64)])
+def test_gpu_proof_streamed_extended_columns(h2v, monkeypatch, k, gate_cols, lookup_cols, degree, scr):
+    """The k = 20 path: the key keeps no extended-coset columns and evaluate_h rebuilds them in slices of `scr` columns
+    (forced here at small k); the proof must be the same bytes as with everything resident, and as the CPU restatement's."""
+    t = Toy(k, seed=k * 100 + gate_cols, n_gate_cols=gate_cols, n_lookup_cols=lookup_cols, degree=degree)
+    params = PL.Params.setup(k, SECRET)
+    srs, pk = _gpu_setup(h2v, k, t, params)
+    resident = _gpu_proof(pk, t)
+    pk.close()
+    monkeypatch.setenv("H2V_STREAM_EXT", "1")
+    monkeypatch.setenv("H2V_STREAM_COLS", str(scr))
+    pk = h2v.ProvingKey(srs, t.cs, [fr_arr(c) for c in t.fixed], [fr_arr(c) for c in t.sigma], fr_arr([t.vk_repr])[0])
+    streamed = _gpu_proof(pk, t)
+    assert streamed == resident == _oracle_proof(params, t)
+    assert _gpu_proof(pk, t) == streamed          # workspace reuse (num / den are released and re-made in this mode)
+    pk.close()
+    srs.close()
+
+
+@pytest.mark.gpu
 def test_gpu_proof_k16(h2v):
     """BASELINE configs[2]'s size: k = 16, LOOKUP_BITS = 15 (few columns, so that the CPU restatement finishes)"""
     k = 16
