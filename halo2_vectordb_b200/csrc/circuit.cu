@@ -11,6 +11,7 @@
 //   * `RangeWithInstanceCircuitBuilder`: one instance column tied to the `make_public` cells (mod.rs:400, 427-433).
 #include <algorithm>
 #include <memory>
+#include <chrono>
 #include <thread>
 
 #include "internal.hpp"
@@ -94,9 +95,17 @@ template <class F> void parallel_for(size_t n, F &&f) {
 // halo2 permutation keygen `Assembly`: union of cycles, smaller merged into larger, in the order of the copy() calls
 struct Cycles {
     size_t rows;
-    std::vector<uint32_t> mapping, aux, sizes;      // flattened (column * rows + row)
-    Cycles(size_t cols, size_t rows_) : rows(rows_), mapping(cols * rows_), aux(cols * rows_), sizes(cols * rows_, 1) {
-        for (size_t i = 0; i < mapping.size(); ++i) mapping[i] = aux[i] = (uint32_t)i;
+    // flattened (column * rows + row); 40 M entries each for the kmeans circuit: allocated raw and initialised by all cores
+    // (first-touch page faults are most of the cost of a serial fill)
+    std::unique_ptr<uint32_t[]> mapping, aux, sizes;
+    Cycles(size_t cols, size_t rows_) : rows(rows_), mapping(new uint32_t[cols * rows_]), aux(new uint32_t[cols * rows_]), sizes(new uint32_t[cols * rows_]) {
+        uint32_t *m = mapping.get(), *a = aux.get(), *z = sizes.get();
+        parallel_for(cols, [&](size_t c) {
+            for (size_t i = c * rows_; i < (c + 1) * rows_; ++i) {
+                m[i] = a[i] = (uint32_t)i;
+                z[i] = 1;
+            }
+        });
     }
     void copy(size_t lc, size_t lr, size_t rc, size_t rr) {
         uint32_t left = (uint32_t)(lc * rows + lr), right = (uint32_t)(rc * rows + rr);
@@ -118,6 +127,14 @@ struct Cycles {
 
 int do_layout(const h2v_builder *b, uint32_t k, uint32_t minimum_rows, h2v_layout *L) {
     const Context &ctx = b->ctx;
+    const bool timing = getenv("H2V_LAYOUT_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto tick = [&](const char *what) {
+        if (!timing) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "layout: %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
     if (k < 3 || k > 26) throw std::runtime_error("k out of range");
     const size_t n = (size_t)1 << k;
     if (minimum_rows >= n) throw std::runtime_error("minimum_rows >= 2^k");
@@ -145,34 +162,55 @@ int do_layout(const h2v_builder *b, uint32_t k, uint32_t minimum_rows, h2v_layou
     const size_t P = num_fixed + A + 1;
     const size_t pc_const = 0, pc_adv = num_fixed, pc_inst = num_fixed + A;
     // columns are written as canonical limbs first and converted to Montgomery form in place at the end
-    L->advice.assign(A, std::vector<uint64_t>(n * 4, 0));
-    L->fixed.assign(F, std::vector<uint64_t>(n * 4, 0));
+    L->advice.assign(A, std::vector<uint64_t>());
+    L->fixed.assign(F, std::vector<uint64_t>());
+    parallel_for(A + F, [&](size_t j) { (j < A ? L->advice[j] : L->fixed[j - A]).assign(n * 4, 0); });      // 2.3 GB at kmeans size: first touch by all cores
     auto put = [](std::vector<uint64_t> &col, size_t row, const U256 &v) { memcpy(&col[4 * row], v.l, 32); };
     std::vector<std::vector<uint64_t>> &adv = L->advice, &fix = L->fixed;
+    tick("allocate columns");
     Cycles cyc(P, n);
+    tick("cycles init");
     // ---- assign_all, first loop: the trace down the gate columns
     std::vector<uint32_t> pos_col(total_advice), pos_row(total_advice);
     {
+        // positions and break points first (serial, selectors only), then the values and selector cells by all cores
+        struct Break { size_t cell; uint32_t col, row; };
+        std::vector<Break> breaks;
         size_t gate_index = 0, row = 0;
         for (size_t i = 0; i < total_advice; ++i) {
             if (gate_index >= num_advice) throw std::runtime_error("NOT ENOUGH ADVICE COLUMNS IN PHASE 0. Perhaps blinding factors were not taken into account.");
-            put(adv[gate_index], row, ctx.advice[i]);
             pos_col[i] = (uint32_t)gate_index;
             pos_row[i] = (uint32_t)row;
             const bool q = ctx.selector[i] != 0;
             if ((q && row + 4 > max_rows) || row >= max_rows - 1) {
+                // the cell closes this column; it is repeated on row 0 of the next one (where its gate, if any, lives)
+                // and tied to the original, which stays the cell's position for the equality constraints
                 L->break_points.push_back((uint32_t)row);
-                const size_t old_col = gate_index, old_row = row;
+                breaks.push_back(Break{i, (uint32_t)gate_index, (uint32_t)row});
                 row = 0;
                 ++gate_index;
                 if (gate_index >= num_advice) throw std::runtime_error("NOT ENOUGH ADVICE COLUMNS IN PHASE 0. Perhaps blinding factors were not taken into account.");
-                put(adv[gate_index], 0, ctx.advice[i]);
-                cyc.copy(pc_adv + gate_index, 0, pc_adv + old_col, old_row);
             }
-            if (q) put(fix[1 + num_fixed + gate_index], row, u_from(1));
             ++row;
         }
+        const size_t parts = 64;
+        parallel_for(parts, [&](size_t part) {
+            const size_t i0 = total_advice * part / parts, i1 = total_advice * (part + 1) / parts;
+            for (size_t i = i0; i < i1; ++i) {
+                put(adv[pos_col[i]], pos_row[i], ctx.advice[i]);
+                if (ctx.selector[i]) put(fix[1 + num_fixed + pos_col[i]], pos_row[i], u_from(1));
+            }
+        });
+        for (const Break &bk : breaks) {
+            put(adv[bk.col + 1], 0, ctx.advice[bk.cell]);
+            if (ctx.selector[bk.cell]) {        // the gate starts on the repeated cell, not on the closing one
+                put(fix[1 + num_fixed + bk.col], bk.row, u_from(0));
+                put(fix[1 + num_fixed + bk.col + 1], 0, u_from(1));
+            }
+            cyc.copy(pc_adv + bk.col + 1, 0, pc_adv + bk.col, bk.row);
+        }
     }
+    tick("trace -> gate columns");
     // constants: one fixed cell per distinct value, column-cyclic
     if (!const_order.empty() && num_fixed == 0) throw std::runtime_error("no fixed column for constants");
     {
@@ -189,6 +227,8 @@ int do_layout(const h2v_builder *b, uint32_t k, uint32_t minimum_rows, h2v_layou
     // ---- second loop: equality constraints, then the lookup copies
     for (const auto &e : ctx.advice_eq)
         cyc.copy(pc_adv + pos_col[(size_t)e.first], pos_row[(size_t)e.first], pc_adv + pos_col[(size_t)e.second], pos_row[(size_t)e.second]);
+    tick("advice equalities");
+    if (timing) fprintf(stderr, "layout: %zu advice equalities, %zu constant equalities, %zu lookup cells\n", ctx.advice_eq.size(), ctx.constant_eq.size(), ctx.cells_to_lookup.size());
     for (const auto &e : ctx.constant_eq) {
         const auto fc = assigned_constants[e.first];
         cyc.copy(pc_const + fc.first, fc.second, pc_adv + pos_col[(size_t)e.second], pos_row[(size_t)e.second]);
@@ -205,6 +245,7 @@ int do_layout(const h2v_builder *b, uint32_t k, uint32_t minimum_rows, h2v_layou
             ++loff;
         }
     }
+    tick("constant + lookup copies");
     // lookup table 0 .. 2^lookup_bits - 1 (the remaining rows hold the default 0)
     for (size_t i = 0; i < ((size_t)1 << b->fp.lookup_bits); ++i) put(fix[0], i, u_from(i));
     // instance column
@@ -227,6 +268,7 @@ int do_layout(const h2v_builder *b, uint32_t k, uint32_t minimum_rows, h2v_layou
     dp[0] = frh::ONE;
     for (size_t c = 1; c < P; ++c) dp[c] = frh::mul(dp[c - 1], delta);
     L->sigma.assign(P, std::vector<uint64_t>());
+    tick("tables, powers");
     parallel_for(A + F + P, [&](size_t j) {
         if (j < A + F) {
             std::vector<uint64_t> &col = j < A ? L->advice[j] : L->fixed[j - A];
@@ -244,6 +286,7 @@ int do_layout(const h2v_builder *b, uint32_t k, uint32_t minimum_rows, h2v_layou
             }
         }
     });
+    tick("montgomery + sigma");
     for (int kind = 0; kind < 3; ++kind) {
         auto &cols = kind == 0 ? L->advice : kind == 1 ? L->fixed : L->sigma;
         L->ptrs[kind].clear();

@@ -193,7 +193,8 @@ int run_ntt(cudaStream_t st, const fe *src, size_t src_stride, fe *dst, size_t d
     if (n_cols == 0) return H2V_OK;
     if ((const void *)src == (const void *)dst) return fail(H2V_EINVAL, "run_ntt: in-place transform needs distinct buffers");
     std::call_once(g_ntt_attr_once[cur_dev()], [] {
-        cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM_BYTES);
+        cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM_BYTES);
+        cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM_BYTES);
     });
     NttPass p;
     memset(&p, 0, sizeof p);
@@ -238,7 +239,12 @@ int run_ntt(cudaStream_t st, const fe *src, size_t src_stride, fe *dst, size_t d
             unsigned threads = 1u << (S + p.logT - 3);
             unsigned tiles = 1u << (L - S - p.logT);
             size_t smem = ((size_t)2 * (1u << (S + p.logT)) + H2V_NTT_PLANE_PAD) * 16;
-            ntt_pass_kernel<<<dim3(tiles, cols), threads, smem, st>>>(p);
+            static const int shoup_max_l = [] {      // H2V_NTT_SHOUP_MAX_L: tuning (0 = never, 30 = always)
+                const char *e = getenv("H2V_NTT_SHOUP_MAX_L");
+                return e ? atoi(e) : 18;
+            }();
+            if (L <= shoup_max_l) ntt_pass_kernel<true><<<dim3(tiles, cols), threads, smem, st>>>(p);
+            else ntt_pass_kernel<false><<<dim3(tiles, cols), threads, smem, st>>>(p);
             LAUNCHED();
             t0 += S;
         }

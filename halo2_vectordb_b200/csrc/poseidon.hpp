@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <future>
 #include <vector>
 
 #include "ec.cuh"
@@ -254,17 +255,38 @@ template <int T, int RATE> struct PoseidonSponge {
     const PoseidonSpec<T> *spec;
     Fr64 state[T];
     std::vector<Fr64> buf;
+    // absorb_async(): the full RATE-word chunks buffered so far are absorbed on a worker thread (a full chunk is absorbed
+    // the same way whatever follows it), so that the prover can queue kernels meanwhile; squeeze() joins it first
+    std::vector<Fr64> work;
+    std::future<void> job;
     explicit PoseidonSponge(const PoseidonSpec<T> *s) : spec(s) {
         for (int i = 0; i < T; ++i) state[i] = frh::zero();
         state[0] = frh::to_mont(Fr64{{0, 1, 0, 0}});      // 2^64
     }
+    PoseidonSponge(const PoseidonSponge &) = delete;
+    PoseidonSponge &operator=(const PoseidonSponge &) = delete;
+    ~PoseidonSponge() { join(); }
     void update(const Fr64 &x) { buf.push_back(x); }
     void permute_chunk(const Fr64 *chunk, size_t len) {
         for (size_t i = 0; i < len; ++i) state[1 + i] = frh::add(state[1 + i], chunk[i]);
         if (len + 1 < (size_t)T) state[len + 1] = frh::add(state[len + 1], frh::ONE);
         poseidon_permute<T>(*spec, state);
     }
+    void join() {
+        if (job.valid()) job.get();
+    }
+    void absorb_async() {
+        join();
+        const size_t full = buf.size() / RATE * RATE;
+        if (!full) return;
+        work.assign(buf.begin(), buf.begin() + full);
+        buf.erase(buf.begin(), buf.begin() + full);
+        job = std::async(std::launch::async, [this] {
+            for (size_t i = 0; i < work.size(); i += RATE) permute_chunk(work.data() + i, RATE);
+        });
+    }
     Fr64 squeeze() {
+        join();
         std::vector<Fr64> b;
         b.swap(buf);
         const bool exact = b.size() % RATE == 0;
@@ -302,6 +324,7 @@ struct PoseidonTranscript {
     std::vector<uint8_t> out;
     PoseidonTranscript() : sponge(&poseidon_transcript_spec()) {}
     Fr64 squeeze_challenge() { return sponge.squeeze(); }
+    void absorb_async() { sponge.absorb_async(); }      // hash what has been written so far while the caller goes on
     // false: the identity cannot be absorbed (upstream: Error::Transcript "Cannot write points at infinity to the transcript")
     bool common_point(const affine &p) {
         if (affine_is_identity(p)) return false;

@@ -574,6 +574,7 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
         H2V_CU(cudaMemcpy(pts.data(), pk->commits.p, (size_t)A * sizeof(affine), cudaMemcpyDeviceToHost));
     }
     H2V_TRY(write_points(T, pts));
+    T.absorb_async();      // the advice commitments are hashed on a worker thread while the lookup permutations run
     lap();   // phase 0: upload + advice commitments
     // column pointer helpers
     auto col_L = [&](uint8_t kind, uint32_t idx) -> const fe * {
@@ -583,8 +584,8 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
         return kind == 0 ? pk->adv_E.f() + (size_t)idx * ne : kind == 1 ? pk->fixed_E.f() + (size_t)idx * ne : pk->inst_E.f() + (size_t)idx * ne;
     };
     // ---- 5. theta; lookups: permuted input / table columns                   (lookup/prover.rs commit_permuted)
-    const Fr64 theta = T.squeeze_challenge();
-    (void)theta;       // single-expression lookups: nothing to compress
+    // theta is squeezed at its place in the transcript (below, before A' / S' are written); single-expression lookups
+    // have nothing to compress, so the permutations do not wait for it
     H2V_TRY(pk->pa_L.ensure(std::max<size_t>(1, L) * n * sizeof(fe)));
     H2V_TRY(pk->ps_L.ensure(std::max<size_t>(1, L) * n * sizeof(fe)));
     if (L) {
@@ -609,11 +610,13 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
         std::vector<affine> ca, cs_;
         H2V_TRY(commit_dev(pk, H2V_BASIS_LAGRANGE, pk->pa_L.f(), L, ca));
         H2V_TRY(commit_dev(pk, H2V_BASIS_LAGRANGE, pk->ps_L.f(), L, cs_));
+        (void)T.squeeze_challenge();      // theta
         for (uint32_t l = 0; l < L; ++l) {
             if (!T.write_point(ca[l]) || !T.write_point(cs_[l]))
                 return failf(H2V_EINVAL, "create_proof: Cannot write points at infinity to the transcript");
         }
     }
+    else (void)T.squeeze_challenge();     // theta
     lap();   // phase 1: lookup permutations
     // ---- 6. beta, gamma; permutation grand products                          (permutation/prover.rs commit)
     const Fr64 beta = T.squeeze_challenge(), gamma = T.squeeze_challenge();
@@ -667,6 +670,7 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
         H2V_TRY(write_rows(pk, pk->z_L.f(), n, n - bf, bf, NS, tails));
         H2V_TRY(commit_dev(pk, H2V_BASIS_LAGRANGE, pk->z_L.f(), NS, pts));
         H2V_TRY(write_points(T, pts));
+        T.absorb_async();      // hashed while the lookup products are built and committed
     }
     // ---- 7. lookup grand products                                             (lookup/prover.rs commit_product)
     H2V_TRY(pk->zl_L.ensure(std::max<size_t>(1, L) * n * sizeof(fe)));
@@ -690,6 +694,7 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
         H2V_TRY(write_rows(pk, pk->zl_L.f(), n, n - bf, bf, L, tails));
         H2V_TRY(commit_dev(pk, H2V_BASIS_LAGRANGE, pk->zl_L.f(), L, pts));
         H2V_TRY(write_points(T, pts));
+        T.absorb_async();
     }
     lap();   // phase 2: grand products
     // ---- 8. vanishing argument: random polynomial                             (vanishing/prover.rs commit)
@@ -705,9 +710,10 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
         H2V_TRY(sync(pk));
         H2V_TRY(commit_dev(pk, H2V_BASIS_MONOMIAL, pk->rnd_C.f(), 1, pts));
         H2V_TRY(write_points(T, pts));
+        T.absorb_async();
     }
-    // ---- 9-11. y; coefficient and extended forms; evaluate_h; quotient pieces
-    const Fr64 y = T.squeeze_challenge();
+    // ---- 9-11. coefficient and extended forms (no challenge involved: they run while the commitments above are hashed);
+    //            then y, evaluate_h, quotient pieces
     const int L2C = H2V_OP_LAGRANGE_TO_COEFF, C2E = H2V_OP_COEFF_TO_EXTENDED;
     const bool stream = pk->stream_ext;
     if (stream) {       // the products' numerators / denominators are dead by now: their memory goes to the extended forms
@@ -728,6 +734,7 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
         H2V_TRY(h2v_domain_transform_dev(pk->dom, L2C, t.Lb->p, n, t.Cb->p, n, t.cnt));
         H2V_TRY(h2v_domain_transform_dev(pk->dom, C2E, t.Cb->p, n, t.Eb->p, ne, t.cnt));
     }
+    const Fr64 y = T.squeeze_challenge();
     lap();   // phase 3: random poly + transforms
     H2V_TRY(pk->hq.ensure(2 * ne * sizeof(fe)));
     fe *h_ext = pk->hq.f(), *h_out = pk->hq.f() + ne;
