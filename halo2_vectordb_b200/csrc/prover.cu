@@ -716,12 +716,9 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
     //            then y, evaluate_h, quotient pieces
     const int L2C = H2V_OP_LAGRANGE_TO_COEFF, C2E = H2V_OP_COEFF_TO_EXTENDED;
     const bool stream = pk->stream_ext;
-    if (stream) {       // the products' numerators / denominators are dead by now: their memory goes to the extended forms
-        pk->num.release();
-        pk->den.release();
-    } else {
-        H2V_TRY(pk->adv_E.ensure((size_t)A * ne * sizeof(fe)));
-    }
+    // (the per-proof buffers are kept between proofs, also in streamed mode: with peer access enabled, freeing and
+    // re-allocating gigabytes every proof costs more than the transforms themselves -- measured on two devices)
+    if (!stream) H2V_TRY(pk->adv_E.ensure((size_t)A * ne * sizeof(fe)));
     H2V_TRY(h2v_domain_transform_dev(pk->dom, L2C, pk->adv_L.p, n, pk->adv_C.p, n, A));
     if (!stream) H2V_TRY(h2v_domain_transform_dev(pk->dom, C2E, pk->adv_C.p, n, pk->adv_E.p, ne, A));
     if (I) H2V_TRY(h2v_domain_transform_dev(pk->dom, C2E, pk->inst_C.p, n, pk->inst_E.p, ne, I));

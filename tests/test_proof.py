@@ -149,7 +149,7 @@ def test_gpu_proof_streamed_extended_columns(h2v, monkeypatch, k, gate_cols, loo
     pk = h2v.ProvingKey(srs, t.cs, [fr_arr(c) for c in t.fixed], [fr_arr(c) for c in t.sigma], fr_arr([t.vk_repr])[0])
     streamed = _gpu_proof(pk, t)
     assert streamed == resident == _oracle_proof(params, t)
-    assert _gpu_proof(pk, t) == streamed          # workspace reuse (num / den are released and re-made in this mode)
+    assert _gpu_proof(pk, t) == streamed          # workspace reuse
     pk.close()
     srs.close()
 
