@@ -305,6 +305,20 @@ def _main(args, real_stdout):
     # ---- strong scaling: ONE fixed commit phase of the kmeans k = 16 proof (1 150 columns of 2^16) split
     # over the ranks by column index, host columns in, commitments gathered back in column order inside the timed region
     line["strong"] = bench_strong_phase(h, torch, dev, srs, host_np, rank, world, barrier, max_over_ranks)
+    if not args.no_extras:
+        # the same for BASELINE configs[3] (SIFT-shaped, k = 20: ~360 commits of 2^20 per proof)
+        try:
+            n20 = 1 << 20
+            from halo2_vectordb_b200.synthetic import uniform_scalars
+            srs20 = h.ParamsKZG(20, None, h.synthetic_bases(n20, SYN_A, SYN_B))
+            host20 = torch.from_numpy(uniform_scalars(8, n20, 20 + rank).view(np.int64)).pin_memory().numpy().view(np.uint64)
+            line["strong_k20"] = bench_strong_phase(h, torch, dev, srs20, host20, rank, world, barrier, max_over_ranks, total_cols=STRONG_COLS_K20,
+                                                    n=n20, what="one SIFT-shaped k=20 proof's commits")
+            srs20.close()
+            del host20
+            torch.cuda.empty_cache()
+        except Exception as e:      # never lose the headline line to an extra
+            line["strong_k20"] = {"error": str(e)[:200]}
 
     if not args.no_extras and rank == 0:
         line["ntt"] = bench_ntt(h, torch, dev, peak)
@@ -344,9 +358,10 @@ def _main(args, real_stdout):
 
 
 STRONG_COLS = 1150     # commit_lagrange calls of one kmeans k = 16 proof
+STRONG_COLS_K20 = 360  # ... of one SIFT-shaped k = 20 proof
 
 
-def bench_strong_phase(h, torch, dev, srs, host_np, rank, world, barrier, max_over_ranks):
+def bench_strong_phase(h, torch, dev, srs, host_np, rank, world, barrier, max_over_ranks, total_cols=None, n=None, what=None):
     """One fixed phase split over the ranks (scaling = strong): column j of STRONG_COLS goes to rank j mod world; every rank
     commits its share through the host-facing entry point (pinned host columns, H2D inside), then the commitments are
     all-gathered and put back in column order -- what the host transcript of ONE proof needs before the next challenge.
@@ -354,6 +369,8 @@ def bench_strong_phase(h, torch, dev, srs, host_np, rank, world, barrier, max_ov
     uniform scalars).  Timed as max over ranks, gather included."""
     import ctypes as C
     import numpy as np
+    STRONG_COLS = total_cols or globals()["STRONG_COLS"]
+    N = n or globals()["N"]
     mine = [j for j in range(STRONG_COLS) if j % world == rank]
     per = (STRONG_COLS + world - 1) // world
     ptrs = (C.c_void_p * len(mine))(*[host_np[j % host_np.shape[0]].ctypes.data for j in mine])
@@ -384,7 +401,8 @@ def bench_strong_phase(h, torch, dev, srs, host_np, rank, world, barrier, max_ov
         torch.cuda.synchronize()
         ts.append(max_over_ranks(time.perf_counter() - t0))
     t = min(ts)
-    return {"scaling": "strong", "phase": f"commit_lagrange of {STRONG_COLS} columns x 2^16 (one kmeans k=16 proof's commits), host columns in, "
+    what = what or "one kmeans k=16 proof's commits"
+    return {"scaling": "strong", "phase": f"commit_lagrange of {STRONG_COLS} columns x 2^{N.bit_length() - 1} ({what}), host columns in, "
                                           "commitments gathered in column order", "n_gpus": world, "ms": t * 1e3,
             "mpts_per_s": STRONG_COLS * N / t / 1e6, "cols_per_rank": len(mine)}
 
@@ -887,11 +905,15 @@ def bench_witness(h, torch, dev, srs, peak):
     a = torch.from_numpy(witness_like(cols, N, 15, 7).view(np.int64)).to(dev)
     out = torch.zeros((cols, 8), dtype=torch.int64, device=dev)
     ms, kms = [], {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(8):
-        srs.commit_batch_dev(a.data_ptr(), N, cols, N, out.data_ptr())
+        e0.record()
+        srs.commit_batch_dev(a.data_ptr(), N, cols, N, out.data_ptr())      # blocks until the result is there
+        e1.record()
+        e1.synchronize()
         if i >= 2:
             k = h.last_kernel_ms()
-            ms.append(sum(k.values()))
+            ms.append(e0.elapsed_time(e1))
             for kk, v in k.items():
                 kms.setdefault(kk, []).append(v)
     t = statistics.median(ms) * 1e-3
@@ -901,7 +923,10 @@ def bench_witness(h, torch, dev, srs, peak):
     acc_s = kmed["msm_accumulate"] * 1e-3
     res = {"msm_mpts_per_s": cols * N / t / 1e6, "ms_per_step": t * 1e3, "cols_per_step": cols, "lookup_bits": 15,
            "kernel_ms_per_step": {kk: round(v, 4) for kk, v in kmed.items() if v},
-           "non_accumulate_share": 1.0 - kmed["msm_accumulate"] / sum(kmed.values()),
+           # the step time is the wall clock of the call (CUDA events around it); the share is the part of it not covered
+           # by the accumulate kernel
+           "non_accumulate_share": max(0.0, 1.0 - kmed["msm_accumulate"] * 1e-3 / t),
+           "kernel_span_sum_ms": sum(kmed.values()),
            "window_bits": c, "windows": w}
     entries = h.last_msm_entries()
     if entries and acc_s > 0:

@@ -104,6 +104,11 @@ extern "C" {
                                         d_sigma: *const c_void, sigma_stride: usize, d_z: *const c_void, z_stride: usize,
                                         d_l0: *const c_void, d_l_last: *const c_void, d_l_active: *const c_void,
                                         blinding_factors: u32) -> c_int;
+    pub fn h2v_quotient_permutation_range_ptrs_dev(dom: *mut H2vDomain, d_h: *mut c_void, y: *const u64, beta: *const u64, gamma: *const u64,
+                                                   n_cols: usize, chunk_len: usize, set_begin: usize, set_end: usize, with_head: c_int,
+                                                   d_col_ptrs: *const *const c_void, d_sigma_ptrs: *const *const c_void,
+                                                   d_z: *const c_void, z_stride: usize, d_l0: *const c_void, d_l_last: *const c_void,
+                                                   d_l_active: *const c_void, blinding_factors: u32) -> c_int;
     pub fn h2v_quotient_lookup_dev(dom: *mut H2vDomain, d_h: *mut c_void, y: *const u64, beta: *const u64, gamma: *const u64,
                                    d_input: *const c_void, d_table: *const c_void, d_perm_input: *const c_void,
                                    d_perm_table: *const c_void, d_z: *const c_void, d_l0: *const c_void, d_l_last: *const c_void,

@@ -164,6 +164,27 @@ __device__ __forceinline__ fe ntt_finish(fe x, const fe *post, uint32_t shift) {
     return x;
 }
 
+// Later passes (t0 > 0) read twiddles that are spread over the whole table -- every butterfly of a stage its own entry --
+// and the round's products wait for them (ncu: a quarter of the stall samples of pass 1 were long-scoreboard waits on
+// IMAD.WIDE).  The round's <= 7 twiddle lines are therefore requested with prefetch.global.L1 one barrier ahead: before
+// the tile load for the first round, before the closing barrier of a round for the next one.  No registers are held.
+template <bool SHOUP>
+__device__ __forceinline__ void ntt_prefetch_twiddles(const NttPass &p, int bp, int u0, uint32_t jlow) {
+    const fe *tw = SHOUP ? p.tws : p.tw;
+#pragma unroll
+    for (int U = 0; U < 3; ++U) {
+        if (U < u0) continue;
+        const int t = p.t0 + bp + U;
+        const uint32_t e_base = jlow << (p.L - 1 - t);
+#pragma unroll
+        for (int kk = 0; kk < (1 << U); ++kk) {
+            const uint32_t e = e_base + ((uint32_t)kk << (p.L - 1 - U));
+            const fe *a = SHOUP ? tw + 2 * (size_t)e : tw + e;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+        }
+    }
+}
+
 // SHOUP (transforms of up to 2^18 points): Shoup twiddle products from the (w, w') table -- 3-5 % faster there; larger
 // transforms keep the Montgomery product, whose twiddle stream is half as wide (measured 4 % faster at 2^20 / 2^22)
 template <bool SHOUP>
@@ -207,6 +228,10 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
         // element (mid, q): index hi * 2^(t0+S) + mid * 2^t0 + lo_tile*T + q, in place on dst
         hi = tile >> (t0 - logT);
         lo_tile = tile & ((1u << (t0 - logT)) - 1);
+        if (tid < (nelem >> 3)) {      // twiddles of the first round: bp = 0 (S >= 3), every in-thread stage
+            const int bp0 = (3 <= S) ? 0 : S - 3;
+            ntt_prefetch_twiddles<SHOUP>(p, bp0, 0 - bp0, lo_tile * T + (tid & (T - 1)));
+        }
         const fe *base = dst + ((size_t)hi << (t0 + S)) + (size_t)lo_tile * T;
         fe xs[8];
 #pragma unroll
@@ -266,6 +291,11 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(NttPass p) {
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) ntt_sm_store_slot(ntt_sm, plane1, slot[k], x[k]);
+        }
+        if (!p.first && b + 3 < S && tid < (nelem >> 3)) {
+            const int nb = b + 3, nbp = (nb + 3 <= S) ? nb : S - 3;
+            const uint32_t q = tid & (T - 1), low = (tid >> logT) & ((1u << nbp) - 1);
+            ntt_prefetch_twiddles<SHOUP>(p, nbp, nb - nbp, (lo_tile * T + q) + (low << t0));
         }
         __syncthreads();
     }

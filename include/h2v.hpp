@@ -168,6 +168,14 @@ class EvaluationDomain {
         check(h2v_quotient_permutation_dev(h_, d_h, y.l, beta.l, gamma.l, n_cols, chunk_len, d_cols, cols_stride, d_sigma, sigma_stride,
                                            d_z, z_stride, d_l0, d_l_last, d_l_active, blinding_factors));
     }
+    // the same fold over the permutation sets [set_begin, set_end) only (extended columns streamed in slices, k = 20)
+    void quotient_permutation_range(void *d_h, const Fr &y, const Fr &beta, const Fr &gamma, size_t n_cols, size_t chunk_len, size_t set_begin,
+                                    size_t set_end, bool with_head, const void *const *d_col_ptrs, const void *const *d_sigma_ptrs,
+                                    const void *d_z, size_t z_stride, const void *d_l0, const void *d_l_last, const void *d_l_active,
+                                    uint32_t blinding_factors) const {
+        check(h2v_quotient_permutation_range_ptrs_dev(h_, d_h, y.l, beta.l, gamma.l, n_cols, chunk_len, set_begin, set_end, with_head ? 1 : 0,
+                                                      d_col_ptrs, d_sigma_ptrs, d_z, z_stride, d_l0, d_l_last, d_l_active, blinding_factors));
+    }
     void quotient_lookup(void *d_h, const Fr &y, const Fr &beta, const Fr &gamma, const void *d_input, const void *d_table,
                          const void *d_perm_input, const void *d_perm_table, const void *d_z, const void *d_l0, const void *d_l_last,
                          const void *d_l_active) const {
