@@ -804,15 +804,22 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
             H2V_TRY(h2v_quotient_permutation_range_ptrs_dev(pk->dom, h_ext, u64(y), u64(beta), u64(gamma), NP, pk->chunk, s0, s1, s0 == 0,
                                                             tab, tab + cnt, pk->z_E.p, ne, l0, ll, la, bf));
         }
+        // lookups: the table's extended form in slot 0 (one table for all of halo2-base's range lookups), the inputs of up
+        // to SC - 1 lookups extended together (a single 2^22-point column transforms four times slower per column than a batch)
         uint32_t table_in_slot = UINT32_MAX;
-        for (uint32_t l = 0; l < L; ++l) {
-            if (pk->lookup_table[l] != table_in_slot) {
-                H2V_TRY(h2v_domain_transform_dev(pk->dom, C2E, col_C(1, pk->lookup_table[l]), n, scr, ne, 1));
-                table_in_slot = pk->lookup_table[l];
+        for (uint32_t l0_ = 0; l0_ < L;) {
+            if (pk->lookup_table[l0_] != table_in_slot) {
+                H2V_TRY(h2v_domain_transform_dev(pk->dom, C2E, col_C(1, pk->lookup_table[l0_]), n, scr, ne, 1));
+                table_in_slot = pk->lookup_table[l0_];
             }
-            H2V_TRY(h2v_domain_transform_dev(pk->dom, C2E, col_C(0, pk->lookup_input[l]), n, scr + ne, ne, 1));
-            H2V_TRY(h2v_quotient_lookup_dev(pk->dom, h_ext, u64(y), u64(beta), u64(gamma), scr + ne, scr, pk->pa_E.f() + (size_t)l * ne,
-                                            pk->ps_E.f() + (size_t)l * ne, pk->zl_E.f() + (size_t)l * ne, l0, ll, la));
+            uint32_t l1_ = l0_;
+            src.clear();
+            while (l1_ < L && pk->lookup_table[l1_] == table_in_slot && src.size() + 1 < SC) src.push_back(col_C(0, pk->lookup_input[l1_++]));
+            H2V_TRY(extend(src, scr + ne));
+            for (uint32_t l = l0_; l < l1_; ++l)
+                H2V_TRY(h2v_quotient_lookup_dev(pk->dom, h_ext, u64(y), u64(beta), u64(gamma), scr + (size_t)(1 + l - l0_) * ne, scr,
+                                                pk->pa_E.f() + (size_t)l * ne, pk->ps_E.f() + (size_t)l * ne, pk->zl_E.f() + (size_t)l * ne, l0, ll, la));
+            l0_ = l1_;
         }
     }
     H2V_TRY(h2v_domain_transform_dev(pk->dom, H2V_OP_DIVIDE_BY_VANISHING, h_ext, ne, h_out, ne, 1));
