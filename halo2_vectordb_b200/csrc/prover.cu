@@ -768,6 +768,15 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
             return kind == 0 ? pk->adv_C.f() + (size_t)idx * n : kind == 1 ? pk->fixed_C.f() + (size_t)idx * n : pk->inst_C.f() + (size_t)idx * n;
         };
         // coeff_to_extended of a list of coefficient columns into consecutive scratch slots; neighbours share one launch
+        const bool timing = getenv("H2V_PROVE_TIMING") != nullptr;
+        double t_ext = 0, t_fold = 0, t_mark = PhaseClock::now();
+        auto mark = [&](double &acc) {
+            if (!timing) return;
+            cudaDeviceSynchronize();
+            const double t = PhaseClock::now();
+            acc += t - t_mark;
+            t_mark = t;
+        };
         auto extend = [&](const std::vector<const fe *> &src, fe *dst) -> int {
             for (size_t i = 0; i < src.size();) {
                 size_t j = i + 1;
@@ -779,6 +788,61 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
         };
         const void *const *tab = (const void *const *)pk->ptrs.p;
         std::vector<const fe *> src, hp;
+        // Gate j reads one advice column, and (in halo2-base's constraint system) every gate column is also a permutation
+        // column: when the gates meet their columns in gate order along the permutation, one pass over the permutation
+        // slices serves both folds -- the gates into h, the permutation into a second accumulator hp (the memory of the
+        // quotient's output, free until the division), joined as h <- h y^(permutation terms) + hp.  Each advice column is
+        // then extended once instead of twice.  Any other constraint system takes the two separate loops below.
+        std::vector<int32_t> gate_of_adv(A, -1);
+        for (uint32_t j = 0; j < G; ++j) gate_of_adv[pk->gate_advice[j]] = gate_of_adv[pk->gate_advice[j]] == -1 ? (int32_t)j : -2;
+        bool fused = NP > 0 && G > 0;
+        {
+            uint32_t next_gate = 0;
+            for (uint32_t c = 0; c < NP && fused; ++c)
+                if (pk->perm_kind[c] == 0 && gate_of_adv[pk->perm_index[c]] != -1) fused = gate_of_adv[pk->perm_index[c]] == (int32_t)next_gate++;
+            fused = fused && next_gate == G;
+        }
+        if (fused) {
+            fe *hp_acc = h_out;
+            H2V_CU(cudaMemsetAsync(hp_acc, 0, ne * sizeof(fe), st));
+            H2V_TRY(sync(pk));
+            const size_t BS = std::max<size_t>(1, SC / (3 * (size_t)pk->chunk));
+            for (size_t s0 = 0; s0 < NS; s0 += BS) {
+                const size_t s1 = std::min<size_t>(NS, s0 + BS), c0 = s0 * pk->chunk, c1 = std::min<size_t>(NP, s1 * pk->chunk), cnt = c1 - c0;
+                src.clear();
+                for (size_t c = c0; c < c1; ++c) src.push_back(col_C(pk->perm_kind[c], pk->perm_index[c]));
+                for (size_t c = c0; c < c1; ++c) src.push_back(pk->sigma_C.f() + c * n);
+                std::vector<const fe *> gq, ga;      // this slice's gates: selector (extended behind the slice), advice (already in it)
+                for (size_t c = c0; c < c1; ++c) {
+                    if (pk->perm_kind[c] != 0 || gate_of_adv[pk->perm_index[c]] < 0) continue;
+                    src.push_back(col_C(1, pk->gate_selector[gate_of_adv[pk->perm_index[c]]]));
+                    gq.push_back(scr + (2 * cnt + gq.size()) * ne);
+                    ga.push_back(scr + (c - c0) * ne);
+                }
+                H2V_TRY(extend(src, scr));
+                mark(t_ext);
+                hp.assign(2 * cnt + 2 * gq.size(), nullptr);
+                for (size_t j = 0; j < 2 * cnt; ++j) hp[j] = scr + j * ne;
+                for (size_t j = 0; j < gq.size(); ++j) {
+                    hp[2 * cnt + j] = gq[j];
+                    hp[2 * cnt + gq.size() + j] = ga[j];
+                }
+                H2V_TRY(upload(pk, pk->ptrs, 0, hp.data(), hp.size() * sizeof(void *)));
+                H2V_TRY(h2v_quotient_permutation_range_ptrs_dev(pk->dom, hp_acc, u64(y), u64(beta), u64(gamma), NP, pk->chunk, s0, s1, s0 == 0,
+                                                                tab, tab + cnt, pk->z_E.p, ne, l0, ll, la, bf));
+                if (!gq.empty()) H2V_TRY(h2v_quotient_gates_ptrs_dev(pk->dom, h_ext, u64(y), gq.size(), tab + 2 * cnt, tab + 2 * cnt + gq.size()));
+                mark(t_fold);
+            }
+            // h <- h y^T + hp, T = the permutation argument's terms: 2 + (NS - 1) + NS
+            const fe *two[2] = {h_ext, hp_acc};
+            const Fr64 cf[2] = {frh::pow_u64(y, 2ull * NS + 1), frh::ONE};
+            H2V_TRY(upload(pk, pk->ptrs, 0, two, sizeof two));
+            H2V_TRY(upload(pk, pk->scal, 0, cf, sizeof cf));
+            lincomb_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>((const fe *const *)pk->ptrs.p, pk->scal.f(), 2, (uint32_t)ne, h_ext);
+            H2V_LAUNCHED();
+            H2V_TRY(sync(pk));
+            mark(t_fold);
+        } else {
         const size_t BG = SC / 2;
         for (size_t g0 = 0; g0 < G; g0 += BG) {
             const size_t b = std::min<size_t>(BG, G - g0);
@@ -787,9 +851,11 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
             for (size_t j = 0; j < b; ++j) src.push_back(col_C(1, pk->gate_selector[g0 + j]));
             for (size_t j = 0; j < b; ++j) src.push_back(col_C(0, pk->gate_advice[g0 + j]));
             H2V_TRY(extend(src, scr));
+            mark(t_ext);
             for (size_t j = 0; j < 2 * b; ++j) hp[j] = scr + j * ne;
             H2V_TRY(upload(pk, pk->ptrs, 0, hp.data(), hp.size() * sizeof(void *)));
             H2V_TRY(h2v_quotient_gates_ptrs_dev(pk->dom, h_ext, u64(y), b, tab, tab + b));
+            mark(t_fold);
         }
         const size_t BS = std::max<size_t>(1, SC / (2 * (size_t)pk->chunk));
         for (size_t s0 = 0; s0 < NS; s0 += BS) {
@@ -799,10 +865,13 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
             for (size_t c = c0; c < c1; ++c) src.push_back(col_C(pk->perm_kind[c], pk->perm_index[c]));
             for (size_t c = c0; c < c1; ++c) src.push_back(pk->sigma_C.f() + c * n);
             H2V_TRY(extend(src, scr));
+            mark(t_ext);
             for (size_t j = 0; j < 2 * cnt; ++j) hp[j] = scr + j * ne;
             H2V_TRY(upload(pk, pk->ptrs, 0, hp.data(), hp.size() * sizeof(void *)));
             H2V_TRY(h2v_quotient_permutation_range_ptrs_dev(pk->dom, h_ext, u64(y), u64(beta), u64(gamma), NP, pk->chunk, s0, s1, s0 == 0,
                                                             tab, tab + cnt, pk->z_E.p, ne, l0, ll, la, bf));
+            mark(t_fold);
+        }
         }
         // lookups: the table's extended form in slot 0 (one table for all of halo2-base's range lookups), the inputs of up
         // to SC - 1 lookups extended together (a single 2^22-point column transforms four times slower per column than a batch)
@@ -816,11 +885,14 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
             src.clear();
             while (l1_ < L && pk->lookup_table[l1_] == table_in_slot && src.size() + 1 < SC) src.push_back(col_C(0, pk->lookup_input[l1_++]));
             H2V_TRY(extend(src, scr + ne));
+            mark(t_ext);
             for (uint32_t l = l0_; l < l1_; ++l)
                 H2V_TRY(h2v_quotient_lookup_dev(pk->dom, h_ext, u64(y), u64(beta), u64(gamma), scr + (size_t)(1 + l - l0_) * ne, scr,
                                                 pk->pa_E.f() + (size_t)l * ne, pk->ps_E.f() + (size_t)l * ne, pk->zl_E.f() + (size_t)l * ne, l0, ll, la));
+            mark(t_fold);
             l0_ = l1_;
         }
+        if (timing) fprintf(stderr, "evaluate_h (streamed): coeff_to_extended of the slices %.1f ms, folds %.1f ms\n", t_ext, t_fold);
     }
     H2V_TRY(h2v_domain_transform_dev(pk->dom, H2V_OP_DIVIDE_BY_VANISHING, h_ext, ne, h_out, ne, 1));
     const uint32_t NH = pk->degree - 1;          // quotient pieces of n coefficients each

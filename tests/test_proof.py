@@ -135,11 +135,16 @@ def test_gpu_proof_bytes_equal_oracle(h2v, k, gate_cols, lookup_cols, degree):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k,gate_cols,lookup_cols,degree,scr", [(8, 5, 3, 4, 6), (7, 3, 2, 5, 8), (10, 6, 2, 4, 7), (6, 4, 0, 4, 64)])
-def test_gpu_proof_streamed_extended_columns(h2v, monkeypatch, k, gate_cols, lookup_cols, degree, scr):
+@pytest.mark.parametrize("k,gate_cols,lookup_cols,degree,scr,reverse_gates",
+                         [(8, 5, 3, 4, 6, False), (7, 3, 2, 5, 8, False), (10, 6, 2, 4, 7, False), (6, 4, 0, 4, 64, False), (8, 5, 3, 4, 6, True), (9, 7, 1, 4, 9, True)])
+def test_gpu_proof_streamed_extended_columns(h2v, monkeypatch, k, gate_cols, lookup_cols, degree, scr, reverse_gates):
     """The k = 20 path: the key keeps no extended-coset columns and evaluate_h rebuilds them in slices of `scr` columns
-    (forced here at small k); the proof must be the same bytes as with everything resident, and as the CPU restatement's."""
+    (forced here at small k); the proof must be the same bytes as with everything resident, and as the CPU restatement's.
+    With the gates in the order of their columns, one pass over the permutation slices folds gates and permutation together
+    (each advice column extended once); `reverse_gates` lists the gates backwards, which takes the two separate loops."""
     t = Toy(k, seed=k * 100 + gate_cols, n_gate_cols=gate_cols, n_lookup_cols=lookup_cols, degree=degree)
+    if reverse_gates:
+        t.cs["gates"] = list(reversed(t.cs["gates"]))
     params = PL.Params.setup(k, SECRET)
     srs, pk = _gpu_setup(h2v, k, t, params)
     resident = _gpu_proof(pk, t)
