@@ -284,6 +284,11 @@ struct h2v_pk {
     bool stream_ext = false;
     size_t scr_cols = 0;
     DevBuf scr_E;
+    // ... and what is left of the device's memory after the first proof's buffers exist keeps the extended forms of the first
+    // `cached_sigma` sigma polynomials (they belong to the key: every later proof skips their coeff_to_extended)
+    DevBuf ext_cache;
+    size_t cached_sigma = 0;
+    bool cache_tried = false;
     cudaStream_t st = nullptr;
     int dev = 0;                 // the proof runs on the primary device (columns and key resident there)
     std::mutex mu;
@@ -345,7 +350,7 @@ void h2v_pk_free(h2v_pk_t pk) {
                      &pk->adv_L, &pk->adv_C, &pk->adv_E, &pk->inst_L, &pk->inst_C, &pk->inst_E, &pk->pa_L, &pk->ps_L, &pk->pa_C, &pk->ps_C,
                      &pk->pa_E, &pk->ps_E, &pk->z_L, &pk->z_C, &pk->z_E, &pk->zl_L, &pk->zl_C, &pk->zl_E, &pk->num, &pk->den, &pk->tails,
                      &pk->ptrs, &pk->scal, &pk->pts, &pk->rnd_C, &pk->hq, &pk->hx_pieces, &pk->evals, &pk->pairs, &pk->sh_S, &pk->sh_A,
-                     &pk->sh_B, &pk->sh_h, &pk->commits, &pk->scr_E};
+                     &pk->sh_B, &pk->sh_h, &pk->commits, &pk->scr_E, &pk->ext_cache};
     for (DevBuf *b : all) b->release();
     if (pk->dom) h2v_domain_free(pk->dom);
     if (pk->st) cudaStreamDestroy(pk->st);
@@ -806,27 +811,51 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
             fe *hp_acc = h_out;
             H2V_CU(cudaMemsetAsync(hp_acc, 0, ne * sizeof(fe), st));
             H2V_TRY(sync(pk));
+            if (!pk->cache_tried) {
+                pk->cache_tried = true;
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                const char *e = getenv("H2V_EXT_CACHE_COLS");
+                const size_t margin = (size_t)8 << 30;
+                size_t want = e ? (size_t)atoi(e) : (free_b > margin ? (free_b - margin) / (ne * sizeof(fe)) : 0);
+                want = std::min<size_t>(want, NP);
+                if (want >= (e ? 1u : 8u) && pk->ext_cache.ensure(want * ne * sizeof(fe)) == H2V_OK) {
+                    H2V_TRY(h2v_domain_transform_dev(pk->dom, C2E, pk->sigma_C.p, n, pk->ext_cache.p, ne, want));
+                    pk->cached_sigma = want;
+                }
+            }
             const size_t BS = std::max<size_t>(1, SC / (3 * (size_t)pk->chunk));
+            std::vector<const fe *> pc, sg, gq, ga;
             for (size_t s0 = 0; s0 < NS; s0 += BS) {
                 const size_t s1 = std::min<size_t>(NS, s0 + BS), c0 = s0 * pk->chunk, c1 = std::min<size_t>(NP, s1 * pk->chunk), cnt = c1 - c0;
-                src.clear();
-                for (size_t c = c0; c < c1; ++c) src.push_back(col_C(pk->perm_kind[c], pk->perm_index[c]));
-                for (size_t c = c0; c < c1; ++c) src.push_back(pk->sigma_C.f() + c * n);
-                std::vector<const fe *> gq, ga;      // this slice's gates: selector (extended behind the slice), advice (already in it)
+                src.clear(); pc.clear(); sg.clear(); gq.clear(); ga.clear();
+                size_t slot = 0;
+                for (size_t c = c0; c < c1; ++c) {
+                    src.push_back(col_C(pk->perm_kind[c], pk->perm_index[c]));
+                    pc.push_back(scr + slot++ * ne);
+                }
+                for (size_t c = c0; c < c1; ++c) {
+                    if (c < pk->cached_sigma) {
+                        sg.push_back(pk->ext_cache.f() + c * ne);
+                    } else {
+                        src.push_back(pk->sigma_C.f() + c * n);
+                        sg.push_back(scr + slot++ * ne);
+                    }
+                }
+                // this slice's gates: selector extended behind the slice, advice already in it
                 for (size_t c = c0; c < c1; ++c) {
                     if (pk->perm_kind[c] != 0 || gate_of_adv[pk->perm_index[c]] < 0) continue;
                     src.push_back(col_C(1, pk->gate_selector[gate_of_adv[pk->perm_index[c]]]));
-                    gq.push_back(scr + (2 * cnt + gq.size()) * ne);
-                    ga.push_back(scr + (c - c0) * ne);
+                    gq.push_back(scr + slot++ * ne);
+                    ga.push_back(pc[c - c0]);
                 }
                 H2V_TRY(extend(src, scr));
                 mark(t_ext);
-                hp.assign(2 * cnt + 2 * gq.size(), nullptr);
-                for (size_t j = 0; j < 2 * cnt; ++j) hp[j] = scr + j * ne;
-                for (size_t j = 0; j < gq.size(); ++j) {
-                    hp[2 * cnt + j] = gq[j];
-                    hp[2 * cnt + gq.size() + j] = ga[j];
-                }
+                hp.clear();
+                hp.insert(hp.end(), pc.begin(), pc.end());
+                hp.insert(hp.end(), sg.begin(), sg.end());
+                hp.insert(hp.end(), gq.begin(), gq.end());
+                hp.insert(hp.end(), ga.begin(), ga.end());
                 H2V_TRY(upload(pk, pk->ptrs, 0, hp.data(), hp.size() * sizeof(void *)));
                 H2V_TRY(h2v_quotient_permutation_range_ptrs_dev(pk->dom, hp_acc, u64(y), u64(beta), u64(gamma), NP, pk->chunk, s0, s1, s0 == 0,
                                                                 tab, tab + cnt, pk->z_E.p, ne, l0, ll, la, bf));

@@ -151,6 +151,8 @@ def test_gpu_proof_streamed_extended_columns(h2v, monkeypatch, k, gate_cols, loo
     pk.close()
     monkeypatch.setenv("H2V_STREAM_EXT", "1")
     monkeypatch.setenv("H2V_STREAM_COLS", str(scr))
+    if k != 8:      # how many extended sigma columns the key caches once the first proof's buffers exist: some / none / all that fit
+        monkeypatch.setenv("H2V_EXT_CACHE_COLS", "3" if k == 10 else "0")
     pk = h2v.ProvingKey(srs, t.cs, [fr_arr(c) for c in t.fixed], [fr_arr(c) for c in t.sigma], fr_arr([t.vk_repr])[0])
     streamed = _gpu_proof(pk, t)
     assert streamed == resident == _oracle_proof(params, t)
