@@ -698,7 +698,7 @@ struct SrsRep {
     DevBuf stage, out;
     DevBuf peer_stage, peer_out;      // columns of another device's batch pulled over NVLink (h2v_commit_batch_dev with several devices)
     std::mutex peer_mu;               // held from the pull to the write-back
-    cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr, up_stream = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, computed[2] = {nullptr, nullptr};
     std::mutex mu;
     // Small calls (a single commit_lagrange from one of the caller's worker threads -- stock create_proof
@@ -985,6 +985,7 @@ static void rep_srs_free(SrsRep *s) {
     s->peer_stage.release();
     s->peer_out.release();
     if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->up_stream) cudaStreamDestroy(s->up_stream);
     if (s->copy_stream) {
         cudaStreamDestroy(s->copy_stream);
         cudaStreamDestroy(s->stream2);
@@ -2617,6 +2618,76 @@ int h2v_commit_batch_dev(h2v_srs_t h, int basis, const void *d_polys, size_t col
     t_dev = r->dev;
     return rc;
 }
+// Host columns that are committed AND left resident (the advice phase of create_proof): every device uploads a contiguous
+// block of the columns over its own PCIe link in sub-batches (the next one crosses while the previous one is committed),
+// overwrites the blinding rows, commits against its SRS replica and forwards the block to the destination buffer on the
+// owning device over NVLink; commitments land in the host array in column order.
+int h2v_commit_batch_resident(h2v_srs_t h, int basis, const uint64_t *const *polys, size_t n_polys, size_t len, const uint64_t *tails,
+                              size_t row0, size_t n_rows, void *d_dst, size_t dst_stride, uint64_t *out_affine) {
+    if (!h) return fail(H2V_EINVAL, "commit: NULL srs");
+    if (n_polys == 0) return H2V_OK;
+    if (!polys || !d_dst || !out_affine || (n_rows && !tails)) return fail(H2V_EINVAL, "commit_resident: NULL buffer");
+    if (len == 0 || dst_stride < len || row0 + n_rows > len) return fail(H2V_EINVAL, "commit_resident: bad length / stride / row range");
+    for (size_t c = 0; c < n_polys; ++c)
+        if (!polys[c]) return fail(H2V_EINVAL, "commit_resident: polys[%zu] is NULL", c);
+    SrsRep *r = srs_on(h, device_of(d_dst));
+    if (!r) return fail(H2V_EINVAL, "commit_resident: the destination lives on device %d, which is not in the h2v_init list", device_of(d_dst));
+    const size_t G = (h->rep.size() > 1 && n_polys >= 8 * h->rep.size()) ? h->rep.size() : 1;
+    const size_t per = (n_polys + G - 1) / G;
+    fe *dst = (fe *)d_dst;
+    int rc = fan_out(G, [&](size_t d) -> int {
+        SrsRep *rep = G == 1 ? r : h->rep[d];
+        const size_t c0 = std::min(n_polys, d * per), cnt = std::min(n_polys, c0 + per) - c0;
+        if (!cnt) return H2V_OK;
+        t_dev = rep->dev;
+        int rc2 = use_device();
+        if (rc2) return rc2;
+        const bool owner = rep == r;
+        std::lock_guard<std::mutex> plk(rep->peer_mu);
+        if (!owner && (rc2 = rep->peer_stage.ensure(cnt * len * sizeof(fe)))) return rc2;
+        if ((rc2 = rep->peer_out.ensure(cnt * sizeof(affine)))) return rc2;
+        if (!rep->up_stream) CU(cudaStreamCreateWithFlags(&rep->up_stream, cudaStreamNonBlocking));
+        fe *stage = owner ? dst + c0 * dst_stride : rep->peer_stage.as<fe>();
+        const size_t sstride = owner ? dst_stride : len;
+        const size_t nsub = std::min<size_t>(4, cnt), sub = (cnt + nsub - 1) / nsub;
+        std::vector<cudaEvent_t> ev(nsub, nullptr);
+        cudaError_t e = cudaSuccess;
+        for (size_t b = 0; b < nsub && e == cudaSuccess; ++b) {
+            const size_t off = std::min(cnt, b * sub), m = std::min(cnt, off + sub) - off;
+            if (m) e = stage_columns(true, stage + off * sstride, sstride, polys + c0 + off, m, len, rep->up_stream);
+            if (m && n_rows && e == cudaSuccess)
+                e = cudaMemcpy2DAsync(stage + off * sstride + row0, sstride * sizeof(fe), tails + (c0 + off) * n_rows * 4, n_rows * sizeof(fe),
+                                      n_rows * sizeof(fe), m, cudaMemcpyHostToDevice, rep->up_stream);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[b], rep->up_stream);
+        }
+        for (size_t b = 0; b < nsub && e == cudaSuccess && !rc2; ++b) {
+            const size_t off = std::min(cnt, b * sub), m = std::min(cnt, off + sub) - off;
+            if (!m) continue;
+            e = cudaEventSynchronize(ev[b]);
+            if (e != cudaSuccess) break;
+            rc2 = rep_commit_batch_dev(rep, basis, stage + off * sstride, sstride, m, len, rep->peer_out.as<affine>() + off);
+            if (rc2 || owner) continue;
+            if (dst_stride == len) {
+                e = cudaMemcpyPeerAsync(dst + (c0 + off) * dst_stride, r->dev, stage + off * len, rep->dev, m * len * sizeof(fe), rep->up_stream);
+            } else {
+                for (size_t c = 0; c < m && e == cudaSuccess; ++c)
+                    e = cudaMemcpyPeerAsync(dst + (c0 + off + c) * dst_stride, r->dev, stage + (off + c) * len, rep->dev, len * sizeof(fe), rep->up_stream);
+            }
+        }
+        if (e == cudaSuccess && !rc2)
+            e = cudaMemcpyAsync(out_affine + 8 * c0, rep->peer_out.p, cnt * sizeof(affine), cudaMemcpyDeviceToHost, rep->up_stream);
+        cudaError_t e2 = cudaStreamSynchronize(rep->up_stream);
+        for (cudaEvent_t x : ev)
+            if (x) cudaEventDestroy(x);
+        if (rc2) return rc2;
+        if (e != cudaSuccess || e2 != cudaSuccess)
+            return fail(H2V_ECUDA, "commit_resident: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return H2V_OK;
+    });
+    t_dev = r->dev;
+    return rc;
+}
 // Host columns: with several devices column j goes to device j mod G (each device has its own PCIe link and SRS
 // replica, no collective); the commitments come back in column order.
 int h2v_commit_batch(h2v_srs_t h, int basis, const uint64_t *const *polys, size_t n_polys, size_t len, uint64_t *out_affine) {
@@ -2698,7 +2769,11 @@ int h2v_domain_transform_dev(h2v_domain_t h, int op, const void *d_in, size_t in
     H2V_DOM_ON(d_in)
     const size_t G = h->rep.size();
     static const bool no_split = getenv("H2V_NO_PEER_SPLIT") != nullptr;
-    if (G == 1 || no_split || n_cols < 8 * G || op < 0 || op > H2V_OP_DIVIDE_BY_VANISHING || !d_out || device_of(d_out) != r->dev)
+    // worth splitting when every device gets about 2^21 points of transform: 8 columns of a 2^18-point extended domain
+    // (k = 16), a single column from 2^21 points up (k = 20: one coset transform is 0.8 ms, its NVLink round trip 0.2 ms)
+    const size_t pts = op >= 0 && op <= H2V_OP_DIVIDE_BY_VANISHING ? ((size_t)1 << (op >= H2V_OP_COEFF_TO_EXTENDED ? r->ek : r->k)) : 1;
+    const size_t min_per_dev = std::min<size_t>(8, std::max<size_t>(1, ((size_t)1 << 21) / pts));
+    if (G == 1 || no_split || n_cols < min_per_dev * G || op < 0 || op > H2V_OP_DIVIDE_BY_VANISHING || !d_out || device_of(d_out) != r->dev)
         return rep_domain_transform_dev(r, op, d_in, in_stride, d_out, out_stride, n_cols);
     // Several devices, one resident batch: contiguous blocks of columns, as h2v_commit_batch_dev splits them.  A device
     // other than the owner pulls its input columns over NVLink, transforms them with its own twiddle tables and pushes

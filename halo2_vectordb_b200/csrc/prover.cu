@@ -543,6 +543,17 @@ int create_proof_locked(h2v_pk *pk, const uint64_t *const *advice, const uint64_
     for (uint32_t c = 0; c < A; ++c)
         if (!advice[c]) return failf(H2V_EINVAL, "create_proof: advice[%u] is NULL", c);
     std::vector<affine> pts;
+    if (h2v_device_list(nullptr, 0) > 1 && A >= 8u * (uint32_t)h2v_device_list(nullptr, 0)) {
+        // several devices: every device uploads its block of the columns over its own PCIe link, blinds and commits it, and
+        // forwards it to adv_L over NVLink (h2v_commit_batch_resident); same draws, same bytes
+        std::vector<Fr64> tails((size_t)A * (bf + 1));
+        for (auto &t : tails) t = rng.fr_random();                       // column by column, rows u .. n-1
+        for (uint32_t c = 0; c < A; ++c) (void)rng.fr_random();          // one Blind per column (unused by KZG, but drawn)
+        pts.resize(A);
+        H2V_TRY(h2v_commit_batch_resident(pk->srs, H2V_BASIS_LAGRANGE, advice, A, n, (const uint64_t *)tails.data(), u, bf + 1, pk->adv_L.p, n,
+                                          (uint64_t *)pts.data()));
+        H2V_CU(cudaSetDevice(pk->dev));
+    } else
     {
         // the columns cross PCIe in sub-batches on the proof's stream while the previous sub-batch is being committed
         // (the commit entry point blocks the host, the copies were queued before it)

@@ -101,6 +101,13 @@ int h2v_commit_batch(h2v_srs_t srs, int basis, const uint64_t *const *polys, siz
  * d_out_affine = n_polys x 64 B on the device.  Asynchronous work is complete on return. */
 int h2v_commit_batch_dev(h2v_srs_t srs, int basis, const void *d_polys, size_t col_stride, size_t n_polys, size_t len,
                          void *d_out_affine);
+/* The advice phase of create_proof in one call: host columns that are committed AND left resident.  Column j is uploaded,
+ * its rows [row0, row0 + n_rows) are overwritten with tails[j * n_rows ...] (the blinding rows; n_rows may be 0), it is
+ * committed, and it is stored at d_dst + j * dst_stride (Fr elements; a buffer on one of the h2v_init devices).  With
+ * several devices the columns are cut into contiguous blocks: every device uploads its block over its own PCIe link,
+ * commits it against its SRS replica and forwards it to d_dst over NVLink.  out_affine: n_polys host G1Affine. */
+int h2v_commit_batch_resident(h2v_srs_t srs, int basis, const uint64_t *const *polys, size_t n_polys, size_t len, const uint64_t *tails,
+                              size_t row0, size_t n_rows, void *d_dst, size_t dst_stride, uint64_t *out_affine);
 /* halo2-axiom arithmetic.rs best_multiexp(coeffs, bases) -> C::Curve, exact shape: arbitrary bases,
  * no handle, Jacobian result (any representative; compare after to_affine). */
 int h2v_best_multiexp(const uint64_t *coeffs, const uint64_t *bases, size_t n, uint64_t out_jacobian[12]);
