@@ -73,6 +73,8 @@ extern "C" {
     pub fn h2v_dev_free(d_ptr: *mut c_void) -> c_int;
     pub fn h2v_dev_upload(d_dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
     pub fn h2v_dev_download(dst: *mut c_void, d_src: *const c_void, bytes: usize) -> c_int;
+    pub fn h2v_commit_batch_resident(srs: *mut H2vSrs, basis: c_int, polys: *const *const u64, n_polys: usize, len: usize, tails: *const u64,
+                                     row0: usize, n_rows: usize, d_dst: *mut c_void, dst_stride: usize, out_affine: *mut u64) -> c_int;
     pub fn h2v_commit_batch_dev(srs: *mut H2vSrs, basis: c_int, d_polys: *const c_void, col_stride: usize, n_polys: usize,
                                 len: usize, d_out_affine: *mut c_void) -> c_int;
     pub fn h2v_domain_transform_dev(dom: *mut H2vDomain, op: c_int, d_in: *const c_void, in_stride: usize,

@@ -121,6 +121,8 @@ def lib():
         L.h2v_quotient_lookup_dev.argtypes = [C.c_void_p] * 13
         L.h2v_g1_to_bytes.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_fr_to_repr.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.h2v_commit_batch_resident.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t,
+                                                C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_selftest_field.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_selftest_group.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.h2v_synthetic_bases.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p]
@@ -551,6 +553,19 @@ class ParamsKZG:
         arr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
         out = np.zeros((len(cols), 8), dtype=np.uint64)
         _check(lib().h2v_commit_batch(self._h, basis, arr, len(cols), ln, _ptr(out)))
+        return out
+
+    def commit_batch_resident(self, polys, tails, row0, d_dst_ptr, dst_stride, basis=H2V_BASIS_LAGRANGE):
+        """Host columns committed AND left resident at d_dst (one of the h2v_init devices); rows row0.. of column j are
+        overwritten with tails[j] (shape (n_polys, n_rows, 4), the blinding rows of create_proof) before the commit."""
+        polys = [np.ascontiguousarray(p, dtype=np.uint64) for p in polys]
+        n_polys, length = len(polys), (polys[0].shape[0] if polys else 0)
+        tails = np.ascontiguousarray(tails, dtype=np.uint64) if tails is not None else None
+        n_rows = 0 if tails is None else tails.shape[1]
+        arr = (C.c_void_p * max(1, n_polys))(*[p.ctypes.data for p in polys])
+        out = np.zeros((n_polys, 8), dtype=np.uint64)
+        _check(lib().h2v_commit_batch_resident(self._h, basis, arr, n_polys, length, _ptr(tails) if n_rows else None, row0, n_rows,
+                                               C.c_void_p(d_dst_ptr), dst_stride, _ptr(out)))
         return out
 
     def commit_batch_dev(self, d_polys_ptr, col_stride, n_polys, length, d_out_ptr, basis=H2V_BASIS_LAGRANGE):

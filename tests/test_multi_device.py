@@ -150,3 +150,32 @@ def test_proof_bytes_do_not_depend_on_the_device_count(h2v):
     h2v.init(0)
     assert proofs[0] == proofs[1]
     assert proofs[0] == PL.create_proof(params, t.cs, t.fixed, t.sigma, t.vk_repr, t.advice, t.instances, seed)
+
+
+@pytest.mark.parametrize("devices", [1, 2])
+def test_commit_batch_resident(h2v, devices):
+    """h2v_commit_batch_resident: host columns are blinded, committed and left on the device (the advice phase of
+    create_proof); with two devices each uploads and commits a block and forwards it to the owner."""
+    import torch
+    if h2v.device_count() < devices:
+        pytest.skip("needs 2 GPUs")
+    h2v.init(list(range(devices)) if devices > 1 else 0)
+    try:
+        k, n, cols_n, rows = 9, 1 << 9, 19, 6
+        bases = O.gen_bases(n)
+        srs = h2v.ParamsKZG(k, None, bases)
+        cols = [O.fr_fill(n, 700 + i, mode=i % 2) for i in range(cols_n)]
+        tails = np.stack([O.fr_fill(rows, 900 + i) for i in range(cols_n)])
+        stride = n + 8
+        dst = torch.zeros((cols_n, stride, 4), dtype=torch.int64, device="cuda:0")
+        got = srs.commit_batch_resident(cols, tails, n - rows, dst.data_ptr(), stride)
+        torch.cuda.synchronize(0)
+        res = dst.cpu().numpy().view(np.uint64)
+        for j in range(cols_n):
+            want = cols[j].copy()
+            want[n - rows:] = tails[j]
+            assert (res[j, :n] == want).all() and not res[j, n:].any(), j
+            assert (got[j] == O.best_multiexp_affine(want, bases)).all(), j
+        srs.close()
+    finally:
+        h2v.init(0)
