@@ -186,6 +186,9 @@ def _main(args, real_stdout):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        # the ranks that have no extras to run wait for rank 0 on the CPU: a NCCL barrier would park a spinning kernel on
+        # their GPUs, which rank 0 drives itself in the in-process N-GPU proof (real_flow_n_gpus)
+        cpu_group = dist.new_group(backend="gloo")
     h.init(local_rank)
     cols = args.cols
 
@@ -349,7 +352,8 @@ def _main(args, real_stdout):
                                     "prove_shaped_note": "extrapolated from the sampled per-call times with the same call counts as prove_shaped.kmeans_k16",
                                     "sample": f"24 of the {cols} columns (2^16 uniform Fr each), restated halo2-axiom best_multiexp, {secs:.1f} s"}
     if world > 1:
-        dist.barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
     if rank == 0:
         print(json.dumps(line), file=real_stdout)
     srs.close()
