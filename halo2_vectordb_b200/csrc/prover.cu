@@ -1230,6 +1230,15 @@ int h2v_create_proof(h2v_pk_t pk, const uint64_t *const *advice, const uint64_t 
     std::lock_guard<std::mutex> lk(pk->mu);
     std::vector<uint8_t> proof;
     int rc = create_proof_locked(pk, advice, instances, instance_len, rng_seed, proof);
+    if (rc == H2V_ENOMEM && pk->cached_sigma) {
+        // the key's opportunistic cache of extended sigma columns (streamed mode) took memory something else now needs:
+        // give it back for good and run the proof again
+        cudaStreamSynchronize(pk->st);
+        pk->ext_cache.release();
+        pk->cached_sigma = 0;
+        proof.clear();
+        rc = create_proof_locked(pk, advice, instances, instance_len, rng_seed, proof);
+    }
     if (rc) {
         cudaStreamSynchronize(pk->st);
         return rc;
