@@ -27,7 +27,22 @@ struct h2v_builder {
     VectorDBChip vdb;
     std::unique_ptr<PoseidonChip3> poseidon;
     std::vector<int64_t> instances;      // `make_public`
-    h2v_builder(unsigned p, unsigned lb) : fp(p, lb), dist(fp), vdb(fp) {}
+    h2v_builder(unsigned p, unsigned lb) : fp(p, lb), dist(fp), vdb(fp) {
+        // the trace of a real circuit has 10^7 - 10^8 cells: reserve address space once (untouched pages cost nothing) instead
+        // of re-copying gigabytes at every doubling of the vectors; H2V_TRACE_RESERVE = cells (0 = let them grow)
+        const char *e = getenv("H2V_TRACE_RESERVE");
+        const size_t cells = e ? (size_t)atoll(e) : ((size_t)1 << 26);
+        if (cells) {
+            try {
+                ctx.advice.reserve(cells);
+                ctx.selector.reserve(cells);
+                ctx.advice_eq.reserve(cells / 3);
+                ctx.constant_eq.reserve(cells / 3);
+                ctx.cells_to_lookup.reserve(cells / 6);
+            } catch (const std::bad_alloc &) {      // no address space to spare: grow on demand
+            }
+        }
+    }
 };
 
 struct h2v_layout {

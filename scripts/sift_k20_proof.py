@@ -56,6 +56,8 @@ def main():
     rnd = random.Random(20)
     inp = dict(query=[rnd.uniform(0.0, 2.0) for _ in range(args.dim)],
                database=[[rnd.uniform(0.0, 2.0) for _ in range(args.dim)] for _ in range(args.vectors)])
+    # the trace has about 2 200 cells per vector coordinate: reserve its address space once (h2v_builder_new reads this)
+    os.environ.setdefault("H2V_TRACE_RESERVE", str(int(args.vectors * args.dim * 2200)))
     t0 = time.perf_counter()
     builder = Z.GateThreadBuilder(args.bits)
     public = []
