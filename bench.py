@@ -38,7 +38,7 @@ FQ_MUL_MACS = 136
 SHOUP_MUL_MACS = 107         # twiddle product of the NTT (csrc/shoup.cuh): 99 IMAD.WIDE + 16 low-only IMAD at half the pipe time
 FQ_SQR_MACS = 108                 # the dedicated squaring: 28 + 8 products, 64 + 8 reduction
 MIXED_ADD_MACS = 8 * FQ_MUL_MACS + 2 * FQ_SQR_MACS      # what msm_accumulate executes per sorted entry (SURVEY counts 10 x 136 = 1360)
-ACC_DRAM_BYTES_PER_LAUNCH = 4.17e9   # msm_accumulate_kernel, 96 columns x 2^16, c = 15: 3.761 GB read + 0.411 GB written (ncu, r01)
+ACC_DRAM_BYTES_PER_LAUNCH = 4.13e9   # msm_accumulate_kernel, 96 columns x 2^16, c = 15: 3.709 GB read + 0.421 GB written (ncu --set full, final build of round 2)
 SYN_A, SYN_B = 0x9E3779B97F4A7C15 >> 2, 0x632BE59BD9B4E019 >> 2
 
 
@@ -297,7 +297,7 @@ def _main(args, real_stdout):
                      "frac_algorithmic": (achieved / (peak / 1e12)) if achieved else None,
                      "executed": executed,
                      "traffic": ACC_DRAM_BYTES_PER_LAUNCH if cols == COLS else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full of this command (profiles/r01_bench_launches_ncu.txt)",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full of this launch (profiles/r02_final2_ncu_summary.txt)",
                      "peak_probes": {"imad_wide_x_rows": peak_row / 1e12, "fq_product_chain_x136": peak_chain / 1e12,
                                      "r01_mad_wide_stream": peak_r01 / 1e12, "nominal_148sm_x_32_per_clk_at_1965mhz": 9.31},
                      "peak_source": "measured live, max of the probes (none of them is the kernel under test); MEASURED_PEAKS.json has no integer peak",
