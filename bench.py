@@ -984,7 +984,10 @@ def bench_ntt(h, torch, dev, peak):
             exec_macs = ((size // 2) * (L - 2) - (size // 8)) * SHOUP_MUL_MACS * cols + N * FQ_MUL_MACS * cols
         res[name] = {"gelem_per_s": cols * size / t / 1e9, "ms": t * 1e3, "cols": cols, "log_n": L,
                      "roofline": {"bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": hbm, "unit": "GB/s",
-                                  "frac": alg_bytes / t / 1e9 / hbm, "peak_source": hbm_src, "traffic": None},
+                                  "frac": alg_bytes / t / 1e9 / hbm, "peak_source": hbm_src,
+                                  # both passes of lagrange_to_coeff 2^16 x 64: 134.3 + 89.6 and 136.4 + 88.8 MB read + written
+                                  # (ncu --set full, profiles/r02_final2_ncu_summary.txt) against 537 MB algorithmic
+                                  "traffic": 4.49e8 if name == "lagrange_to_coeff" else None},
                      "roofline_int": {"achieved": alg_macs / t / 1e12, "peak": peak / 1e12, "unit": "T wide-MAC/s",
                                       "frac": alg_macs / t / peak, "frac_butterflies_only": bfly_macs / t / peak,
                                       "frac_executed": exec_macs / t / peak,
